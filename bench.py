@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- window-graphs/s, forward+backward, of the detector's message-passing path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2] as restated by SURVEY.md 8d "Config 3"): the real L-TOWN-A
+topology (N=661 nodes, 1532 directed edges, nnz 2193 with GCN self loops), B = 4096 windows of
+288 five-minute steps per GPU, hidden 64, all P = 764 pipes as classes, synthetic inputs
+(residual ~ N(0,1), seed 198 + rank; time features on a 5-minute grid from 2018-01-02),
+random-init weights (seed 42), train mode (dropout on), fp32.
+
+One STEP = one pass of the hot path over one batch of B windows:
+  * `value`  : GNN stack only -- node init -> 2 x (GCN conv, ReLU, dropout) -> pipe head + mean-pool
+               no-leak head -> cross-entropy -> backward to every non-GRU parameter and to the sensor
+               embeddings (reference detector.py:178-218 + autograd), with the
+               sensor embeddings h_s already resident in HBM.  At N > 1 the step also averages the
+               gradients with one flat-bucket NCCL all-reduce (data parallel over windows).
+  * `e2e`    : the call a user makes -- LeakDetector.forward(residual, tfeat) (includes the cuDNN GRU
+               encoder over L = 288), cross-entropy, backward -- with residual/tfeat copied from pinned
+               host memory and the loss read back to the host inside the timed region.
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+L2: every step writes and re-reads ~5 GB of activations (693 MB per (B,N,64) tensor), far above
+the 126 MB L2, so nothing survives between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent
+if str(REPO) not in sys.path:
+    sys.path.insert(0, str(REPO))
+GOLDEN = REPO / "tests" / "golden"
+
+METRIC = "window_graphs_per_sec_fwd_bwd"
+UNIT = "window-graphs/s"
+N_NODES, NNZ, HIDDEN, SENSORS = 661, 2193, 64, 29
+
+
+def time_features(n_steps: int, start_step: int = 0) -> np.ndarray:
+    """(n_steps, 9): hour sin/cos + day-of-week one-hot on a 5-minute grid from 2018-01-02 00:00
+    (Tuesday) -- the arithmetic of reference models/datasets.py:49-59."""
+    minutes = 5 * (start_step + np.arange(n_steps))
+    hour = ((minutes // 60) % 24).astype(np.float32) + ((minutes % 60).astype(np.float32) / 60.0)
+    angle = (2.0 * np.pi) * (hour / 24.0)
+    dow = (1 + minutes // 1440) % 7
+    return np.concatenate([np.sin(angle).astype(np.float32)[:, None], np.cos(angle).astype(np.float32)[:, None],
+                           np.eye(7, dtype=np.float32)[dow]], axis=1).astype(np.float32)
+
+
+def synthetic_batch(batch: int, l_det: int, n_classes: int, seed: int):
+    gen = torch.Generator().manual_seed(seed)
+    residual = torch.randn(batch, l_det, SENSORS, generator=gen)
+    tf = torch.from_numpy(time_features(l_det + batch))
+    idx = torch.arange(l_det).unsqueeze(0) + torch.arange(batch).unsqueeze(1)  # window b starts at step b
+    tfeat = tf[idx]
+    label = torch.randint(0, n_classes, (batch,), generator=gen)
+    return residual, tfeat, label
+
+
+def graph_fixture():
+    z = np.load(GOLDEN / "graph_LTA.npz")
+    return {k: z[k] for k in z.files}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def result(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.path:
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in Path(self.path).read_text().splitlines():
+                c = [t.strip() for t in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    sm.append(float(c[0]))
+                    mx.append(float(c[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, c[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def peaks() -> dict:
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": float(d["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference path; PyG is not installable here) on host cores
+# ----------------------------------------------------------------------------------------------
+def build_oracle(n_pipes: int):
+    from oracle.detector_oracle import OracleLeakDetector
+
+    g = graph_fixture()
+    torch.manual_seed(42)
+    m = OracleLeakDetector(len(g["node_names"]), torch.from_numpy(g["edge_index"]),
+                           torch.from_numpy(g["pipe_ends"][:n_pipes]), g["sensor_node_idx"].tolist(),
+                           HIDDEN, HIDDEN, 2, 0.1, True)
+    return m.train()
+
+
+def cpu_gnn_stack(sample_b: int, n_pipes: int, iters: int = 3) -> dict:
+    """cpu_baseline of the `value` scope: oracle GNN stack fwd+bwd from resident h_s."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = build_oracle(n_pipes)
+    gen = torch.Generator().manual_seed(198)
+    h_s = torch.randn(sample_b, SENSORS, HIDDEN, generator=gen).requires_grad_(True)
+    label = torch.randint(0, n_pipes + 1, (sample_b,), generator=gen)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        h_s.grad = None
+        torch.nn.functional.cross_entropy(m.gnn_stack(h_s), label).backward()
+
+    step()
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    return {"value": sample_b / t, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle (torch CPU restatement of reference detector.py:178-218 + PyG GCNConv) GNN stack "
+                      f"fwd+bwd, B={sample_b} windows of the same workload, median of {iters} after 1 warm-up, "
+                      f"{t * 1e3:.1f} ms/iter"}
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference path on the host cores (oracle port), full detector call
+    (GRU encoder + GNN stack + loss + backward) on a bounded sample of the workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    n_pipes = args.pipes
+    sample_b = args.cpu_sample
+    m = build_oracle(n_pipes)
+    residual, tfeat, label = synthetic_batch(sample_b, args.l_det, n_pipes + 1, 198)
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(m(residual, tfeat), label)
+        loss.backward()
+        return loss.item()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample_b * args.steps / dt
+    sample = (f"B={sample_b} windows x L={args.l_det} per step (bounded sample of the B={args.batch} workload), "
+              f"full detector forward + cross-entropy + backward, train mode")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "torch_geometric is not installable offline; this arm runs oracle/ (CPU restatement of the "
+                "reference LeakDetector + PyG GCNConv/global_mean_pool) on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int) -> dict:
+    return {
+        "workload": f"synthetic L-TOWN-A graph (N={N_NODES}, E=1532, nnz={NNZ}), {args.batch} windows x "
+                    f"{args.l_det} timesteps per GPU, hidden {HIDDEN}, P={args.pipes} pipe classes, "
+                    f"detector GNN stack fwd+bwd (BASELINE configs[2] per SURVEY 8d)",
+        "windows_per_gpu": args.batch, "global_windows": args.batch * world, "l_det": args.l_det,
+        "nodes": N_NODES, "nnz": NNZ, "hidden": HIDDEN, "pipes": args.pipes, "mode": "train (dropout 0.1)",
+        "parallelism": f"dp{world}" if world > 1 else "single",
+        "l2": "working set per step ~5 GB (693 MB per activation tensor) >> 126 MB L2; no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch.distributed as dist
+
+    from leak_det_gnn_b200 import instrument as inst
+    from leak_det_gnn_b200.models import LeakDetector
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    g = graph_fixture()
+    pipe_ids = [str(p) for p in g["pipe_ids"]][: args.pipes]
+    sensors = [str(s) for s in g["sensor_node_ids"]]
+    torch.manual_seed(42)
+    model = LeakDetector(GOLDEN / "L-TOWN-A.topo.inp", sensors, pipe_ids, sensor_hidden=HIDDEN, node_hidden=HIDDEN,
+                         gnn_layers=2, dropout=0.1, use_time=True).to(dev).train()
+    params = [p for p in model.parameters()]
+    stack_params = [p for n, p in model.named_parameters() if not n.startswith("sensor_encoder.")]
+
+    residual_h, tfeat_h, label_h = synthetic_batch(args.batch, args.l_det, args.pipes + 1, 198 + rank)
+    residual_h, tfeat_h = residual_h.pin_memory(), tfeat_h.pin_memory()
+    label = label_h.to(dev)
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+
+    # flat gradient bucket for the data-parallel all-reduce (one collective per step)
+    def allreduce_grads(ps):
+        if world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in ps if p.grad is not None])
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        off = 0
+        for p in ps:
+            if p.grad is not None:
+                n = p.grad.numel()
+                p.grad.copy_(flat[off:off + n].view_as(p.grad))
+                off += n
+
+    # ---- scope `value`: GNN stack with h_s resident ----
+    with torch.no_grad():
+        h_s = model.sensor_encoder(residual_h.to(dev), tfeat_h.to(dev))
+    h_s = h_s.detach().clone().requires_grad_(True)
+
+    def stack_step():
+        for p in stack_params:
+            p.grad = None
+        h_s.grad = None
+        loss = torch.nn.functional.cross_entropy(model.gnn_stack(h_s), label)
+        loss.backward()
+        allreduce_grads(stack_params)
+
+    def e2e_step():
+        for p in params:
+            p.grad = None
+        r = residual_h.to(dev, non_blocking=True)
+        t = tfeat_h.to(dev, non_blocking=True)
+        loss = torch.nn.functional.cross_entropy(model(r, t), label)
+        loss.backward()
+        allreduce_grads(params)
+        loss_h.copy_(loss.detach(), non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, timing_kernels=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        inst.reset(timing=timing_kernels)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, inst.launches, inst.summary()
+
+    with ClockSampler(local) as clk:
+        ms_stack, launches, ksum = timed(stack_step, args.steps, args.warmup, timing_kernels=True)
+    clocks = clk.result()
+    ms_e2e, _, _ = timed(e2e_step, max(1, min(args.steps, args.e2e_steps)), max(3, min(args.warmup, 3)))
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    value = args.batch * world * args.steps / (ms_stack * 1e-3)
+    e2e_value = args.batch * world * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant hand-written kernel: the aggregation (SpMM), timed live above ----
+    pk = peaks()
+    agg = [v for k, v in ksum.items() if k.startswith("spmm")]
+    alg_bytes = 2 * N_NODES * HIDDEN * 4 * args.batch  # read X once + write Y once
+    roof = None
+    if agg:
+        mean_ms = sum(v["total_ms"] for v in agg) / sum(v["count"] for v in agg)
+        achieved = alg_bytes / (mean_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "kernel": "spmm_staged_kernel (fwd + transpose)",
+                "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_ms,
+                "launches_timed": sum(v["count"] for v in agg), "peak_source": pk["source"],
+                "share_of_step": sum(v["total_ms"] for v in agg) / ms_stack}
+
+    if rank == 0:
+        cpu = cpu_gnn_stack(args.cpu_sample, args.pipes) if world == 1 and not args.no_cpu_baseline else None
+        h2d = residual_h.numel() * 4 + tfeat_h.numel() * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_stack / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
+                    "scope": "LeakDetector.forward(residual, tfeat) incl. cuDNN GRU over L + CE + backward, "
+                             "pinned-host inputs copied H2D and loss copied D2H every step"},
+            "gpu_launches": launches, "clocks": clocks,
+            "kernels": {k: {"count": v["count"], "mean_ms": round(v["mean_ms"], 4)} for k, v in ksum.items()},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=4096, help="windows per GPU")
+    ap.add_argument("--l-det", type=int, default=288)
+    ap.add_argument("--pipes", type=int, default=764)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample", type=int, default=32, help="windows per CPU-arm step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29541", __file__] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

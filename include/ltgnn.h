@@ -1,0 +1,87 @@
+/* ltgnn.h -- C ABI of libltgnn.so: sm_100a kernels for the pipe-graph message-passing path
+ * of Mateng0228/Leak-det-gnn's leak detector.
+ *
+ * The reference has NO native code and no FFI; the boundary it offers is the Python
+ * operator API of torch_geometric (GCNConv / global_mean_pool) called from
+ * models/detector.py:170-218.  Each entry point below names the reference lines it
+ * replaces.  INTEGRATION.md shows the ctypes binding and the 3-line reference patch.
+ *
+ * Conventions
+ *   - plain C types only; every function returns an ltgnn_status (0 = ok, <0 = error);
+ *     ltgnn_last_error() returns the thread's last message.  No exception crosses the ABI.
+ *   - the caller owns every tensor: device pointers to fp32, contiguous, row-major,
+ *     16-byte aligned.  The library never allocates activations; it owns only the device
+ *     copy of the graph held by a handle (immutable after create -> shareable by threads).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ *     asynchronous on that stream.  Safe to call from any host thread (torch's autograd
+ *     worker calls the *_bwd functions).
+ *   - activations are [B, N, D]: B independent windows over the SAME N-node graph
+ *     (the reference's B-times replicated disjoint union, detector.py:105-114, kept dense).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     LTGNN_E_CUDA.
+ */
+#ifndef LTGNN_H_
+#define LTGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTGNN_VERSION 100 /* major*10000 + minor*100 + patch : 0.1.0 */
+
+typedef enum ltgnn_status {
+    LTGNN_OK = 0,
+    LTGNN_E_ARG = -1,         /* null pointer / negative size / bad flag                 */
+    LTGNN_E_SHAPE = -2,       /* shape not supported by the kernels (see each function)  */
+    LTGNN_E_ALIGN = -3,       /* pointer not 16-byte aligned                             */
+    LTGNN_E_CUDA = -4,        /* CUDA runtime / driver error (message has the detail)    */
+    LTGNN_E_UNSUPPORTED = -5  /* device is not sm_100                                    */
+} ltgnn_status;
+
+typedef struct ltgnn_graph* ltgnn_graph_t;
+
+int ltgnn_version(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf; returns its length. */
+size_t ltgnn_last_error(char* buf, size_t cap);
+
+/* ---- graph handle -------------------------------------------------------------------
+ * Replaces the per-forward work of detector.py:195-196 (_batchify_edge_index) and of
+ * torch_geometric gcn_norm inside every GCNConv.forward (detector.py:199): the normalised
+ * adjacency A_hat of ONE graph is uploaded once, as CSR (row = message target) and as the
+ * CSR of A_hat^T ("CSC transpose", row = message source) used by every backward.
+ * Host arrays: rowptr int32[N+1], col int32[nnz], val fp32[nnz]; same for t_*.
+ * Row entries are consumed in array order (the summation order is part of the contract).
+ */
+int ltgnn_graph_create(int device, int32_t n_nodes, int32_t nnz,
+                       const int32_t* rowptr, const int32_t* col, const float* val,
+                       const int32_t* t_rowptr, const int32_t* t_col, const float* t_val,
+                       ltgnn_graph_t* out);
+int ltgnn_graph_destroy(ltgnn_graph_t g);
+int ltgnn_graph_info(ltgnn_graph_t g, int32_t* n_nodes, int32_t* nnz, int32_t* device, int32_t* sm_count);
+
+/* ---- aggregation (SpMM) ---------------------------------------------------------------
+ * Y[b,i,:] = sum_k val[k] * X[b, col[k], :]   over row i of A_hat (transpose=0)
+ *                                              or of A_hat^T        (transpose=1).
+ * transpose=0 replaces GCNConv.propagate (gather x_j, multiply by norm, scatter_add at the
+ * target; detector.py:199) for all B windows; transpose=1 is its adjoint, i.e. the
+ * backward of propagate wrt x, as a deterministic gather (no atomics).
+ * Each entry is one fp32 multiply then one fp32 add in row order -- bit-identical to a
+ * sequential scatter-add over PyG's edge list.
+ * D must be a multiple of 4.  X and Y must not alias.
+ * algo: LTGNN_SPMM_AUTO picks; the others force a kernel (testing / benchmarking).
+ */
+enum {
+    LTGNN_SPMM_AUTO = 0,
+    LTGNN_SPMM_STAGED = 1, /* whole-graph feature slices staged in shared memory by TMA    */
+    LTGNN_SPMM_GATHER = 2  /* neighbour rows gathered straight from L2 (any graph size)    */
+};
+int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTGNN_H_ */

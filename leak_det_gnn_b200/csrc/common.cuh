@@ -1,0 +1,141 @@
+// common.cuh -- shared host/device helpers for libltgnn (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "ltgnn.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libltgnn is written for sm_100a (Blackwell B200) only"
+#endif
+
+// ------------------------------------------------------------------------------------
+// host side: error reporting + graph handle
+// ------------------------------------------------------------------------------------
+namespace ltgnn {
+
+int fail(int code, const char* fmt, ...);  // records the thread-local message, returns code
+
+#define LTGNN_CUDA_TRY(expr)                                                                         \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return ::ltgnn::fail(LTGNN_E_CUDA, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(e__),   \
+                                 __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define LTGNN_REQUIRE(cond, code, ...)                      \
+    do {                                                    \
+        if (!(cond)) return ::ltgnn::fail(code, __VA_ARGS__); \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cuTensorMapEncodeTiled resolved through the runtime (no -lcuda link dependency)
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmapEncodeTiled tmap_encode_fn();
+
+}  // namespace ltgnn
+
+struct ltgnn_graph {
+    int device = 0;
+    int sm_count = 0;
+    int smem_optin = 0;  // max dynamic shared memory per block (opt-in), bytes
+    int32_t n = 0;
+    int32_t nnz = 0;
+    // index 0: A_hat (row = target), index 1: A_hat^T (row = source)
+    int32_t* rowptr[2] = {nullptr, nullptr};
+    int2* colval[2] = {nullptr, nullptr};  // .x = column, .y = fp32 bits of the weight
+    int32_t max_row_len[2] = {0, 0};
+};
+
+// ------------------------------------------------------------------------------------
+// device side: PTX wrappers (mbarrier, TMA, tcgen05)
+// ------------------------------------------------------------------------------------
+namespace ltgnn {
+namespace ptx {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make mbarrier.init visible to the async (TMA / tcgen05) proxy
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// order generic-proxy smem writes before async-proxy reads (tcgen05.mma / TMA store)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Blocking wait with a watchdog: a lost arrival traps (launch fails with an error) instead
+// of hanging the GPU.  ~2^31 cycles is > 1 s at any B200 clock; real waits are microseconds.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (1ll << 31)) __trap();
+    }
+}
+
+// 3-D tiled TMA load global -> shared, completion on an mbarrier (coordinates innermost first)
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+
+// streaming 128-bit global accesses (data touched once: keep it out of L1)
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+}  // namespace ptx
+}  // namespace ltgnn

@@ -1,0 +1,135 @@
+// graph.cu -- error plumbing and the immutable device-side graph handle.
+//
+// Replaces the per-forward index work of the reference: _batchify_edge_index
+// (models/detector.py:105-114,195-196) and PyG's gcn_norm inside each GCNConv.forward
+// (models/detector.py:199).  The handle is created once per model per device.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ltgnn {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+PFN_tmapEncodeTiled tmap_encode_fn() {
+    static PFN_tmapEncodeTiled fn = []() -> PFN_tmapEncodeTiled {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }();
+    return fn;
+}
+
+}  // namespace ltgnn
+
+using namespace ltgnn;
+
+extern "C" int ltgnn_version(void) { return LTGNN_VERSION; }
+
+extern "C" size_t ltgnn_last_error(char* buf, size_t cap) {
+    size_t n = strlen(g_err);
+    if (buf && cap) {
+        size_t m = n < cap - 1 ? n : cap - 1;
+        memcpy(buf, g_err, m);
+        buf[m] = 0;
+    }
+    return n;
+}
+
+static int check_csr(int32_t n, int32_t nnz, const int32_t* rowptr, const int32_t* col, const char* what,
+                     int32_t* max_len) {
+    LTGNN_REQUIRE(rowptr[0] == 0 && rowptr[n] == nnz, LTGNN_E_ARG, "%s: rowptr[0]=%d rowptr[N]=%d, expected 0 and %d",
+                  what, rowptr[0], rowptr[n], nnz);
+    int32_t ml = 0;
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t len = rowptr[i + 1] - rowptr[i];
+        LTGNN_REQUIRE(len >= 0, LTGNN_E_ARG, "%s: rowptr not monotone at row %d", what, i);
+        if (len > ml) ml = len;
+    }
+    for (int32_t k = 0; k < nnz; ++k)
+        LTGNN_REQUIRE(col[k] >= 0 && col[k] < n, LTGNN_E_ARG, "%s: col[%d]=%d out of range [0,%d)", what, k, col[k], n);
+    *max_len = ml;
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_graph_create(int device, int32_t n_nodes, int32_t nnz, const int32_t* rowptr, const int32_t* col,
+                                  const float* val, const int32_t* t_rowptr, const int32_t* t_col, const float* t_val,
+                                  ltgnn_graph_t* out) {
+    LTGNN_REQUIRE(out != nullptr, LTGNN_E_ARG, "graph_create: out is null");
+    *out = nullptr;
+    LTGNN_REQUIRE(rowptr && col && val && t_rowptr && t_col && t_val, LTGNN_E_ARG, "graph_create: null array");
+    LTGNN_REQUIRE(n_nodes > 0 && nnz >= 0, LTGNN_E_ARG, "graph_create: n_nodes=%d nnz=%d", n_nodes, nnz);
+
+    int ndev = 0;
+    LTGNN_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    LTGNN_REQUIRE(device >= 0 && device < ndev, LTGNN_E_ARG, "graph_create: device %d of %d", device, ndev);
+    cudaDeviceProp prop;
+    LTGNN_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    LTGNN_REQUIRE(prop.major == 10, LTGNN_E_UNSUPPORTED,
+                  "device %d is sm_%d%d; libltgnn carries sm_100a code only (no fallback path)", device, prop.major,
+                  prop.minor);
+
+    ltgnn_graph g;
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    g.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    g.n = n_nodes;
+    g.nnz = nnz;
+    int rc = check_csr(n_nodes, nnz, rowptr, col, "A_hat", &g.max_row_len[0]);
+    if (rc) return rc;
+    rc = check_csr(n_nodes, nnz, t_rowptr, t_col, "A_hat^T", &g.max_row_len[1]);
+    if (rc) return rc;
+
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    const int32_t* rp[2] = {rowptr, t_rowptr};
+    const int32_t* cc[2] = {col, t_col};
+    const float* vv[2] = {val, t_val};
+    std::vector<int2> packed(static_cast<size_t>(nnz) + 1);
+    for (int t = 0; t < 2; ++t) {
+        for (int32_t k = 0; k < nnz; ++k) {
+            int bits;
+            memcpy(&bits, &vv[t][k], 4);
+            packed[k] = make_int2(cc[t][k], bits);
+        }
+        LTGNN_CUDA_TRY(cudaMalloc(&g.rowptr[t], sizeof(int32_t) * (static_cast<size_t>(n_nodes) + 1)));
+        LTGNN_CUDA_TRY(cudaMalloc(&g.colval[t], sizeof(int2) * (static_cast<size_t>(nnz) + 1)));
+        LTGNN_CUDA_TRY(cudaMemcpy(g.rowptr[t], rp[t], sizeof(int32_t) * (static_cast<size_t>(n_nodes) + 1),
+                                  cudaMemcpyHostToDevice));
+        LTGNN_CUDA_TRY(cudaMemcpy(g.colval[t], packed.data(), sizeof(int2) * static_cast<size_t>(nnz),
+                                  cudaMemcpyHostToDevice));
+    }
+    *out = new ltgnn_graph(g);
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_graph_destroy(ltgnn_graph_t g) {
+    if (!g) return LTGNN_OK;
+    cudaSetDevice(g->device);
+    for (int t = 0; t < 2; ++t) {
+        cudaFree(g->rowptr[t]);
+        cudaFree(g->colval[t]);
+    }
+    delete g;
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_graph_info(ltgnn_graph_t g, int32_t* n_nodes, int32_t* nnz, int32_t* device, int32_t* sm_count) {
+    LTGNN_REQUIRE(g != nullptr, LTGNN_E_ARG, "graph_info: null handle");
+    if (n_nodes) *n_nodes = g->n;
+    if (nnz) *nnz = g->nnz;
+    if (device) *device = g->device;
+    if (sm_count) *sm_count = g->sm_count;
+    return LTGNN_OK;
+}

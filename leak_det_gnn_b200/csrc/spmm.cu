@@ -1,0 +1,272 @@
+// spmm.cu -- batched aggregation  Y[b] = A_hat * X[b]  (or A_hat^T * X[b]) over a fixed graph.
+//
+// Replaces torch_geometric's GCNConv.propagate as the reference runs it for the B-times
+// replicated graph (models/detector.py:199): index_select of (B*nnz, D) messages, multiply
+// by norm, scatter_add_ with atomics -- and its autograd adjoint (index_add_ with atomics).
+// Here: CSR gather for the forward, CSR-of-the-transpose gather for the backward, no atomics,
+// fixed summation order (edge order, self loop last), one fp32 mul + one fp32 add per entry
+// so the result is bit-identical to a sequential CPU scatter-add.
+//
+// Two kernels:
+//   STAGED  (graphs whose 32-feature slice fits shared memory, e.g. L-TOWN 661/785 nodes):
+//           persistent CTAs, one per SM.  Topology (rowptr + packed col/weight) is staged in
+//           shared memory once per CTA.  A work unit is (window b, 32-feature slice): the
+//           N x 128 B slice is pulled HBM -> smem by TMA (3-D tensor map, zero-filled rows
+//           past N) into a multi-stage ring by one producer thread; 16 consumer warps gather
+//           neighbour rows from smem with conflict-free LDS.128 (8 lanes = one 128 B row),
+//           and stream the result out with 128-bit stores.  HBM traffic = read X once +
+//           write Y once; every re-read of a neighbour row is a shared-memory hit.
+//   GATHER  (any size, e.g. the 100k-node network): one thread per float4 of output, neighbour
+//           rows read through L2; topology read through the read-only path.
+#include "common.cuh"
+
+using namespace ltgnn;
+using namespace ltgnn::ptx;
+
+namespace {
+
+constexpr int kSliceFloats = 32;  // 128 B of each node row per work unit
+constexpr int kSliceBytes = kSliceFloats * 4;
+constexpr int kConsumerWarps = 16;
+constexpr int kStagedThreads = (kConsumerWarps + 1) * 32;  // + 1 producer warp
+constexpr int kMaxStages = 4;
+constexpr int kRowsPerPass = kConsumerWarps * 4;  // 8 lanes per row, 4 rows per warp
+
+struct StagedParams {
+    const int32_t* rowptr;
+    const int2* colval;
+    float* Y;
+    int64_t n_units;  // B * n_slices
+    int32_t n, nnz, d4, n_slices;
+    int32_t box_rows, n_boxes, n_stages;
+    uint32_t stage_bytes, off_rowptr, off_colval, off_stage0;
+};
+
+__device__ __forceinline__ void fma2(float4& acc, float w, const float4& x) {
+    // two roundings per entry, as ATen's mul followed by index_add_ (see file header)
+    acc.x = __fadd_rn(acc.x, __fmul_rn(w, x.x));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(w, x.y));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(w, x.z));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(w, x.w));
+}
+
+__global__ void __launch_bounds__(kStagedThreads, 1)
+spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty = full + kMaxStages;
+    int32_t* s_rowptr = reinterpret_cast<int32_t*>(smem + p.off_rowptr);
+    int2* s_colval = reinterpret_cast<int2*>(smem + p.off_colval);
+    uint8_t* s_stage = smem + p.off_stage0;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int S = p.n_stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i <= p.n; i += kStagedThreads) s_rowptr[i] = __ldg(p.rowptr + i);
+    for (int i = threadIdx.x; i < p.nnz; i += kStagedThreads) s_colval[i] = __ldg(p.colval + i);
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer: one thread drives TMA ----------------
+        if (lane == 0) {
+            tma_prefetch_desc(&tmap);
+            int it = 0;
+            for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+                const int s = it % S;
+                const uint32_t ph = (it / S) & 1;
+                mbar_wait(empty + s, ph ^ 1);  // slot free (passes at once on first use)
+                mbar_arrive_expect_tx(full + s, p.stage_bytes);
+                const int64_t b = u / p.n_slices;
+                const int sl = static_cast<int>(u - b * p.n_slices);
+                uint8_t* dst = s_stage + static_cast<size_t>(s) * p.stage_bytes;
+                for (int bx = 0; bx < p.n_boxes; ++bx)
+                    tma_load_3d(dst + static_cast<size_t>(bx) * p.box_rows * kSliceBytes, &tmap, full + s,
+                                sl * kSliceFloats, bx * p.box_rows, static_cast<int>(b));
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: gather from smem, stream out ----------------
+    const int g = lane >> 3;  // row within the warp's group of 4
+    const int q = lane & 7;   // float4 within the 128 B slice
+    int it = 0;
+    for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        mbar_wait(full + s, ph);
+        const float4* xs = reinterpret_cast<const float4*>(s_stage + static_cast<size_t>(s) * p.stage_bytes) + q;
+        const int64_t b = u / p.n_slices;
+        const int sl = static_cast<int>(u - b * p.n_slices);
+        float4* y = reinterpret_cast<float4*>(p.Y) + (b * p.n) * p.d4 + sl * (kSliceFloats / 4) + q;
+
+        // two rows in flight per lane group for memory-level parallelism on the LDS chain
+        for (int r0 = warp * 4 + g; r0 < p.n; r0 += 2 * kRowsPerPass) {
+            const int r1 = r0 + kRowsPerPass;
+            int k0 = s_rowptr[r0];
+            const int e0 = s_rowptr[r0 + 1];
+            int k1 = 0, e1 = 0;
+            if (r1 < p.n) {
+                k1 = s_rowptr[r1];
+                e1 = s_rowptr[r1 + 1];
+            }
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 a1 = a0;
+            while (k0 < e0 && k1 < e1) {
+                const int2 c0 = s_colval[k0++];
+                const int2 c1 = s_colval[k1++];
+                const float4 x0 = xs[c0.x * 8];
+                const float4 x1 = xs[c1.x * 8];
+                fma2(a0, __int_as_float(c0.y), x0);
+                fma2(a1, __int_as_float(c1.y), x1);
+            }
+            for (; k0 < e0; ++k0) {
+                const int2 c0 = s_colval[k0];
+                fma2(a0, __int_as_float(c0.y), xs[c0.x * 8]);
+            }
+            for (; k1 < e1; ++k1) {
+                const int2 c1 = s_colval[k1];
+                fma2(a1, __int_as_float(c1.y), xs[c1.x * 8]);
+            }
+            stg_stream(y + static_cast<int64_t>(r0) * p.d4, a0);
+            if (r1 < p.n) stg_stream(y + static_cast<int64_t>(r1) * p.d4, a1);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+spmm_gather_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ colval,
+                   const float4* __restrict__ X, float4* __restrict__ Y, int32_t n, int32_t d4, int64_t total) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const int64_t row = e / d4;
+        const int c4 = static_cast<int>(e - row * d4);
+        const int64_t b = row / n;
+        const int r = static_cast<int>(row - b * n);
+        const float4* xb = X + b * n * d4 + c4;
+        int k = __ldg(rowptr + r);
+        const int end = __ldg(rowptr + r + 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; k + 1 < end; k += 2) {
+            const int2 c0 = __ldg(colval + k);
+            const int2 c1 = __ldg(colval + k + 1);
+            const float4 x0 = __ldg(xb + static_cast<int64_t>(c0.x) * d4);
+            const float4 x1 = __ldg(xb + static_cast<int64_t>(c1.x) * d4);
+            fma2(acc, __int_as_float(c0.y), x0);
+            fma2(acc, __int_as_float(c1.y), x1);
+        }
+        if (k < end) {
+            const int2 c0 = __ldg(colval + k);
+            fma2(acc, __int_as_float(c0.y), __ldg(xb + static_cast<int64_t>(c0.x) * d4));
+        }
+        stg_stream(Y + e, acc);
+    }
+}
+
+struct StagedPlan {
+    bool ok = false;
+    int box_rows = 0, n_boxes = 0, n_stages = 0;
+    uint32_t stage_bytes = 0, off_rowptr = 0, off_colval = 0, off_stage0 = 0, smem_bytes = 0;
+};
+
+inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
+
+StagedPlan plan_staged(const ltgnn_graph* g, int32_t D) {
+    StagedPlan pl;
+    if (D % kSliceFloats != 0) return pl;
+    pl.n_boxes = (g->n + 255) / 256;
+    pl.box_rows = (g->n + pl.n_boxes - 1) / pl.n_boxes;
+    pl.stage_bytes = static_cast<uint32_t>(pl.n_boxes) * pl.box_rows * kSliceBytes;
+    pl.off_rowptr = 128;  // after the barriers
+    pl.off_colval = align_up(pl.off_rowptr + 4u * (g->n + 1), 16);
+    pl.off_stage0 = align_up(pl.off_colval + 8u * g->nnz, 128);
+    const int64_t avail = static_cast<int64_t>(g->smem_optin) - 128 /*alignment slack*/ - pl.off_stage0;
+    if (avail < static_cast<int64_t>(pl.stage_bytes)) return pl;
+    pl.n_stages = static_cast<int>(avail / pl.stage_bytes);
+    if (pl.n_stages > kMaxStages) pl.n_stages = kMaxStages;
+    pl.smem_bytes = 128 + pl.off_stage0 + pl.n_stages * pl.stage_bytes;
+    pl.ok = true;
+    return pl;
+}
+
+}  // namespace
+
+extern "C" int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
+                          void* stream_) {
+    LTGNN_REQUIRE(g != nullptr, LTGNN_E_ARG, "spmm: null graph handle");
+    LTGNN_REQUIRE(transpose == 0 || transpose == 1, LTGNN_E_ARG, "spmm: transpose must be 0 or 1");
+    LTGNN_REQUIRE(B >= 0 && D > 0, LTGNN_E_ARG, "spmm: B=%lld D=%d", static_cast<long long>(B), D);
+    LTGNN_REQUIRE(D % 4 == 0, LTGNN_E_SHAPE, "spmm: D=%d must be a multiple of 4", D);
+    LTGNN_REQUIRE(B < (1ll << 31), LTGNN_E_SHAPE, "spmm: B too large");
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(X && Y, LTGNN_E_ARG, "spmm: null tensor");
+    LTGNN_REQUIRE(X != Y, LTGNN_E_ARG, "spmm: X and Y must not alias");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(Y), LTGNN_E_ALIGN, "spmm: X/Y must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    LTGNN_CUDA_TRY(cudaSetDevice(g->device));
+
+    const StagedPlan pl = plan_staged(g, D);
+    const bool want_staged = (algo == LTGNN_SPMM_STAGED) || (algo == LTGNN_SPMM_AUTO && pl.ok && pl.n_stages >= 2);
+    if (algo == LTGNN_SPMM_STAGED)
+        LTGNN_REQUIRE(pl.ok, LTGNN_E_SHAPE, "spmm: STAGED needs D %% 32 == 0 and a 32-feature slice of the graph (%d rows) "
+                      "to fit shared memory", g->n);
+
+    if (want_staged) {
+        PFN_tmapEncodeTiled enc = tmap_encode_fn();
+        LTGNN_REQUIRE(enc != nullptr, LTGNN_E_CUDA, "spmm: cuTensorMapEncodeTiled not available from the driver");
+        CUtensorMap tmap;
+        const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(g->n),
+                                    static_cast<cuuint64_t>(B)};
+        const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(D) * 4, static_cast<cuuint64_t>(g->n) * D * 4};
+        const cuuint32_t box[3] = {kSliceFloats, static_cast<cuuint32_t>(pl.box_rows), 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        LTGNN_REQUIRE(cr == CUDA_SUCCESS, LTGNN_E_CUDA, "spmm: cuTensorMapEncodeTiled failed with CUresult %d",
+                      static_cast<int>(cr));
+        StagedParams p;
+        p.rowptr = g->rowptr[transpose];
+        p.colval = g->colval[transpose];
+        p.Y = Y;
+        p.n = g->n;
+        p.nnz = g->nnz;
+        p.d4 = D / 4;
+        p.n_slices = D / kSliceFloats;
+        p.n_units = B * p.n_slices;
+        p.box_rows = pl.box_rows;
+        p.n_boxes = pl.n_boxes;
+        p.n_stages = pl.n_stages;
+        p.stage_bytes = pl.stage_bytes;
+        p.off_rowptr = pl.off_rowptr;
+        p.off_colval = pl.off_colval;
+        p.off_stage0 = pl.off_stage0;
+        LTGNN_CUDA_TRY(cudaFuncSetAttribute(spmm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(pl.smem_bytes)));
+        const int grid = static_cast<int>(p.n_units < g->sm_count ? p.n_units : g->sm_count);
+        spmm_staged_kernel<<<grid, kStagedThreads, pl.smem_bytes, stream>>>(tmap, p);
+        LTGNN_CUDA_TRY(cudaGetLastError());
+        return LTGNN_OK;
+    }
+
+    const int64_t total = B * g->n * (D / 4);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(g->sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    spmm_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
+        g->rowptr[transpose], g->colval[transpose], reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+        g->n, D / 4, total);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}

@@ -1,0 +1,148 @@
+"""torch.autograd bindings of the libltgnn kernels.
+
+Everything here runs on CUDA tensors only and calls straight into the C ABI with raw
+device pointers and the current torch stream.  Non-CUDA / non-fp32 inputs are a
+``ValueError``; a missing extension is a ``RuntimeError`` -- there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import instrument as _inst
+from . import lib as _lib
+from .graph import GCNCsr, build_gcn_csr
+
+__all__ = ["PipeGraph", "spmm", "aggregate"]
+
+
+def _ptr(a: np.ndarray) -> ctypes.c_void_p:
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class PipeGraph:
+    """The normalised adjacency of ONE pipe network, uploaded once per device.
+
+    Stands in for what the reference rebuilds on every forward: the B-times replicated
+    ``edge_index`` (models/detector.py:105-114,195-196) and PyG's ``gcn_norm`` inside each
+    ``GCNConv`` call (models/detector.py:199).
+    """
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int) -> None:
+        self.num_nodes = int(num_nodes)
+        self.csr: GCNCsr = build_gcn_csr(edge_index, self.num_nodes)
+        self._handles: Dict[int, ctypes.c_void_p] = {}
+        self._lock = threading.Lock()
+
+    @property
+    def nnz(self) -> int:
+        return self.csr.nnz
+
+    def handle(self, device: torch.device) -> ctypes.c_void_p:
+        if device.type != "cuda":
+            raise ValueError(f"PipeGraph needs a CUDA device, got {device}")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
+            with self._lock:
+                h = self._handles.get(idx)
+                if h is None:
+                    c = self.csr
+                    out = ctypes.c_void_p()
+                    L = _lib.load()
+                    _lib.check(L.ltgnn_graph_create(idx, c.num_nodes, c.nnz, _ptr(c.rowptr), _ptr(c.col), _ptr(c.val),
+                                                    _ptr(c.t_rowptr), _ptr(c.t_col), _ptr(c.t_val), ctypes.byref(out)))
+                    self._handles[idx] = h = out
+        return h
+
+    def __del__(self) -> None:  # best effort; the handle only owns ~40 KB of device memory
+        try:
+            L = _lib.load()
+            for h in self._handles.values():
+                L.ltgnn_graph_destroy(h)
+        except Exception:
+            pass
+
+
+def _check_act(x: torch.Tensor, name: str) -> None:
+    if not x.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (libltgnn has no CPU path), got {x.device}")
+    if x.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {x.dtype}")
+    if not x.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def _stream(x: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+
+
+def spmm(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, algo: int = _lib.SPMM_AUTO,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw (non-differentiable) batched aggregation.  x: (B, N, D) or (B*N, D) fp32 CUDA."""
+    _check_act(x, "x")
+    n = graph.num_nodes
+    d = x.shape[-1]
+    if x.numel() % (n * d) != 0:
+        raise ValueError(f"x with shape {tuple(x.shape)} is not a whole number of {n}-node graphs")
+    b = x.numel() // (n * d)
+    y = torch.empty_like(x) if out is None else out
+    if out is not None:
+        _check_act(out, "out")
+        if out.shape != x.shape:
+            raise ValueError("out shape mismatch")
+    L = _lib.load()
+    h = graph.handle(x.device)
+    tok = _inst.begin("spmm_bwd" if transpose else "spmm_fwd")
+    _lib.check(L.ltgnn_spmm(h, int(bool(transpose)), b, d, x.data_ptr(), y.data_ptr(), int(algo), _stream(x)))
+    _inst.end(tok)
+    return y
+
+
+class _Aggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, graph: PipeGraph) -> torch.Tensor:
+        ctx.graph = graph
+        return spmm(graph, x.contiguous(), transpose=False)
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        return spmm(ctx.graph, dy.contiguous(), transpose=True), None
+
+
+def aggregate(x: torch.Tensor, graph: PipeGraph) -> torch.Tensor:
+    """Differentiable ``A_hat @ x`` per window; backward is the CSC-transpose gather."""
+    return _Aggregate.apply(x, graph)
+
+
+def gcn_conv(x: torch.Tensor, graph: PipeGraph, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """``A_hat (x W^T) + b`` -- the operator ``torch_geometric.nn.GCNConv.forward`` computes
+    (reference call site models/detector.py:199).  x: (B, N, Din) or (B*N, Din)."""
+    n = graph.num_nodes
+    xw = torch.nn.functional.linear(x, weight)
+    y = aggregate(xw.reshape(-1, n, xw.shape[-1]), graph).view(*x.shape[:-1], xw.shape[-1])
+    return y if bias is None else y + bias
+
+
+def mean_pool(x: torch.Tensor) -> torch.Tensor:
+    """(B, N, D) -> (B, D): ``global_mean_pool`` for equal-sized graphs (detector.py:214-215)."""
+    return x.mean(dim=1)
+
+
+def node_init(h_s: torch.Tensor, sensor_idx: torch.Tensor, num_nodes: int, weight: torch.Tensor,
+              bias: torch.Tensor) -> torch.Tensor:
+    """Node-feature initialisation, reference models/detector.py:178-189:
+    ``relu(Linear([h0 | mask]))`` with ``h0`` = zeros except the sensor rows (= h_s) and ``mask`` the
+    sensor indicator.  Never materialises the zero-padded (B, N, d_s+1) tensor: a non-sensor row is
+    the batch-independent constant ``relu(bias)``; a sensor row is
+    ``relu(W[:, :d_s] h_s + W[:, d_s] + bias)``.  Returns (B, N, D)."""
+    b, s, ds = h_s.shape
+    base = torch.relu(bias)
+    x = base.expand(b, num_nodes, base.shape[0]).contiguous()
+    sens = torch.relu(torch.nn.functional.linear(h_s, weight[:, :ds], weight[:, ds] + bias))
+    x[:, sensor_idx, :] = sens
+    return x

@@ -1,0 +1,52 @@
+"""The C-ABI shared library: loads, exports exactly what include/ltgnn.h declares, and fails
+loudly (never falls back) when there is no CUDA device.  No compute calls here."""
+import ctypes
+import re
+
+import pytest
+import torch
+
+from conftest import REPO
+from leak_det_gnn_b200 import lib as L
+
+
+def _declared():
+    text = (REPO / "include" / "ltgnn.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ltgnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert "ltgnn_spmm" in names and "ltgnn_graph_create" in names
+    lib = L.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in ltgnn.h but not exported"
+    assert sorted(L.SIGNATURES) == names, "lib.SIGNATURES must mirror ltgnn.h"
+    assert lib.ltgnn_version() == 100
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package never imports the oracle."""
+    for p in (REPO / "leak_det_gnn_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu(graph_golden):
+    from leak_det_gnn_b200.ops import PipeGraph, spmm
+    g0 = graph_golden("LTA")
+    pg = PipeGraph(torch.from_numpy(g0["edge_index"]), 661)
+    with pytest.raises(ValueError, match="CUDA"):
+        spmm(pg, torch.zeros(1, 661, 64))
+    import numpy as np
+    c = pg.csr
+    out = ctypes.c_void_p()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = L.load().ltgnn_graph_create(0, c.num_nodes, c.nnz, p(c.rowptr), p(c.col), p(c.val), p(c.t_rowptr),
+                                     p(c.t_col), p(c.t_val), ctypes.byref(out))
+    assert rc == -4 and not out.value
+    assert "cuda" in L.last_error().lower()
+    with pytest.raises(L.LtgnnError):
+        L.check(rc)
