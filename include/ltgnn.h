@@ -81,6 +81,15 @@ enum {
 int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
                void* stream);
 
+/* ---- dense row-wise layer on tensor cores --------------------------------------------------
+ * Y[M,N] = act(X[M,K] W[N,K]^T + bias[N])  (bias may be NULL; relu = 0/1), W in torch.nn.Linear layout.
+ * tcgen05 3xTF32 with fp32 accumulation: fp32-faithful (error ~1e-6 relative to |x||w|), the
+ * reference runs these in full fp32 (GCNConv.lin detector.py:199; NoLeakHead detector.py:94-99).
+ * K multiple of 32 (<= 256), N multiple of 16 (<= 256).
+ */
+int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const float* X, const float* W, const float* bias,
+                 int relu, float* Y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,116 @@
+// umma.cuh -- tcgen05 (5th-gen tensor core) building blocks for fp32-faithful GEMM tiles.
+//
+// The reference computes every Linear in full fp32 (torch's allow_tf32 default is off and it is
+// never changed).  tcgen05 has no fp32 kind, so the product uses the error-compensated
+// 3xTF32 scheme: each fp32 operand is split a = hi + lo with hi = rna_tf32(a), lo = rna_tf32(a - hi)
+// and   a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b   accumulated in fp32 in tensor memory.
+// The dropped lo*lo term is <= 2^-22 |a||b|, i.e. at fp32 rounding level.
+//
+// Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B layout:
+//   atom  = 8 rows x 128 B (32 fp32 of K); 16-byte chunk c of row r is stored at chunk c ^ (r & 7);
+//   a tile of R rows x K fp32 = K/32 "k-atoms" blocks of R*128 B each, rows grouped by 8 (1024 B).
+// One tcgen05.mma.kind::tf32 consumes K = 8 fp32 (32 B) per operand row.
+#pragma once
+
+#include "common.cuh"
+
+namespace ltgnn {
+namespace umma {
+
+using ptx::smem_u32;
+
+// ---- fp32 -> (hi, lo) TF32 split ------------------------------------------------------------
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y);
+    lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+}
+
+// byte offset of 16-byte chunk `c16` (0..K/4-1) of row `r` in an R-row K-major SW128 tile
+__device__ __forceinline__ uint32_t sw128_offset(int r, int c16, int rows) {
+    const int katom = c16 >> 3;
+    const int c = c16 & 7;
+    return static_cast<uint32_t>(katom * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// ---- descriptors --------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4)  // start address   [0,14)
+           | (1ull << 16)                                    // LBO (unused for swizzled K-major)
+           | (64ull << 32)                                   // SBO = 1024 B >> 4 [32,46)
+           | (1ull << 46)                                    // descriptor version (sm_100)
+           | (2ull << 61);                                   // SWIZZLE_128B
+}
+// instruction descriptor: D fp32, A/B TF32, both K-major, M x N tile
+__host__ __device__ constexpr uint32_t idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ---- tensor memory -------------------------------------------------------------------------
+// whole warp: allocate `cols` (power of two >= 32) TMEM columns, base address written to *dst_smem
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one K=8 step, issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 3xTF32 product of one (rows_a x 32) by (rows_b x 32) k-atom: 4 K-steps x 3 MMAs.
+// a_hi/a_lo/b_hi/b_lo: shared addresses of the k-atom blocks; first==1 overwrites D.
+__device__ __forceinline__ void mma_katom_3x(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                             uint32_t b_lo, uint32_t idesc, bool first) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t ah = smem_desc_sw128(a_hi + k * 32), al = smem_desc_sw128(a_lo + k * 32);
+        const uint64_t bh = smem_desc_sw128(b_hi + k * 32), bl = smem_desc_sw128(b_lo + k * 32);
+        mma_tf32(d_tmem, al, bh, idesc, (first && k == 0) ? 0u : 1u);  // small terms first
+        mma_tf32(d_tmem, ah, bl, idesc, 1u);
+        mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    }
+}
+
+// warp-collective: 16 consecutive fp32 columns of this thread's TMEM lane -> registers.
+// Load and wait sit in ONE asm statement so no use of the registers can be scheduled in between.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace umma
+}  // namespace ltgnn

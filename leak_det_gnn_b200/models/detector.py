@@ -37,6 +37,7 @@ class SharedSensorGRUEncoder(nn.Module):
         super().__init__()
         self.use_time = bool(use_time)
         self.hidden_size = int(hidden_size)
+        self.max_seqs_per_call = 8192
         self.gru = nn.GRU(input_size=1 + (time_dim if self.use_time else 0), hidden_size=self.hidden_size,
                           num_layers=num_layers, batch_first=True, dropout=dropout if num_layers > 1 else 0.0)
 
@@ -47,8 +48,13 @@ class SharedSensorGRUEncoder(nn.Module):
             if tfeat is None:
                 raise ValueError("tfeat required when use_time=True")
             seq = torch.cat([seq, tfeat.unsqueeze(1).expand(b, s, l, tfeat.shape[-1]).reshape(b * s, l, -1)], dim=-1)
-        out, _ = self.gru(seq)
-        return out[:, -1, :].view(b, s, -1)
+        # cuDNN's RNN workspace + reserve grow with (sequences x steps); at B*S ~ 1e5 sequences of 288
+        # steps one call asks for > 150 GB.  Sequences are independent, so run them in slabs.
+        if seq.shape[0] <= self.max_seqs_per_call:
+            out, _ = self.gru(seq)
+            return out[:, -1, :].view(b, s, -1)
+        last = [self.gru(chunk)[0][:, -1, :] for chunk in seq.split(self.max_seqs_per_call, dim=0)]
+        return torch.cat(last, dim=0).view(b, s, -1)
 
 
 class EdgeHead(nn.Module):

@@ -146,3 +146,20 @@ def node_init(h_s: torch.Tensor, sensor_idx: torch.Tensor, num_nodes: int, weigh
     sens = torch.relu(torch.nn.functional.linear(h_s, weight[:, :ds], weight[:, ds] + bias))
     x[:, sensor_idx, :] = sens
     return x
+
+
+def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """Raw (non-differentiable) ``act(x @ weight.T + bias)`` on tcgen05 tensor cores (3xTF32)."""
+    _check_act(x, "x")
+    _check_act(weight, "weight")
+    k = x.shape[-1]
+    n = weight.shape[0]
+    m = x.numel() // k
+    y = torch.empty(*x.shape[:-1], n, device=x.device, dtype=torch.float32)
+    L = _lib.load()
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    tok = _inst.begin("linear_tc")
+    _lib.check(L.ltgnn_linear(idx, m, k, n, x.data_ptr(), weight.data_ptr(),
+                              None if bias is None else bias.data_ptr(), int(relu), y.data_ptr(), _stream(x)))
+    _inst.end(tok)
+    return y

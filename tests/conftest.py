@@ -17,6 +17,12 @@ REFERENCE_INP = {
 }
 
 
+# fp32 parity: cuDNN's RNN may otherwise run TF32 tensor-core math (torch default allow_tf32=True for
+# cuDNN), which alone costs ~1e-3 on the GRU gradients; torch.matmul already defaults to full fp32.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

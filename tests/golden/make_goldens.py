@@ -143,9 +143,19 @@ def make_detector_golden(ref_detector, case: str, net: str, pipe_ids, sensors, b
     tfeat = torch.from_numpy(np.stack([tf[i:i + l_det] for i in range(batch)]))
     label = torch.randint(0, len(pipe_ids) + 1, (batch,), generator=gen)
 
+    # capture the sensor embeddings that enter the message-passing path, and the gradient that leaves it
+    cap = {}
+
+    def _hook(_mod, _inp, out):
+        out.retain_grad()
+        cap["h_s"] = out
+
+    handle = model.sensor_encoder.register_forward_hook(_hook)
     logits = model(residual, tfeat)
     loss = torch.nn.functional.cross_entropy(logits, label)
     loss.backward()
+    handle.remove()
+    h_s, grad_h_s = cap["h_s"].detach().clone(), cap["h_s"].grad.detach().clone()
     state = {k: v.detach().clone() for k, v in model.state_dict().items()}
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
     assert len(state) == 4 + 2 + 2 * gnn_layers + 8, len(state)
@@ -159,7 +169,27 @@ def make_detector_golden(ref_detector, case: str, net: str, pipe_ids, sensors, b
     bit_equal = bool(torch.equal(o_logits, logits))
     assert bit_equal, (o_logits - logits).abs().max()
 
+    # fp64 run of the same algorithm: the truth both fp32 implementations are measured against
+    orc64 = OracleLeakDetector(len(model.node_names), model.edge_index_single, model.pipe_ends,
+                               model.sensor_node_idx, sensor_hidden, node_hidden, gnn_layers, 0.1, True).double()
+    orc64.load_state_dict({k: v.double() for k, v in state.items()}, strict=True)
+    orc64.eval()
+    logits64 = orc64(residual.double(), tfeat.double())
+    loss64 = torch.nn.functional.cross_entropy(logits64, label)
+    loss64.backward()
+    grads64 = {k: p.grad.detach().clone() for k, p in orc64.named_parameters()}
+    # fp64 truth of the stack alone, driven by the fp32 embeddings (what the GPU stack is handed)
+    orc64.zero_grad()
+    hs64 = h_s.double().requires_grad_(True)
+    stack_logits64 = orc64.gnn_stack(hs64)
+    torch.nn.functional.cross_entropy(stack_logits64, label).backward()
+    stack_grads64 = {k: p.grad.detach().clone() for k, p in orc64.named_parameters() if p.grad is not None}
+    stack_grad_h_s64 = hs64.grad.detach().clone()
+
     torch.save({
+        "logits64": logits64.detach(), "loss64": loss64.detach(), "grads64": grads64,
+        "h_s": h_s, "grad_h_s": grad_h_s, "stack_logits64": stack_logits64.detach(),
+        "stack_grads64": stack_grads64, "stack_grad_h_s64": stack_grad_h_s64,
         "case": case, "net": net, "pipe_ids": list(pipe_ids), "sensor_node_ids": list(sensors),
         "hparams": dict(sensor_hidden=sensor_hidden, node_hidden=node_hidden, gnn_layers=gnn_layers, dropout=0.1,
                         use_time=True),
