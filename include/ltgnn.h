@@ -82,13 +82,18 @@ int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float
                void* stream);
 
 /* ---- dense row-wise layer on tensor cores --------------------------------------------------
- * Y[M,N] = act(X[M,K] W[N,K]^T + bias[N])  (bias may be NULL; relu = 0/1), W in torch.nn.Linear layout.
- * tcgen05 3xTF32 with fp32 accumulation: fp32-faithful (error ~1e-6 relative to |x||w|), the
- * reference runs these in full fp32 (GCNConv.lin detector.py:199; NoLeakHead detector.py:94-99).
- * K multiple of 32 (<= 256), N multiple of 16 (<= 256).
+ * Y[M,N] = gate( act( X[M,K] op(W) + bias[N] ) )
+ *   op(W) = W^T with W [N,K] row-major (w_transposed = 0, torch.nn.Linear layout)
+ *         = W   with W [K,N] row-major (w_transposed = 1; the input-gradient GEMM dX = dY W)
+ *   bias may be NULL; relu = 0/1;
+ *   gate (NULL or [M,N]): Y *= gate > 0 ? gate_scale : 0 -- the backward of an upstream
+ *   ReLU(+inverted dropout) whose OUTPUT is `gate` (detector.py:189-190,200-201).
+ * tcgen05 3xTF32 with fp32 accumulation in tensor memory: fp32-faithful (the reference runs these in
+ * full fp32: GCNConv.lin detector.py:199; NoLeakHead detector.py:94-99).
+ * K multiple of 32 (<= 256), N multiple of 16 (<= 256), operands must fit shared memory.
  */
-int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const float* X, const float* W, const float* bias,
-                 int relu, float* Y, void* stream);
+int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const float* X, const float* W, int w_transposed,
+                 const float* bias, int relu, const float* gate, float gate_scale, float* Y, void* stream);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,17 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_tmapEncodeTiled tmap_encode_fn();
 
+// per-device facts, queried once (cudaGetDeviceProperties costs ~1 ms per call)
+struct DeviceInfo {
+    bool ok = false;
+    int cc_major = 0, cc_minor = 0;
+    int sm_count = 0;
+    int smem_optin = 0;   // max dynamic shared memory per block
+    int smem_per_sm = 0;
+};
+// returns nullptr (and records the error) if the device cannot be queried
+const DeviceInfo* device_info(int device);
+
 }  // namespace ltgnn
 
 struct ltgnn_graph {

@@ -4,6 +4,7 @@
 // (models/detector.py:105-114,195-196) and PyG's gcn_norm inside each GCNConv.forward
 // (models/detector.py:199).  The handle is created once per model per device.
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -30,6 +31,40 @@ PFN_tmapEncodeTiled tmap_encode_fn() {
         return reinterpret_cast<PFN_tmapEncodeTiled>(p);
     }();
     return fn;
+}
+
+const DeviceInfo* device_info(int device) {
+    constexpr int kMax = 64;
+    static DeviceInfo table[kMax];
+    static std::mutex mu;
+    if (device < 0 || device >= kMax) {
+        fail(LTGNN_E_ARG, "device ordinal %d out of range", device);
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    DeviceInfo& d = table[device];
+    if (!d.ok) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || device >= ndev) {
+            fail(LTGNN_E_CUDA, "no usable CUDA device %d (%s; %d devices visible)", device,
+                 e == cudaSuccess ? "ordinal out of range" : cudaGetErrorString(e), ndev);
+            return nullptr;
+        }
+        cudaDeviceProp prop;
+        e = cudaGetDeviceProperties(&prop, device);
+        if (e != cudaSuccess) {
+            fail(LTGNN_E_CUDA, "cudaGetDeviceProperties(%d) -> %s", device, cudaGetErrorString(e));
+            return nullptr;
+        }
+        d.cc_major = prop.major;
+        d.cc_minor = prop.minor;
+        d.sm_count = prop.multiProcessorCount;
+        d.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+        d.smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
+        d.ok = true;
+    }
+    return &d;
 }
 
 }  // namespace ltgnn
@@ -72,19 +107,16 @@ extern "C" int ltgnn_graph_create(int device, int32_t n_nodes, int32_t nnz, cons
     LTGNN_REQUIRE(rowptr && col && val && t_rowptr && t_col && t_val, LTGNN_E_ARG, "graph_create: null array");
     LTGNN_REQUIRE(n_nodes > 0 && nnz >= 0, LTGNN_E_ARG, "graph_create: n_nodes=%d nnz=%d", n_nodes, nnz);
 
-    int ndev = 0;
-    LTGNN_CUDA_TRY(cudaGetDeviceCount(&ndev));
-    LTGNN_REQUIRE(device >= 0 && device < ndev, LTGNN_E_ARG, "graph_create: device %d of %d", device, ndev);
-    cudaDeviceProp prop;
-    LTGNN_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    LTGNN_REQUIRE(prop.major == 10, LTGNN_E_UNSUPPORTED,
-                  "device %d is sm_%d%d; libltgnn carries sm_100a code only (no fallback path)", device, prop.major,
-                  prop.minor);
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED,
+                  "device %d is sm_%d%d; libltgnn carries sm_100a code only (no fallback path)", device, di->cc_major,
+                  di->cc_minor);
 
     ltgnn_graph g;
     g.device = device;
-    g.sm_count = prop.multiProcessorCount;
-    g.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    g.sm_count = di->sm_count;
+    g.smem_optin = di->smem_optin;
     g.n = n_nodes;
     g.nnz = nnz;
     int rc = check_csr(n_nodes, nnz, rowptr, col, "A_hat", &g.max_row_len[0]);

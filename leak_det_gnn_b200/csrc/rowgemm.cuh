@@ -1,0 +1,229 @@
+// rowgemm.cuh -- warp-specialised, pipelined row-tile GEMM skeleton on tcgen05 (3xTF32).
+//
+//   D[128 x N] = A_tile[128 x K] * B[N x K]^T      per 128-row tile, persistent CTAs, one per SM
+//
+//   warps 0-7  LOADERS   produce the A tile: a `Loader` functor returns 4 consecutive fp32 of a row
+//                        (a plain coalesced global load, a neighbour aggregation, a pipe-end gather...);
+//                        values are split into TF32 hi/lo and stored K-major SWIZZLE_128B in a 2-stage ring
+//   warp  8    MMA       one elected lane issues the tcgen05.mma chain into one of two TMEM accumulators and
+//                        commits to the "stage free" and "accumulator full" mbarriers
+//   warps 9-12 EPILOGUE  tcgen05.ld their 32 TMEM lanes (lane = tile row), hand 16 columns at a time to an
+//                        `Epilogue` functor (bias, activation, masks, stores), release the accumulator
+//
+// B (the weight, N x K) is split once per CTA and stays resident in shared memory.
+// All hand-offs are mbarriers; no __syncthreads after the prologue.
+#pragma once
+
+#include "umma.cuh"
+
+namespace ltgnn {
+namespace rowgemm {
+
+using namespace ltgnn::ptx;
+using namespace ltgnn::umma;
+
+constexpr int kTileM = 128;
+constexpr int kLoaderWarps = 8;
+constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kMmaWarp = kLoaderWarps;
+constexpr int kEpiWarp0 = kMmaWarp + 1;
+constexpr int kEpiWarps = 4;
+constexpr int kThreads = (kLoaderWarps + 1 + kEpiWarps) * 32;
+constexpr int kStages = 2;
+
+// the A ring moves "k-groups" of KG = 64 (or 32) columns of K, so a stage is at most 64 KB whatever K is
+__host__ __device__ inline int k_group(int K) { return (K % 64 == 0) ? 64 : 32; }
+__host__ __device__ inline uint32_t a_stage_bytes(int K) { return 2u * kTileM * k_group(K) * 4; }
+__host__ __device__ inline uint32_t b_bytes(int K, int N) { return 2u * N * K * 4; }
+__host__ inline size_t smem_bytes(int K, int N) { return 1024 + kStages * a_stage_bytes(K) + b_bytes(K, N); }
+__host__ inline uint32_t tmem_cols_for(int N) {
+    uint32_t c = 32;
+    while (c < 2u * N) c <<= 1;
+    return c;
+}
+
+// Fill the resident B operand.  W is [N x K] row-major (w_transposed = 0, torch.nn.Linear layout) or
+// [K x N] row-major (w_transposed = 1: computes A * W instead of A * W^T).
+__device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const float* __restrict__ W, int K, int N, int w_transposed,
+                              int tid, int nthreads) {
+    if (!w_transposed) {
+        const int k4 = K >> 2;
+        for (int i = tid; i < N * k4; i += nthreads) {
+            const int r = i / k4, c = i - r * k4;
+            float4 hi, lo;
+            split4(__ldg(reinterpret_cast<const float4*>(W) + i), hi, lo);
+            const uint32_t off = sw128_offset(r, c, N);
+            *reinterpret_cast<float4*>(b_hi + off) = hi;
+            *reinterpret_cast<float4*>(b_lo + off) = lo;
+        }
+    } else {
+        for (int i = tid; i < N * K; i += nthreads) {
+            const int k = i / N, n = i - k * N;  // coalesced read of W[k][n]
+            const float w = __ldg(W + i);
+            const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+            const uint32_t off = sw128_offset(n, k >> 2, N) + (k & 3) * 4;
+            *reinterpret_cast<float*>(b_hi + off) = hi;
+            *reinterpret_cast<float*>(b_lo + off) = lo;
+        }
+    }
+}
+
+template <class Loader, class Epilogue>
+__global__ void __launch_bounds__(kThreads, 1)
+rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __restrict__ W, int w_transposed, int64_t M,
+               int K, int N, uint32_t tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int KG = k_group(K);
+    const int n_kg = K / KG;
+    const uint32_t a_half = kTileM * KG * 4;  // hi block, then lo block
+    uint8_t* b_hi = smem + kStages * 2 * a_half;
+    uint8_t* b_lo = b_hi + N * K * 4;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bar_full[s], kLoaderWarps);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tfull[a], 1);
+            mbar_init(&bar_tempty[a], kEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    fill_b(b_hi, b_lo, W, K, N, w_transposed, tid, kThreads);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+
+    if (warp < kLoaderWarps) {
+        // ------------------------------- loaders -------------------------------
+        const int g4 = KG >> 2;  // 16-byte chunks per row per k-group
+        const int items = kTileM * g4;
+        int it = 0;  // counts (tile, k-group) stages
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row0 = tile * kTileM;
+            for (int kg = 0; kg < n_kg; ++kg, ++it) {
+                const int s = it % kStages;
+                const uint32_t ph = (it / kStages) & 1;
+                mbar_wait(&bar_empty[s], ph ^ 1);
+                uint8_t* a_hi = smem + s * 2 * a_half;
+                uint8_t* a_lo = a_hi + a_half;
+                // all of this thread's loads are issued before the first is consumed (8 x 16 B in flight
+                // per thread, 32 KB per SM) -- the loads, not the math, bound this kernel
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = tid + j * kLoaderThreads;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < items) {
+                        const int r = idx / g4, c = idx - r * g4;
+                        if (row0 + r < M) v[j] = loader(row0 + r, kg * g4 + c);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = tid + j * kLoaderThreads;
+                    if (idx < items) {
+                        const int r = idx / g4, c = idx - r * g4;
+                        float4 hi, lo;
+                        split4(v[j], hi, lo);
+                        const uint32_t off = sw128_offset(r, c, kTileM);
+                        *reinterpret_cast<float4*>(a_hi + off) = hi;
+                        *reinterpret_cast<float4*>(a_lo + off) = lo;
+                    }
+                }
+                fence_proxy_async_smem();  // this thread's smem writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[s]);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ------------------------------- MMA issuer -------------------------------
+        if (lane == 0) {
+            const uint32_t idesc = idesc_tf32(kTileM, N);
+            const int katoms_per_group = KG >> 5;
+            int it = 0, t = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+                const int a = t & 1;
+                const uint32_t pha = (t >> 1) & 1;
+                mbar_wait(&bar_tempty[a], pha ^ 1);  // epilogue drained this accumulator
+                const uint32_t d = tmem_base + a * N;
+                for (int kg = 0; kg < n_kg; ++kg, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1;
+                    mbar_wait(&bar_full[s], ph);  // operands landed
+                    fence_after_sync();
+                    const uint32_t a_hi = smem_u32(smem + s * 2 * a_half), a_lo = a_hi + a_half;
+                    for (int ka = 0; ka < katoms_per_group; ++ka) {
+                        const int kb = kg * katoms_per_group + ka;  // k-atom index into the resident B
+                        mma_katom_3x(d, a_hi + ka * kTileM * 128, a_lo + ka * kTileM * 128,
+                                     smem_u32(b_hi) + kb * N * 128, smem_u32(b_lo) + kb * N * 128, idesc, kb == 0);
+                    }
+                    commit(&bar_empty[s]);  // smem stage reusable once these MMAs retire
+                }
+                commit(&bar_tfull[a]);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ------------------------------- epilogue -------------------------------
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        int t = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const int a = t & 1;
+            const uint32_t pha = (t >> 1) & 1;
+            mbar_wait(&bar_tfull[a], pha);
+            fence_after_sync();
+            const uint32_t taddr = tmem_base + a * N + (static_cast<uint32_t>(q * 32) << 16);
+            const int64_t row = tile * kTileM + q * 32 + lane;
+            for (int c0 = 0; c0 < N; c0 += 16) {
+                float v[16];
+                tmem_ld16(taddr + c0, v);
+                if (row < M) epilogue(row, c0, v);
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[a]);
+        }
+    }
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// host-side launch helper: validates shapes against the device, sets the smem attribute, launches
+template <class Loader, class Epilogue>
+int launch(int device, const Loader& loader, const Epilogue& epilogue, const float* W, int w_transposed, int64_t M, int K,
+           int N, cudaStream_t stream, const char* who) {
+    LTGNN_REQUIRE(K % 32 == 0 && K > 0 && K <= 256, LTGNN_E_SHAPE, "%s: K=%d must be a multiple of 32, <= 256", who, K);
+    LTGNN_REQUIRE(N % 16 == 0 && N > 0 && N <= 256, LTGNN_E_SHAPE, "%s: N=%d must be a multiple of 16, <= 256", who, N);
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
+                  di->cc_minor);
+    const size_t smem = smem_bytes(K, N);
+    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE,
+                  "%s: K=%d N=%d needs %zu B of shared memory (limit %d)", who, K, N, smem, di->smem_optin);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    auto kern = rowgemm_kernel<Loader, Epilogue>;
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles = (M + kTileM - 1) / kTileM;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    kern<<<grid, kThreads, smem, stream>>>(loader, epilogue, W, w_transposed, M, K, N, tmem_cols_for(N));
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+}  // namespace rowgemm
+}  // namespace ltgnn

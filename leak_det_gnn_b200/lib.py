@@ -27,8 +27,8 @@ SIGNATURES = {
     "ltgnn_graph_destroy": (c_int, [c_void_p]),
     "ltgnn_graph_info": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "ltgnn_spmm": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_int, c_void_p]),
-    "ltgnn_linear": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                             c_void_p]),
+    "ltgnn_linear": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                             c_float, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -148,18 +148,30 @@ def node_init(h_s: torch.Tensor, sensor_idx: torch.Tensor, num_nodes: int, weigh
     return x
 
 
-def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
-    """Raw (non-differentiable) ``act(x @ weight.T + bias)`` on tcgen05 tensor cores (3xTF32)."""
+def _dev_index(x: torch.Tensor) -> int:
+    return x.device.index if x.device.index is not None else torch.cuda.current_device()
+
+
+def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
+              transposed: bool = False, gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0) -> torch.Tensor:
+    """Raw (non-differentiable) tensor-core dense layer (tcgen05, 3xTF32):
+    ``gate(act(x @ weight.T + bias))``, or ``x @ weight`` when ``transposed``; see ltgnn_linear."""
     _check_act(x, "x")
     _check_act(weight, "weight")
     k = x.shape[-1]
-    n = weight.shape[0]
+    n = weight.shape[1] if transposed else weight.shape[0]
+    if (weight.shape[0] if transposed else weight.shape[1]) != k:
+        raise ValueError(f"weight {tuple(weight.shape)} does not match x[..., {k}] (transposed={transposed})")
     m = x.numel() // k
     y = torch.empty(*x.shape[:-1], n, device=x.device, dtype=torch.float32)
+    if gate is not None:
+        _check_act(gate, "gate")
+        if gate.numel() != y.numel():
+            raise ValueError("gate must have the shape of the output")
     L = _lib.load()
-    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
     tok = _inst.begin("linear_tc")
-    _lib.check(L.ltgnn_linear(idx, m, k, n, x.data_ptr(), weight.data_ptr(),
-                              None if bias is None else bias.data_ptr(), int(relu), y.data_ptr(), _stream(x)))
+    _lib.check(L.ltgnn_linear(_dev_index(x), m, k, n, x.data_ptr(), weight.data_ptr(), int(transposed),
+                              None if bias is None else bias.data_ptr(), int(relu),
+                              None if gate is None else gate.data_ptr(), float(gate_scale), y.data_ptr(), _stream(x)))
     _inst.end(tok)
     return y

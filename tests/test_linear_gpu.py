@@ -49,3 +49,14 @@ def test_linear_shape_errors():
         linear_tc(x, torch.zeros(16, 48, device="cuda"))
     with pytest.raises(L.LtgnnError, match="multiple of 16"):
         linear_tc(torch.zeros(4, 64, device="cuda"), torch.zeros(8, 64, device="cuda"))
+
+
+def test_linear_transposed_and_gate():
+    gen = torch.Generator().manual_seed(11)
+    g = torch.randn(1500, 64, generator=gen)
+    w = torch.randn(64, 96, generator=gen) * 0.3   # [K, N]: dX = G @ W
+    gate = torch.randn(1500, 96, generator=gen)
+    want = (g.double() @ w.double()) * (gate > 0).double() * 1.25
+    got = linear_tc(g.cuda(), w.cuda(), transposed=True, gate=gate.cuda(), gate_scale=1.25)
+    assert rel_err(got, want) <= 1e-5
+    assert bool(((got.cpu() == 0) | (gate > 0)).all())  # gated-off entries are exact zeros
