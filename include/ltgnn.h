@@ -81,6 +81,23 @@ enum {
 int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
                void* stream);
 
+/* Fused variant of the STAGED kernel (D % 32 == 0 and the graph slice must fit shared memory,
+ * otherwise LTGNN_E_SHAPE and the caller composes the unfused pieces):
+ *   input gate   (gate != NULL): X is multiplied by (gate > 0 ? gate_scale : 0) BEFORE aggregation --
+ *                the backward of an upstream ReLU(+inverted dropout) whose output is `gate`
+ *                (detector.py:200-201); colsum[D] (optional) receives the column sums of the gated X
+ *                over all B*N rows, i.e. d loss / d bias of that layer.  `ws` must hold
+ *                ltgnn_spmm_ws_floats(g) floats.  Deterministic (fixed reduction order).
+ *   output epilogue: Y = dropout(relu(A X + bias)); bias NULL / relu 0 / drop_p 0 switch parts off
+ *                (GCNConv's `out + bias`, F.relu, nn.Dropout: detector.py:199-201).  Dropout is
+ *                inverted dropout from a counter-based Philox stream keyed by drop_seed:
+ *                statistically equivalent to torch's, not bit-identical.
+ */
+int64_t ltgnn_spmm_ws_floats(ltgnn_graph_t g);
+int ltgnn_spmm_fused(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y,
+                     const float* bias, int relu, float drop_p, uint64_t drop_seed, const float* gate,
+                     float gate_scale, float* colsum, float* ws, void* stream);
+
 /* ---- dense row-wise layer on tensor cores --------------------------------------------------
  * Y[M,N] = gate( act( X[M,K] op(W) + bias[N] ) )
  *   op(W) = W^T with W [N,K] row-major (w_transposed = 0, torch.nn.Linear layout)

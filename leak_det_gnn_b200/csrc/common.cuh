@@ -138,6 +138,34 @@ __device__ __forceinline__ void stg_stream(float4* p, const float4& v) {
                  : "memory");
 }
 
+// ---- counter-based RNG for dropout: Philox4x32 with 7 rounds (Salmon et al. 2011; 7 rounds pass
+// BigCrush).  One call yields the four keep/drop decisions of one float4.  Statistically equivalent to,
+// not bit-identical with, torch's dropout stream (SURVEY.md section 7 "Dropout RNG parity").
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1) {
+    uint32_t c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c1 = l1;
+        c2 = h0 ^ c3 ^ k1;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// inverted dropout on the float4 whose linear float4 index is `idx4`; thresh = p * 2^32
+__device__ __forceinline__ void dropout4(float4& v, uint64_t idx4, uint64_t seed, uint32_t thresh, float keep_scale) {
+    const uint4 r = philox4x32_7(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32),
+                                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    v.x = r.x >= thresh ? v.x * keep_scale : 0.f;
+    v.y = r.y >= thresh ? v.y * keep_scale : 0.f;
+    v.z = r.z >= thresh ? v.z * keep_scale : 0.f;
+    v.w = r.w >= thresh ? v.w * keep_scale : 0.f;
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

@@ -40,6 +40,16 @@ struct StagedParams {
     int32_t n, nnz, d4, n_slices;
     int32_t box_rows, n_boxes, n_stages;
     uint32_t stage_bytes, off_rowptr, off_colval, off_stage0;
+    // output epilogue (kEpi): y = dropout(relu(acc + bias))
+    const float* bias;
+    int32_t relu;
+    uint32_t drop_thresh;  // p * 2^32, 0 = no dropout
+    float keep_scale;      // 1 / (1 - p)
+    uint64_t drop_seed;
+    // input gate (kGate): x *= gate > 0 ? gate_scale : 0 before aggregation; column sums of the gated x
+    const float* gate;
+    float gate_scale;
+    float* colsum_ws;  // [gridDim.x][32] per-CTA partial column sums, or nullptr
 };
 
 __device__ __forceinline__ void fma2(float4& acc, float w, const float4& x) {
@@ -50,6 +60,9 @@ __device__ __forceinline__ void fma2(float4& acc, float w, const float4& x) {
     acc.w = __fadd_rn(acc.w, __fmul_rn(w, x.w));
 }
 
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
+
+template <bool kEpi, bool kGate>
 __global__ void __launch_bounds__(kStagedThreads, 1)
 spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -96,18 +109,41 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
         return;
     }
 
-    // ---------------- consumers: gather from smem, stream out ----------------
+    // ---------------- consumers: (gate,) gather from smem, (epilogue,) stream out ----------------
     const int g = lane >> 3;  // row within the warp's group of 4
     const int q = lane & 7;   // float4 within the 128 B slice
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     int it = 0;
     for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         mbar_wait(full + s, ph);
-        const float4* xs = reinterpret_cast<const float4*>(s_stage + static_cast<size_t>(s) * p.stage_bytes) + q;
+        float4* stage = reinterpret_cast<float4*>(s_stage + static_cast<size_t>(s) * p.stage_bytes);
+        const float4* xs = stage + q;
         const int64_t b = u / p.n_slices;
         const int sl = static_cast<int>(u - b * p.n_slices);
-        float4* y = reinterpret_cast<float4*>(p.Y) + (b * p.n) * p.d4 + sl * (kSliceFloats / 4) + q;
+        const int64_t base4 = (b * p.n) * p.d4 + sl * (kSliceFloats / 4) + q;  // float4 index of (b, row 0, this lane)
+
+        if (kGate) {
+            // backward of the upstream ReLU(+dropout): its OUTPUT `gate` says which entries were live.
+            // Each thread owns column group q for rows tid/8, tid/8 + 64, ...; then all consumers sync.
+            const float4* gt = reinterpret_cast<const float4*>(p.gate) + base4;
+            for (int r = threadIdx.x >> 3; r < p.n; r += kConsumerWarps * 4) {
+                const float4 m = ldg_stream(gt + static_cast<int64_t>(r) * p.d4);
+                float4 x = stage[r * 8 + q];
+                x.x = m.x > 0.f ? x.x * p.gate_scale : 0.f;
+                x.y = m.y > 0.f ? x.y * p.gate_scale : 0.f;
+                x.z = m.z > 0.f ? x.z * p.gate_scale : 0.f;
+                x.w = m.w > 0.f ? x.w * p.gate_scale : 0.f;
+                stage[r * 8 + q] = x;
+                csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w;
+            }
+            consumer_bar();
+        }
+
+        float4* y = reinterpret_cast<float4*>(p.Y) + base4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kEpi && p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias) + sl * (kSliceFloats / 4) + q);
 
         // two rows in flight per lane group for memory-level parallelism on the LDS chain
         for (int r0 = warp * 4 + g; r0 < p.n; r0 += 2 * kRowsPerPass) {
@@ -137,12 +173,58 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
                 const int2 c1 = s_colval[k1];
                 fma2(a1, __int_as_float(c1.y), xs[c1.x * 8]);
             }
+            if (kEpi) {
+                a0.x = __fadd_rn(a0.x, bias4.x); a0.y = __fadd_rn(a0.y, bias4.y);
+                a0.z = __fadd_rn(a0.z, bias4.z); a0.w = __fadd_rn(a0.w, bias4.w);
+                a1.x = __fadd_rn(a1.x, bias4.x); a1.y = __fadd_rn(a1.y, bias4.y);
+                a1.z = __fadd_rn(a1.z, bias4.z); a1.w = __fadd_rn(a1.w, bias4.w);
+                if (p.relu) {
+                    a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a0.z = fmaxf(a0.z, 0.f); a0.w = fmaxf(a0.w, 0.f);
+                    a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); a1.z = fmaxf(a1.z, 0.f); a1.w = fmaxf(a1.w, 0.f);
+                }
+                if (p.drop_thresh) {
+                    dropout4(a0, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * p.d4), p.drop_seed,
+                             p.drop_thresh, p.keep_scale);
+                    dropout4(a1, static_cast<uint64_t>(base4 + static_cast<int64_t>(r1) * p.d4), p.drop_seed,
+                             p.drop_thresh, p.keep_scale);
+                }
+            }
             stg_stream(y + static_cast<int64_t>(r0) * p.d4, a0);
             if (r1 < p.n) stg_stream(y + static_cast<int64_t>(r1) * p.d4, a1);
         }
+        if (kGate) fence_proxy_async_smem();  // our generic-proxy writes to the stage precede the next TMA fill
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
     }
+
+    if (kGate && p.colsum_ws) {
+        // lanes q, q+8, q+16, q+24 share a column group; then 16 warps through shared memory, fixed order
+        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 8);  csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 8);
+        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 8);  csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 8);
+        csum.x += __shfl_xor_sync(0xffffffffu, csum.x, 16); csum.y += __shfl_xor_sync(0xffffffffu, csum.y, 16);
+        csum.z += __shfl_xor_sync(0xffffffffu, csum.z, 16); csum.w += __shfl_xor_sync(0xffffffffu, csum.w, 16);
+        consumer_bar();  // every consumer is done with the stage buffers (all its units consumed)
+        float4* red = reinterpret_cast<float4*>(s_stage);
+        if (lane < 8) red[warp * 8 + lane] = csum;
+        consumer_bar();
+        if (warp == 0 && lane < 8) {
+            float4 t = red[lane];
+            for (int w = 1; w < kConsumerWarps; ++w) {
+                const float4 o = red[w * 8 + lane];
+                t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+            }
+            reinterpret_cast<float4*>(p.colsum_ws)[blockIdx.x * 8 + lane] = t;
+        }
+    }
+}
+
+// colsum[sl*32 + c] = sum over CTAs that worked on slice sl (cta % n_slices == sl) of ws[cta][c], fixed order
+__global__ void colsum_reduce_kernel(const float* __restrict__ ws, float* __restrict__ colsum, int n_ctas, int n_slices) {
+    const int col = threadIdx.x;  // 0 .. D-1
+    const int sl = col >> 5, c = col & 31;
+    float t = 0.f;
+    for (int cta = sl; cta < n_ctas; cta += n_slices) t += ws[cta * 32 + c];
+    colsum[col] = t;
 }
 
 __global__ void __launch_bounds__(256)
@@ -200,31 +282,49 @@ StagedPlan plan_staged(const ltgnn_graph* g, int32_t D) {
     return pl;
 }
 
-}  // namespace
+struct FusedArgs {
+    const float* bias = nullptr;
+    int relu = 0;
+    float drop_p = 0.f;
+    uint64_t drop_seed = 0;
+    const float* gate = nullptr;
+    float gate_scale = 1.f;
+    float* colsum = nullptr;
+    float* ws = nullptr;
+};
 
-extern "C" int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
-                          void* stream_) {
-    LTGNN_REQUIRE(g != nullptr, LTGNN_E_ARG, "spmm: null graph handle");
-    LTGNN_REQUIRE(transpose == 0 || transpose == 1, LTGNN_E_ARG, "spmm: transpose must be 0 or 1");
-    LTGNN_REQUIRE(B >= 0 && D > 0, LTGNN_E_ARG, "spmm: B=%lld D=%d", static_cast<long long>(B), D);
-    LTGNN_REQUIRE(D % 4 == 0, LTGNN_E_SHAPE, "spmm: D=%d must be a multiple of 4", D);
-    LTGNN_REQUIRE(B < (1ll << 31), LTGNN_E_SHAPE, "spmm: B too large");
-    if (B == 0) return LTGNN_OK;
-    LTGNN_REQUIRE(X && Y, LTGNN_E_ARG, "spmm: null tensor");
-    LTGNN_REQUIRE(X != Y, LTGNN_E_ARG, "spmm: X and Y must not alias");
-    LTGNN_REQUIRE(aligned16(X) && aligned16(Y), LTGNN_E_ALIGN, "spmm: X/Y must be 16-byte aligned");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
+              const FusedArgs& f, cudaStream_t stream, const char* who) {
+    LTGNN_REQUIRE(g != nullptr, LTGNN_E_ARG, "%s: null graph handle", who);
+    LTGNN_REQUIRE(transpose == 0 || transpose == 1, LTGNN_E_ARG, "%s: transpose must be 0 or 1", who);
+    LTGNN_REQUIRE(B >= 0 && D > 0, LTGNN_E_ARG, "%s: B=%lld D=%d", who, static_cast<long long>(B), D);
+    LTGNN_REQUIRE(D % 4 == 0, LTGNN_E_SHAPE, "%s: D=%d must be a multiple of 4", who, D);
+    LTGNN_REQUIRE(B < (1ll << 31), LTGNN_E_SHAPE, "%s: B too large", who);
+    LTGNN_REQUIRE(f.drop_p >= 0.f && f.drop_p < 1.f, LTGNN_E_ARG, "%s: dropout p=%f not in [0,1)", who, f.drop_p);
+    const bool epi = f.bias || f.relu || f.drop_p > 0.f;
+    const bool gated = f.gate != nullptr;
+    LTGNN_REQUIRE(!f.colsum || (gated && f.ws), LTGNN_E_ARG, "%s: colsum needs gate and workspace", who);
+    if (B == 0) {
+        if (f.colsum) LTGNN_CUDA_TRY(cudaMemsetAsync(f.colsum, 0, sizeof(float) * D, stream));
+        return LTGNN_OK;
+    }
+    LTGNN_REQUIRE(X && Y, LTGNN_E_ARG, "%s: null tensor", who);
+    LTGNN_REQUIRE(X != Y, LTGNN_E_ARG, "%s: X and Y must not alias", who);
+    LTGNN_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(f.bias) && aligned16(f.gate), LTGNN_E_ALIGN,
+                  "%s: tensors must be 16-byte aligned", who);
     LTGNN_CUDA_TRY(cudaSetDevice(g->device));
 
     const StagedPlan pl = plan_staged(g, D);
-    const bool want_staged = (algo == LTGNN_SPMM_STAGED) || (algo == LTGNN_SPMM_AUTO && pl.ok && pl.n_stages >= 2);
-    if (algo == LTGNN_SPMM_STAGED)
-        LTGNN_REQUIRE(pl.ok, LTGNN_E_SHAPE, "spmm: STAGED needs D %% 32 == 0 and a 32-feature slice of the graph (%d rows) "
-                      "to fit shared memory", g->n);
+    const bool fused = epi || gated;
+    const bool want_staged = (algo == LTGNN_SPMM_STAGED) || fused ||
+                             (algo == LTGNN_SPMM_AUTO && pl.ok && pl.n_stages >= 2);
+    if (algo == LTGNN_SPMM_STAGED || fused)
+        LTGNN_REQUIRE(pl.ok, LTGNN_E_SHAPE, "%s: the STAGED kernel needs D %% 32 == 0 and a 32-feature slice of the "
+                      "graph (%d rows) to fit shared memory", who, g->n);
 
     if (want_staged) {
         PFN_tmapEncodeTiled enc = tmap_encode_fn();
-        LTGNN_REQUIRE(enc != nullptr, LTGNN_E_CUDA, "spmm: cuTensorMapEncodeTiled not available from the driver");
+        LTGNN_REQUIRE(enc != nullptr, LTGNN_E_CUDA, "%s: cuTensorMapEncodeTiled not available from the driver", who);
         CUtensorMap tmap;
         const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(g->n),
                                     static_cast<cuuint64_t>(B)};
@@ -234,7 +334,7 @@ extern "C" int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, 
         CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), gdim, gstr, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        LTGNN_REQUIRE(cr == CUDA_SUCCESS, LTGNN_E_CUDA, "spmm: cuTensorMapEncodeTiled failed with CUresult %d",
+        LTGNN_REQUIRE(cr == CUDA_SUCCESS, LTGNN_E_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who,
                       static_cast<int>(cr));
         StagedParams p;
         p.rowptr = g->rowptr[transpose];
@@ -252,11 +352,34 @@ extern "C" int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, 
         p.off_rowptr = pl.off_rowptr;
         p.off_colval = pl.off_colval;
         p.off_stage0 = pl.off_stage0;
-        LTGNN_CUDA_TRY(cudaFuncSetAttribute(spmm_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            static_cast<int>(pl.smem_bytes)));
-        const int grid = static_cast<int>(p.n_units < g->sm_count ? p.n_units : g->sm_count);
-        spmm_staged_kernel<<<grid, kStagedThreads, pl.smem_bytes, stream>>>(tmap, p);
-        LTGNN_CUDA_TRY(cudaGetLastError());
+        p.bias = f.bias;
+        p.relu = f.relu;
+        p.drop_thresh = f.drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(f.drop_p) * 4294967296.0) : 0u;
+        p.keep_scale = 1.f / (1.f - f.drop_p);
+        p.drop_seed = f.drop_seed;
+        p.gate = f.gate;
+        p.gate_scale = f.gate_scale;
+        p.colsum_ws = f.colsum ? f.ws : nullptr;
+        // a CTA must keep one feature slice for its whole life when it accumulates column sums
+        int64_t grid = p.n_units < g->sm_count ? p.n_units : g->sm_count;
+        grid -= grid % p.n_slices;
+        LTGNN_REQUIRE(grid > 0, LTGNN_E_SHAPE, "%s: fewer SMs (%d) than feature slices (%d)", who, g->sm_count,
+                      p.n_slices);
+        auto launch = [&](auto kern) -> int {
+            LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                static_cast<int>(pl.smem_bytes)));
+            kern<<<static_cast<int>(grid), kStagedThreads, pl.smem_bytes, stream>>>(tmap, p);
+            LTGNN_CUDA_TRY(cudaGetLastError());
+            return LTGNN_OK;
+        };
+        int rc;
+        if (gated) rc = epi ? launch(spmm_staged_kernel<true, true>) : launch(spmm_staged_kernel<false, true>);
+        else rc = epi ? launch(spmm_staged_kernel<true, false>) : launch(spmm_staged_kernel<false, false>);
+        if (rc) return rc;
+        if (f.colsum) {
+            colsum_reduce_kernel<<<1, D, 0, stream>>>(f.ws, f.colsum, static_cast<int>(grid), p.n_slices);
+            LTGNN_CUDA_TRY(cudaGetLastError());
+        }
         return LTGNN_OK;
     }
 
@@ -269,4 +392,28 @@ extern "C" int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, 
         g->n, D / 4, total);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
+}
+
+}  // namespace
+
+extern "C" int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
+                          void* stream_) {
+    return spmm_impl(g, transpose, B, D, X, Y, algo, FusedArgs{}, static_cast<cudaStream_t>(stream_), "spmm");
+}
+
+extern "C" int64_t ltgnn_spmm_ws_floats(ltgnn_graph_t g) { return g ? static_cast<int64_t>(g->sm_count) * 32 : 0; }
+
+extern "C" int ltgnn_spmm_fused(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y,
+                                const float* bias, int relu, float drop_p, uint64_t drop_seed, const float* gate,
+                                float gate_scale, float* colsum, float* ws, void* stream_) {
+    FusedArgs f;
+    f.bias = bias;
+    f.relu = relu;
+    f.drop_p = drop_p;
+    f.drop_seed = drop_seed;
+    f.gate = gate;
+    f.gate_scale = gate_scale;
+    f.colsum = colsum;
+    f.ws = ws;
+    return spmm_impl(g, transpose, B, D, X, Y, LTGNN_SPMM_STAGED, f, static_cast<cudaStream_t>(stream_), "spmm_fused");
 }

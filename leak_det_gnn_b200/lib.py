@@ -6,7 +6,7 @@ There is deliberately no fallback: if the shared library is missing or a call fa
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -27,6 +27,9 @@ SIGNATURES = {
     "ltgnn_graph_destroy": (c_int, [c_void_p]),
     "ltgnn_graph_info": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
     "ltgnn_spmm": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_int, c_void_p]),
+    "ltgnn_spmm_ws_floats": (c_int64, [c_void_p]),
+    "ltgnn_spmm_fused": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                 c_uint64, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "ltgnn_linear": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                              c_float, c_void_p, c_void_p]),
 }

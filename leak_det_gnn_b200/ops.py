@@ -175,3 +175,44 @@ def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
                               None if gate is None else gate.data_ptr(), float(gate_scale), y.data_ptr(), _stream(x)))
     _inst.end(tok)
     return y
+
+
+def new_dropout_seed() -> int:
+    """A fresh 63-bit key for one in-kernel dropout stream, drawn from torch's CPU generator so that
+    ``torch.manual_seed`` makes training runs reproducible."""
+    return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+def spmm_fused(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, bias: Optional[torch.Tensor] = None,
+               relu: bool = False, drop_p: float = 0.0, drop_seed: int = 0, gate: Optional[torch.Tensor] = None,
+               gate_scale: float = 1.0, want_colsum: bool = False):
+    """Raw fused aggregation (see ltgnn_spmm_fused): ``dropout(relu(A (x * gatemask) + bias))``.
+    Returns ``y`` or ``(y, colsum)`` when ``want_colsum`` (column sums of the gated input)."""
+    _check_act(x, "x")
+    n, d = graph.num_nodes, x.shape[-1]
+    if x.numel() % (n * d) != 0:
+        raise ValueError(f"x with shape {tuple(x.shape)} is not a whole number of {n}-node graphs")
+    b = x.numel() // (n * d)
+    if gate is not None:
+        _check_act(gate, "gate")
+        if gate.shape != x.shape:
+            raise ValueError("gate must have the shape of x")
+    if bias is not None:
+        _check_act(bias, "bias")
+    y = torch.empty_like(x)
+    L = _lib.load()
+    h = graph.handle(x.device)
+    colsum = ws = None
+    if want_colsum:
+        if gate is None:
+            raise ValueError("want_colsum needs a gate")
+        colsum = torch.empty(d, device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(L.ltgnn_spmm_ws_floats(h)), device=x.device, dtype=torch.float32)
+    tok = _inst.begin("spmm_fused_bwd" if transpose else "spmm_fused_fwd")
+    _lib.check(L.ltgnn_spmm_fused(h, int(bool(transpose)), b, d, x.data_ptr(), y.data_ptr(),
+                                  None if bias is None else bias.data_ptr(), int(relu), float(drop_p),
+                                  int(drop_seed) & (2**64 - 1), None if gate is None else gate.data_ptr(),
+                                  float(gate_scale), None if colsum is None else colsum.data_ptr(),
+                                  None if ws is None else ws.data_ptr(), _stream(x)))
+    _inst.end(tok)
+    return (y, colsum) if want_colsum else y

@@ -120,3 +120,54 @@ def test_aggregate_autograd(graph_golden):
     w = torch.randn(3, 661, 64, device="cuda")
     (aggregate(x, pg) * w).sum().backward()
     assert torch.equal(x.grad, spmm(pg, w, transpose=True))
+
+
+@pytest.mark.parametrize("net,b,d", [("LTA", 5, 64), ("LT", 3, 64), ("LTA", 300, 128), ("LTA", 2, 32)])
+def test_spmm_fused_epilogue_and_gate_bit_exact(graph_golden, net, b, d):
+    from leak_det_gnn_b200.ops import spmm_fused
+    pg = _graph(graph_golden, net)
+    c = pg.csr
+    gen = torch.Generator().manual_seed(77 + b)
+    x = torch.randn(b, pg.num_nodes, d, generator=gen)
+    bias = torch.randn(d, generator=gen)
+    # forward epilogue: relu(A x + bias), same roundings as the oracle
+    want = np.maximum(c_oracle.spmm(c.rowptr, c.col, c.val, x.numpy()) + bias.numpy(), 0.0).astype(np.float32)
+    got = spmm_fused(pg, x.cuda(), bias=bias.cuda(), relu=True)
+    assert np.array_equal(_bits(got), want.view(np.int32))
+    # input gate on the transposed (backward) aggregation + column sums of the gated input
+    gate = torch.randn(b, pg.num_nodes, d, generator=gen).relu()  # an upstream ReLU output: ~half exact zeros
+    scale = 1.0 / 0.9
+    xg = torch.where(gate > 0, x * np.float32(scale), torch.zeros(()))
+    want = c_oracle.spmm(c.t_rowptr, c.t_col, c.t_val, xg.numpy())
+    got, colsum = spmm_fused(pg, x.cuda(), transpose=True, gate=gate.cuda(), gate_scale=scale, want_colsum=True)
+    assert np.array_equal(_bits(got), want.view(np.int32))
+    truth = xg.double().sum(dim=(0, 1))
+    assert (colsum.cpu().double() - truth).abs().max() <= 1e-5 * xg.double().abs().sum(dim=(0, 1)).max()
+    # run-to-run deterministic
+    got2, colsum2 = spmm_fused(pg, x.cuda(), transpose=True, gate=gate.cuda(), gate_scale=scale, want_colsum=True)
+    assert torch.equal(got, got2) and torch.equal(colsum, colsum2)
+
+
+def test_spmm_fused_dropout_statistics(graph_golden):
+    from leak_det_gnn_b200.ops import spmm_fused
+    pg = _graph(graph_golden, "LTA")
+    x = torch.randn(64, 661, 64, device="cuda").abs() + 0.1   # strictly positive -> relu never zeroes
+    base = spmm_fused(pg, x, relu=True)
+    assert (base > 0).all()
+    p = 0.1
+    a = spmm_fused(pg, x, relu=True, drop_p=p, drop_seed=1234)
+    b = spmm_fused(pg, x, relu=True, drop_p=p, drop_seed=1234)
+    c2 = spmm_fused(pg, x, relu=True, drop_p=p, drop_seed=1235)
+    assert torch.equal(a, b) and not torch.equal(a, c2)          # keyed, reproducible
+    dropped = (a == 0)
+    frac = dropped.float().mean().item()
+    assert abs(frac - p) < 2e-3, frac                            # 2.7M samples: sigma ~ 1.8e-4
+    kept = ~dropped
+    assert torch.equal(a[kept], (base * np.float32(1.0 / (1.0 - p)))[kept])   # inverted dropout scaling, exact
+    # no structure across features / nodes / windows
+    for dim in (0, 1, 2):
+        other = tuple(i for i in range(3) if i != dim)
+        m = dropped.float().mean(dim=other)
+        assert (m - p).abs().max() < 0.02
+    both = ((a == 0) & (c2 == 0)).float().mean().item()
+    assert abs(both - p * p) < 2e-3                              # independent streams
