@@ -112,6 +112,31 @@ int ltgnn_spmm_fused(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const
 int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const float* X, const float* W, int w_transposed,
                  const float* bias, int relu, const float* gate, float gate_scale, float* Y, void* stream);
 
+/* ---- weight gradient of a row-wise linear map ---------------------------------------------
+ * dW[Do,Di] (+)= sum over the M rows of G[row,:]^T X[row,:]   (accumulate = 0/1)
+ * Replaces autograd's grad_weight of GCNConv.lin (detector.py:199) over the B*N node rows.
+ * (Do/8)*(Di/8) must divide 256 (64x64, 128x128, 64x128, ...).  ws: ltgnn_wgrad_ws_floats() floats.
+ * Deterministic: per-CTA partials are added in a fixed order.
+ */
+int64_t ltgnn_wgrad_ws_floats(int device, int32_t Do, int32_t Di);
+int ltgnn_wgrad(int device, int64_t M, int32_t Do, int32_t Di, const float* G, const float* X, float* dW,
+                int accumulate, float* ws, void* stream);
+
+/* ---- node-feature initialisation (detector.py:178-190) and its backward ---------------------
+ * fwd: X0[b,i,:] = dropout(relu(W[:, :ds] h + W[:, ds] m + bias)), (h, m) = (hs[b, slot[i], :], 1) for a
+ *      sensor node (slot[i] >= 0) and (0, 0) otherwise.  hs [B,S,ds]; W [D, ds+1] (sensor_to_node.weight);
+ *      slot int32[N] on the device.  Never builds the zero-padded (B,N,ds+1) tensor.
+ * bwd: gate = (X0 > 0) * gate_scale applied to dX0; dhs [B,S,ds], dW [D, ds+1], dbias [D].
+ *      ws: ltgnn_node_init_ws_floats() floats.  Deterministic.
+ */
+int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
+                        const int32_t* slot, const float* W, const float* bias, float drop_p, uint64_t drop_seed,
+                        float* X0, void* stream);
+int64_t ltgnn_node_init_ws_floats(int device, int32_t ds, int32_t D);
+int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
+                        const int32_t* slot, const float* W, const float* dX0, const float* X0, float gate_scale,
+                        float* dhs, float* dW, float* dbias, float* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,11 @@ struct DeviceInfo {
 // returns nullptr (and records the error) if the device cannot be queried
 const DeviceInfo* device_info(int device);
 
+// out[i] (+)= sum_{c < n_parts} parts[c * stride + i], i < n, added in index order: the deterministic
+// second stage of every cross-CTA reduction in this library (no float atomics anywhere)
+int reduce_parts(const float* parts, int64_t stride, float* out, int n_parts, int n, int accumulate,
+                 cudaStream_t stream);
+
 }  // namespace ltgnn
 
 struct ltgnn_graph {

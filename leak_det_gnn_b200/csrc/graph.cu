@@ -67,6 +67,25 @@ const DeviceInfo* device_info(int device) {
     return &d;
 }
 
+namespace {
+__global__ void reduce_parts_kernel(const float* __restrict__ parts, int64_t stride, float* __restrict__ out,
+                                    int n_parts, int n, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t = accumulate ? out[i] : 0.f;
+    for (int c = 0; c < n_parts; ++c) t += parts[c * stride + i];
+    out[i] = t;
+}
+}  // namespace
+
+int reduce_parts(const float* parts, int64_t stride, float* out, int n_parts, int n, int accumulate,
+                 cudaStream_t stream) {
+    if (n <= 0) return LTGNN_OK;
+    reduce_parts_kernel<<<(n + 127) / 128, 128, 0, stream>>>(parts, stride, out, n_parts, n, accumulate);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
 }  // namespace ltgnn
 
 using namespace ltgnn;

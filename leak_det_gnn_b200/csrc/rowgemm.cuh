@@ -31,11 +31,13 @@ constexpr int kEpiWarps = 4;
 constexpr int kThreads = (kLoaderWarps + 1 + kEpiWarps) * 32;
 constexpr int kStages = 2;
 
-// the A ring moves "k-groups" of KG = 64 (or 32) columns of K, so a stage is at most 64 KB whatever K is
-__host__ __device__ inline int k_group(int K) { return (K % 64 == 0) ? 64 : 32; }
-__host__ __device__ inline uint32_t a_stage_bytes(int K) { return 2u * kTileM * k_group(K) * 4; }
-__host__ __device__ inline uint32_t b_bytes(int K, int N) { return 2u * N * K * 4; }
-__host__ inline size_t smem_bytes(int K, int N) { return 1024 + kStages * a_stage_bytes(K) + b_bytes(K, N); }
+// the A ring moves "k-groups" of KG = 64 (or 32) columns of K, so a stage is at most 64 KB whatever K is;
+// 32 is used when K is not a multiple of 64 or when the resident B leaves no room for 64-wide stages
+__host__ inline size_t smem_bytes(int K, int N, int KG) { return 1024 + kStages * 2ull * kTileM * KG * 4 + 2ull * N * K * 4; }
+__host__ inline int k_group(int K, int N, size_t limit) {
+    if (K % 64 == 0 && smem_bytes(K, N, 64) <= limit) return 64;
+    return 32;
+}
 __host__ inline uint32_t tmem_cols_for(int N) {
     uint32_t c = 32;
     while (c < 2u * N) c <<= 1;
@@ -71,13 +73,12 @@ __device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const float* __restr
 template <class Loader, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
 rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __restrict__ W, int w_transposed, int64_t M,
-               int K, int N, uint32_t tmem_cols) {
+               int K, int N, int KG, uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int KG = k_group(K);
     const int n_kg = K / KG;
     const uint32_t a_half = kTileM * KG * 4;  // hi block, then lo block
     uint8_t* b_hi = smem + kStages * 2 * a_half;
@@ -212,7 +213,8 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const flo
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
                   di->cc_minor);
-    const size_t smem = smem_bytes(K, N);
+    const int KG = k_group(K, N, static_cast<size_t>(di->smem_optin));
+    const size_t smem = smem_bytes(K, N, KG);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE,
                   "%s: K=%d N=%d needs %zu B of shared memory (limit %d)", who, K, N, smem, di->smem_optin);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
@@ -220,7 +222,7 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const flo
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t tiles = (M + kTileM - 1) / kTileM;
     const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
-    kern<<<grid, kThreads, smem, stream>>>(loader, epilogue, W, w_transposed, M, K, N, tmem_cols_for(N));
+    kern<<<grid, kThreads, smem, stream>>>(loader, epilogue, W, w_transposed, M, K, N, KG, tmem_cols_for(N));
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

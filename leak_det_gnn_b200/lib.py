@@ -32,6 +32,13 @@ SIGNATURES = {
                                  c_uint64, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
     "ltgnn_linear": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                              c_float, c_void_p, c_void_p]),
+    "ltgnn_wgrad_ws_floats": (c_int64, [c_int, c_int32, c_int32]),
+    "ltgnn_wgrad": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "ltgnn_node_init_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_float, c_uint64, c_void_p, c_void_p]),
+    "ltgnn_node_init_ws_floats": (c_int64, [c_int, c_int32, c_int32]),
+    "ltgnn_node_init_bwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

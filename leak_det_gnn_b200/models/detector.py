@@ -117,7 +117,9 @@ class LeakDetector(nn.Module):
         key = (device.type, device.index)
         hit = self._dev_cache.get(key)
         if hit is None:
-            hit = (self.sensor_node_idx.to(device), self.pipe_ends.to(device))
+            slot = torch.full((len(self.node_names),), -1, dtype=torch.int32)
+            slot[self.sensor_node_idx] = torch.arange(len(self.sensor_node_ids), dtype=torch.int32)
+            hit = (slot.to(device), self.pipe_ends.to(device))
             self._dev_cache[key] = hit
         return hit
 
@@ -126,12 +128,10 @@ class LeakDetector(nn.Module):
         message-passing hot path."""
         if not h_s.is_cuda:
             raise ValueError("LeakDetector runs on CUDA only (sm_100a kernels; no CPU fallback)")
-        sensor_idx, ends = self._index_tensors(h_s.device)
-        n = len(self.node_names)
-        x = ops.node_init(h_s, sensor_idx, n, self.sensor_to_node.weight, self.sensor_to_node.bias)
-        x = self.dropout(x)
-        for conv in self.convs:
-            x = self.dropout(F.relu(conv(x, self.pipe_graph)))
+        slot, ends = self._index_tensors(h_s.device)
+        conv_params = [t for conv in self.convs for t in (conv.lin.weight, conv.bias)]
+        x = ops.gnn_body(h_s, slot, self.pipe_graph, self.dropout.p, self.training, self.sensor_to_node.weight,
+                         self.sensor_to_node.bias, conv_params)
         h_u = x[:, ends[:, 0], :]
         h_v = x[:, ends[:, 1], :]
         pipe_logits = self.edge_head(h_u, h_v)

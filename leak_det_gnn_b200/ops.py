@@ -17,7 +17,7 @@ from . import instrument as _inst
 from . import lib as _lib
 from .graph import GCNCsr, build_gcn_csr
 
-__all__ = ["PipeGraph", "spmm", "aggregate"]
+__all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body"]
 
 
 def _ptr(a: np.ndarray) -> ctypes.c_void_p:
@@ -119,35 +119,6 @@ def aggregate(x: torch.Tensor, graph: PipeGraph) -> torch.Tensor:
     return _Aggregate.apply(x, graph)
 
 
-def gcn_conv(x: torch.Tensor, graph: PipeGraph, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """``A_hat (x W^T) + b`` -- the operator ``torch_geometric.nn.GCNConv.forward`` computes
-    (reference call site models/detector.py:199).  x: (B, N, Din) or (B*N, Din)."""
-    n = graph.num_nodes
-    xw = torch.nn.functional.linear(x, weight)
-    y = aggregate(xw.reshape(-1, n, xw.shape[-1]), graph).view(*x.shape[:-1], xw.shape[-1])
-    return y if bias is None else y + bias
-
-
-def mean_pool(x: torch.Tensor) -> torch.Tensor:
-    """(B, N, D) -> (B, D): ``global_mean_pool`` for equal-sized graphs (detector.py:214-215)."""
-    return x.mean(dim=1)
-
-
-def node_init(h_s: torch.Tensor, sensor_idx: torch.Tensor, num_nodes: int, weight: torch.Tensor,
-              bias: torch.Tensor) -> torch.Tensor:
-    """Node-feature initialisation, reference models/detector.py:178-189:
-    ``relu(Linear([h0 | mask]))`` with ``h0`` = zeros except the sensor rows (= h_s) and ``mask`` the
-    sensor indicator.  Never materialises the zero-padded (B, N, d_s+1) tensor: a non-sensor row is
-    the batch-independent constant ``relu(bias)``; a sensor row is
-    ``relu(W[:, :d_s] h_s + W[:, d_s] + bias)``.  Returns (B, N, D)."""
-    b, s, ds = h_s.shape
-    base = torch.relu(bias)
-    x = base.expand(b, num_nodes, base.shape[0]).contiguous()
-    sens = torch.relu(torch.nn.functional.linear(h_s, weight[:, :ds], weight[:, ds] + bias))
-    x[:, sensor_idx, :] = sens
-    return x
-
-
 def _dev_index(x: torch.Tensor) -> int:
     return x.device.index if x.device.index is not None else torch.cuda.current_device()
 
@@ -216,3 +187,211 @@ def spmm_fused(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, bias:
                                   None if ws is None else ws.data_ptr(), _stream(x)))
     _inst.end(tok)
     return (y, colsum) if want_colsum else y
+
+
+# ----------------------------------------------------------------------------------------------
+# shape support predicates (mirrors of the checks in csrc/; unsupported shapes use cuBLAS via torch
+# for the plain GEMMs -- still on the GPU, never on the CPU)
+# ----------------------------------------------------------------------------------------------
+_SMEM_LIMIT = 232448  # sm_100: 227 KB opt-in dynamic shared memory per block
+
+
+def _linear_tc_ok(k: int, n: int) -> bool:
+    if k % 32 or n % 16 or not (0 < k <= 256) or not (0 < n <= 256):
+        return False
+    return 1024 + 2 * 2 * 128 * 32 * 4 + 2 * n * k * 4 <= _SMEM_LIMIT
+
+
+def _wgrad_ok(do: int, di: int) -> bool:
+    if do % 8 or di % 8:
+        return False
+    tpg = (do // 8) * (di // 8)
+    return tpg <= 256 and 256 % tpg == 0
+
+
+def _staged_ok(graph: PipeGraph, d: int) -> bool:
+    if d % 32:
+        return False
+    n = graph.num_nodes
+    boxes = (n + 255) // 256
+    rows = (n + boxes - 1) // boxes
+    stage = boxes * rows * 128
+    off = ((128 + 4 * (n + 1) + 15) // 16 * 16 + 8 * graph.nnz + 127) // 128 * 128
+    return _SMEM_LIMIT - 128 - off >= stage
+
+
+def _linear_any(x, weight, transposed=False):
+    k = x.shape[-1]
+    n = weight.shape[1] if transposed else weight.shape[0]
+    if _linear_tc_ok(k, n):
+        return linear_tc(x, weight, transposed=transposed)
+    return x @ weight if transposed else torch.nn.functional.linear(x, weight)
+
+
+def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW[Do, Di] = sum_rows g[row, :]^T x[row, :]; g: (..., Do), x: (..., Di), same leading shape."""
+    _check_act(g, "g")
+    _check_act(x, "x")
+    do, di = g.shape[-1], x.shape[-1]
+    m = g.numel() // do
+    if x.numel() // di != m:
+        raise ValueError("wgrad: row counts differ")
+    if not _wgrad_ok(do, di):
+        return g.reshape(m, do).t() @ x.reshape(m, di)
+    L = _lib.load()
+    dev = _dev_index(g)
+    dw = torch.empty(do, di, device=g.device, dtype=torch.float32)
+    ws = torch.empty(int(L.ltgnn_wgrad_ws_floats(dev, do, di)), device=g.device, dtype=torch.float32)
+    tok = _inst.begin("wgrad")
+    _lib.check(L.ltgnn_wgrad(dev, m, do, di, g.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), _stream(g)))
+    _inst.end(tok)
+    return dw
+
+
+def node_init_fwd(h_s, slot, num_nodes, weight, bias, drop_p=0.0, drop_seed=0):
+    """Raw node-feature initialisation (see ltgnn_node_init_fwd).  h_s (B,S,ds) -> (B,N,D)."""
+    _check_act(h_s, "h_s")
+    _check_act(weight, "weight")
+    _check_act(bias, "bias")
+    b, s, ds = h_s.shape
+    d = weight.shape[0]
+    x0 = torch.empty(b, num_nodes, d, device=h_s.device, dtype=torch.float32)
+    L = _lib.load()
+    tok = _inst.begin("node_init_fwd")
+    _lib.check(L.ltgnn_node_init_fwd(_dev_index(h_s), b, num_nodes, s, ds, d, h_s.data_ptr(), slot.data_ptr(),
+                                     weight.data_ptr(), bias.data_ptr(), float(drop_p), int(drop_seed) & (2**64 - 1),
+                                     x0.data_ptr(), _stream(h_s)))
+    _inst.end(tok)
+    return x0
+
+
+def node_init_bwd(h_s, slot, weight, dx0, x0, gate_scale):
+    """Raw backward of node_init: returns (dh_s, dW, dbias); dx0 is gated by (x0 > 0) * gate_scale."""
+    for t, nm in ((h_s, "h_s"), (weight, "weight"), (dx0, "dx0"), (x0, "x0")):
+        _check_act(t, nm)
+    b, s, ds = h_s.shape
+    n, d = x0.shape[1], x0.shape[2]
+    L = _lib.load()
+    dev = _dev_index(h_s)
+    dhs = torch.empty_like(h_s)
+    dw = torch.empty_like(weight)
+    db = torch.empty(d, device=h_s.device, dtype=torch.float32)
+    ws = torch.empty(int(L.ltgnn_node_init_ws_floats(dev, ds, d)), device=h_s.device, dtype=torch.float32)
+    tok = _inst.begin("node_init_bwd")
+    _lib.check(L.ltgnn_node_init_bwd(dev, b, n, s, ds, d, h_s.data_ptr(), slot.data_ptr(), weight.data_ptr(),
+                                     dx0.data_ptr(), x0.data_ptr(), float(gate_scale), dhs.data_ptr(), dw.data_ptr(),
+                                     db.data_ptr(), ws.data_ptr(), _stream(h_s)))
+    _inst.end(tok)
+    return dhs, dw, db
+
+
+# ----------------------------------------------------------------------------------------------
+# operator-level autograd: GCNConv  (reference call site models/detector.py:199)
+# ----------------------------------------------------------------------------------------------
+class _GcnConv(torch.autograd.Function):
+    """out = A_hat (x W^T) + b, PyG's operation order; backward: G = A_hat^T dout (CSC gather),
+    dW = G^T x, dx = G W, db = column sums of dout."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph):
+        x = x.contiguous()
+        n = graph.num_nodes
+        xw = _linear_any(x, weight)
+        xw3 = xw.view(-1, n, xw.shape[-1])
+        if bias is not None and _staged_ok(graph, xw.shape[-1]):
+            y = spmm_fused(graph, xw3, bias=bias)
+        else:
+            y = spmm(graph, xw3)
+            if bias is not None:
+                y += bias
+        ctx.save_for_backward(x, weight)
+        ctx.graph, ctx.has_bias = graph, bias is not None
+        return y.view(*x.shape[:-1], xw.shape[-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        g = spmm(ctx.graph, dy.view(-1, ctx.graph.num_nodes, dy.shape[-1]), transpose=True).view(dy.shape)
+        dw = wgrad(g, x) if ctx.needs_input_grad[1] else None
+        dx = _linear_any(g, weight, transposed=True) if ctx.needs_input_grad[0] else None
+        db = dy.reshape(-1, dy.shape[-1]).sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
+
+
+def gcn_conv(x: torch.Tensor, graph: PipeGraph, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """``A_hat (x W^T) + b`` -- the operator ``torch_geometric.nn.GCNConv.forward`` computes
+    (reference call site models/detector.py:199).  x: (B, N, Din) or (B*N, Din), fp32 CUDA."""
+    _check_act(x.contiguous(), "x")
+    return _GcnConv.apply(x, weight, bias, graph)
+
+
+def mean_pool(x: torch.Tensor) -> torch.Tensor:
+    """(B, N, D) -> (B, D): ``global_mean_pool`` for equal-sized graphs (detector.py:214-215)."""
+    return x.mean(dim=1)
+
+
+# ----------------------------------------------------------------------------------------------
+# the message-passing body of the detector as ONE autograd node
+#   h_s -> node init -> L x [GCNConv -> ReLU -> Dropout] -> x_L        (detector.py:178-201)
+# ----------------------------------------------------------------------------------------------
+class _GnnBody(torch.autograd.Function):
+    """Forward keeps only the layer outputs x_0..x_L (each doubles as the ReLU/dropout mask of its own
+    layer: x > 0 <=> unit was active and kept).  Backward per layer: gate + CSC-transpose aggregation +
+    bias gradient in one staged kernel, weight gradient, input gradient on tensor cores."""
+
+    @staticmethod
+    def forward(ctx, h_s, slot, graph, drop_p, training, w0, b0, *conv_params):
+        h_s = h_s.contiguous()
+        n = graph.num_nodes
+        p = float(drop_p) if training else 0.0
+        n_layers = len(conv_params) // 2
+        x = node_init_fwd(h_s, slot, n, w0, b0, p, new_dropout_seed() if p > 0 else 0)
+        xs = [x]
+        for l in range(n_layers):
+            w, b = conv_params[2 * l], conv_params[2 * l + 1]
+            xw = _linear_any(x, w)
+            if _staged_ok(graph, xw.shape[-1]):
+                x = spmm_fused(graph, xw, bias=b, relu=True, drop_p=p, drop_seed=new_dropout_seed() if p > 0 else 0)
+            else:  # graph too large for shared memory: L2-gather kernel + elementwise tail
+                x = torch.relu_(spmm(graph, xw).add_(b))
+                if p > 0:
+                    x = torch.nn.functional.dropout(x, p, True)
+            del xw
+            xs.append(x)
+        ctx.save_for_backward(h_s, slot, w0, *conv_params[0::2], *xs)
+        ctx.graph, ctx.n_layers, ctx.scale = graph, n_layers, 1.0 / (1.0 - p)
+        return xs[-1]
+
+    @staticmethod
+    def backward(ctx, dx):
+        saved = ctx.saved_tensors
+        L_ = ctx.n_layers
+        h_s, slot, w0 = saved[0], saved[1], saved[2]
+        ws_ = saved[3:3 + L_]
+        xs = saved[3 + L_:]
+        graph, scale = ctx.graph, ctx.scale
+        g = dx.contiguous()
+        grads = [None] * (2 * L_)
+        for l in range(L_ - 1, -1, -1):
+            x_out, x_in, w = xs[l + 1], xs[l], ws_[l]
+            if _staged_ok(graph, g.shape[-1]):
+                gz, db = spmm_fused(graph, g, transpose=True, gate=x_out, gate_scale=scale, want_colsum=True)
+            else:
+                dz = torch.where(x_out > 0, g * scale, torch.zeros((), device=g.device))
+                db = dz.sum(dim=(0, 1))
+                gz = spmm(graph, dz, transpose=True)
+                del dz
+            grads[2 * l] = wgrad(gz, x_in)
+            grads[2 * l + 1] = db
+            g = _linear_any(gz, w, transposed=True)
+            del gz
+        dhs, dw0, db0 = node_init_bwd(h_s, slot, w0, g, xs[0], scale)
+        return (dhs, None, None, None, None, dw0, db0, *grads)
+
+
+def gnn_body(h_s: torch.Tensor, slot: torch.Tensor, graph: PipeGraph, drop_p: float, training: bool,
+             w0: torch.Tensor, b0: torch.Tensor, conv_params) -> torch.Tensor:
+    """Sensor embeddings (B,S,ds) -> node states after the last GCN layer (B,N,D)."""
+    _check_act(h_s.contiguous(), "h_s")
+    return _GnnBody.apply(h_s, slot, graph, drop_p, training, w0, b0, *conv_params)

@@ -1,0 +1,93 @@
+"""Unit parity of the remaining hand-written kernels vs plain fp64 torch restatements of the reference ops."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from leak_det_gnn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("m,do,di", [(1, 64, 64), (31, 64, 64), (33, 64, 64), (84608, 64, 64), (5000, 128, 128),
+                                     (777, 64, 128), (100, 32, 64), (1000, 24, 40)])
+def test_wgrad(m, do, di):
+    gen = torch.Generator().manual_seed(m + do)
+    g = torch.randn(m, do, generator=gen)
+    x = torch.randn(m, di, generator=gen)
+    want = g.double().t() @ x.double()
+    got = ops.wgrad(g.cuda(), x.cuda())
+    assert got.shape == (do, di)
+    # a sum of m products: compare to fp64 relative to the size of the terms (sqrt(m) growth)
+    assert (got.cpu().double() - want).abs().max() <= TOL * max(want.abs().max().item(), m ** 0.5)
+    assert rel_err(got, want) <= 1e-4
+    assert torch.equal(got, ops.wgrad(g.cuda(), x.cuda()))  # deterministic
+
+
+def _node_init_ref(h_s, idx, n, w, b):
+    """reference detector.py:178-189 in fp64 (dropout off)."""
+    bsz, s, ds = h_s.shape
+    h0 = torch.zeros(bsz, n, ds, dtype=torch.float64)
+    h0[:, idx, :] = h_s
+    mask = torch.zeros(n, 1, dtype=torch.float64)
+    mask[idx, 0] = 1.0
+    h = torch.cat([h0, mask.unsqueeze(0).expand(bsz, -1, -1)], dim=-1)
+    return torch.relu(torch.nn.functional.linear(h, w, b))
+
+
+@pytest.mark.parametrize("bsz,n,s,ds,d", [(1, 661, 29, 64, 64), (37, 661, 29, 64, 64), (3, 785, 29, 32, 128),
+                                          (700, 50, 7, 16, 32)])
+def test_node_init_fwd_bwd(bsz, n, s, ds, d):
+    gen = torch.Generator().manual_seed(bsz + n)
+    idx = torch.randperm(n, generator=gen)[:s]
+    slot = torch.full((n,), -1, dtype=torch.int32)
+    slot[idx] = torch.arange(s, dtype=torch.int32)
+    h_s = torch.randn(bsz, s, ds, generator=gen)
+    w = torch.randn(d, ds + 1, generator=gen) * 0.2
+    b = torch.randn(d, generator=gen) * 0.5
+    x64 = _node_init_ref(h_s.double(), idx, n, w.double(), b.double())
+    dx = torch.randn(bsz, n, d, generator=gen)
+
+    x0 = ops.node_init_fwd(h_s.cuda(), slot.cuda(), n, w.cuda(), b.cuda())
+    assert rel_err(x0, x64) <= TOL
+    # fp64 truth of the backward, through autograd, with the ReLU mask the fp32 forward actually produced
+    # (a pre-activation within fp32 rounding of zero may land on the other side in fp64; the backward is
+    # defined by the forward that ran)
+    h64 = h_s.double().requires_grad_(True)
+    w64 = w.double().requires_grad_(True)
+    b64 = b.double().requires_grad_(True)
+    h0 = torch.zeros(bsz, n, ds, dtype=torch.float64)
+    h0 = h0.index_copy(1, idx, h64)
+    mask = torch.zeros(n, 1, dtype=torch.float64)
+    mask[idx, 0] = 1.0
+    pre = torch.nn.functional.linear(torch.cat([h0, mask.unsqueeze(0).expand(bsz, -1, -1)], dim=-1), w64, b64)
+    (pre * (x0.cpu() > 0).double()).backward(dx.double())
+    # non-sensor rows are exactly relu(bias)
+    non = torch.ones(n, dtype=torch.bool)
+    non[idx] = False
+    assert torch.equal(x0[:, non.cuda(), :].cpu(), torch.relu(b).expand(bsz, int(non.sum()), d))
+    dhs, dw, db = ops.node_init_bwd(h_s.cuda(), slot.cuda(), w.cuda(), dx.cuda(), x0, 1.0)
+    assert rel_err(dhs, h64.grad) <= TOL
+    assert rel_err(dw, w64.grad) <= 5 * TOL
+    assert rel_err(db, b64.grad) <= 5 * TOL
+    a = ops.node_init_bwd(h_s.cuda(), slot.cuda(), w.cuda(), dx.cuda(), x0, 1.0)
+    assert all(torch.equal(u, v) for u, v in zip(a, (dhs, dw, db)))  # deterministic
+
+
+def test_node_init_dropout():
+    n, s, ds, d, bsz = 661, 29, 64, 64, 200
+    idx = torch.arange(0, n, 23)[:s]
+    slot = torch.full((n,), -1, dtype=torch.int32)
+    slot[idx] = torch.arange(s, dtype=torch.int32)
+    h_s = torch.randn(bsz, s, ds).cuda()
+    w = (torch.randn(d, ds + 1) * 0.2).cuda()
+    b = (torch.rand(d) + 0.1).cuda()       # positive bias -> every non-sensor entry is live before dropout
+    base = ops.node_init_fwd(h_s, slot.cuda(), n, w, b)
+    dr = ops.node_init_fwd(h_s, slot.cuda(), n, w, b, 0.1, 99)
+    live = base > 0
+    frac = ((dr == 0) & live).float().sum().item() / live.float().sum().item()
+    assert abs(frac - 0.1) < 3e-3
+    kept = dr != 0
+    assert torch.equal(dr[kept], (base * np.float32(1 / 0.9))[kept])
+    assert torch.equal(dr, ops.node_init_fwd(h_s, slot.cuda(), n, w, b, 0.1, 99))
