@@ -1,0 +1,264 @@
+// heads.cu -- the two read-out heads of the detector on top of the last GCN layer.
+//
+//   pipe head  (models/detector.py:76-88, 204-211): for every class pipe p = (u, v)
+//              feat = [h_u, h_v, |h_u - h_v|] -> Linear(3D, H) -> ReLU -> Dropout -> Linear(H, 1)
+//              The reference gathers h_u / h_v into (B, P, D) tensors, concatenates a (B, P, 3D) feature
+//              tensor (2.4 GB at B = 4096, P = 764) and runs cuBLAS on it.  Here the features are formed
+//              on the fly by the loader warps of the tcgen05 row-GEMM (rowgemm.cuh) straight from the
+//              L2-resident node states; the hidden layer never leaves the SM in the forward except as the
+//              saved post-activation the backward needs.
+//   mean pool  (models/detector.py:214-215, PyG global_mean_pool over equal-sized graphs).
+//
+// Shared-memory budget forces the H = 128 hidden units to be processed as two "variants" of 64 (forward:
+// rows of W1) and the 3D = 192 feature gradients as two variants of 96 (backward: columns of W1); a CTA
+// keeps its variant for life, the two CTAs working on the same row tile run side by side so the second
+// read of the tile's inputs is an L2 hit.
+#include "rowgemm.cuh"
+
+using namespace ltgnn;
+
+namespace {
+
+// ------------------------------------------------------------------ forward
+struct PipeFeatLoader {
+    const float4* x;   // node states [B*N, d4]
+    const int2* ends;  // [P] (u, v)
+    int P, N, d4;
+    __device__ __forceinline__ float4 operator()(int64_t row, int c16) const {
+        const int b = static_cast<int>(row / P), p = static_cast<int>(row - static_cast<int64_t>(b) * P);
+        const int2 e = __ldg(ends + p);
+        const int seg = c16 / d4, cc = c16 - seg * d4;
+        const float4* xb = x + static_cast<int64_t>(b) * N * d4 + cc;
+        if (seg == 0) return __ldg(xb + static_cast<int64_t>(e.x) * d4);
+        if (seg == 1) return __ldg(xb + static_cast<int64_t>(e.y) * d4);
+        const float4 a = __ldg(xb + static_cast<int64_t>(e.x) * d4), c = __ldg(xb + static_cast<int64_t>(e.y) * d4);
+        return make_float4(fabsf(a.x - c.x), fabsf(a.y - c.y), fabsf(a.z - c.z), fabsf(a.w - c.w));
+    }
+};
+
+// hidden = dropout(relu(acc + b1)); part[var][row] = sum over this variant's 64 hidden units of hidden * w2
+struct HeadFwdEpilogue {
+    const float* b1;   // [H]
+    const float* w2;   // [H]
+    float* part;       // [nvar][M]
+    float* hpost;      // [M][H] saved post-activation, or nullptr (inference)
+    int64_t M;
+    int H, nh;         // hidden units in total / per variant
+    uint32_t drop_thresh;
+    float keep_scale;
+    uint64_t drop_seed;
+    template <class Pull>
+    __device__ __forceinline__ void operator()(int64_t row, bool valid, int var, Pull&& pull) const {
+        float acc = 0.f;
+        for (int c0 = 0; c0 < nh; c0 += 16) {
+            float v[16];
+            pull(c0, v);
+            const int col = var * nh + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col) + j);
+                float4 h = make_float4(fmaxf(v[4 * j] + bb.x, 0.f), fmaxf(v[4 * j + 1] + bb.y, 0.f),
+                                       fmaxf(v[4 * j + 2] + bb.z, 0.f), fmaxf(v[4 * j + 3] + bb.w, 0.f));
+                if (drop_thresh)
+                    ptx::dropout4(h, static_cast<uint64_t>(row) * (H >> 2) + ((col >> 2) + j), drop_seed, drop_thresh,
+                                  keep_scale);
+                if (hpost && valid) reinterpret_cast<float4*>(hpost + row * H + col)[j] = h;
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + col) + j);
+                acc = fmaf(h.x, ww.x, acc);
+                acc = fmaf(h.y, ww.y, acc);
+                acc = fmaf(h.z, ww.z, acc);
+                acc = fmaf(h.w, ww.w, acc);
+            }
+        }
+        if (valid) part[static_cast<int64_t>(var) * M + row] = acc;
+    }
+};
+
+// ------------------------------------------------------------------ backward (input gradient)
+// A[row, j] = d loss / d pre[row, j] = dlogit[row] * w2[j] * (hpost[row, j] > 0 ? scale : 0)
+struct DpreLoader {
+    const float4* hpost;   // [M][H/4]
+    const float* dlogit;   // [M]
+    const float4* w2;      // [H/4]
+    float scale;
+    int h4;
+    __device__ __forceinline__ float4 operator()(int64_t row, int c16) const {
+        const float4 h = ptx::ldg_stream(hpost + row * h4 + c16);
+        const float4 w = __ldg(w2 + c16);
+        const float g = __ldg(dlogit + row) * scale;
+        return make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
+                           h.w > 0.f ? g * w.w : 0.f);
+    }
+};
+
+__device__ __forceinline__ float sgn(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
+
+// dfeat[row, 0:3D] is scattered back to the two end nodes: +u for the h_u block, +v for the h_v block,
+// +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0).  Several pipes share a node, so the
+// adds are fp32 reductions in L2 (red.global.add.v4.f32) -- like the reference's index_add_ in autograd.
+struct HeadBwdEpilogue {
+    float* dx;          // [B*N, D], pre-filled with the mean-pool gradient
+    const float* x;     // node states (for the sign of h_u - h_v)
+    const int2* ends;
+    int P, N, D, ncols;  // ncols = feature-gradient columns per variant
+    template <class Pull>
+    __device__ __forceinline__ void operator()(int64_t row, bool valid, int var, Pull&& pull) const {
+        int b = 0;
+        int2 e = make_int2(0, 0);
+        if (valid) {
+            b = static_cast<int>(row / P);
+            e = __ldg(ends + static_cast<int>(row - static_cast<int64_t>(b) * P));
+        }
+        const int64_t ru = (static_cast<int64_t>(b) * N + e.x) * D, rv = (static_cast<int64_t>(b) * N + e.y) * D;
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+            float v[16];
+            pull(c0, v);
+            if (!valid) continue;
+            const int gc = var * ncols + c0;
+            const int blk = gc / D, cb = gc - blk * D;
+            if (blk < 2) {
+                float4* dst = reinterpret_cast<float4*>(dx + (blk == 0 ? ru : rv) + cb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(dst + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            } else {
+                const float4* hu = reinterpret_cast<const float4*>(x + ru + cb);
+                const float4* hv = reinterpret_cast<const float4*>(x + rv + cb);
+                float4* du = reinterpret_cast<float4*>(dx + ru + cb);
+                float4* dv = reinterpret_cast<float4*>(dx + rv + cb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 a = __ldg(hu + j), c = __ldg(hv + j);
+                    const float4 g = make_float4(sgn(a.x - c.x) * v[4 * j], sgn(a.y - c.y) * v[4 * j + 1],
+                                                 sgn(a.z - c.z) * v[4 * j + 2], sgn(a.w - c.w) * v[4 * j + 3]);
+                    atomicAdd(du + j, g);
+                    atomicAdd(dv + j, make_float4(-g.x, -g.y, -g.z, -g.w));
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------ mean pool and its adjoint
+__global__ void __launch_bounds__(256)
+mean_pool_kernel(const float4* __restrict__ x, float4* __restrict__ pooled, int64_t B, int N, int d4) {
+    __shared__ float4 red[256];
+    const int tid = threadIdx.x;
+    const int c = tid % d4, r0 = tid / d4, rstep = 256 / d4;
+    const float inv = 1.f / static_cast<float>(N);
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const float4* xb = x + b * N * d4 + c;
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = r0; r < N; r += rstep) {
+            const float4 v = ptx::ldg_stream(xb + static_cast<int64_t>(r) * d4);
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        red[tid] = s;
+        __syncthreads();
+        if (tid < d4) {
+            float4 t = red[tid];
+            for (int k = tid + d4; k < 256; k += d4) {
+                const float4 o = red[k];
+                t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+            }
+            pooled[b * d4 + tid] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+        }
+        __syncthreads();
+    }
+}
+
+// dx[b, i, :] = dpooled[b, :] / N   (adjoint of the mean; also the initial value the pipe-head scatter adds onto)
+__global__ void __launch_bounds__(256)
+pool_bwd_fill_kernel(const float4* __restrict__ dpooled, float4* __restrict__ dx, int64_t total4, int N, int d4) {
+    const float inv = 1.f / static_cast<float>(N);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    const int64_t per_b = static_cast<int64_t>(N) * d4;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const int64_t b = i / per_b;
+        const int c = static_cast<int>(i % d4);
+        const float4 g = __ldg(dpooled + b * d4 + c);
+        ptx::stg_stream(dx + i, make_float4(g.x * inv, g.y * inv, g.z * inv, g.w * inv));
+    }
+}
+
+int head_shape_check(int D, int H, const char* who) {
+    LTGNN_REQUIRE(D == 64, LTGNN_E_SHAPE, "%s: node width D=%d not supported by the fused head (64 only)", who, D);
+    LTGNN_REQUIRE(H == 128, LTGNN_E_SHAPE, "%s: hidden width H=%d not supported by the fused head (128 only)", who, H);
+    return LTGNN_OK;
+}
+
+}  // namespace
+
+extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
+                                   const int32_t* ends, const float* W1, const float* b1, const float* w2,
+                                   float drop_p, uint64_t drop_seed, float* part, float* hpost, void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_fwd: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
+    int rc = head_shape_check(D, H, "pipe_head_fwd");
+    if (rc) return rc;
+    LTGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LTGNN_E_ARG, "pipe_head_fwd: dropout p=%f", drop_p);
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(X && ends && W1 && b1 && w2 && part, LTGNN_E_ARG, "pipe_head_fwd: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(b1) && aligned16(w2) && aligned16(hpost), LTGNN_E_ALIGN,
+                  "pipe_head_fwd: 16-byte alignment required");
+    const int64_t M = B * P;
+    LTGNN_REQUIRE(M < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*P too large");
+    PipeFeatLoader ld{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), P, N, D / 4};
+    HeadFwdEpilogue ep{b1, w2, part, hpost, M, H, H / 2,
+                       drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 4294967296.0) : 0u,
+                       1.f / (1.f - drop_p), drop_seed};
+    rowgemm::BSpec bs{W1, 3 * D, 0, 2};
+    return rowgemm::launch(device, ld, ep, bs, M, 3 * D, H / 2, static_cast<cudaStream_t>(stream_), "pipe_head_fwd");
+}
+
+extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
+                                      const int32_t* ends, const float* W1, const float* w2, const float* hpost,
+                                      const float* dlogit, float gate_scale, float* dX, void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_bwd_dx: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
+    int rc = head_shape_check(D, H, "pipe_head_bwd_dx");
+    if (rc) return rc;
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(X && ends && W1 && w2 && hpost && dlogit && dX, LTGNN_E_ARG, "pipe_head_bwd_dx: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(w2) && aligned16(hpost) && aligned16(dX), LTGNN_E_ALIGN,
+                  "pipe_head_bwd_dx: 16-byte alignment required");
+    const int64_t M = B * P;
+    DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, H / 4};
+    HeadBwdEpilogue ep{dX, X, reinterpret_cast<const int2*>(ends), P, N, D, 3 * D / 2};
+    rowgemm::BSpec bs{W1, 3 * D, 1, 2};
+    return rowgemm::launch(device, ld, ep, bs, M, H, 3 * D / 2, static_cast<cudaStream_t>(stream_), "pipe_head_bwd_dx");
+}
+
+extern "C" int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, const float* X, float* pooled,
+                                   void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && N > 0 && D > 0, LTGNN_E_ARG, "mean_pool_fwd: B=%lld N=%d D=%d", static_cast<long long>(B), N, D);
+    LTGNN_REQUIRE(D % 4 == 0 && 256 % (D / 4) == 0, LTGNN_E_SHAPE, "mean_pool_fwd: D=%d must be 4 * a divisor of 256", D);
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(X && pooled, LTGNN_E_ARG, "mean_pool_fwd: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(pooled), LTGNN_E_ALIGN, "mean_pool_fwd: 16-byte alignment required");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    const int64_t cap = static_cast<int64_t>(di->sm_count) * 8;
+    mean_pool_kernel<<<static_cast<int>(B < cap ? B : cap), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(pooled), B, N, D / 4);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_mean_pool_bwd_fill(int device, int64_t B, int32_t N, int32_t D, const float* dpooled, float* dX,
+                                        void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && N > 0 && D > 0 && D % 4 == 0, LTGNN_E_ARG, "mean_pool_bwd_fill: B=%lld N=%d D=%d",
+                  static_cast<long long>(B), N, D);
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(dpooled && dX, LTGNN_E_ARG, "mean_pool_bwd_fill: null tensor");
+    LTGNN_REQUIRE(aligned16(dpooled) && aligned16(dX), LTGNN_E_ALIGN, "mean_pool_bwd_fill: 16-byte alignment required");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    const int64_t total4 = B * N * (D / 4);
+    int64_t blocks = (total4 + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(di->sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    pool_bwd_fill_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        reinterpret_cast<const float4*>(dpooled), reinterpret_cast<float4*>(dX), total4, N, D / 4);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}

@@ -26,7 +26,15 @@ struct StoreEpilogue {
     float gate_scale;
     int n;
     int relu;
-    __device__ __forceinline__ void operator()(int64_t row, int c0, float (&v)[16]) const {
+    template <class Pull>
+    __device__ __forceinline__ void operator()(int64_t row, bool valid, int /*var*/, Pull&& pull) const {
+        for (int c0 = 0; c0 < n; c0 += 16) {
+            float v[16];
+            pull(c0, v);
+            if (valid) chunk(row, c0, v);
+        }
+    }
+    __device__ __forceinline__ void chunk(int64_t row, int c0, float (&v)[16]) const {
         if (bias) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
@@ -64,5 +72,6 @@ extern "C" int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const f
                   "linear: 16-byte alignment required");
     RowLoader ld{reinterpret_cast<const float4*>(X), K / 4};
     StoreEpilogue ep{Y, bias, gate, gate_scale, N, relu};
-    return rowgemm::launch(device, ld, ep, W, w_transposed, M, K, N, static_cast<cudaStream_t>(stream_), "linear");
+    rowgemm::BSpec bs{W, w_transposed ? N : K, w_transposed, 1};
+    return rowgemm::launch(device, ld, ep, bs, M, K, N, static_cast<cudaStream_t>(stream_), "linear");
 }

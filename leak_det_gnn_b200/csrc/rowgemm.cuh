@@ -44,24 +44,33 @@ __host__ inline uint32_t tmem_cols_for(int N) {
     return c;
 }
 
-// Fill the resident B operand.  W is [N x K] row-major (w_transposed = 0, torch.nn.Linear layout) or
-// [K x N] row-major (w_transposed = 1: computes A * W instead of A * W^T).
-__device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const float* __restrict__ W, int K, int N, int w_transposed,
-                              int tid, int nthreads) {
-    if (!w_transposed) {
+// Where the resident B operand comes from.  A launch may carry several B "variants" (disjoint slices of one
+// weight): CTA c works with variant c % nvar for its whole life and walks row tiles c / nvar, c / nvar + grid / nvar, ...
+//   transposed = 0:  B_var[n][k] = W[(var * N + n) * ldw + k]      (rows of a torch.nn.Linear weight [N_total, K])
+//   transposed = 1:  B_var[n][k] = W[k * ldw + var * N + n]        (columns of a [K, N_total] matrix: A * W)
+struct BSpec {
+    const float* W;
+    int ldw;
+    int transposed;
+    int nvar;
+};
+
+__device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const BSpec& bs, int var, int K, int N, int tid,
+                              int nthreads) {
+    if (!bs.transposed) {
         const int k4 = K >> 2;
         for (int i = tid; i < N * k4; i += nthreads) {
             const int r = i / k4, c = i - r * k4;
             float4 hi, lo;
-            split4(__ldg(reinterpret_cast<const float4*>(W) + i), hi, lo);
+            split4(__ldg(reinterpret_cast<const float4*>(bs.W + static_cast<size_t>(var * N + r) * bs.ldw) + c), hi, lo);
             const uint32_t off = sw128_offset(r, c, N);
             *reinterpret_cast<float4*>(b_hi + off) = hi;
             *reinterpret_cast<float4*>(b_lo + off) = lo;
         }
     } else {
         for (int i = tid; i < N * K; i += nthreads) {
-            const int k = i / N, n = i - k * N;  // coalesced read of W[k][n]
-            const float w = __ldg(W + i);
+            const int k = i / N, n = i - k * N;  // coalesced along n
+            const float w = __ldg(bs.W + static_cast<size_t>(k) * bs.ldw + var * N + n);
             const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
             const uint32_t off = sw128_offset(n, k >> 2, N) + (k & 3) * 4;
             *reinterpret_cast<float*>(b_hi + off) = hi;
@@ -72,8 +81,8 @@ __device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const float* __restr
 
 template <class Loader, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
-rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __restrict__ W, int w_transposed, int64_t M,
-               int K, int N, int KG, uint32_t tmem_cols) {
+rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, int64_t M, int K, int N, int KG,
+               uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -98,7 +107,9 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __rest
         }
         fence_mbar_init();
     }
-    fill_b(b_hi, b_lo, W, K, N, w_transposed, tid, kThreads);
+    const int var = blockIdx.x % bspec.nvar;
+    const int64_t tile0 = blockIdx.x / bspec.nvar, tile_step = gridDim.x / bspec.nvar;
+    fill_b(b_hi, b_lo, bspec, var, K, N, tid, kThreads);
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -111,7 +122,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __rest
         const int g4 = KG >> 2;  // 16-byte chunks per row per k-group
         const int items = kTileM * g4;
         int it = 0;  // counts (tile, k-group) stages
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
             const int64_t row0 = tile * kTileM;
             for (int kg = 0; kg < n_kg; ++kg, ++it) {
                 const int s = it % kStages;
@@ -154,7 +165,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __rest
             const uint32_t idesc = idesc_tf32(kTileM, N);
             const int katoms_per_group = KG >> 5;
             int it = 0, t = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
                 const int a = t & 1;
                 const uint32_t pha = (t >> 1) & 1;
                 mbar_wait(&bar_tempty[a], pha ^ 1);  // epilogue drained this accumulator
@@ -179,18 +190,16 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __rest
         // ------------------------------- epilogue -------------------------------
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
         int t = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
             const int a = t & 1;
             const uint32_t pha = (t >> 1) & 1;
             mbar_wait(&bar_tfull[a], pha);
             fence_after_sync();
             const uint32_t taddr = tmem_base + a * N + (static_cast<uint32_t>(q * 32) << 16);
             const int64_t row = tile * kTileM + q * 32 + lane;
-            for (int c0 = 0; c0 < N; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
-                if (row < M) epilogue(row, c0, v);
-            }
+            // the epilogue pulls 16-column chunks itself (tcgen05.ld is warp-collective: every lane must pull
+            // every chunk, valid row or not) and may keep per-row state across chunks
+            epilogue(row, row < M, var, [&](int c0, float (&v)[16]) { tmem_ld16(taddr + c0, v); });
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);
@@ -205,10 +214,11 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const float* __rest
 
 // host-side launch helper: validates shapes against the device, sets the smem attribute, launches
 template <class Loader, class Epilogue>
-int launch(int device, const Loader& loader, const Epilogue& epilogue, const float* W, int w_transposed, int64_t M, int K,
-           int N, cudaStream_t stream, const char* who) {
+int launch(int device, const Loader& loader, const Epilogue& epilogue, const BSpec& bspec, int64_t M, int K, int N,
+           cudaStream_t stream, const char* who) {
     LTGNN_REQUIRE(K % 32 == 0 && K > 0 && K <= 256, LTGNN_E_SHAPE, "%s: K=%d must be a multiple of 32, <= 256", who, K);
     LTGNN_REQUIRE(N % 16 == 0 && N > 0 && N <= 256, LTGNN_E_SHAPE, "%s: N=%d must be a multiple of 16, <= 256", who, N);
+    LTGNN_REQUIRE(bspec.nvar >= 1, LTGNN_E_ARG, "%s: nvar=%d", who, bspec.nvar);
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
@@ -221,8 +231,10 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const flo
     auto kern = rowgemm_kernel<Loader, Epilogue>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t tiles = (M + kTileM - 1) / kTileM;
-    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
-    kern<<<grid, kThreads, smem, stream>>>(loader, epilogue, W, w_transposed, M, K, N, KG, tmem_cols_for(N));
+    int64_t grid = tiles * bspec.nvar < di->sm_count ? tiles * bspec.nvar : di->sm_count;
+    grid -= grid % bspec.nvar;
+    LTGNN_REQUIRE(grid > 0, LTGNN_E_SHAPE, "%s: nvar=%d exceeds the SM count", who, bspec.nvar);
+    kern<<<static_cast<int>(grid), kThreads, smem, stream>>>(loader, epilogue, bspec, M, K, N, KG, tmem_cols_for(N));
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

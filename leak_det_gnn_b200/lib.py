@@ -39,6 +39,12 @@ SIGNATURES = {
     "ltgnn_node_init_ws_floats": (c_int64, [c_int, c_int32, c_int32]),
     "ltgnn_node_init_bwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ltgnn_pipe_head_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p]),
+    "ltgnn_pipe_head_bwd_dx": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "ltgnn_mean_pool_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "ltgnn_mean_pool_bwd_fill": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

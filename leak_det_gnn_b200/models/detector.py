@@ -119,7 +119,7 @@ class LeakDetector(nn.Module):
         if hit is None:
             slot = torch.full((len(self.node_names),), -1, dtype=torch.int32)
             slot[self.sensor_node_idx] = torch.arange(len(self.sensor_node_ids), dtype=torch.int32)
-            hit = (slot.to(device), self.pipe_ends.to(device))
+            hit = (slot.to(device), self.pipe_ends.to(device), self.pipe_ends.to(device=device, dtype=torch.int32))
             self._dev_cache[key] = hit
         return hit
 
@@ -128,14 +128,20 @@ class LeakDetector(nn.Module):
         message-passing hot path."""
         if not h_s.is_cuda:
             raise ValueError("LeakDetector runs on CUDA only (sm_100a kernels; no CPU fallback)")
-        slot, ends = self._index_tensors(h_s.device)
+        slot, ends, ends32 = self._index_tensors(h_s.device)
         conv_params = [t for conv in self.convs for t in (conv.lin.weight, conv.bias)]
         x = ops.gnn_body(h_s, slot, self.pipe_graph, self.dropout.p, self.training, self.sensor_to_node.weight,
                          self.sensor_to_node.bias, conv_params)
-        h_u = x[:, ends[:, 0], :]
-        h_v = x[:, ends[:, 1], :]
-        pipe_logits = self.edge_head(h_u, h_v)
-        noleak_logit = self.noleak_head(ops.mean_pool(x)).unsqueeze(-1)
+        lin1, lin2 = self.edge_head.mlp[0], self.edge_head.mlp[3]
+        if ops.heads_supported(x.shape[-1], lin1.out_features):
+            # fused pipe head (features formed on the fly, tcgen05) + mean pool; the H -> 1 layer's bias and the
+            # tiny no-leak MLP on the pooled (B, D) vector stay in torch
+            part, pooled = ops.heads(x, ends32, lin1.weight, lin1.bias, lin2.weight, self.dropout.p, self.training)
+            pipe_logits = part.sum(0) + lin2.bias
+        else:
+            pipe_logits = self.edge_head(x[:, ends[:, 0], :], x[:, ends[:, 1], :])
+            pooled = ops.mean_pool(x)
+        noleak_logit = self.noleak_head(pooled).unsqueeze(-1)
         return torch.cat([pipe_logits, noleak_logit], dim=-1)
 
     def forward(self, residual: torch.Tensor, tfeat: Optional[torch.Tensor] = None) -> torch.Tensor:

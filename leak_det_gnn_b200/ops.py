@@ -17,7 +17,7 @@ from . import instrument as _inst
 from . import lib as _lib
 from .graph import GCNCsr, build_gcn_csr
 
-__all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body"]
+__all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported"]
 
 
 def _ptr(a: np.ndarray) -> ctypes.c_void_p:
@@ -326,9 +326,112 @@ def gcn_conv(x: torch.Tensor, graph: PipeGraph, weight: torch.Tensor, bias: Opti
     return _GcnConv.apply(x, weight, bias, graph)
 
 
+class _MeanPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        b, n, d = x.shape
+        pooled = torch.empty(b, d, device=x.device, dtype=torch.float32)
+        L = _lib.load()
+        tok = _inst.begin("mean_pool_fwd")
+        _lib.check(L.ltgnn_mean_pool_fwd(_dev_index(x), b, n, d, x.data_ptr(), pooled.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        ctx.shape = (b, n, d)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        b, n, d = ctx.shape
+        dpooled = dpooled.contiguous()
+        dx = torch.empty(b, n, d, device=dpooled.device, dtype=torch.float32)
+        L = _lib.load()
+        tok = _inst.begin("mean_pool_bwd")
+        _lib.check(L.ltgnn_mean_pool_bwd_fill(_dev_index(dpooled), b, n, d, dpooled.data_ptr(), dx.data_ptr(),
+                                              _stream(dpooled)))
+        _inst.end(tok)
+        return dx
+
+
 def mean_pool(x: torch.Tensor) -> torch.Tensor:
     """(B, N, D) -> (B, D): ``global_mean_pool`` for equal-sized graphs (detector.py:214-215)."""
-    return x.mean(dim=1)
+    _check_act(x.contiguous(), "x")
+    if x.shape[-1] % 4 or 256 % (x.shape[-1] // 4):
+        return x.mean(dim=1)
+    return _MeanPool.apply(x)
+
+
+def heads_supported(d: int, h: int) -> bool:
+    return d == 64 and h == 128
+
+
+class _Heads(torch.autograd.Function):
+    """Pipe head partial logits + mean pool of the last node states as one autograd node, so that the backward
+    writes d loss / d x exactly once: the pool gradient initialises it, the pipe-head scatter adds onto it."""
+
+    @staticmethod
+    def forward(ctx, x, ends, w1, b1, w2, drop_p, training):
+        x = x.contiguous()
+        b, n, d = x.shape
+        p_cnt, h = ends.shape[0], w1.shape[0]
+        dev = _dev_index(x)
+        L = _lib.load()
+        p = float(drop_p) if training else 0.0
+        need_grad = any(ctx.needs_input_grad)
+        part = torch.empty(2, b, p_cnt, device=x.device, dtype=torch.float32)
+        hpost = torch.empty(b * p_cnt, h, device=x.device, dtype=torch.float32) if need_grad else None
+        w2v = w2.reshape(-1).contiguous()
+        tok = _inst.begin("pipe_head_fwd")
+        _lib.check(L.ltgnn_pipe_head_fwd(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), w1.data_ptr(),
+                                         b1.data_ptr(), w2v.data_ptr(), p, new_dropout_seed() if p > 0 else 0,
+                                         part.data_ptr(), None if hpost is None else hpost.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        pooled = torch.empty(b, d, device=x.device, dtype=torch.float32)
+        tok = _inst.begin("mean_pool_fwd")
+        _lib.check(L.ltgnn_mean_pool_fwd(dev, b, n, d, x.data_ptr(), pooled.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        if need_grad:
+            ctx.save_for_backward(x, ends, w1, w2v, hpost)
+        ctx.scale = 1.0 / (1.0 - p)
+        return part, pooled
+
+    @staticmethod
+    def backward(ctx, dpart, dpooled):
+        x, ends, w1, w2v, hpost = ctx.saved_tensors
+        b, n, d = x.shape
+        p_cnt, h = ends.shape[0], w1.shape[0]
+        dev = _dev_index(x)
+        L = _lib.load()
+        # both halves of `part` feed one sum, so their gradients are the same tensor: d loss / d pipe_logit
+        dlogit = dpart[0].contiguous().view(-1)
+        dx = torch.empty_like(x)
+        tok = _inst.begin("mean_pool_bwd")
+        if dpooled is None:
+            dx.zero_()
+        else:
+            dpooled = dpooled.contiguous()
+            _lib.check(L.ltgnn_mean_pool_bwd_fill(dev, b, n, d, dpooled.data_ptr(), dx.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        tok = _inst.begin("pipe_head_bwd_dx")
+        _lib.check(L.ltgnn_pipe_head_bwd_dx(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), w1.data_ptr(),
+                                            w2v.data_ptr(), hpost.data_ptr(), dlogit.data_ptr(), ctx.scale,
+                                            dx.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        # parameter gradients (interim: cuBLAS through torch on materialised operands)
+        dpre = torch.where(hpost > 0, dlogit.unsqueeze(1) * (w2v * ctx.scale), torch.zeros((), device=x.device))
+        e = ends.long()
+        h_u, h_v = x[:, e[:, 0], :], x[:, e[:, 1], :]
+        feat = torch.cat([h_u, h_v, (h_u - h_v).abs()], dim=-1).view(b * p_cnt, 3 * d)
+        dw1 = dpre.t() @ feat
+        db1 = dpre.sum(0)
+        dw2 = (dlogit.unsqueeze(1) * hpost).sum(0).view(1, h)
+        return dx, None, dw1, db1, dw2, None, None
+
+
+def heads(x: torch.Tensor, ends: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, drop_p: float,
+          training: bool):
+    """x (B,N,64), ends int32 (P,2) -> (part (2,B,P), pooled (B,64)); pipe_logits = part.sum(0) + b2."""
+    _check_act(x.contiguous(), "x")
+    return _Heads.apply(x, ends, w1, b1, w2, drop_p, training)
 
 
 # ----------------------------------------------------------------------------------------------

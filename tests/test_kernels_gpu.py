@@ -91,3 +91,61 @@ def test_node_init_dropout():
     kept = dr != 0
     assert torch.equal(dr[kept], (base * np.float32(1 / 0.9))[kept])
     assert torch.equal(dr, ops.node_init_fwd(h_s, slot.cuda(), n, w, b, 0.1, 99))
+
+
+def _head_ref(x, ends, w1, b1, w2, b2):
+    h_u, h_v = x[:, ends[:, 0], :], x[:, ends[:, 1], :]
+    feat = torch.cat([h_u, h_v, (h_u - h_v).abs()], dim=-1)
+    hid = torch.relu(torch.nn.functional.linear(feat, w1, b1))
+    return torch.nn.functional.linear(hid, w2, b2).squeeze(-1), x.mean(dim=1)
+
+
+@pytest.mark.parametrize("bsz,n,p", [(3, 661, 764), (1, 661, 2), (5, 785, 905), (40, 100, 37)])
+def test_heads_fwd_bwd(bsz, n, p):
+    gen = torch.Generator().manual_seed(bsz * 7 + p)
+    x = torch.randn(bsz, n, 64, generator=gen).relu()
+    ends = torch.randint(0, n, (p, 2), generator=gen)
+    ends[0, 1] = ends[0, 0]  # a degenerate pipe: |h_u - h_v| = 0 and sign(0) = 0
+    w1 = torch.randn(128, 192, generator=gen) * 0.1
+    b1 = torch.randn(128, generator=gen) * 0.1
+    w2 = torch.randn(1, 128, generator=gen) * 0.2
+    b2 = torch.randn(1, generator=gen)
+    dlog = torch.randn(bsz, p, generator=gen)
+    dpool = torch.randn(bsz, 64, generator=gen)
+
+    t = [v.double().requires_grad_(True) for v in (x, w1, b1, w2, b2)]
+    lr, pr = _head_ref(t[0], ends, *t[1:])
+    ((lr * dlog.double()).sum() + (pr * dpool.double()).sum()).backward()
+
+    o = [v.cuda().requires_grad_(True) for v in (x, w1, b1, w2)]
+    b2c = b2.cuda().requires_grad_(True)
+    part, pooled = ops.heads(o[0], ends.to(torch.int32).cuda(), o[1], o[2], o[3], 0.1, False)
+    logits = part.sum(0) + b2c
+    assert rel_err(logits, lr) <= TOL and rel_err(pooled, pr) <= TOL
+    ((logits * dlog.cuda()).sum() + (pooled * dpool.cuda()).sum()).backward()
+    assert rel_err(o[0].grad, t[0].grad) <= TOL
+    assert rel_err(o[1].grad, t[1].grad) <= TOL
+    assert rel_err(o[2].grad, t[2].grad) <= TOL
+    assert rel_err(o[3].grad, t[3].grad) <= TOL
+    assert rel_err(b2c.grad, t[4].grad) <= TOL
+
+
+def test_heads_dropout_train_mode():
+    gen = torch.Generator().manual_seed(5)
+    x = (torch.randn(16, 661, 64, generator=gen).relu()).cuda()
+    ends = torch.randint(0, 661, (764, 2), generator=gen).to(torch.int32).cuda()
+    w1 = (torch.randn(128, 192, generator=gen) * 0.1).cuda()
+    b1 = (torch.rand(128, generator=gen) + 5.0).cuda()     # all hidden units live: dropout is the only zero source
+    w2 = (torch.rand(1, 128, generator=gen) + 0.5).cuda().requires_grad_(True)
+    torch.manual_seed(1)
+    part, _ = ops.heads(x, ends, w1, b1, w2, 0.1, True)
+    base, _ = ops.heads(x, ends, w1, b1, w2, 0.1, False)
+    torch.manual_seed(1)
+    part2, _ = ops.heads(x, ends, w1, b1, w2, 0.1, True)
+    assert torch.equal(part, part2)                         # torch.manual_seed reproduces the masks
+    assert not torch.equal(part, base)
+    ratio = (part.sum(0) / base.sum(0)).mean().item()
+    assert abs(ratio - 1.0) < 5e-3                          # inverted dropout is unbiased
+    # backward uses the saved post-dropout activations: d/dw2 = sum dlogit * hidden
+    part.sum().backward()
+    assert w2.grad.shape == (1, 128) and torch.isfinite(w2.grad).all()
