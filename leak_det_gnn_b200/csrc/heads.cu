@@ -24,8 +24,8 @@ struct PipeFeatLoader {
     const float4* x;   // node states [B*N, d4]
     const int2* ends;  // [P] (u, v)
     int P, N, d4;
-    __device__ __forceinline__ float4 operator()(int64_t row, int c16) const {
-        const int b = static_cast<int>(row / P), p = static_cast<int>(row - static_cast<int64_t>(b) * P);
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c16) const {
+        const uint32_t b = row / static_cast<uint32_t>(P), p = row - b * static_cast<uint32_t>(P);
         const int2 e = __ldg(ends + p);
         const int seg = c16 / d4, cc = c16 - seg * d4;
         const float4* xb = x + static_cast<int64_t>(b) * N * d4 + cc;
@@ -48,7 +48,7 @@ struct HeadFwdEpilogue {
     float keep_scale;
     uint64_t drop_seed;
     template <class Pull>
-    __device__ __forceinline__ void operator()(int64_t row, bool valid, int var, Pull&& pull) const {
+    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int var, Pull&& pull) const {
         float acc = 0.f;
         for (int c0 = 0; c0 < nh; c0 += 16) {
             float v[16];
@@ -62,7 +62,7 @@ struct HeadFwdEpilogue {
                 if (drop_thresh)
                     ptx::dropout4(h, static_cast<uint64_t>(row) * (H >> 2) + ((col >> 2) + j), drop_seed, drop_thresh,
                                   keep_scale);
-                if (hpost && valid) reinterpret_cast<float4*>(hpost + row * H + col)[j] = h;
+                if (hpost && valid) reinterpret_cast<float4*>(hpost + static_cast<int64_t>(row) * H + col)[j] = h;
                 const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + col) + j);
                 acc = fmaf(h.x, ww.x, acc);
                 acc = fmaf(h.y, ww.y, acc);
@@ -82,8 +82,8 @@ struct DpreLoader {
     const float4* w2;      // [H/4]
     float scale;
     int h4;
-    __device__ __forceinline__ float4 operator()(int64_t row, int c16) const {
-        const float4 h = ptx::ldg_stream(hpost + row * h4 + c16);
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c16) const {
+        const float4 h = ptx::ldg_stream(hpost + static_cast<int64_t>(row) * h4 + c16);
         const float4 w = __ldg(w2 + c16);
         const float g = __ldg(dlogit + row) * scale;
         return make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
@@ -102,12 +102,12 @@ struct HeadBwdEpilogue {
     const int2* ends;
     int P, N, D, ncols;  // ncols = feature-gradient columns per variant
     template <class Pull>
-    __device__ __forceinline__ void operator()(int64_t row, bool valid, int var, Pull&& pull) const {
-        int b = 0;
+    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int var, Pull&& pull) const {
+        uint32_t b = 0;
         int2 e = make_int2(0, 0);
         if (valid) {
-            b = static_cast<int>(row / P);
-            e = __ldg(ends + static_cast<int>(row - static_cast<int64_t>(b) * P));
+            b = row / static_cast<uint32_t>(P);
+            e = __ldg(ends + (row - b * static_cast<uint32_t>(P)));
         }
         const int64_t ru = (static_cast<int64_t>(b) * N + e.x) * D, rv = (static_cast<int64_t>(b) * N + e.y) * D;
         for (int c0 = 0; c0 < ncols; c0 += 16) {

@@ -14,7 +14,9 @@ namespace {
 struct RowLoader {
     const float4* x;
     int k4;
-    __device__ __forceinline__ float4 operator()(int64_t row, int c) const { return ptx::ldg_stream(x + row * k4 + c); }
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        return ptx::ldg_stream(x + static_cast<int64_t>(row) * k4 + c);
+    }
 };
 
 // bias -> ReLU -> optional gate: y *= (gate[row, col] > 0) ? gate_scale : 0
@@ -27,7 +29,7 @@ struct StoreEpilogue {
     int n;
     int relu;
     template <class Pull>
-    __device__ __forceinline__ void operator()(int64_t row, bool valid, int /*var*/, Pull&& pull) const {
+    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int /*var*/, Pull&& pull) const {
         for (int c0 = 0; c0 < n; c0 += 16) {
             float v[16];
             pull(c0, v);

@@ -2,13 +2,14 @@
 //
 //   D[128 x N] = A_tile[128 x K] * B[N x K]^T      per 128-row tile, persistent CTAs, one per SM
 //
-//   warps 0-7  LOADERS   produce the A tile: a `Loader` functor returns 4 consecutive fp32 of a row
-//                        (a plain coalesced global load, a neighbour aggregation, a pipe-end gather...);
-//                        values are split into TF32 hi/lo and stored K-major SWIZZLE_128B in a 2-stage ring
-//   warp  8    MMA       one elected lane issues the tcgen05.mma chain into one of two TMEM accumulators and
+//   warps 0-15  LOADERS  produce the A tile 32 K-columns at a time: a `Loader` functor returns 4 consecutive fp32
+//                        of a row (a plain coalesced global load, a pipe-end gather, an on-the-fly gradient...);
+//                        values are split into TF32 hi/lo and stored K-major SWIZZLE_128B into a 4-stage ring,
+//                        one group of loader warps per stage
+//   warp  16    MMA      one elected lane issues the tcgen05.mma chain into one of two TMEM accumulators and
 //                        commits to the "stage free" and "accumulator full" mbarriers
-//   warps 9-12 EPILOGUE  tcgen05.ld their 32 TMEM lanes (lane = tile row), hand 16 columns at a time to an
-//                        `Epilogue` functor (bias, activation, masks, stores), release the accumulator
+//   warps 17-20 EPILOGUE tcgen05.ld their 32 TMEM lanes (lane = tile row) 16 columns at a time inside an
+//                        `Epilogue` functor (bias, activation, masks, reductions, stores), release the accumulator
 //
 // B (the weight, N x K) is split once per CTA and stays resident in shared memory.
 // All hand-offs are mbarriers; no __syncthreads after the prologue.
@@ -23,20 +24,23 @@ using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
 
 constexpr int kTileM = 128;
-constexpr int kLoaderWarps = 8;
-constexpr int kLoaderThreads = kLoaderWarps * 32;
+constexpr int kLoaderWarps = 16;
 constexpr int kMmaWarp = kLoaderWarps;
 constexpr int kEpiWarp0 = kMmaWarp + 1;
 constexpr int kEpiWarps = 4;
 constexpr int kThreads = (kLoaderWarps + 1 + kEpiWarps) * 32;
-constexpr int kStages = 2;
+constexpr int kMaxStages = 4;
+constexpr int kKG = 32;                              // K columns per ring stage = one 128-byte swizzle atom
+constexpr uint32_t kStageBytes = 2u * kTileM * kKG * 4;  // hi block + lo block = 32 KB
 
-// the A ring moves "k-groups" of KG = 64 (or 32) columns of K, so a stage is at most 64 KB whatever K is;
-// 32 is used when K is not a multiple of 64 or when the resident B leaves no room for 64-wide stages
-__host__ inline size_t smem_bytes(int K, int N, int KG) { return 1024 + kStages * 2ull * kTileM * KG * 4 + 2ull * N * K * 4; }
-__host__ inline int k_group(int K, int N, size_t limit) {
-    if (K % 64 == 0 && smem_bytes(K, N, 64) <= limit) return 64;
-    return 32;
+// The A ring has 4 stages (2 when the resident B leaves no room).  Each stage is owned by its own group of
+// loader warps, so the global loads / gathers of up to 4 stages are in flight at once -- the loaders are
+// latency-bound, and this is what keeps the tensor pipe and HBM busy.
+__host__ inline size_t smem_bytes(int K, int N, int stages) { return 1024 + static_cast<size_t>(stages) * kStageBytes + 2ull * N * K * 4; }
+__host__ inline int pick_stages(int K, int N, size_t limit) {
+    if (smem_bytes(K, N, 4) <= limit) return 4;
+    if (smem_bytes(K, N, 2) <= limit) return 2;
+    return 0;
 }
 __host__ inline uint32_t tmem_cols_for(int N) {
     uint32_t c = 32;
@@ -81,24 +85,25 @@ __device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const BSpec& bs, int
 
 template <class Loader, class Epilogue>
 __global__ void __launch_bounds__(kThreads, 1)
-rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, int64_t M, int K, int N, int KG,
+rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, uint32_t M, int K, int N, int n_stages,
                uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
 
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int n_kg = K / KG;
-    const uint32_t a_half = kTileM * KG * 4;  // hi block, then lo block
-    uint8_t* b_hi = smem + kStages * 2 * a_half;
+    const int n_kg = K / kKG;
+    constexpr uint32_t a_half = kTileM * kKG * 4;  // hi block, then lo block
+    uint8_t* b_hi = smem + n_stages * kStageBytes;
     uint8_t* b_lo = b_hi + N * K * 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int warps_per_group = kLoaderWarps / n_stages;
 
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&bar_full[s], kLoaderWarps);
+        for (int s = 0; s < n_stages; ++s) {
+            mbar_init(&bar_full[s], warps_per_group);
             mbar_init(&bar_empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -108,45 +113,47 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
         fence_mbar_init();
     }
     const int var = blockIdx.x % bspec.nvar;
-    const int64_t tile0 = blockIdx.x / bspec.nvar, tile_step = gridDim.x / bspec.nvar;
+    const uint32_t tile0 = blockIdx.x / bspec.nvar, tile_step = gridDim.x / bspec.nvar;
     fill_b(b_hi, b_lo, bspec, var, K, N, tid, kThreads);
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
-    const int64_t n_tiles = (M + kTileM - 1) / kTileM;
+    const uint32_t n_tiles = (M + kTileM - 1) / kTileM;
 
     if (warp < kLoaderWarps) {
         // ------------------------------- loaders -------------------------------
-        const int g4 = KG >> 2;  // 16-byte chunks per row per k-group
-        const int items = kTileM * g4;
-        int it = 0;  // counts (tile, k-group) stages
-        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step) {
-            const int64_t row0 = tile * kTileM;
+        // group g owns ring stage g and fills it for every (tile, k-group) step `it` with it % n_stages == g
+        const int grp = warp / warps_per_group;
+        const int gtid = tid - grp * warps_per_group * 32;
+        const int gthreads = warps_per_group * 32;
+        const int per_thread = (kTileM * 8) / gthreads;  // 16-byte chunks per thread per stage: 8 or 4
+        uint8_t* a_hi = smem + grp * kStageBytes;
+        uint8_t* a_lo = a_hi + a_half;
+        uint32_t it = 0, use = 0;
+        for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step) {
+            const uint32_t row0 = tile * kTileM;
             for (int kg = 0; kg < n_kg; ++kg, ++it) {
-                const int s = it % kStages;
-                const uint32_t ph = (it / kStages) & 1;
-                mbar_wait(&bar_empty[s], ph ^ 1);
-                uint8_t* a_hi = smem + s * 2 * a_half;
-                uint8_t* a_lo = a_hi + a_half;
-                // all of this thread's loads are issued before the first is consumed (8 x 16 B in flight
-                // per thread, 32 KB per SM) -- the loads, not the math, bound this kernel
+                if (static_cast<int>(it % n_stages) != grp) continue;
+                mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
+                ++use;
+                // every load of this thread is issued before the first is consumed
                 float4 v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int idx = tid + j * kLoaderThreads;
                     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < items) {
-                        const int r = idx / g4, c = idx - r * g4;
-                        if (row0 + r < M) v[j] = loader(row0 + r, kg * g4 + c);
+                    if (j < per_thread) {
+                        const int idx = gtid + j * gthreads;
+                        const int r = idx >> 3, c = idx & 7;
+                        if (row0 + r < M) v[j] = loader(row0 + r, kg * 8 + c);
                     }
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int idx = tid + j * kLoaderThreads;
-                    if (idx < items) {
-                        const int r = idx / g4, c = idx - r * g4;
+                    if (j < per_thread) {
+                        const int idx = gtid + j * gthreads;
+                        const int r = idx >> 3, c = idx & 7;
                         float4 hi, lo;
                         split4(v[j], hi, lo);
                         const uint32_t off = sw128_offset(r, c, kTileM);
@@ -156,31 +163,27 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
                 }
                 fence_proxy_async_smem();  // this thread's smem writes -> visible to the tensor core
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_full[s]);
+                if (lane == 0) mbar_arrive(&bar_full[grp]);
             }
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------- MMA issuer -------------------------------
         if (lane == 0) {
             const uint32_t idesc = idesc_tf32(kTileM, N);
-            const int katoms_per_group = KG >> 5;
-            int it = 0, t = 0;
-            for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
+            uint32_t it = 0, t = 0;
+            for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
                 const int a = t & 1;
                 const uint32_t pha = (t >> 1) & 1;
                 mbar_wait(&bar_tempty[a], pha ^ 1);  // epilogue drained this accumulator
                 const uint32_t d = tmem_base + a * N;
                 for (int kg = 0; kg < n_kg; ++kg, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t ph = (it / kStages) & 1;
+                    const int s = it % n_stages;
+                    const uint32_t ph = (it / n_stages) & 1;
                     mbar_wait(&bar_full[s], ph);  // operands landed
                     fence_after_sync();
-                    const uint32_t a_hi = smem_u32(smem + s * 2 * a_half), a_lo = a_hi + a_half;
-                    for (int ka = 0; ka < katoms_per_group; ++ka) {
-                        const int kb = kg * katoms_per_group + ka;  // k-atom index into the resident B
-                        mma_katom_3x(d, a_hi + ka * kTileM * 128, a_lo + ka * kTileM * 128,
-                                     smem_u32(b_hi) + kb * N * 128, smem_u32(b_lo) + kb * N * 128, idesc, kb == 0);
-                    }
+                    const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + a_half;
+                    mma_katom_3x(d, a_hi, a_lo, smem_u32(b_hi) + kg * N * 128, smem_u32(b_lo) + kg * N * 128, idesc,
+                                 kg == 0);
                     commit(&bar_empty[s]);  // smem stage reusable once these MMAs retire
                 }
                 commit(&bar_tfull[a]);  // accumulator ready for the epilogue
@@ -189,14 +192,14 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
     } else {
         // ------------------------------- epilogue -------------------------------
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
-        int t = 0;
-        for (int64_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
+        uint32_t t = 0;
+        for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
             const int a = t & 1;
             const uint32_t pha = (t >> 1) & 1;
             mbar_wait(&bar_tfull[a], pha);
             fence_after_sync();
             const uint32_t taddr = tmem_base + a * N + (static_cast<uint32_t>(q * 32) << 16);
-            const int64_t row = tile * kTileM + q * 32 + lane;
+            const uint32_t row = tile * kTileM + q * 32 + lane;
             // the epilogue pulls 16-column chunks itself (tcgen05.ld is warp-collective: every lane must pull
             // every chunk, valid row or not) and may keep per-row state across chunks
             epilogue(row, row < M, var, [&](int c0, float (&v)[16]) { tmem_ld16(taddr + c0, v); });
@@ -223,10 +226,12 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const BSp
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
                   di->cc_minor);
-    const int KG = k_group(K, N, static_cast<size_t>(di->smem_optin));
-    const size_t smem = smem_bytes(K, N, KG);
-    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE,
-                  "%s: K=%d N=%d needs %zu B of shared memory (limit %d)", who, K, N, smem, di->smem_optin);
+    const int stages = pick_stages(K, N, static_cast<size_t>(di->smem_optin));
+    LTGNN_REQUIRE(stages > 0, LTGNN_E_SHAPE, "%s: K=%d N=%d needs %zu B of shared memory (limit %d)", who, K, N,
+                  smem_bytes(K, N, 2), di->smem_optin);
+    LTGNN_REQUIRE(M < (1ll << 31) - kTileM, LTGNN_E_SHAPE, "%s: M=%lld rows exceed the 32-bit row index", who,
+                  static_cast<long long>(M));
+    const size_t smem = smem_bytes(K, N, stages);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
     auto kern = rowgemm_kernel<Loader, Epilogue>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -234,7 +239,8 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const BSp
     int64_t grid = tiles * bspec.nvar < di->sm_count ? tiles * bspec.nvar : di->sm_count;
     grid -= grid % bspec.nvar;
     LTGNN_REQUIRE(grid > 0, LTGNN_E_SHAPE, "%s: nvar=%d exceeds the SM count", who, bspec.nvar);
-    kern<<<static_cast<int>(grid), kThreads, smem, stream>>>(loader, epilogue, bspec, M, K, N, KG, tmem_cols_for(N));
+    kern<<<static_cast<int>(grid), kThreads, smem, stream>>>(loader, epilogue, bspec, static_cast<uint32_t>(M), K, N,
+                                                            stages, tmem_cols_for(N));
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""One GNN-stack forward+backward at bench shapes, for ncu:  python tools/prof_step.py [B] [iters]"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(REPO))
+from leak_det_gnn_b200.models import LeakDetector  # noqa: E402
+
+b = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+g = np.load(REPO / "tests/golden/graph_LTA.npz")
+torch.manual_seed(42)
+m = LeakDetector(REPO / "tests/golden/L-TOWN-A.topo.inp", [str(s) for s in g["sensor_node_ids"]],
+                 [str(p) for p in g["pipe_ids"]]).cuda().train()
+h_s = torch.randn(b, 29, 64, device="cuda", requires_grad=True)
+label = torch.randint(0, 765, (b,), device="cuda")
+for _ in range(iters):
+    m.zero_grad(set_to_none=True)
+    h_s.grad = None
+    torch.nn.functional.cross_entropy(m.gnn_stack(h_s), label).backward()
+torch.cuda.synchronize()
+print("ok")
