@@ -107,13 +107,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Blocking wait with a watchdog: a lost arrival traps (launch fails with an error) instead
-// of hanging the GPU.  ~2^31 cycles is > 1 s at any B200 clock; real waits are microseconds.
+// Blocking wait with a watchdog: a lost arrival traps (launch fails with an error) instead of hanging
+// the GPU.  try_wait itself suspends the warp in hardware for a bounded time, so the loop body is cold;
+// 2^26 failed probes is seconds, real waits are microseconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 31)) __trap();
+        if (++spins > (1u << 26)) __trap();
     }
 }
 
@@ -169,6 +169,22 @@ __device__ __forceinline__ void dropout4(float4& v, uint64_t idx4, uint64_t seed
     v.y = r.y >= thresh ? v.y * keep_scale : 0.f;
     v.z = r.z >= thresh ? v.z * keep_scale : 0.f;
     v.w = r.w >= thresh ? v.w * keep_scale : 0.f;
+}
+// Same, 16 random bits per element: one Philox call decides 8 elements (v[0..7]); thresh16 = round(p * 2^16)
+// and the caller scales by 1 / (1 - thresh16 / 2^16) so the estimator stays exactly unbiased.
+__device__ __forceinline__ void dropout8(float* v, uint64_t idx8, uint64_t seed, uint32_t thresh16, float keep_scale) {
+    const uint4 r = philox4x32_7(static_cast<uint32_t>(idx8), static_cast<uint32_t>(idx8 >> 32) ^ 0x5bd1e995u,
+                                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = (w[i] & 0xffffu) >= thresh16 ? v[2 * i] * keep_scale : 0.f;
+        v[2 * i + 1] = (w[i] >> 16) >= thresh16 ? v[2 * i + 1] * keep_scale : 0.f;
+    }
+}
+// exact floor(x / d) for any 32-bit x: magic = floor((2^64 - 1) / d) + 1 (host side, d >= 2)
+__device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint64_t magic) {
+    return static_cast<uint32_t>(__umul64hi(static_cast<uint64_t>(x), magic));
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -20,18 +20,23 @@ using namespace ltgnn;
 namespace {
 
 // ------------------------------------------------------------------ forward
+constexpr int kD = 64;        // node width supported by the fused head
+constexpr int kD4 = kD / 4;
+
 struct PipeFeatLoader {
-    const float4* x;   // node states [B*N, d4]
+    const float4* x;   // node states [B*N, kD4]
     const int2* ends;  // [P] (u, v)
-    int P, N, d4;
+    uint32_t P, N;
+    uint64_t magic;    // fastdiv constant of P (P >= 2), 0 when P == 1
     __device__ __forceinline__ float4 operator()(uint32_t row, int c16) const {
-        const uint32_t b = row / static_cast<uint32_t>(P), p = row - b * static_cast<uint32_t>(P);
+        const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
+        const uint32_t p = row - b * P;
         const int2 e = __ldg(ends + p);
-        const int seg = c16 / d4, cc = c16 - seg * d4;
-        const float4* xb = x + static_cast<int64_t>(b) * N * d4 + cc;
-        if (seg == 0) return __ldg(xb + static_cast<int64_t>(e.x) * d4);
-        if (seg == 1) return __ldg(xb + static_cast<int64_t>(e.y) * d4);
-        const float4 a = __ldg(xb + static_cast<int64_t>(e.x) * d4), c = __ldg(xb + static_cast<int64_t>(e.y) * d4);
+        const int seg = c16 / kD4, cc = c16 % kD4;  // uniform across the CTA for a ring stage
+        const float4* xb = x + static_cast<int64_t>(b) * N * kD4 + cc;
+        if (seg == 0) return __ldg(xb + e.x * kD4);
+        if (seg == 1) return __ldg(xb + e.y * kD4);
+        const float4 a = __ldg(xb + e.x * kD4), c = __ldg(xb + e.y * kD4);
         return make_float4(fabsf(a.x - c.x), fabsf(a.y - c.y), fabsf(a.z - c.z), fabsf(a.w - c.w));
     }
 };
@@ -44,8 +49,8 @@ struct HeadFwdEpilogue {
     float* hpost;      // [M][H] saved post-activation, or nullptr (inference)
     int64_t M;
     int H, nh;         // hidden units in total / per variant
-    uint32_t drop_thresh;
-    float keep_scale;
+    uint32_t drop_thresh16;  // round(p * 2^16), 0 = no dropout
+    float keep_scale;        // 1 / (1 - drop_thresh16 / 2^16)
     uint64_t drop_seed;
     template <class Pull>
     __device__ __forceinline__ void operator()(uint32_t row, bool valid, int var, Pull&& pull) const {
@@ -57,17 +62,26 @@ struct HeadFwdEpilogue {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col) + j);
-                float4 h = make_float4(fmaxf(v[4 * j] + bb.x, 0.f), fmaxf(v[4 * j + 1] + bb.y, 0.f),
-                                       fmaxf(v[4 * j + 2] + bb.z, 0.f), fmaxf(v[4 * j + 3] + bb.w, 0.f));
-                if (drop_thresh)
-                    ptx::dropout4(h, static_cast<uint64_t>(row) * (H >> 2) + ((col >> 2) + j), drop_seed, drop_thresh,
-                                  keep_scale);
-                if (hpost && valid) reinterpret_cast<float4*>(hpost + static_cast<int64_t>(row) * H + col)[j] = h;
+                v[4 * j + 0] = fmaxf(v[4 * j + 0] + bb.x, 0.f);
+                v[4 * j + 1] = fmaxf(v[4 * j + 1] + bb.y, 0.f);
+                v[4 * j + 2] = fmaxf(v[4 * j + 2] + bb.z, 0.f);
+                v[4 * j + 3] = fmaxf(v[4 * j + 3] + bb.w, 0.f);
+            }
+            if (drop_thresh16) {
+                const uint64_t i8 = static_cast<uint64_t>(row) * (H >> 3) + (col >> 3);
+                ptx::dropout8(v, i8, drop_seed, drop_thresh16, keep_scale);
+                ptx::dropout8(v + 8, i8 + 1, drop_seed, drop_thresh16, keep_scale);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (hpost && valid)
+                    reinterpret_cast<float4*>(hpost + static_cast<int64_t>(row) * H + col)[j] =
+                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + col) + j);
-                acc = fmaf(h.x, ww.x, acc);
-                acc = fmaf(h.y, ww.y, acc);
-                acc = fmaf(h.z, ww.z, acc);
-                acc = fmaf(h.w, ww.w, acc);
+                acc = fmaf(v[4 * j + 0], ww.x, acc);
+                acc = fmaf(v[4 * j + 1], ww.y, acc);
+                acc = fmaf(v[4 * j + 2], ww.z, acc);
+                acc = fmaf(v[4 * j + 3], ww.w, acc);
             }
         }
         if (valid) part[static_cast<int64_t>(var) * M + row] = acc;
@@ -100,14 +114,16 @@ struct HeadBwdEpilogue {
     float* dx;          // [B*N, D], pre-filled with the mean-pool gradient
     const float* x;     // node states (for the sign of h_u - h_v)
     const int2* ends;
-    int P, N, D, ncols;  // ncols = feature-gradient columns per variant
+    uint32_t P, N;
+    int D, ncols;       // ncols = feature-gradient columns per variant
+    uint64_t magic;
     template <class Pull>
     __device__ __forceinline__ void operator()(uint32_t row, bool valid, int var, Pull&& pull) const {
         uint32_t b = 0;
         int2 e = make_int2(0, 0);
         if (valid) {
-            b = row / static_cast<uint32_t>(P);
-            e = __ldg(ends + (row - b * static_cast<uint32_t>(P)));
+            b = magic ? ptx::fastdiv(row, magic) : row;
+            e = __ldg(ends + (row - b * P));
         }
         const int64_t ru = (static_cast<int64_t>(b) * N + e.x) * D, rv = (static_cast<int64_t>(b) * N + e.y) * D;
         for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -180,6 +196,8 @@ pool_bwd_fill_kernel(const float4* __restrict__ dpooled, float4* __restrict__ dx
     }
 }
 
+uint64_t magic_of(int P) { return P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull; }
+
 int head_shape_check(int D, int H, const char* who) {
     LTGNN_REQUIRE(D == 64, LTGNN_E_SHAPE, "%s: node width D=%d not supported by the fused head (64 only)", who, D);
     LTGNN_REQUIRE(H == 128, LTGNN_E_SHAPE, "%s: hidden width H=%d not supported by the fused head (128 only)", who, H);
@@ -201,10 +219,10 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
                   "pipe_head_fwd: 16-byte alignment required");
     const int64_t M = B * P;
     LTGNN_REQUIRE(M < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*P too large");
-    PipeFeatLoader ld{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), P, N, D / 4};
-    HeadFwdEpilogue ep{b1, w2, part, hpost, M, H, H / 2,
-                       drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 4294967296.0) : 0u,
-                       1.f / (1.f - drop_p), drop_seed};
+    PipeFeatLoader ld{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends),
+                      static_cast<uint32_t>(P), static_cast<uint32_t>(N), magic_of(P)};
+    const uint32_t t16 = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
+    HeadFwdEpilogue ep{b1, w2, part, hpost, M, H, H / 2, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
     rowgemm::BSpec bs{W1, 3 * D, 0, 2};
     return rowgemm::launch(device, ld, ep, bs, M, 3 * D, H / 2, static_cast<cudaStream_t>(stream_), "pipe_head_fwd");
 }
@@ -221,7 +239,8 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
                   "pipe_head_bwd_dx: 16-byte alignment required");
     const int64_t M = B * P;
     DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, H / 4};
-    HeadBwdEpilogue ep{dX, X, reinterpret_cast<const int2*>(ends), P, N, D, 3 * D / 2};
+    HeadBwdEpilogue ep{dX, X, reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P), static_cast<uint32_t>(N),
+                       D, 3 * D / 2, magic_of(P)};
     rowgemm::BSpec bs{W1, 3 * D, 1, 2};
     return rowgemm::launch(device, ld, ep, bs, M, H, 3 * D / 2, static_cast<cudaStream_t>(stream_), "pipe_head_bwd_dx");
 }

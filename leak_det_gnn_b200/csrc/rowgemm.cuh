@@ -129,11 +129,15 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
         const int gtid = tid - grp * warps_per_group * 32;
         const int gthreads = warps_per_group * 32;
         const int per_thread = (kTileM * 8) / gthreads;  // 16-byte chunks per thread per stage: 8 or 4
+        // a thread always owns 16-byte column c of rows r0, r0 + rstep, ...; rstep is a multiple of 8, so the
+        // swizzled offset only advances by whole 8-row groups
+        const int r0 = gtid >> 3, c = gtid & 7, rstep = gthreads >> 3;
+        const uint32_t off0 = sw128_offset(r0, c, kTileM), offstep = static_cast<uint32_t>(rstep >> 3) * 1024u;
         uint8_t* a_hi = smem + grp * kStageBytes;
         uint8_t* a_lo = a_hi + a_half;
         uint32_t it = 0, use = 0;
         for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step) {
-            const uint32_t row0 = tile * kTileM;
+            const uint32_t row0 = tile * kTileM + r0;
             for (int kg = 0; kg < n_kg; ++kg, ++it) {
                 if (static_cast<int>(it % n_stages) != grp) continue;
                 mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
@@ -143,22 +147,15 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (j < per_thread) {
-                        const int idx = gtid + j * gthreads;
-                        const int r = idx >> 3, c = idx & 7;
-                        if (row0 + r < M) v[j] = loader(row0 + r, kg * 8 + c);
-                    }
+                    if (j < per_thread && row0 + j * rstep < M) v[j] = loader(row0 + j * rstep, kg * 8 + c);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     if (j < per_thread) {
-                        const int idx = gtid + j * gthreads;
-                        const int r = idx >> 3, c = idx & 7;
                         float4 hi, lo;
                         split4(v[j], hi, lo);
-                        const uint32_t off = sw128_offset(r, c, kTileM);
-                        *reinterpret_cast<float4*>(a_hi + off) = hi;
-                        *reinterpret_cast<float4*>(a_lo + off) = lo;
+                        *reinterpret_cast<float4*>(a_hi + off0 + j * offstep) = hi;
+                        *reinterpret_cast<float4*>(a_lo + off0 + j * offstep) = lo;
                     }
                 }
                 fence_proxy_async_smem();  // this thread's smem writes -> visible to the tensor core
@@ -168,25 +165,26 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
         }
     } else if (warp == kMmaWarp) {
         // ------------------------------- MMA issuer -------------------------------
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(kTileM, N);
-            uint32_t it = 0, t = 0;
-            for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
-                const int a = t & 1;
-                const uint32_t pha = (t >> 1) & 1;
-                mbar_wait(&bar_tempty[a], pha ^ 1);  // epilogue drained this accumulator
-                const uint32_t d = tmem_base + a * N;
-                for (int kg = 0; kg < n_kg; ++kg, ++it) {
-                    const int s = it % n_stages;
-                    const uint32_t ph = (it / n_stages) & 1;
-                    mbar_wait(&bar_full[s], ph);  // operands landed
-                    fence_after_sync();
-                    const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + a_half;
-                    mma_katom_3x(d, a_hi, a_lo, smem_u32(b_hi) + kg * N * 128, smem_u32(b_lo) + kg * N * 128, idesc,
-                                 kg == 0);
-                    commit(&bar_empty[s]);  // smem stage reusable once these MMAs retire
+        // The whole warp walks the loop (warp-uniform control flow keeps addresses and descriptors in uniform
+        // registers); one elected lane issues the tcgen05 instructions.
+        const uint32_t idesc = idesc_tf32(kTileM, N);
+        const uint32_t a_base = smem_u32(smem), bh_base = smem_u32(b_hi), bl_base = smem_u32(b_lo);
+        uint32_t it = 0, t = 0;
+        for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
+            const uint32_t a = t & 1;
+            mbar_wait(&bar_tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+            const uint32_t d = tmem_base + a * N;
+            for (int kg = 0; kg < n_kg; ++kg, ++it) {
+                const uint32_t s = it % n_stages;
+                mbar_wait(&bar_full[s], (it / n_stages) & 1);  // operands landed
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = a_base + s * kStageBytes;
+                    mma_katom_3x(d, a_hi, a_hi + a_half, bh_base + kg * N * 128, bl_base + kg * N * 128, idesc, kg == 0);
+                    commit(&bar_empty[s]);                    // smem stage reusable once these MMAs retire
+                    if (kg == n_kg - 1) commit(&bar_tfull[a]);  // accumulator ready for the epilogue
                 }
-                commit(&bar_tfull[a]);  // accumulator ready for the epilogue
+                __syncwarp();
             }
         }
     } else {

@@ -67,7 +67,24 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem]^T, one K=8 step, issued by ONE thread
+// D[tmem] (+)= A[smem] * B[smem]^T, one K=8 step, issued by ONE thread.
+// The single issuing thread is a serial bottleneck (a few dozen dependent integer instructions per MMA
+// cost more than the MMA itself at N = 64), so descriptors are passed as their 32-bit low word (the only
+// part that changes: start address >> 4) plus a constant high word, and assembled inside the asm block.
+constexpr uint32_t kDescHi = (64u /*SBO*/) | (1u << 14) /*version*/ | (2u << 29) /*SWIZZLE_128B*/;
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+
+__device__ __forceinline__ void mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi)
+        : "memory");
+}
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
     asm volatile(
@@ -84,16 +101,15 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 }
 
 // 3xTF32 product of one (rows_a x 32) by (rows_b x 32) k-atom: 4 K-steps x 3 MMAs.
-// a_hi/a_lo/b_hi/b_lo: shared addresses of the k-atom blocks; first==1 overwrites D.
+// a_hi/a_lo/b_hi/b_lo: shared addresses of the k-atom blocks (1024-byte aligned); first==1 overwrites D.
 __device__ __forceinline__ void mma_katom_3x(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
                                              uint32_t b_lo, uint32_t idesc, bool first) {
+    const uint32_t ah = desc_lo(a_hi), al = desc_lo(a_lo), bh = desc_lo(b_hi), bl = desc_lo(b_lo);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint64_t ah = smem_desc_sw128(a_hi + k * 32), al = smem_desc_sw128(a_lo + k * 32);
-        const uint64_t bh = smem_desc_sw128(b_hi + k * 32), bl = smem_desc_sw128(b_lo + k * 32);
-        mma_tf32(d_tmem, al, bh, idesc, (first && k == 0) ? 0u : 1u);  // small terms first
-        mma_tf32(d_tmem, ah, bl, idesc, 1u);
-        mma_tf32(d_tmem, ah, bh, idesc, 1u);
+    for (uint32_t k = 0; k < 4; ++k) {  // one K = 8 step is 32 bytes = 2 descriptor units
+        mma_tf32_lo(d_tmem, al + 2 * k, bh + 2 * k, idesc, (first && k == 0) ? 0u : 1u);  // small terms first
+        mma_tf32_lo(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
+        mma_tf32_lo(d_tmem, ah + 2 * k, bh + 2 * k, idesc, 1u);
     }
 }
 

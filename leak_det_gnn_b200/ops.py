@@ -391,7 +391,8 @@ class _Heads(torch.autograd.Function):
         _inst.end(tok)
         if need_grad:
             ctx.save_for_backward(x, ends, w1, w2v, hpost)
-        ctx.scale = 1.0 / (1.0 - p)
+        # the kernel draws 16 random bits per hidden unit: its keep probability is 1 - round(p * 2^16) / 2^16
+        ctx.scale = 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
         return part, pooled
 
     @staticmethod
