@@ -1,0 +1,131 @@
+// tgrad.cu -- tensor-core weight gradients (see tgrad.cuh) for
+//   * GCNConv.lin:   dW[Do, Di] = G^T X over the B*N node rows      (autograd of models/detector.py:199)
+//   * EdgeHead.mlp.0: dW1[H, 3D] = dpre^T feat and db1 = column sums of dpre over the B*P pipe rows
+//                     (autograd of models/detector.py:79-87), with dpre and feat formed on the fly from the
+//                     saved hidden activations / the node states -- neither (B*P, H) nor (B*P, 3D) exists.
+#include "tgrad.cuh"
+
+using namespace ltgnn;
+
+namespace {
+
+// ---- plain row-major operands, optionally two matrices stacked side by side to fill the 128 accumulator rows
+struct StackedRows {
+    const float4* a;  // [M, wa4]
+    const float4* b;  // [M, wb4] (columns wa4.. of the stacked operand) or nullptr
+    int wa4, wb4;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        if (c < wa4) return ptx::ldg_stream(a + static_cast<int64_t>(row) * wa4 + c);
+        if (b && c - wa4 < wb4) return ptx::ldg_stream(b + static_cast<int64_t>(row) * wb4 + (c - wa4));
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+};
+
+// ---- pipe head: G = d loss / d pre (from the saved post-activation), X = [feat | 1 | 0...]
+struct HeadDpre {
+    const float4* hpost;  // [M][32]
+    const float* dlogit;  // [M]
+    const float4* w2;     // [32]
+    float scale;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        const float4 h = ptx::ldg_stream(hpost + static_cast<int64_t>(row) * 32 + c);
+        const float4 w = __ldg(w2 + c);
+        const float g = __ldg(dlogit + row) * scale;
+        return make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
+                           h.w > 0.f ? g * w.w : 0.f);
+    }
+};
+struct HeadFeatOnes {
+    const float4* x;   // node states [B*N, 16]
+    const int2* ends;
+    uint32_t P, N;
+    uint64_t magic;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        if (c >= 48) return make_float4(c == 48 ? 1.f : 0.f, 0.f, 0.f, 0.f);  // column 192 = 1 -> db1
+        const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
+        const int2 e = __ldg(ends + (row - b * P));
+        const int seg = c >> 4, cc = c & 15;
+        const float4* xb = x + static_cast<int64_t>(b) * N * 16 + cc;
+        if (seg == 0) return __ldg(xb + e.x * 16);
+        if (seg == 1) return __ldg(xb + e.y * 16);
+        const float4 a = __ldg(xb + e.x * 16), d = __ldg(xb + e.y * 16);
+        return make_float4(fabsf(a.x - d.x), fabsf(a.y - d.y), fabsf(a.z - d.z), fabsf(a.w - d.w));
+    }
+};
+
+// out[r][c] (+)= sum_p ws[p][r][c_src] for a sub-rectangle of the [128][No] accumulator
+__global__ void gather_partials_kernel(const float* __restrict__ ws, int n_parts, int No, int r0, int rows, int c0,
+                                       int cols, float* __restrict__ out, int ld_out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i - r * cols;
+    const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c;
+    float t = accumulate ? out[r * ld_out + c] : 0.f;
+    for (int p = 0; p < n_parts; ++p) t += ws[static_cast<size_t>(p) * tgrad::kMo * No + src];
+    out[r * ld_out + c] = t;
+}
+
+int gather(const float* ws, int n_parts, int No, int r0, int rows, int c0, int cols, float* out, int ld_out,
+           int accumulate, cudaStream_t stream) {
+    const int n = rows * cols;
+    gather_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ws, n_parts, No, r0, rows, c0, cols, out, ld_out, accumulate);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t ltgnn_tgrad_ws_floats(int device, int32_t No) {
+    const DeviceInfo* di = device_info(device);
+    return di ? static_cast<int64_t>(di->sm_count) * tgrad::kMo * No : -1;
+}
+
+// dW[Do, Di] = G[M, Do]^T X[M, Di];  (Do, Di) in {(64, 64), (128, 128), (128, 64), (64, 128), ...}: Do in {64, 128},
+// Di a multiple of 32 <= 256.  ws: ltgnn_tgrad_ws_floats(device, Di) floats.
+extern "C" int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, const float* G, const float* X, float* dW,
+                              int accumulate, float* ws, void* stream_) {
+    LTGNN_REQUIRE(M >= 0, LTGNN_E_ARG, "wgrad_tc: M=%lld", static_cast<long long>(M));
+    LTGNN_REQUIRE(Do == 64 || Do == 128, LTGNN_E_SHAPE, "wgrad_tc: Do=%d must be 64 or 128", Do);
+    LTGNN_REQUIRE(Di % 32 == 0 && Di > 0 && Di <= 256, LTGNN_E_SHAPE, "wgrad_tc: Di=%d must be a multiple of 32, <= 256", Di);
+    LTGNN_REQUIRE(G && X && dW && ws, LTGNN_E_ARG, "wgrad_tc: null tensor");
+    LTGNN_REQUIRE(aligned16(G) && aligned16(X), LTGNN_E_ALIGN, "wgrad_tc: G/X must be 16-byte aligned");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (M == 0) {
+        if (!accumulate) LTGNN_CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * Do * Di, stream));
+        return LTGNN_OK;
+    }
+    // Do = 64 fills only half of the 128 accumulator rows: the other half is fed with zeros
+    StackedRows g{reinterpret_cast<const float4*>(G), nullptr, Do / 4, 0};
+    StackedRows x{reinterpret_cast<const float4*>(X), nullptr, Di / 4, 0};
+    int grid = 0;
+    int rc = tgrad::launch(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc");
+    if (rc) return rc;
+    return gather(ws, grid, Di, 0, Do, 0, Di, dW, Di, accumulate, stream);
+}
+
+// Pipe-head parameter gradients: dW1 [128, 192] and db1 [128].  ws: ltgnn_tgrad_ws_floats(device, 224) floats.
+extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
+                                     const int32_t* ends, const float* w2, const float* hpost, const float* dlogit,
+                                     float gate_scale, float* dW1, float* db1, float* ws, void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_bwd_w: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
+    LTGNN_REQUIRE(D == 64 && H == 128, LTGNN_E_SHAPE, "pipe_head_bwd_w: D=%d H=%d (64 / 128 only)", D, H);
+    LTGNN_REQUIRE(X && ends && w2 && hpost && dlogit && dW1 && db1 && ws, LTGNN_E_ARG, "pipe_head_bwd_w: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(w2) && aligned16(hpost), LTGNN_E_ALIGN, "pipe_head_bwd_w: alignment");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0) {
+        LTGNN_CUDA_TRY(cudaMemsetAsync(dW1, 0, sizeof(float) * H * 3 * D, stream));
+        LTGNN_CUDA_TRY(cudaMemsetAsync(db1, 0, sizeof(float) * H, stream));
+        return LTGNN_OK;
+    }
+    const int64_t M = B * P;
+    HeadDpre g{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale};
+    HeadFeatOnes x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
+                   static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
+    const int No = 224;  // 192 feature columns + a ones column (-> db1) padded to a whole 32-column block
+    int grid = 0;
+    int rc = tgrad::launch(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
+    if (rc) return rc;
+    rc = gather(ws, grid, No, 0, H, 0, 3 * D, dW1, 3 * D, 0, stream);
+    if (rc) return rc;
+    return gather(ws, grid, No, 0, H, 3 * D, 1, db1, 1, 0, stream);
+}

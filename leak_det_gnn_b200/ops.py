@@ -236,11 +236,18 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     m = g.numel() // do
     if x.numel() // di != m:
         raise ValueError("wgrad: row counts differ")
-    if not _wgrad_ok(do, di):
-        return g.reshape(m, do).t() @ x.reshape(m, di)
     L = _lib.load()
     dev = _dev_index(g)
     dw = torch.empty(do, di, device=g.device, dtype=torch.float32)
+    if do in (64, 128) and di % 32 == 0 and 0 < di <= 256 and m > 0:
+        ws = torch.empty(int(L.ltgnn_tgrad_ws_floats(dev, di)), device=g.device, dtype=torch.float32)
+        tok = _inst.begin("wgrad_tc")
+        _lib.check(L.ltgnn_wgrad_tc(dev, m, do, di, g.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(),
+                                    _stream(g)))
+        _inst.end(tok)
+        return dw
+    if not _wgrad_ok(do, di):
+        return g.reshape(m, do).t() @ x.reshape(m, di)
     ws = torch.empty(int(L.ltgnn_wgrad_ws_floats(dev, do, di)), device=g.device, dtype=torch.float32)
     tok = _inst.begin("wgrad")
     _lib.check(L.ltgnn_wgrad(dev, m, do, di, g.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), _stream(g)))
@@ -417,14 +424,16 @@ class _Heads(torch.autograd.Function):
                                             w2v.data_ptr(), hpost.data_ptr(), dlogit.data_ptr(), ctx.scale,
                                             dx.data_ptr(), _stream(x)))
         _inst.end(tok)
-        # parameter gradients (interim: cuBLAS through torch on materialised operands)
-        dpre = torch.where(hpost > 0, dlogit.unsqueeze(1) * (w2v * ctx.scale), torch.zeros((), device=x.device))
-        e = ends.long()
-        h_u, h_v = x[:, e[:, 0], :], x[:, e[:, 1], :]
-        feat = torch.cat([h_u, h_v, (h_u - h_v).abs()], dim=-1).view(b * p_cnt, 3 * d)
-        dw1 = dpre.t() @ feat
-        db1 = dpre.sum(0)
-        dw2 = (dlogit.unsqueeze(1) * hpost).sum(0).view(1, h)
+        # parameter gradients: dW1 / db1 on tensor cores with operands formed on the fly; dw2 is one GEMV
+        dw1 = torch.empty_like(w1)
+        db1 = torch.empty(h, device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(L.ltgnn_tgrad_ws_floats(dev, 224)), device=x.device, dtype=torch.float32)
+        tok = _inst.begin("pipe_head_bwd_w")
+        _lib.check(L.ltgnn_pipe_head_bwd_w(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), w2v.data_ptr(),
+                                           hpost.data_ptr(), dlogit.data_ptr(), ctx.scale, dw1.data_ptr(),
+                                           db1.data_ptr(), ws.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        dw2 = torch.mv(hpost.t(), dlogit).view(1, h)
         return dx, None, dw1, db1, dw2, None, None
 
 
