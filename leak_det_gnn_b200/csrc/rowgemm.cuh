@@ -75,7 +75,7 @@ __device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const BSpec& bs, int
         for (int i = tid; i < N * K; i += nthreads) {
             const int k = i / N, n = i - k * N;  // coalesced along n
             const float w = __ldg(bs.W + static_cast<size_t>(k) * bs.ldw + var * N + n);
-            const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
+            const float hi = tf32_hi(w), lo = w - hi;
             const uint32_t off = sw128_offset(n, k >> 2, N) + (k & 3) * 4;
             *reinterpret_cast<float*>(b_hi + off) = hi;
             *reinterpret_cast<float*>(b_lo + off) = lo;

@@ -2,7 +2,7 @@
 //
 // The reference computes every Linear in full fp32 (torch's allow_tf32 default is off and it is
 // never changed).  tcgen05 has no fp32 kind, so the product uses the error-compensated
-// 3xTF32 scheme: each fp32 operand is split a = hi + lo with hi = rna_tf32(a), lo = rna_tf32(a - hi)
+// 3xTF32 scheme: each fp32 operand is split a = hi + lo with hi = round_tf32(a), lo = a - hi (exact)
 // and   a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b   accumulated in fp32 in tensor memory.
 // The dropped lo*lo term is <= 2^-22 |a||b|, i.e. at fp32 rounding level.
 //
@@ -20,15 +20,18 @@ namespace umma {
 using ptx::smem_u32;
 
 // ---- fp32 -> (hi, lo) TF32 split ------------------------------------------------------------
-__device__ __forceinline__ float tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+// hi = x rounded to TF32 (10-bit mantissa) with two integer ops (add half an ulp of TF32, clear the 13 low
+// bits: round-half-away, finite inputs); lo = x - hi is exact in fp32 and is handed to the tensor core as
+// is -- kind::tf32 reads the upper 19 bits of the container, so lo is truncated to TF32 there, an error of
+// at most 2^-11 |lo| <= 2^-23 |x|.  (cvt.rna.tf32.f32 expands to ~4 SASS instructions with NaN handling;
+// the loaders are instruction-bound, so this matters.)
+__device__ __forceinline__ float tf32_hi(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
+__device__ __forceinline__ float tf32_rna(float x) { return tf32_hi(x); }
 __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
-    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
-    lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y);
-    lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
+    hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
 }
 
 // byte offset of 16-byte chunk `c16` (0..K/4-1) of row `r` in an R-row K-major SW128 tile
