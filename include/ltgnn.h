@@ -140,8 +140,8 @@ int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds,
 /* ---- read-out heads (detector.py:76-102, 204-216) ---------------------------------------------
  * pipe_head_fwd: for every window b and class pipe p with end nodes ends[p] = (u, v):
  *      hidden = dropout(relu(W1 [x_u, x_v, |x_u - x_v|] + b1)),   W1 [H, 3D] (edge_head.mlp.0.weight)
- *      part[v][b*P + p] = sum over hidden units [v*H/2, (v+1)*H/2) of hidden * w2      (v = 0, 1)
- *   so pipe_logit = part[0] + part[1] + b2 (edge_head.mlp.3).  hpost [B*P, H] (optional) receives `hidden`
+ *      part[b*P + p] = sum over the H hidden units of hidden * w2
+ *   so pipe_logit = part + b2 (edge_head.mlp.3).  hpost [B*P, H] (optional) receives `hidden`
  *   for the backward.  X [B,N,D] node states; ends int32 [P,2] on the device.  D = 64, H = 128.
  * pipe_head_bwd_dx: dX[b, u/v, :] += the input gradient of the pipe head given dlogit [B*P]; dX must hold the
  *   gradient arriving from other consumers (ltgnn_mean_pool_bwd_fill, or zeros).  fp32 reductions in L2.

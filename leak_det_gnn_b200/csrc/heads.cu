@@ -9,11 +9,10 @@
 //              saved post-activation the backward needs.
 //   mean pool  (models/detector.py:214-215, PyG global_mean_pool over equal-sized graphs).
 //
-// Shared-memory budget forces the H = 128 hidden units to be processed as two "variants" of 64 (forward:
-// rows of W1) and the 3D = 192 feature gradients as two variants of 96 (backward: columns of W1); a CTA
-// keeps its variant for life, the two CTAs working on the same row tile run side by side so the second
-// read of the tile's inputs is an L2 hit.
-#include "rowgemm.cuh"
+// Both GEMMs run on the tensor-memory-operand skeleton (rowgemm_ts.cuh): the loaders keep one pipe row per
+// thread, split it into TF32 hi/lo in registers and tcgen05.st it into TMEM, so shared memory only holds the
+// whole weight W1 (192 KB as hi + lo) and every tile is produced exactly once.
+#include "rowgemm_ts.cuh"
 
 using namespace ltgnn;
 
@@ -23,25 +22,38 @@ namespace {
 constexpr int kD = 64;        // node width supported by the fused head
 constexpr int kD4 = kD / 4;
 
+// one row = one class pipe of one window; K values [32 kg, 32 kg + 32) of [x_u | x_v | |x_u - x_v|]
 struct PipeFeatLoader {
     const float4* x;   // node states [B*N, kD4]
     const int2* ends;  // [P] (u, v)
     uint32_t P, N;
     uint64_t magic;    // fastdiv constant of P (P >= 2), 0 when P == 1
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c16) const {
+    __device__ __forceinline__ void operator()(uint32_t row, int kg, float (&v)[32]) const {
         const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
-        const uint32_t p = row - b * P;
-        const int2 e = __ldg(ends + p);
-        const int seg = c16 / kD4, cc = c16 % kD4;  // uniform across the CTA for a ring stage
-        const float4* xb = x + static_cast<int64_t>(b) * N * kD4 + cc;
-        if (seg == 0) return __ldg(xb + e.x * kD4);
-        if (seg == 1) return __ldg(xb + e.y * kD4);
-        const float4 a = __ldg(xb + e.x * kD4), c = __ldg(xb + e.y * kD4);
-        return make_float4(fabsf(a.x - c.x), fabsf(a.y - c.y), fabsf(a.z - c.z), fabsf(a.w - c.w));
+        const int2 e = __ldg(ends + (row - b * P));
+        const int seg = kg >> 1, half = kg & 1;  // uniform across the CTA for a ring stage
+        const float4* xb = x + static_cast<int64_t>(b) * N * kD4 + half * 8;
+        const float4* pu = xb + e.x * kD4;
+        const float4* pv = xb + e.y * kD4;
+        if (seg < 2) {
+            const float4* src = seg == 0 ? pu : pv;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(src + j);
+                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 a = __ldg(pu + j), c = __ldg(pv + j);
+                v[4 * j] = fabsf(a.x - c.x); v[4 * j + 1] = fabsf(a.y - c.y);
+                v[4 * j + 2] = fabsf(a.z - c.z); v[4 * j + 3] = fabsf(a.w - c.w);
+            }
+        }
     }
 };
 
-// hidden = dropout(relu(acc + b1)); part[var][row] = sum over this variant's 64 hidden units of hidden * w2
+// hidden = dropout(relu(acc + b1)); part[row] = sum over the hidden units of hidden * w2
 struct HeadFwdEpilogue {
     const float* b1;   // [H]
     const float* w2;   // [H]
@@ -96,12 +108,18 @@ struct DpreLoader {
     const float4* w2;      // [H/4]
     float scale;
     int h4;
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c16) const {
-        const float4 h = ptx::ldg_stream(hpost + static_cast<int64_t>(row) * h4 + c16);
-        const float4 w = __ldg(w2 + c16);
+    __device__ __forceinline__ void operator()(uint32_t row, int kg, float (&v)[32]) const {
+        const float4* h = hpost + static_cast<int64_t>(row) * h4 + kg * 8;
         const float g = __ldg(dlogit + row) * scale;
-        return make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
-                           h.w > 0.f ? g * w.w : 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 t = ptx::ldg_stream(h + j);
+            const float4 w = __ldg(w2 + kg * 8 + j);
+            v[4 * j] = t.x > 0.f ? g * w.x : 0.f;
+            v[4 * j + 1] = t.y > 0.f ? g * w.y : 0.f;
+            v[4 * j + 2] = t.z > 0.f ? g * w.z : 0.f;
+            v[4 * j + 3] = t.w > 0.f ? g * w.w : 0.f;
+        }
     }
 };
 
@@ -222,9 +240,9 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
     PipeFeatLoader ld{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends),
                       static_cast<uint32_t>(P), static_cast<uint32_t>(N), magic_of(P)};
     const uint32_t t16 = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
-    HeadFwdEpilogue ep{b1, w2, part, hpost, M, H, H / 2, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
-    rowgemm::BSpec bs{W1, 3 * D, 0, 2};
-    return rowgemm::launch(device, ld, ep, bs, M, 3 * D, H / 2, static_cast<cudaStream_t>(stream_), "pipe_head_fwd");
+    HeadFwdEpilogue ep{b1, w2, part, hpost, M, H, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
+    return rowgemm_ts::launch(device, ld, ep, W1, 3 * D, 0, M, 3 * D, H, static_cast<cudaStream_t>(stream_),
+                              "pipe_head_fwd");
 }
 
 extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
@@ -240,9 +258,9 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
     const int64_t M = B * P;
     DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, H / 4};
     HeadBwdEpilogue ep{dX, X, reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P), static_cast<uint32_t>(N),
-                       D, 3 * D / 2, magic_of(P)};
-    rowgemm::BSpec bs{W1, 3 * D, 1, 2};
-    return rowgemm::launch(device, ld, ep, bs, M, H, 3 * D / 2, static_cast<cudaStream_t>(stream_), "pipe_head_bwd_dx");
+                       D, 3 * D, magic_of(P)};
+    return rowgemm_ts::launch(device, ld, ep, W1, 3 * D, 1, M, H, 3 * D, static_cast<cudaStream_t>(stream_),
+                              "pipe_head_bwd_dx");
 }
 
 extern "C" int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, const float* X, float* pooled,

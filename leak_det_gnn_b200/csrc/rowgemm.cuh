@@ -37,7 +37,8 @@ constexpr uint32_t kStageBytes = 2u * kTileM * kKG * 4;  // hi block + lo block 
 // loader warps, so the global loads / gathers of up to 4 stages are in flight at once -- the loaders are
 // latency-bound, and this is what keeps the tensor pipe and HBM busy.
 __host__ inline size_t smem_bytes(int K, int N, int stages) { return 1024 + static_cast<size_t>(stages) * kStageBytes + 2ull * N * K * 4; }
-__host__ inline int pick_stages(int K, int N, size_t limit) {
+__host__ inline int pick_stages(int K, int N, size_t limit, int prefer = 4) {
+    if (prefer == 3 && smem_bytes(K, N, 3) <= limit) return 3;
     if (smem_bytes(K, N, 4) <= limit) return 4;
     if (smem_bytes(K, N, 2) <= limit) return 2;
     return 0;
@@ -98,7 +99,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
     uint8_t* b_lo = b_hi + N * K * 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int warps_per_group = kLoaderWarps / n_stages;
+    const int warps_per_group = n_stages >= 3 ? 4 : 8;  // 3 stages: warps 12-15 idle
 
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
@@ -122,7 +123,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t n_tiles = (M + kTileM - 1) / kTileM;
 
-    if (warp < kLoaderWarps) {
+    if (warp < warps_per_group * n_stages) {
         // ------------------------------- loaders -------------------------------
         // group g owns ring stage g and fills it for every (tile, k-group) step `it` with it % n_stages == g
         const int grp = warp / warps_per_group;
@@ -163,6 +164,8 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
                 if (lane == 0) mbar_arrive(&bar_full[grp]);
             }
         }
+    } else if (warp < kLoaderWarps) {
+        // spare loader warps (3-stage configuration)
     } else if (warp == kMmaWarp) {
         // ------------------------------- MMA issuer -------------------------------
         // The whole warp walks the loop (warp-uniform control flow keeps addresses and descriptors in uniform
@@ -216,7 +219,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
 // host-side launch helper: validates shapes against the device, sets the smem attribute, launches
 template <class Loader, class Epilogue>
 int launch(int device, const Loader& loader, const Epilogue& epilogue, const BSpec& bspec, int64_t M, int K, int N,
-           cudaStream_t stream, const char* who) {
+           cudaStream_t stream, const char* who, int prefer_stages = 4) {
     LTGNN_REQUIRE(K % 32 == 0 && K > 0 && K <= 256, LTGNN_E_SHAPE, "%s: K=%d must be a multiple of 32, <= 256", who, K);
     LTGNN_REQUIRE(N % 16 == 0 && N > 0 && N <= 256, LTGNN_E_SHAPE, "%s: N=%d must be a multiple of 16, <= 256", who, N);
     LTGNN_REQUIRE(bspec.nvar >= 1, LTGNN_E_ARG, "%s: nvar=%d", who, bspec.nvar);
@@ -224,7 +227,7 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const BSp
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
                   di->cc_minor);
-    const int stages = pick_stages(K, N, static_cast<size_t>(di->smem_optin));
+    const int stages = pick_stages(K, N, static_cast<size_t>(di->smem_optin), prefer_stages);
     LTGNN_REQUIRE(stages > 0, LTGNN_E_SHAPE, "%s: K=%d N=%d needs %zu B of shared memory (limit %d)", who, K, N,
                   smem_bytes(K, N, 2), di->smem_optin);
     LTGNN_REQUIRE(M < (1ll << 31) - kTileM, LTGNN_E_SHAPE, "%s: M=%lld rows exceed the 32-bit row index", who,

@@ -384,7 +384,7 @@ class _Heads(torch.autograd.Function):
         L = _lib.load()
         p = float(drop_p) if training else 0.0
         need_grad = any(ctx.needs_input_grad)
-        part = torch.empty(2, b, p_cnt, device=x.device, dtype=torch.float32)
+        part = torch.empty(1, b, p_cnt, device=x.device, dtype=torch.float32)
         hpost = torch.empty(b * p_cnt, h, device=x.device, dtype=torch.float32) if need_grad else None
         w2v = w2.reshape(-1).contiguous()
         tok = _inst.begin("pipe_head_fwd")
@@ -409,7 +409,6 @@ class _Heads(torch.autograd.Function):
         p_cnt, h = ends.shape[0], w1.shape[0]
         dev = _dev_index(x)
         L = _lib.load()
-        # both halves of `part` feed one sum, so their gradients are the same tensor: d loss / d pipe_logit
         dlogit = dpart[0].contiguous().view(-1)
         dx = torch.empty_like(x)
         tok = _inst.begin("mean_pool_bwd")
@@ -439,7 +438,7 @@ class _Heads(torch.autograd.Function):
 
 def heads(x: torch.Tensor, ends: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, drop_p: float,
           training: bool):
-    """x (B,N,64), ends int32 (P,2) -> (part (2,B,P), pooled (B,64)); pipe_logits = part.sum(0) + b2."""
+    """x (B,N,64), ends int32 (P,2) -> (part (1,B,P), pooled (B,64)); pipe_logits = part.sum(0) + b2."""
     _check_act(x.contiguous(), "x")
     return _Heads.apply(x, ends, w1, b1, w2, drop_p, training)
 

@@ -21,3 +21,17 @@ for P in (764, 64):
         print(f"P={P} fwd train no-save: {timeit(lambda: ops.heads(x, e, w1, b1, w2, 0.1, True)):.3f} ms")
     print(f"P={P} fwd eval save    : {timeit(lambda: ops.heads(xg, e, w1, b1, w2, 0.1, False)):.3f} ms")
     print(f"P={P} fwd train save   : {timeit(lambda: ops.heads(xg, e, w1, b1, w2, 0.1, True)):.3f} ms")
+
+# backward pieces
+P = 764
+e = ends[:P].contiguous()
+xg = x.clone().requires_grad_(True)
+w1g = w1.clone().requires_grad_(True); b1g = b1.clone().requires_grad_(True); w2g = w2.clone().requires_grad_(True)
+part, pooled = ops.heads(xg, e, w1g, b1g, w2g, 0.1, True)
+loss = part.sum() + pooled.sum()
+from leak_det_gnn_b200 import instrument as inst
+inst.reset(timing=True)
+for _ in range(5):
+    loss.backward(retain_graph=True)
+torch.cuda.synchronize()
+print({k: round(v["mean_ms"], 3) for k, v in inst.summary().items()})
