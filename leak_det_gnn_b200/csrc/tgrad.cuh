@@ -103,56 +103,37 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         uint8_t* g_lo = g_hi + g_half;
         uint8_t* x_hi = g_lo + g_half;
         uint8_t* x_lo = x_hi + x_half;
-        const int g4 = kMo / 4, x4 = No / 4;
-        const int g_items = kChunk * g4, x_items = kChunk * x4;  // 1024, 32 * No/4
+        // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of both operands, so the
+        // row-dependent part of a gather (division, end-node lookup) is done once and all loads go out together
+        const int r = gtid >> 3, q = gtid & 7;
+        const int x4 = No / 4;
         uint32_t use = 0;
         for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
+            const uint32_t row = ch * kChunk + r;
+            const bool valid = row < M;
+            float4 gv[kMo / 32], xv[8];
+#pragma unroll
+            for (int j = 0; j < kMo / 32; ++j) gv[j] = valid ? gload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                xv[j] = (valid && q + 8 * j < x4) ? xload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
-            const uint32_t row0 = ch * kChunk;
-            // G part: 4 items per thread, all loads first
-            {
-                float4 v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int idx = gtid + j * kGroupThreads;
-                    const int r = idx / g4, c = idx - r * g4;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (row0 + r < M) v[j] = gload(row0 + r, c);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int idx = gtid + j * kGroupThreads;
-                    const int r = idx / g4, c = idx - r * g4;
-                    float4 hi, lo;
-                    split4(v[j], hi, lo);
-                    const uint32_t off = mn_offset(r, c, kChunk);
-                    *reinterpret_cast<float4*>(g_hi + off) = hi;
-                    *reinterpret_cast<float4*>(g_lo + off) = lo;
-                }
+            for (int j = 0; j < kMo / 32; ++j) {
+                float4 hi, lo;
+                split4(gv[j], hi, lo);
+                const uint32_t off = mn_offset(r, q + 8 * j, kChunk);
+                *reinterpret_cast<float4*>(g_hi + off) = hi;
+                *reinterpret_cast<float4*>(g_lo + off) = lo;
             }
-            // X part: up to 8 items per thread (No <= 256)
-            for (int base = 0; base < x_items; base += 4 * kGroupThreads) {
-                float4 v[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int idx = base + gtid + j * kGroupThreads;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (idx < x_items) {
-                        const int r = idx / x4, c = idx - r * x4;
-                        if (row0 + r < M) v[j] = xload(row0 + r, c);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int idx = base + gtid + j * kGroupThreads;
-                    if (idx < x_items) {
-                        const int r = idx / x4, c = idx - r * x4;
-                        float4 hi, lo;
-                        split4(v[j], hi, lo);
-                        const uint32_t off = mn_offset(r, c, kChunk);
-                        *reinterpret_cast<float4*>(x_hi + off) = hi;
-                        *reinterpret_cast<float4*>(x_lo + off) = lo;
-                    }
+            for (int j = 0; j < 8; ++j) {
+                if (q + 8 * j < x4) {
+                    float4 hi, lo;
+                    split4(xv[j], hi, lo);
+                    const uint32_t off = mn_offset(r, q + 8 * j, kChunk);
+                    *reinterpret_cast<float4*>(x_hi + off) = hi;
+                    *reinterpret_cast<float4*>(x_lo + off) = lo;
                 }
             }
             fence_proxy_async_smem();
