@@ -127,12 +127,12 @@ int ltgnn_wgrad(int device, int64_t M, int32_t Do, int32_t Di, const float* G, c
  *      sensor node (slot[i] >= 0) and (0, 0) otherwise.  hs [B,S,ds]; W [D, ds+1] (sensor_to_node.weight);
  *      slot int32[N] on the device.  Never builds the zero-padded (B,N,ds+1) tensor.
  * bwd: gate = (X0 > 0) * gate_scale applied to dX0; dhs [B,S,ds], dW [D, ds+1], dbias [D].
- *      ws: ltgnn_node_init_ws_floats() floats.  Deterministic.
+ *      ws: ltgnn_node_init_ws_floats() floats, 16-byte aligned.  Deterministic.
  */
 int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
                         const int32_t* slot, const float* W, const float* bias, float drop_p, uint64_t drop_seed,
                         float* X0, void* stream);
-int64_t ltgnn_node_init_ws_floats(int device, int32_t ds, int32_t D);
+int64_t ltgnn_node_init_ws_floats(int device, int64_t B, int32_t S, int32_t ds, int32_t D);
 int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
                         const int32_t* slot, const float* W, const float* dX0, const float* X0, float gate_scale,
                         float* dhs, float* dW, float* dbias, float* ws, void* stream);

@@ -1,0 +1,85 @@
+// functors.cuh -- loader / epilogue functors shared by the GEMM skeletons (rowgemm.cuh, tgrad.cuh).
+#pragma once
+
+#include "common.cuh"
+
+namespace ltgnn {
+namespace functors {
+
+struct RowLoader {
+    const float4* x;
+    int k4;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        return ptx::ldg_stream(x + static_cast<int64_t>(row) * k4 + c);
+    }
+};
+
+// bias -> ReLU -> optional gate: y *= (gate[row, col] > 0) ? gate_scale : 0
+// (the gate is the output of an upstream ReLU(+dropout): its positivity IS that layer's backward mask)
+struct StoreEpilogue {
+    float* y;
+    const float* bias;
+    const float* gate;
+    float gate_scale;
+    int n;
+    int relu;
+    template <class Pull>
+    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int /*var*/, Pull&& pull) const {
+        for (int c0 = 0; c0 < n; c0 += 16) {
+            float v[16];
+            pull(c0, v);
+            if (valid) chunk(row, c0, v);
+        }
+    }
+    __device__ __forceinline__ void chunk(int64_t row, int c0, float (&v)[16]) const {
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (gate) {
+            const float4* g = reinterpret_cast<const float4*>(gate + row * n + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 m = ptx::ldg_stream(g + j);
+                v[4 * j + 0] = m.x > 0.f ? v[4 * j + 0] * gate_scale : 0.f;
+                v[4 * j + 1] = m.y > 0.f ? v[4 * j + 1] * gate_scale : 0.f;
+                v[4 * j + 2] = m.z > 0.f ? v[4 * j + 2] * gate_scale : 0.f;
+                v[4 * j + 3] = m.w > 0.f ? v[4 * j + 3] * gate_scale : 0.f;
+            }
+        }
+        float4* out = reinterpret_cast<float4*>(y + row * n + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+};
+
+
+// ---- plain row-major operands, optionally two matrices stacked side by side to fill the 128 accumulator rows
+struct StackedRows {
+    const float4* a;  // [M, wa4]
+    const float4* b;  // [M, wb4] (columns wa4.. of the stacked operand) or nullptr
+    int wa4, wb4;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        if (c < wa4) return ptx::ldg_stream(a + static_cast<int64_t>(row) * wa4 + c);
+        if (b && c - wa4 < wb4) return ptx::ldg_stream(b + static_cast<int64_t>(row) * wb4 + (c - wa4));
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+};
+
+
+// [a | 1 | 0 ...]: operand rows followed by a ones column (its product column is the column sum of the other operand)
+struct RowsThenOne {
+    const float4* a;  // [M, wa4]
+    int wa4;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        if (c < wa4) return ptx::ldg_stream(a + static_cast<int64_t>(row) * wa4 + c);
+        return make_float4(c == wa4 ? 1.f : 0.f, 0.f, 0.f, 0.f);
+    }
+};
+
+}  // namespace functors
+}  // namespace ltgnn

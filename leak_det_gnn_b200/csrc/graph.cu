@@ -68,20 +68,24 @@ const DeviceInfo* device_info(int device) {
 }
 
 namespace {
+// one warp per output element: lane l adds parts l, l + 32, ... in order, then a fixed shuffle tree
 __global__ void reduce_parts_kernel(const float* __restrict__ parts, int64_t stride, float* __restrict__ out,
                                     int n_parts, int n, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= n) return;
-    float t = accumulate ? out[i] : 0.f;
-    for (int c = 0; c < n_parts; ++c) t += parts[c * stride + i];
-    out[i] = t;
+    float t = 0.f;
+    for (int c = lane; c < n_parts; c += 32) t += parts[c * stride + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) out[i] = accumulate ? out[i] + t : t;
 }
 }  // namespace
 
 int reduce_parts(const float* parts, int64_t stride, float* out, int n_parts, int n, int accumulate,
                  cudaStream_t stream) {
     if (n <= 0) return LTGNN_OK;
-    reduce_parts_kernel<<<(n + 127) / 128, 128, 0, stream>>>(parts, stride, out, n_parts, n, accumulate);
+    reduce_parts_kernel<<<(n + 3) / 4, 128, 0, stream>>>(parts, stride, out, n_parts, n, accumulate);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

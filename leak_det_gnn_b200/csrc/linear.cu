@@ -5,62 +5,13 @@
 // input-gradient GEMM dX = dXW * W in the backward (autograd of the same line), NoLeakHead
 // (models/detector.py:94-99).  Built on the pipelined skeleton in rowgemm.cuh; also the validation
 // vehicle for the tensor-core building blocks (tests/test_linear_gpu.py checks it against fp64).
+#include "functors.cuh"
 #include "rowgemm.cuh"
 
 using namespace ltgnn;
+using namespace ltgnn::functors;
 
 namespace {
-
-struct RowLoader {
-    const float4* x;
-    int k4;
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
-        return ptx::ldg_stream(x + static_cast<int64_t>(row) * k4 + c);
-    }
-};
-
-// bias -> ReLU -> optional gate: y *= (gate[row, col] > 0) ? gate_scale : 0
-// (the gate is the output of an upstream ReLU(+dropout): its positivity IS that layer's backward mask)
-struct StoreEpilogue {
-    float* y;
-    const float* bias;
-    const float* gate;
-    float gate_scale;
-    int n;
-    int relu;
-    template <class Pull>
-    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int /*var*/, Pull&& pull) const {
-        for (int c0 = 0; c0 < n; c0 += 16) {
-            float v[16];
-            pull(c0, v);
-            if (valid) chunk(row, c0, v);
-        }
-    }
-    __device__ __forceinline__ void chunk(int64_t row, int c0, float (&v)[16]) const {
-        if (bias) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(bias + c0 + j);
-        }
-        if (relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (gate) {
-            const float4* g = reinterpret_cast<const float4*>(gate + row * n + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 m = ptx::ldg_stream(g + j);
-                v[4 * j + 0] = m.x > 0.f ? v[4 * j + 0] * gate_scale : 0.f;
-                v[4 * j + 1] = m.y > 0.f ? v[4 * j + 1] * gate_scale : 0.f;
-                v[4 * j + 2] = m.z > 0.f ? v[4 * j + 2] * gate_scale : 0.f;
-                v[4 * j + 3] = m.w > 0.f ? v[4 * j + 3] * gate_scale : 0.f;
-            }
-        }
-        float4* out = reinterpret_cast<float4*>(y + row * n + c0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) out[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
-};
 
 }  // namespace
 

@@ -6,7 +6,9 @@
 // Here: a non-sensor row is the batch-independent constant relu(bias); a sensor row is
 // relu(W[:, :d_s] h_s + W[:, d_s] + bias).  HBM traffic = one write of x0 (forward), one read of
 // dx0 and x0 (backward); the 29-row GEMMs run on CUDA cores out of shared memory (0.1 % of the bytes).
-#include "common.cuh"
+#include "functors.cuh"
+#include "rowgemm.cuh"
+#include "tgrad.cuh"
 
 using namespace ltgnn;
 
@@ -77,89 +79,59 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0) {
 }
 
 // ---------------------------------------- backward ----------------------------------------
-// per CTA partial layout in ws: [D*(ds+1) dW | D db]
+// (1) one pure streaming kernel over dx0 / x0: gate, per-column sums (-> d bias) and the gated gradient of the S
+//     sensor rows of every window, written compactly to dz [B, S, D] (4 % of the bytes);
+// (2) d h_s = dz W[:, :ds] on the row-GEMM skeleton and dW = dz^T [h_s | 1] on the tensor-core weight-gradient
+//     skeleton, both over the B*S sensor rows only.
+
+// colsum partial layout: part[cta][D]
 __global__ void __launch_bounds__(kThreads)
-node_init_bwd_kernel(const InitParams p, const float* __restrict__ dX0, const float* __restrict__ X0, float gate_scale,
-                     float* __restrict__ dhs, float* __restrict__ ws) {
-    extern __shared__ __align__(16) float sm[];
-    const int ds = p.ds, ds1 = ds + 1, D = p.D, d4 = D >> 2;
-    float* Wo = sm;                 // [D][ds+1] as stored
-    float* hs = Wo + D * ds1;       // [S][ds]
-    float* dz = hs + p.S * ds;      // [S][D] gated gradient of the sensor rows
-    float* red = dz + p.S * D;      // [kThreads][4] scratch for the db reduction
+gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X0, const int32_t* __restrict__ slot,
+                    float gate_scale, float4* __restrict__ dz, float* __restrict__ part, int64_t B, int N, int S,
+                    int d4) {
+    __shared__ float4 red[kThreads];
     const int tid = threadIdx.x;
-
-    for (int i = tid; i < D * ds1; i += kThreads) Wo[i] = __ldg(p.W + i);
-
-    constexpr int kMaxAcc = 40;  // ceil(D*(ds+1)/256): 17 for 64x65, 33 for 128x65
-    float wacc[kMaxAcc];
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // kThreads % d4 == 0: a thread keeps its column group
+    const int n4 = N * d4;
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const float4* gb = dX0 + b * n4;
+        const float4* xb = X0 + b * n4;
+        float4* dzb = dz + b * S * d4;
+        for (int i0 = tid; i0 < n4; i0 += 4 * kThreads) {
+            float4 g[4], x[4];
 #pragma unroll
-    for (int m = 0; m < kMaxAcc; ++m) wacc[m] = 0.f;
-    const int n_w = D * ds1;
-    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // thread's column group is tid % d4 (kThreads % d4 == 0)
-
-    for (int64_t b = blockIdx.x; b < p.B; b += gridDim.x) {
-        __syncthreads();
-        const float* hsb = p.hs + b * p.S * ds;
-        for (int i = tid; i < p.S * ds; i += kThreads) hs[i] = __ldg(hsb + i);
-        const float4* g4 = reinterpret_cast<const float4*>(dX0) + b * p.N * d4;
-        const float4* x4 = reinterpret_cast<const float4*>(X0) + b * p.N * d4;
-        for (int i = tid; i < p.N * d4; i += kThreads) {
-            const int r = i / d4, c = i - r * d4;
-            float4 g = ptx::ldg_stream(g4 + i);
-            const float4 x = ptx::ldg_stream(x4 + i);
-            g.x = x.x > 0.f ? g.x * gate_scale : 0.f;
-            g.y = x.y > 0.f ? g.y * gate_scale : 0.f;
-            g.z = x.z > 0.f ? g.z * gate_scale : 0.f;
-            g.w = x.w > 0.f ? g.w * gate_scale : 0.f;
-            csum.x += g.x; csum.y += g.y; csum.z += g.z; csum.w += g.w;
-            const int sl = __ldg(p.slot + r);
-            if (sl >= 0) *reinterpret_cast<float4*>(dz + sl * D + c * 4) = g;
-        }
-        __syncthreads();
-        // d h_s[b, s, k] = sum_j dz[s, j] W[j, k]
-        float* out = dhs + b * p.S * ds;
-        for (int i = tid; i < p.S * ds; i += kThreads) {
-            const int s = i / ds, k = i - s * ds;
-            float acc = 0.f;
-            const float* z = dz + s * D;
-#pragma unroll 8
-            for (int j = 0; j < D; ++j) acc = fmaf(z[j], Wo[j * ds1 + k], acc);
-            out[i] = acc;
-        }
-        // dW[j, k] += sum_s dz[s, j] * (k < ds ? hs[s, k] : 1)
-#pragma unroll
-        for (int m = 0; m < kMaxAcc; ++m) {
-            const int e = tid + m * kThreads;
-            if (e < n_w) {
-                const int j = e / ds1, k = e - j * ds1;
-                float acc = wacc[m];
-                if (k < ds) {
-                    for (int s = 0; s < p.S; ++s) acc = fmaf(dz[s * D + j], hs[s * ds + k], acc);
-                } else {
-                    for (int s = 0; s < p.S; ++s) acc += dz[s * D + j];
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kThreads;
+                if (i < n4) {
+                    g[u] = ptx::ldg_stream(gb + i);
+                    x[u] = ptx::ldg_stream(xb + i);
                 }
-                wacc[m] = acc;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * kThreads;
+                if (i < n4) {
+                    g[u].x = x[u].x > 0.f ? g[u].x * gate_scale : 0.f;
+                    g[u].y = x[u].y > 0.f ? g[u].y * gate_scale : 0.f;
+                    g[u].z = x[u].z > 0.f ? g[u].z * gate_scale : 0.f;
+                    g[u].w = x[u].w > 0.f ? g[u].w * gate_scale : 0.f;
+                    csum.x += g[u].x; csum.y += g[u].y; csum.z += g[u].z; csum.w += g[u].w;
+                    const int r = i / d4, c = i - r * d4;
+                    const int sl = __ldg(slot + r);
+                    if (sl >= 0) dzb[sl * d4 + c] = g[u];
+                }
             }
         }
     }
-
-    float* part = ws + static_cast<size_t>(blockIdx.x) * (n_w + D);
-#pragma unroll
-    for (int m = 0; m < kMaxAcc; ++m) {
-        const int e = tid + m * kThreads;
-        if (e < n_w) part[e] = wacc[m];
-    }
-    __syncthreads();
-    *reinterpret_cast<float4*>(red + tid * 4) = csum;
+    red[tid] = csum;
     __syncthreads();
     if (tid < d4) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = tid; k < kThreads; k += d4) {
-            const float4 o = *reinterpret_cast<const float4*>(red + k * 4);
+        float4 t = red[tid];
+        for (int k = tid + d4; k < kThreads; k += d4) {
+            const float4 o = red[k];
             t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
         }
-        *reinterpret_cast<float4*>(part + n_w + tid * 4) = t;
+        reinterpret_cast<float4*>(part)[static_cast<size_t>(blockIdx.x) * d4 + tid] = t;
     }
 }
 
@@ -205,9 +177,15 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     return LTGNN_OK;
 }
 
-extern "C" int64_t ltgnn_node_init_ws_floats(int device, int32_t ds, int32_t D) {
+// workspace: dz [B,S,D] | colsum partials [n_stream_ctas][D] | weight-gradient partials
+static int stream_ctas(const DeviceInfo* di) { return di->sm_count * 8; }
+static int dw_cols(int ds) { return (ds + 1 + 31) / 32 * 32; }  // [h_s | 1] padded to whole 32-column blocks
+
+extern "C" int64_t ltgnn_node_init_ws_floats(int device, int64_t B, int32_t S, int32_t ds, int32_t D) {
     const DeviceInfo* di = device_info(device);
-    return di ? static_cast<int64_t>(di->sm_count) * 2 * (static_cast<int64_t>(D) * (ds + 1) + D) : -1;
+    if (!di) return -1;
+    return B * S * D + static_cast<int64_t>(stream_ctas(di)) * D +
+           static_cast<int64_t>(di->sm_count) * tgrad::kMo * dw_cols(ds);
 }
 
 extern "C" int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
@@ -216,28 +194,45 @@ extern "C" int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, 
     const DeviceInfo* di;
     int rc = check_common(device, B, N, S, ds, D, &di, "node_init_bwd");
     if (rc) return rc;
+    LTGNN_REQUIRE(D == 64 || D == 128, LTGNN_E_SHAPE, "node_init_bwd: D=%d must be 64 or 128", D);
+    LTGNN_REQUIRE(ds % 32 == 0 && ds <= 224, LTGNN_E_SHAPE, "node_init_bwd: ds=%d must be a multiple of 32", ds);
     LTGNN_REQUIRE(hs && slot && W && dX0 && X0 && dhs && dW && dbias && ws, LTGNN_E_ARG, "node_init_bwd: null tensor");
-    LTGNN_REQUIRE(aligned16(dX0) && aligned16(X0), LTGNN_E_ALIGN, "node_init_bwd: dX0/X0 must be 16-byte aligned");
+    LTGNN_REQUIRE(aligned16(dX0) && aligned16(X0) && aligned16(ws) && aligned16(hs) && aligned16(dhs), LTGNN_E_ALIGN,
+                  "node_init_bwd: 16-byte alignment required");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    const int n_w = D * (ds + 1);
+    const int n_w = D * (ds + 1), d4 = D / 4;
     if (B == 0) {
         LTGNN_CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * n_w, stream));
         LTGNN_CUDA_TRY(cudaMemsetAsync(dbias, 0, sizeof(float) * D, stream));
         return LTGNN_OK;
     }
-    InitParams p{hs, W, nullptr, slot, B, N, S, ds, D, 0u, 1.f, 0};
-    const size_t smem = sizeof(float) * (static_cast<size_t>(n_w) + static_cast<size_t>(S) * ds +
-                                         static_cast<size_t>(S) * D + 4 * kThreads);
-    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "node_init_bwd: %zu B of shared memory", smem);
-    LTGNN_CUDA_TRY(cudaFuncSetAttribute(node_init_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    const int64_t cap = static_cast<int64_t>(di->sm_count) * 2;
-    const int grid = static_cast<int>(B < cap ? B : cap);
-    node_init_bwd_kernel<<<grid, kThreads, smem, stream>>>(p, dX0, X0, gate_scale, dhs, ws);
+    float* dz = ws;
+    float* cpart = dz + B * S * D;
+    float* wpart = cpart + static_cast<int64_t>(stream_ctas(di)) * D;
+
+    // (1) streaming pass
+    const int64_t g1 = B < stream_ctas(di) ? B : stream_ctas(di);
+    gate_extract_kernel<<<static_cast<int>(g1), kThreads, 0, stream>>>(
+        reinterpret_cast<const float4*>(dX0), reinterpret_cast<const float4*>(X0), slot, gate_scale,
+        reinterpret_cast<float4*>(dz), cpart, B, N, S, d4);
     LTGNN_CUDA_TRY(cudaGetLastError());
-    // ws rows are [dW | db]
-    rc = reduce_parts(ws, n_w + D, dW, grid, n_w, 0, stream);
+    rc = reduce_parts(cpart, D, dbias, static_cast<int>(g1), D, 0, stream);
     if (rc) return rc;
-    return reduce_parts(ws + n_w, n_w + D, dbias, grid, D, 0, stream);
+
+    // (2a) d h_s [B*S, ds] = dz [B*S, D] * W[:, :ds]   (W is [D, ds+1] row-major: a [K, N] operand with ld = ds+1)
+    const int64_t M = B * S;
+    functors::RowLoader ld{reinterpret_cast<const float4*>(dz), d4};
+    functors::StoreEpilogue ep{dhs, nullptr, nullptr, 1.f, ds, 0};
+    rowgemm::BSpec bs{W, ds + 1, 1, 1};
+    rc = rowgemm::launch(device, ld, ep, bs, M, D, ds, stream, "node_init_bwd(dhs)");
+    if (rc) return rc;
+
+    // (2b) dW [D, ds+1] = dz^T [h_s | 1]
+    functors::StackedRows g{reinterpret_cast<const float4*>(dz), nullptr, d4, 0};
+    functors::RowsThenOne x{reinterpret_cast<const float4*>(hs), ds / 4};
+    int grid = 0;
+    rc = tgrad::launch(device, g, x, wpart, M, dw_cols(ds), &grid, stream, "node_init_bwd(dW)");
+    if (rc) return rc;
+    return tgrad::gather(wpart, grid, dw_cols(ds), 0, D, 0, ds + 1, dW, ds + 1, 0, stream);
 }

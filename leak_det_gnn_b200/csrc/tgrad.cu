@@ -3,23 +3,13 @@
 //   * EdgeHead.mlp.0: dW1[H, 3D] = dpre^T feat and db1 = column sums of dpre over the B*P pipe rows
 //                     (autograd of models/detector.py:79-87), with dpre and feat formed on the fly from the
 //                     saved hidden activations / the node states -- neither (B*P, H) nor (B*P, 3D) exists.
+#include "functors.cuh"
 #include "tgrad.cuh"
 
 using namespace ltgnn;
+using namespace ltgnn::functors;
 
 namespace {
-
-// ---- plain row-major operands, optionally two matrices stacked side by side to fill the 128 accumulator rows
-struct StackedRows {
-    const float4* a;  // [M, wa4]
-    const float4* b;  // [M, wb4] (columns wa4.. of the stacked operand) or nullptr
-    int wa4, wb4;
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
-        if (c < wa4) return ptx::ldg_stream(a + static_cast<int64_t>(row) * wa4 + c);
-        if (b && c - wa4 < wb4) return ptx::ldg_stream(b + static_cast<int64_t>(row) * wb4 + (c - wa4));
-        return make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-};
 
 // ---- pipe head: G = d loss / d pre (from the saved post-activation), X = [feat | 1 | 0...]
 struct HeadDpre {
@@ -53,26 +43,6 @@ struct HeadFeatOnes {
     }
 };
 
-// out[r][c] (+)= sum_p ws[p][r][c_src] for a sub-rectangle of the [128][No] accumulator
-__global__ void gather_partials_kernel(const float* __restrict__ ws, int n_parts, int No, int r0, int rows, int c0,
-                                       int cols, float* __restrict__ out, int ld_out, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    const int r = i / cols, c = i - r * cols;
-    const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c;
-    float t = accumulate ? out[r * ld_out + c] : 0.f;
-    for (int p = 0; p < n_parts; ++p) t += ws[static_cast<size_t>(p) * tgrad::kMo * No + src];
-    out[r * ld_out + c] = t;
-}
-
-int gather(const float* ws, int n_parts, int No, int r0, int rows, int c0, int cols, float* out, int ld_out,
-           int accumulate, cudaStream_t stream) {
-    const int n = rows * cols;
-    gather_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ws, n_parts, No, r0, rows, c0, cols, out, ld_out, accumulate);
-    LTGNN_CUDA_TRY(cudaGetLastError());
-    return LTGNN_OK;
-}
-
 }  // namespace
 
 extern "C" int64_t ltgnn_tgrad_ws_floats(int device, int32_t No) {
@@ -100,7 +70,7 @@ extern "C" int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, con
     int grid = 0;
     int rc = tgrad::launch(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc");
     if (rc) return rc;
-    return gather(ws, grid, Di, 0, Do, 0, Di, dW, Di, accumulate, stream);
+    return tgrad::gather(ws, grid, Di, 0, Do, 0, Di, dW, Di, accumulate, stream);
 }
 
 // Pipe-head parameter gradients: dW1 [128, 192] and db1 [128].  ws: ltgnn_tgrad_ws_floats(device, 224) floats.
@@ -125,7 +95,7 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
     int grid = 0;
     int rc = tgrad::launch(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
     if (rc) return rc;
-    rc = gather(ws, grid, No, 0, H, 0, 3 * D, dW1, 3 * D, 0, stream);
+    rc = tgrad::gather(ws, grid, No, 0, H, 0, 3 * D, dW1, 3 * D, 0, stream);
     if (rc) return rc;
-    return gather(ws, grid, No, 0, H, 3 * D, 1, db1, 1, 0, stream);
+    return tgrad::gather(ws, grid, No, 0, H, 3 * D, 1, db1, 1, 0, stream);
 }

@@ -213,5 +213,26 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     return LTGNN_OK;
 }
 
+// out[r][c] (+)= sum_p ws[p][r][c_src] for a sub-rectangle of the [128][No] accumulator
+static __global__ void gather_partials_kernel(const float* __restrict__ ws, int n_parts, int No, int r0, int rows, int c0,
+                                       int cols, float* __restrict__ out, int ld_out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i - r * cols;
+    const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c;
+    float t = accumulate ? out[r * ld_out + c] : 0.f;
+    for (int p = 0; p < n_parts; ++p) t += ws[static_cast<size_t>(p) * kMo * No + src];
+    out[r * ld_out + c] = t;
+}
+
+inline int gather(const float* ws, int n_parts, int No, int r0, int rows, int c0, int cols, float* out, int ld_out,
+           int accumulate, cudaStream_t stream) {
+    const int n = rows * cols;
+    gather_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ws, n_parts, No, r0, rows, c0, cols, out, ld_out, accumulate);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+
 }  // namespace tgrad
 }  // namespace ltgnn

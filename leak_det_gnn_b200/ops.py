@@ -278,12 +278,20 @@ def node_init_bwd(h_s, slot, weight, dx0, x0, gate_scale):
         _check_act(t, nm)
     b, s, ds = h_s.shape
     n, d = x0.shape[1], x0.shape[2]
+    if d not in (64, 128) or ds % 32:
+        # shapes outside the tensor-core kernels (never the reference's 64/64): same maths with torch ops on the GPU
+        dz = torch.where(x0 > 0, dx0 * gate_scale, torch.zeros((), device=x0.device))
+        rows = torch.nonzero(slot >= 0).flatten()
+        dzs = torch.zeros(b, s, d, device=x0.device)
+        dzs[:, slot[rows].long()] = dz[:, rows]
+        dw = torch.cat([torch.einsum("bsd,bsk->dk", dzs, h_s), dzs.sum(dim=(0, 1)).unsqueeze(1)], dim=1)
+        return dzs @ weight[:, :ds], dw, dz.sum(dim=(0, 1))
     L = _lib.load()
     dev = _dev_index(h_s)
     dhs = torch.empty_like(h_s)
     dw = torch.empty_like(weight)
     db = torch.empty(d, device=h_s.device, dtype=torch.float32)
-    ws = torch.empty(int(L.ltgnn_node_init_ws_floats(dev, ds, d)), device=h_s.device, dtype=torch.float32)
+    ws = torch.empty(int(L.ltgnn_node_init_ws_floats(dev, b, s, ds, d)), device=h_s.device, dtype=torch.float32)
     tok = _inst.begin("node_init_bwd")
     _lib.check(L.ltgnn_node_init_bwd(dev, b, n, s, ds, d, h_s.data_ptr(), slot.data_ptr(), weight.data_ptr(),
                                      dx0.data_ptr(), x0.data_ptr(), float(gate_scale), dhs.data_ptr(), dw.data_ptr(),
