@@ -169,6 +169,16 @@ int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D
                           const int32_t* ends, const float* w2, const float* hpost, const float* dlogit,
                           float gate_scale, float* dW1, float* db1, float* ws, void* stream);
 
+/* ---- shared per-sensor GRU encoder (detector.py:28-73) -----------------------
+ * Sequence q = b*S + s has input [r[b,t,s], tf[b,t,0..F)] at step t (the reference's cat([rr, tf]) order);
+ * weights in torch.nn.GRU layout (gate order r, z, n): w_ih [3H, 1+F], w_hh [3H, H], b_ih, b_hh [3H].
+ * h_last [B*S, H] = hidden state after step L-1 (h_0 = 0); hseq (optional) [L, B*S, H] = every state, saved
+ * for the backward.  H = 64.  State lives in tensor memory; recurrent GEMM on tcgen05 (3xTF32).
+ */
+int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t H, const float* r, const float* tf,
+                  const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* h_last,
+                  float* hseq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,277 @@
+// gru.cu -- the shared per-sensor GRU encoder that feeds the message-passing path.
+//
+// Reference: models/detector.py:28-73 -- `nn.GRU(input_size=1+9, hidden_size=64, batch_first=True)` over
+// B*S sequences of L steps (input = [residual_s(t), 9 time features of the window]); only the last hidden
+// state is used.  The reference (and round-1's drop-in) call cuDNN, which at B*S = 118 784, L = 288 spends
+// ~225 ms forward / ~450 ms backward on 1 TFLOP of recurrent GEMM (per-timestep launches, 4 TFLOP/s).
+//
+// Here: one persistent CTA per SM owns a tile of 128 sequences for all L steps.
+//   * the recurrent weights AND the input weights AND the biases form ONE resident tensor-core operand
+//     B[4H x 96] (rows: r | z | W_hn h + b_hn | W_in x + b_in; columns: h(64) | x(1) | tf(9) | 1 | 0-pad),
+//     split TF32 hi/lo in shared memory (192 KB);
+//   * the state lives in TENSOR MEMORY: A[128 x 96] = [h_{t-1} | x_t | tf_t | 1] as hi/lo columns, written
+//     by the gate warps with tcgen05.st, consumed by tcgen05.mma (A from TMEM, 3xTF32) into a 256-column
+//     accumulator -- the hidden state never touches shared or global memory between steps;
+//   * 8 gate warps (thread = one sequence x 32 hidden units) read the four pre-activation groups with
+//     tcgen05.ld, apply sigmoid/tanh, update h in registers and store the next A.
+// PyTorch gate order and equations (torch.nn.GRU): r, z, n;  n = tanh(W_in x + b_in + r * (W_hn h + b_hn));
+// h' = (1 - z) * n + z * h.
+#include "umma.cuh"
+#include "rowgemm_ts.cuh"
+
+using namespace ltgnn;
+using namespace ltgnn::ptx;
+using namespace ltgnn::umma;
+using ltgnn::rowgemm_ts::mma_tf32_ts;
+using ltgnn::rowgemm_ts::tmem_wait_st;
+
+namespace {
+
+constexpr int H = 64;            // hidden size supported by this kernel
+constexpr int KA = 96;           // augmented K: h(64) | x | tf(F <= 29) | 1 | pad
+constexpr int NG = 4 * H;        // 256 accumulator columns
+constexpr int kGateWarps = 8;
+constexpr int kMmaWarp = kGateWarps;
+constexpr int kThreads = (kGateWarps + 1) * 32;
+constexpr uint32_t kAccCol = 0, kAhiCol = NG, kAloCol = NG + KA;  // TMEM column map (448 of 512 used)
+
+struct GruParams {
+    const float* r;      // [B, L, S]
+    const float* tf;     // [B, L, F] or nullptr (F = 0)
+    const float* w_ih;   // [3H, 1 + F]
+    const float* w_hh;   // [3H, H]
+    const float* b_ih;   // [3H]
+    const float* b_hh;   // [3H]
+    float* h_last;       // [Q, H]
+    float* hseq;         // [L, Q, H] or nullptr
+    uint32_t Q;          // B * S sequences
+    int L, S, F;
+    uint64_t magic_s;    // fastdiv constant of S (S >= 2), 0 when S == 1
+};
+
+__device__ __forceinline__ float sigmoidf_fast(float v) { return __frcp_rn(1.f + __expf(-v)); }
+__device__ __forceinline__ float tanhf_fast(float v) { return 2.f * __frcp_rn(1.f + __expf(-2.f * v)) - 1.f; }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+          "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
+        : "memory");
+}
+
+// element (n, k) of the fused operand described in the file header
+__device__ __forceinline__ float fused_weight(const GruParams& p, int n, int k) {
+    const int g = n / H, j = n - g * H;
+    const int fi = 1 + p.F;  // row length of w_ih
+    const int kx = H, kb = H + 1 + p.F;  // column of x, column of the constant 1
+    if (g < 2) {
+        const int row = g * H + j;
+        if (k < H) return __ldg(p.w_hh + row * H + k);
+        if (k >= kx && k < kb) return __ldg(p.w_ih + row * fi + (k - kx));
+        if (k == kb) return __ldg(p.b_ih + row) + __ldg(p.b_hh + row);
+        return 0.f;
+    }
+    const int row = 2 * H + j;
+    if (g == 2) {
+        if (k < H) return __ldg(p.w_hh + row * H + k);
+        if (k == kb) return __ldg(p.b_hh + row);
+        return 0.f;
+    }
+    if (k >= kx && k < kb) return __ldg(p.w_ih + row * fi + (k - kx));
+    if (k == kb) return __ldg(p.b_ih + row);
+    return 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gru_fwd_kernel(const GruParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_a, bar_d;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_hi = smem;
+    uint8_t* b_lo = b_hi + NG * KA * 4;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        mbar_init(&bar_a, kGateWarps);
+        mbar_init(&bar_d, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < NG * KA; i += kThreads) {
+        const int n = i / KA, k = i - n * KA;
+        const float w = fused_weight(p, n, k);
+        const float hi = tf32_hi(w);
+        const uint32_t off = sw128_offset(n, k >> 2, NG) + (k & 3) * 4;
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = w - hi;
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t n_tiles = (p.Q + 127) / 128;
+    uint32_t ph_a = 0, ph_d = 0;  // phases of the two barriers, advanced identically by every role
+
+    if (warp < kGateWarps) {
+        const int quad = warp & 3, half = warp >> 2;           // TMEM lane quadrant, hidden-unit half
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int j0 = half * 32;                              // this thread's hidden units [j0, j0 + 32)
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t q = tile * 128 + quad * 32 + lane;  // sequence index = b * S + s
+            const bool valid = q < p.Q;
+            const uint32_t b = p.magic_s ? fastdiv(valid ? q : 0, p.magic_s) : (valid ? q : 0);
+            const uint32_t s = (valid ? q : 0) - b * p.S;
+            const float* rp = p.r + static_cast<size_t>(b) * p.L * p.S + s;      // + t * S
+            const float* tp = p.tf ? p.tf + static_cast<size_t>(b) * p.L * p.F : nullptr;  // + t * F
+            float h[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = 0.f;
+
+            // ---- A(0) = [0 | x_0 | tf_0 | 1]
+            {
+                float z16[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) z16[j] = 0.f;
+                tmem_st16(tmem + lane_off + kAhiCol + j0, z16);
+                tmem_st16(tmem + lane_off + kAhiCol + j0 + 16, z16);
+                tmem_st16(tmem + lane_off + kAloCol + j0, z16);
+                tmem_st16(tmem + lane_off + kAloCol + j0 + 16, z16);
+            }
+            auto store_aux = [&](int t) {  // columns 64..95 of A for step t (half 0 warps only)
+                float a[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = 0.f;
+                if (valid && t < p.L) {
+                    a[0] = __ldg(rp + static_cast<size_t>(t) * p.S);
+#pragma unroll
+                    for (int j = 1; j < 31; ++j)  // compile-time register indices; F <= 30
+                        if (j <= p.F) a[j] = __ldg(tp + static_cast<size_t>(t) * p.F + (j - 1));
+                }
+                // the constant-one column sits right after the time features
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j == 1 + p.F) a[j] = 1.f;
+                    const float hi = tf32_hi(a[j]);
+                    lo[j] = a[j] - hi;
+                    a[j] = hi;
+                }
+                rowgemm_ts::tmem_st32(tmem + lane_off + kAhiCol + H, a);
+                rowgemm_ts::tmem_st32(tmem + lane_off + kAloCol + H, lo);
+            };
+            if (half == 0) store_aux(0);
+            tmem_wait_st();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_a);
+
+            for (int t = 0; t < p.L; ++t) {
+                mbar_wait(&bar_d, ph_d);
+                ph_d ^= 1;
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    float rr[16], zz[16], hn[16], in[16];
+                    tmem_ld16(tmem + lane_off + kAccCol + 0 * H + j0 + c, rr);
+                    tmem_ld16(tmem + lane_off + kAccCol + 1 * H + j0 + c, zz);
+                    tmem_ld16(tmem + lane_off + kAccCol + 2 * H + j0 + c, hn);
+                    tmem_ld16(tmem + lane_off + kAccCol + 3 * H + j0 + c, in);
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float r = sigmoidf_fast(rr[j]);
+                        const float z = sigmoidf_fast(zz[j]);
+                        const float n = tanhf_fast(fmaf(r, hn[j], in[j]));
+                        const float hv = fmaf(z, h[c + j] - n, n);  // (1 - z) n + z h
+                        h[c + j] = hv;
+                        hi[j] = tf32_hi(hv);
+                        lo[j] = hv - hi[j];
+                    }
+                    tmem_st16(tmem + lane_off + kAhiCol + j0 + c, hi);
+                    tmem_st16(tmem + lane_off + kAloCol + j0 + c, lo);
+                }
+                if (p.hseq && valid) {
+                    float4* dst = reinterpret_cast<float4*>(p.hseq + (static_cast<size_t>(t) * p.Q + q) * H + j0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                }
+                if (t + 1 < p.L) {
+                    if (half == 0) store_aux(t + 1);
+                    tmem_wait_st();
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_a);
+                }
+            }
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(p.h_last + static_cast<size_t>(q) * H + j0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+            }
+            // the tile's last accumulator has been read: the next tile's first A store may proceed only after
+            // every gate warp is past its tcgen05.ld, which the bar_a count of the next arrival guarantees
+            fence_before_sync();
+        }
+    } else {
+        // ------------------------------- MMA issuer -------------------------------
+        const uint32_t idesc = idesc_tf32(128, NG);
+        const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
+        constexpr uint32_t kg_units = NG * 128u >> 4;  // one 32-column k-atom block of B
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int t = 0; t < p.L; ++t) {
+                mbar_wait(&bar_a, ph_a);
+                ph_a ^= 1;
+                fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < KA / 8; ++ks) {
+                        const uint32_t boff = (ks >> 2) * kg_units + 2 * (ks & 3);
+                        mma_tf32_ts(tmem + kAccCol, tmem + kAloCol + 8 * ks, bh + boff, idesc, ks == 0 ? 0u : 1u);
+                        mma_tf32_ts(tmem + kAccCol, tmem + kAhiCol + 8 * ks, bl + boff, idesc, 1u);
+                        mma_tf32_ts(tmem + kAccCol, tmem + kAhiCol + 8 * ks, bh + boff, idesc, 1u);
+                    }
+                    commit(&bar_d);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace
+
+extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
+                             const float* tf, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                             float* h_last, float* hseq, void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && L > 0 && S > 0 && F >= 0, LTGNN_E_ARG, "gru_fwd: B=%lld L=%d S=%d F=%d",
+                  static_cast<long long>(B), L, S, F);
+    LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_fwd: hidden size %d not supported (64 only)", Hdim);
+    LTGNN_REQUIRE(H + 1 + F + 1 <= KA, LTGNN_E_SHAPE, "gru_fwd: %d time features do not fit the fused operand", F);
+    LTGNN_REQUIRE(B * S < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_fwd: too many sequences");
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(r && w_ih && w_hh && b_ih && b_hh && h_last && (tf || F == 0), LTGNN_E_ARG, "gru_fwd: null tensor");
+    LTGNN_REQUIRE(aligned16(h_last) && aligned16(hseq), LTGNN_E_ALIGN, "gru_fwd: outputs must be 16-byte aligned");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_fwd: device is sm_%d%d, need sm_100", di->cc_major,
+                  di->cc_minor);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, static_cast<uint32_t>(B * S), L, S, F,
+                S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
+    const size_t smem = 1024 + 2ull * NG * KA * 4;
+    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "gru_fwd: %zu B of shared memory", smem);
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles = (B * S + 127) / 128;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    gru_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}

@@ -515,3 +515,29 @@ def gnn_body(h_s: torch.Tensor, slot: torch.Tensor, graph: PipeGraph, drop_p: fl
     """Sensor embeddings (B,S,ds) -> node states after the last GCN layer (B,N,D)."""
     _check_act(h_s.contiguous(), "h_s")
     return _GnnBody.apply(h_s, slot, graph, drop_p, training, w0, b0, *conv_params)
+
+
+# ----------------------------------------------------------------------------------------------
+# shared per-sensor GRU encoder (reference models/detector.py:28-73)
+# ----------------------------------------------------------------------------------------------
+def gru_supported(hidden: int, n_time: int) -> bool:
+    return hidden == 64 and 0 <= n_time <= 30
+
+
+def gru_fwd(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh, save_seq: bool = False):
+    """Raw forward: r (B,L,S), tf (B,L,F) or None -> h_last (B,S,H) [, hseq (L, B*S, H)]."""
+    _check_act(r, "r")
+    b, l, s = r.shape
+    f = 0 if tf is None else tf.shape[-1]
+    if tf is not None:
+        _check_act(tf, "tf")
+    hdim = w_hh.shape[1]
+    h_last = torch.empty(b, s, hdim, device=r.device, dtype=torch.float32)
+    hseq = torch.empty(l, b * s, hdim, device=r.device, dtype=torch.float32) if save_seq else None
+    L = _lib.load()
+    tok = _inst.begin("gru_fwd")
+    _lib.check(L.ltgnn_gru_fwd(_dev_index(r), b, l, s, f, hdim, r.data_ptr(), None if tf is None else tf.data_ptr(),
+                               w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), h_last.data_ptr(),
+                               None if hseq is None else hseq.data_ptr(), _stream(r)))
+    _inst.end(tok)
+    return (h_last, hseq) if save_seq else h_last

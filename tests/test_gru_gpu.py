@@ -1,0 +1,34 @@
+"""Sensor GRU encoder kernel vs torch.nn.GRU in fp64 on the CPU (the reference calls nn.GRU; detector.py:50-73)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from leak_det_gnn_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(r, tf, gru):
+    b, l, s = r.shape
+    seq = r.transpose(1, 2).reshape(b * s, l, 1)
+    if tf is not None:
+        seq = torch.cat([seq, tf.unsqueeze(1).expand(b, s, l, tf.shape[-1]).reshape(b * s, l, -1)], dim=-1)
+    out, _ = gru(seq)
+    return out  # (B*S, L, H)
+
+
+@pytest.mark.parametrize("b,l,s,f", [(1, 1, 1, 0), (3, 36, 29, 9), (10, 36, 29, 9), (2, 288, 29, 9), (5, 12, 7, 3),
+                                     (40, 5, 29, 0)])
+def test_gru_forward(b, l, s, f):
+    torch.manual_seed(b * 100 + l)
+    gru = torch.nn.GRU(input_size=1 + f, hidden_size=64, num_layers=1, batch_first=True).double()
+    r = torch.randn(b, l, s)
+    tf = torch.randn(b, l, f) if f else None
+    out = _ref(r.double(), None if tf is None else tf.double(), gru)
+    w = [getattr(gru, n).detach().float().cuda() for n in ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")]
+    h_last, hseq = ops.gru_fwd(r.cuda(), None if tf is None else tf.cuda(), *w, save_seq=True)
+    assert h_last.shape == (b, s, 64) and hseq.shape == (l, b * s, 64)
+    assert rel_err(hseq.permute(1, 0, 2), out) <= 2e-5
+    assert rel_err(h_last.reshape(b * s, 64), out[:, -1, :]) <= 2e-5
+    h2 = ops.gru_fwd(r.cuda(), None if tf is None else tf.cuda(), *w)
+    assert torch.equal(h2, h_last)
