@@ -171,13 +171,23 @@ int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D
 
 /* ---- shared per-sensor GRU encoder (detector.py:28-73) -----------------------
  * Sequence q = b*S + s has input [r[b,t,s], tf[b,t,0..F)] at step t (the reference's cat([rr, tf]) order);
- * weights in torch.nn.GRU layout (gate order r, z, n): w_ih [3H, 1+F], w_hh [3H, H], b_ih, b_hh [3H].
- * h_last [B*S, H] = hidden state after step L-1 (h_0 = 0); hseq (optional) [L, B*S, H] = every state, saved
- * for the backward.  H = 64.  State lives in tensor memory; recurrent GEMM on tcgen05 (3xTF32).
+ * weights in torch.nn.GRU layout (gate order r, z, n): w_ih [3H, 1+F], w_hh [3H, H], b_ih, b_hh [3H].  H = 64.
+ * gru_fwd:    h_last [B*S, H] = hidden state after step L-1 (h_0 = 0).  For training also pass
+ *             hseq [L, B*S, H] (every state) and gates [L, B*S, 4, H] (r, z, n, W_hn h + b_hn); NULL otherwise.
+ *             State lives in tensor memory; recurrent + input GEMM fused on tcgen05 (3xTF32).
+ * gru_bwd_dg: back-propagation through time given dh_last [B*S, H]: writes dG [L, B*S, 4, H], the gradient wrt
+ *             the four pre-activation groups (r, z, W_hn h + b_hn, W_in x + b_in).
+ * gru_bwd_w:  dBfused [4H, 96] = sum_(t,q) dG^T [h_{t-1} | x | tf | 1 | 0]: columns 0..H-1 are d w_hh, H..H+F
+ *             d w_ih, H+F+1 the bias gradients (rows: r, z, hn-part, in-part).  ws: ltgnn_gru_ws_floats() floats.
  */
 int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t H, const float* r, const float* tf,
                   const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, float* h_last,
-                  float* hseq, void* stream);
+                  float* hseq, float* gates, void* stream);
+int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t H, const float* w_hh, const float* gates,
+                     const float* hseq, const float* dh_last, float* dG, void* stream);
+int64_t ltgnn_gru_ws_floats(int device);
+int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t H, const float* r, const float* tf,
+                    const float* hseq, const float* dG, float* dBfused, float* ws, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@
 // h' = (1 - z) * n + z * h.
 #include "umma.cuh"
 #include "rowgemm_ts.cuh"
+#include "tgrad.cuh"
 
 using namespace ltgnn;
 using namespace ltgnn::ptx;
@@ -44,6 +45,7 @@ struct GruParams {
     const float* b_hh;   // [3H]
     float* h_last;       // [Q, H]
     float* hseq;         // [L, Q, H] or nullptr
+    float* gates;        // [L, Q, 4, H] (r, z, n, W_hn h + b_hn) or nullptr: saved for the backward
     uint32_t Q;          // B * S sequences
     int L, S, F;
     uint64_t magic_s;    // fastdiv constant of S (S >= 2), 0 when S == 1
@@ -188,6 +190,19 @@ gru_fwd_kernel(const GruParams p) {
                         h[c + j] = hv;
                         hi[j] = tf32_hi(hv);
                         lo[j] = hv - hi[j];
+                        rr[j] = r;
+                        zz[j] = z;
+                        in[j] = n;
+                    }
+                    if (p.gates && valid) {
+                        float* gp = p.gates + ((static_cast<size_t>(t) * p.Q + q) * 4) * H + j0 + c;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            reinterpret_cast<float4*>(gp)[j] = make_float4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
+                            reinterpret_cast<float4*>(gp + H)[j] = make_float4(zz[4 * j], zz[4 * j + 1], zz[4 * j + 2], zz[4 * j + 3]);
+                            reinterpret_cast<float4*>(gp + 2 * H)[j] = make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
+                            reinterpret_cast<float4*>(gp + 3 * H)[j] = make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
+                        }
                     }
                     tmem_st16(tmem + lane_off + kAhiCol + j0 + c, hi);
                     tmem_st16(tmem + lane_off + kAloCol + j0 + c, lo);
@@ -246,11 +261,188 @@ gru_fwd_kernel(const GruParams p) {
     }
 }
 
+
+// =====================================================================================================
+// backward through time.  Per step t = L-1 .. 0 and tile of 128 sequences, with dh = d loss / d h_t:
+//   dn = dh (1 - z);  dn_pre = dn (1 - n^2);  dz_pre = dh (h_{t-1} - n) z (1 - z);
+//   dr_pre = dn_pre * hn * r (1 - r);  dhn = dn_pre * r;  din = dn_pre
+//   dG(t) = [dr_pre | dz_pre | dhn | din]  -> written to HBM for the weight-gradient GEMM (tgrad.cuh)
+//   dh_{t-1} = dh z + [dr_pre | dz_pre | dhn] [W_hr; W_hz; W_hn]          (tcgen05, A = dG in TMEM)
+// Gates r, z, n and hn = W_hn h + b_hn were saved by the forward, so no transcendental is recomputed.
+// =====================================================================================================
+constexpr int KB = 3 * H;  // 192: K of the dh_{t-1} GEMM
+constexpr uint32_t kB_acc = 0, kB_hi = H, kB_lo = H + KB;  // TMEM: acc 64 | dG hi 192 | dG lo 192 = 448 columns
+
+struct GruBwdParams {
+    const float* w_hh;   // [3H, H]
+    const float* gates;  // [L, Q, 4, H]
+    const float* hseq;   // [L, Q, H]
+    const float* dh_last;  // [Q, H]
+    float* dG;           // [L, Q, 4, H]
+    uint32_t Q;
+    int L;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gru_bwd_kernel(const GruBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_a, bar_d;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_hi = smem;                 // B2[n = h column (64)][k = gate row (192)] = w_hh[k][n], K-major SW128
+    uint8_t* b_lo = b_hi + H * KB * 4;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        mbar_init(&bar_a, kGateWarps);
+        mbar_init(&bar_d, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < KB * H; i += kThreads) {
+        const int k = i / H, n = i - k * H;  // coalesced read of w_hh[k][n]
+        const float w = __ldg(p.w_hh + i);
+        const float hi = tf32_hi(w);
+        const uint32_t off = sw128_offset(n, k >> 2, H) + (k & 3) * 4;
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = w - hi;
+    }
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t n_tiles = (p.Q + 127) / 128;
+    uint32_t ph_a = 0, ph_d = 0;
+
+    if (warp < kGateWarps) {
+        const int quad = warp & 3, half = warp >> 2;
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int j0 = half * 32;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t q = tile * 128 + quad * 32 + lane;
+            const bool valid = q < p.Q;
+            float dh[32];
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.dh_last + static_cast<size_t>(valid ? q : 0) * H + j0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dh[4 * j] = v.x; dh[4 * j + 1] = v.y; dh[4 * j + 2] = v.z; dh[4 * j + 3] = v.w;
+                }
+            }
+            for (int t = p.L - 1; t >= 0; --t) {
+                const size_t row = static_cast<size_t>(t) * p.Q + (valid ? q : 0);
+                const float4* gp = reinterpret_cast<const float4*>(p.gates + row * 4 * H + j0);
+                const float4* hp = t > 0 ? reinterpret_cast<const float4*>(p.hseq + (row - p.Q) * H + j0) : nullptr;
+                float4* dgp = reinterpret_cast<float4*>(p.dG + row * 4 * H + j0);
+                float zkeep[32];
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    float r[16], z[16], n[16], hn[16], hm[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 a = valid ? ldg_stream(gp + (c >> 2) + j) : zero;
+                        const float4 b = valid ? ldg_stream(gp + (H >> 2) + (c >> 2) + j) : zero;
+                        const float4 d = valid ? ldg_stream(gp + (2 * H >> 2) + (c >> 2) + j) : zero;
+                        const float4 e = valid ? ldg_stream(gp + (3 * H >> 2) + (c >> 2) + j) : zero;
+                        const float4 f = (valid && hp) ? ldg_stream(hp + (c >> 2) + j) : zero;
+                        r[4 * j] = a.x; r[4 * j + 1] = a.y; r[4 * j + 2] = a.z; r[4 * j + 3] = a.w;
+                        z[4 * j] = b.x; z[4 * j + 1] = b.y; z[4 * j + 2] = b.z; z[4 * j + 3] = b.w;
+                        n[4 * j] = d.x; n[4 * j + 1] = d.y; n[4 * j + 2] = d.z; n[4 * j + 3] = d.w;
+                        hn[4 * j] = e.x; hn[4 * j + 1] = e.y; hn[4 * j + 2] = e.z; hn[4 * j + 3] = e.w;
+                        hm[4 * j] = f.x; hm[4 * j + 1] = f.y; hm[4 * j + 2] = f.z; hm[4 * j + 3] = f.w;
+                    }
+                    float dr[16], dz[16], dhn[16], din[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float g = dh[c + j];
+                        const float dnp = g * (1.f - z[j]) * (1.f - n[j] * n[j]);
+                        dz[j] = g * (hm[j] - n[j]) * z[j] * (1.f - z[j]);
+                        dr[j] = dnp * hn[j] * r[j] * (1.f - r[j]);
+                        dhn[j] = dnp * r[j];
+                        din[j] = dnp;
+                        zkeep[c + j] = z[j];
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            stg_stream(dgp + (c >> 2) + j, make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]));
+                            stg_stream(dgp + (H >> 2) + (c >> 2) + j, make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]));
+                            stg_stream(dgp + (2 * H >> 2) + (c >> 2) + j, make_float4(dhn[4 * j], dhn[4 * j + 1], dhn[4 * j + 2], dhn[4 * j + 3]));
+                            stg_stream(dgp + (3 * H >> 2) + (c >> 2) + j, make_float4(din[4 * j], din[4 * j + 1], din[4 * j + 2], din[4 * j + 3]));
+                        }
+                    }
+                    // A operand of the dh_{t-1} GEMM: columns [g * 64 + j0 + c, +16) for g = r, z, hn
+                    float lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float x = dr[j]; dr[j] = tf32_hi(x); lo[j] = x - dr[j]; }
+                    tmem_st16(tmem + lane_off + kB_hi + 0 * H + j0 + c, dr);
+                    tmem_st16(tmem + lane_off + kB_lo + 0 * H + j0 + c, lo);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float x = dz[j]; dz[j] = tf32_hi(x); lo[j] = x - dz[j]; }
+                    tmem_st16(tmem + lane_off + kB_hi + 1 * H + j0 + c, dz);
+                    tmem_st16(tmem + lane_off + kB_lo + 1 * H + j0 + c, lo);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float x = dhn[j]; dhn[j] = tf32_hi(x); lo[j] = x - dhn[j]; }
+                    tmem_st16(tmem + lane_off + kB_hi + 2 * H + j0 + c, dhn);
+                    tmem_st16(tmem + lane_off + kB_lo + 2 * H + j0 + c, lo);
+                }
+                tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a);
+
+                mbar_wait(&bar_d, ph_d);
+                ph_d ^= 1;
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    float acc[16];
+                    tmem_ld16(tmem + lane_off + kB_acc + j0 + c, acc);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dh[c + j] = fmaf(dh[c + j], zkeep[c + j], acc[j]);
+                }
+                fence_before_sync();
+            }
+        }
+    } else {
+        const uint32_t idesc = idesc_tf32(128, H);
+        const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
+        constexpr uint32_t kg_units = H * 128u >> 4;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int t = 0; t < p.L; ++t) {
+                mbar_wait(&bar_a, ph_a);
+                ph_a ^= 1;
+                fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < KB / 8; ++ks) {
+                        const uint32_t boff = (ks >> 2) * kg_units + 2 * (ks & 3);
+                        mma_tf32_ts(tmem + kB_acc, tmem + kB_lo + 8 * ks, bh + boff, idesc, ks == 0 ? 0u : 1u);
+                        mma_tf32_ts(tmem + kB_acc, tmem + kB_hi + 8 * ks, bl + boff, idesc, 1u);
+                        mma_tf32_ts(tmem + kB_acc, tmem + kB_hi + 8 * ks, bh + boff, idesc, 1u);
+                    }
+                    commit(&bar_d);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 }  // namespace
 
 extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
                              const float* tf, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                             float* h_last, float* hseq, void* stream_) {
+                             float* h_last, float* hseq, float* gates, void* stream_) {
     LTGNN_REQUIRE(B >= 0 && L > 0 && S > 0 && F >= 0, LTGNN_E_ARG, "gru_fwd: B=%lld L=%d S=%d F=%d",
                   static_cast<long long>(B), L, S, F);
     LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_fwd: hidden size %d not supported (64 only)", Hdim);
@@ -258,13 +450,13 @@ extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_
     LTGNN_REQUIRE(B * S < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_fwd: too many sequences");
     if (B == 0) return LTGNN_OK;
     LTGNN_REQUIRE(r && w_ih && w_hh && b_ih && b_hh && h_last && (tf || F == 0), LTGNN_E_ARG, "gru_fwd: null tensor");
-    LTGNN_REQUIRE(aligned16(h_last) && aligned16(hseq), LTGNN_E_ALIGN, "gru_fwd: outputs must be 16-byte aligned");
+    LTGNN_REQUIRE(aligned16(h_last) && aligned16(hseq) && aligned16(gates), LTGNN_E_ALIGN, "gru_fwd: outputs must be 16-byte aligned");
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_fwd: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, static_cast<uint32_t>(B * S), L, S, F,
+    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, gates, static_cast<uint32_t>(B * S), L, S, F,
                 S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
     const size_t smem = 1024 + 2ull * NG * KA * 4;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "gru_fwd: %zu B of shared memory", smem);
@@ -273,5 +465,102 @@ extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_
     const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
     gru_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
     LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t Hdim, const float* w_hh, const float* gates,
+                                const float* hseq, const float* dh_last, float* dG, void* stream_) {
+    LTGNN_REQUIRE(Q >= 0 && L > 0, LTGNN_E_ARG, "gru_bwd_dg: Q=%lld L=%d", static_cast<long long>(Q), L);
+    LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_bwd_dg: hidden size %d not supported (64 only)", Hdim);
+    LTGNN_REQUIRE(Q < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_bwd_dg: too many sequences");
+    if (Q == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(w_hh && gates && hseq && dh_last && dG, LTGNN_E_ARG, "gru_bwd_dg: null tensor");
+    LTGNN_REQUIRE(aligned16(gates) && aligned16(hseq) && aligned16(dh_last) && aligned16(dG), LTGNN_E_ALIGN,
+                  "gru_bwd_dg: 16-byte alignment required");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg: device is sm_%d%d, need sm_100", di->cc_major,
+                  di->cc_minor);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    GruBwdParams p{w_hh, gates, hseq, dh_last, dG, static_cast<uint32_t>(Q), L};
+    const size_t smem = 1024 + 2ull * H * KB * 4;
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles = (Q + 127) / 128;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    gru_bwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+// ---- weight gradients: dBfused[4H, 96] = sum over (t, q) of dG(t, q)^T [h_{t-1}(q) | x | tf | 1 | 0]  (tgrad.cuh)
+namespace {
+struct DgRows {  // 128 of the 256 dG columns of row rho = t * Q + q
+    const float4* dg;  // [L*Q, 64] float4
+    int col4;          // first float4 column (0 or 32)
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        return ptx::ldg_stream(dg + static_cast<int64_t>(row) * 64 + col4 + c);
+    }
+};
+struct GruInputRows {  // the forward's A operand, rebuilt on the fly
+    const float4* hseq;  // [L*Q, 16] float4
+    const float* r;      // [B, L, S]
+    const float* tf;     // [B, L, F]
+    uint32_t Q, S;
+    int L, F;
+    uint64_t magic_q, magic_s;
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+        if (c < 16) {
+            if (row < Q) return make_float4(0.f, 0.f, 0.f, 0.f);  // t = 0: h_{-1} = 0
+            return ptx::ldg_stream(hseq + static_cast<int64_t>(row - Q) * 16 + c);
+        }
+        const uint32_t t = magic_q ? ptx::fastdiv(row, magic_q) : row;
+        const uint32_t q = row - t * Q;
+        const uint32_t b = magic_s ? ptx::fastdiv(q, magic_s) : q;
+        const uint32_t s = q - b * S;
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int e = 4 * (c - 16) + i;
+            float x = 0.f;
+            if (e == 0) x = __ldg(r + (static_cast<size_t>(b) * L + t) * S + s);
+            else if (e <= F) x = __ldg(tf + (static_cast<size_t>(b) * L + t) * F + (e - 1));
+            else if (e == F + 1) x = 1.f;
+            v[i] = x;
+        }
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+}  // namespace
+
+extern "C" int64_t ltgnn_gru_ws_floats(int device) {
+    const DeviceInfo* di = device_info(device);
+    return di ? static_cast<int64_t>(di->sm_count) * tgrad::kMo * KA : -1;
+}
+
+extern "C" int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
+                               const float* tf, const float* hseq, const float* dG, float* dBfused, float* ws,
+                               void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && L > 0 && S > 0 && F >= 0, LTGNN_E_ARG, "gru_bwd_w: B=%lld L=%d S=%d F=%d",
+                  static_cast<long long>(B), L, S, F);
+    LTGNN_REQUIRE(Hdim == H && H + 1 + F + 1 <= KA, LTGNN_E_SHAPE, "gru_bwd_w: H=%d F=%d not supported", Hdim, F);
+    LTGNN_REQUIRE(r && hseq && dG && dBfused && ws && (tf || F == 0), LTGNN_E_ARG, "gru_bwd_w: null tensor");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (B == 0) {
+        LTGNN_CUDA_TRY(cudaMemsetAsync(dBfused, 0, sizeof(float) * NG * KA, stream));
+        return LTGNN_OK;
+    }
+    const int64_t Q = B * S, M = Q * L;
+    LTGNN_REQUIRE(M < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_bwd_w: L*B*S=%lld rows exceed the 32-bit row index",
+                  static_cast<long long>(M));
+    GruInputRows x{reinterpret_cast<const float4*>(hseq), r, tf, static_cast<uint32_t>(Q), static_cast<uint32_t>(S), L, F,
+                   Q >= 2 ? (~0ull / static_cast<uint64_t>(Q)) + 1 : 0ull, S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
+    for (int half = 0; half < 2; ++half) {
+        DgRows g{reinterpret_cast<const float4*>(dG), half * 32};
+        int grid = 0;
+        int rc = tgrad::launch(device, g, x, ws, M, KA, &grid, stream, "gru_bwd_w");
+        if (rc) return rc;
+        rc = tgrad::gather(ws, grid, KA, 0, 128, 0, KA, dBfused + half * 128 * KA, KA, 0, stream);
+        if (rc) return rc;
+    }
     return LTGNN_OK;
 }

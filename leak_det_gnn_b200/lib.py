@@ -50,7 +50,12 @@ SIGNATURES = {
     "ltgnn_pipe_head_bwd_w": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ltgnn_gru_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ltgnn_gru_bwd_dg": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
+    "ltgnn_gru_ws_floats": (c_int64, [c_int]),
+    "ltgnn_gru_bwd_w": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -28,9 +28,10 @@ from ..ops import PipeGraph
 
 
 class SharedSensorGRUEncoder(nn.Module):
-    """One GRU shared by all sensors: (B, L, S) residuals [+ (B, L, 9) time features] ->
-    (B, S, hidden).  Kept on cuDNN exactly as the reference (detector.py:28-73); it feeds the
-    hot path but is not graph work (last row)."""
+    """One GRU shared by all sensors: (B, L, S) residuals [+ (B, L, 9) time features] -> (B, S, hidden)
+    (reference detector.py:28-73).  It feeds the hot path: hidden size 64 runs on
+    the persistent tensor-memory GRU kernel (csrc/gru.cu); other sizes, or ``use_native = False``, take the
+    reference's cuDNN route."""
 
     def __init__(self, time_dim: int = 9, hidden_size: int = 64, num_layers: int = 1, dropout: float = 0.0,
                  use_time: bool = True) -> None:
@@ -38,10 +39,19 @@ class SharedSensorGRUEncoder(nn.Module):
         self.use_time = bool(use_time)
         self.hidden_size = int(hidden_size)
         self.max_seqs_per_call = 8192
+        self.use_native = True  # False: run the reference's cuDNN path (kept for comparison)
         self.gru = nn.GRU(input_size=1 + (time_dim if self.use_time else 0), hidden_size=self.hidden_size,
                           num_layers=num_layers, batch_first=True, dropout=dropout if num_layers > 1 else 0.0)
 
     def forward(self, r: torch.Tensor, tfeat: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.use_time and tfeat is None:
+            raise ValueError("tfeat required when use_time=True")
+        g = self.gru
+        if (self.use_native and r.is_cuda and g.num_layers == 1 and
+                ops.gru_supported(self.hidden_size, tfeat.shape[-1] if self.use_time else 0)):
+            # persistent tcgen05 kernel: state in tensor memory, no per-timestep launches (csrc/gru.cu)
+            return ops.gru_encode(r, tfeat if self.use_time else None, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0,
+                                  g.bias_hh_l0)
         b, l, s = r.shape
         seq = r.transpose(1, 2).reshape(b * s, l, 1)
         if self.use_time:

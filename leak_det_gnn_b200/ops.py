@@ -17,7 +17,7 @@ from . import instrument as _inst
 from . import lib as _lib
 from .graph import GCNCsr, build_gcn_csr
 
-__all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported"]
+__all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported", "gru_encode", "gru_supported"]
 
 
 def _ptr(a: np.ndarray) -> ctypes.c_void_p:
@@ -524,8 +524,8 @@ def gru_supported(hidden: int, n_time: int) -> bool:
     return hidden == 64 and 0 <= n_time <= 30
 
 
-def gru_fwd(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh, save_seq: bool = False):
-    """Raw forward: r (B,L,S), tf (B,L,F) or None -> h_last (B,S,H) [, hseq (L, B*S, H)]."""
+def gru_fwd(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh, save: bool = False):
+    """Raw forward: r (B,L,S), tf (B,L,F) or None -> h_last (B,S,H) [, hseq (L,B*S,H), gates (L,B*S,4,H)]."""
     _check_act(r, "r")
     b, l, s = r.shape
     f = 0 if tf is None else tf.shape[-1]
@@ -533,11 +533,67 @@ def gru_fwd(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh,
         _check_act(tf, "tf")
     hdim = w_hh.shape[1]
     h_last = torch.empty(b, s, hdim, device=r.device, dtype=torch.float32)
-    hseq = torch.empty(l, b * s, hdim, device=r.device, dtype=torch.float32) if save_seq else None
+    hseq = torch.empty(l, b * s, hdim, device=r.device, dtype=torch.float32) if save else None
+    gates = torch.empty(l, b * s, 4, hdim, device=r.device, dtype=torch.float32) if save else None
     L = _lib.load()
     tok = _inst.begin("gru_fwd")
     _lib.check(L.ltgnn_gru_fwd(_dev_index(r), b, l, s, f, hdim, r.data_ptr(), None if tf is None else tf.data_ptr(),
                                w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), h_last.data_ptr(),
-                               None if hseq is None else hseq.data_ptr(), _stream(r)))
+                               None if hseq is None else hseq.data_ptr(), None if gates is None else gates.data_ptr(),
+                               _stream(r)))
     _inst.end(tok)
-    return (h_last, hseq) if save_seq else h_last
+    return (h_last, hseq, gates) if save else h_last
+
+
+class _GruEncoder(torch.autograd.Function):
+    """h_last = GRU(cat([r_s, tf]))[:, -1] for every (window, sensor) sequence, with back-propagation through time
+    to the four GRU parameters (the inputs are data: the reference never asks for their gradient either)."""
+
+    @staticmethod
+    def forward(ctx, r, tf, w_ih, w_hh, b_ih, b_hh):
+        r = r.contiguous()
+        tf = None if tf is None else tf.contiguous()
+        params = [t.contiguous() for t in (w_ih, w_hh, b_ih, b_hh)]
+        if any(ctx.needs_input_grad[2:]):
+            h_last, hseq, gates = gru_fwd(r, tf, *params, save=True)
+            ctx.save_for_backward(r, tf, params[1], hseq, gates)
+        else:
+            h_last = gru_fwd(r, tf, *params)
+        return h_last
+
+    @staticmethod
+    def backward(ctx, dh):
+        r, tf, w_hh, hseq, gates = ctx.saved_tensors
+        b, l, s = r.shape
+        f = 0 if tf is None else tf.shape[-1]
+        hd = w_hh.shape[1]
+        q = b * s
+        dev = _dev_index(r)
+        L = _lib.load()
+        dh = dh.contiguous()
+        dg = torch.empty_like(gates)
+        tok = _inst.begin("gru_bwd_dg")
+        _lib.check(L.ltgnn_gru_bwd_dg(dev, q, l, hd, w_hh.data_ptr(), gates.data_ptr(), hseq.data_ptr(), dh.data_ptr(),
+                                      dg.data_ptr(), _stream(r)))
+        _inst.end(tok)
+        del gates
+        fused = torch.empty(4 * hd, 96, device=r.device, dtype=torch.float32)
+        ws = torch.empty(int(L.ltgnn_gru_ws_floats(dev)), device=r.device, dtype=torch.float32)
+        tok = _inst.begin("gru_bwd_w")
+        _lib.check(L.ltgnn_gru_bwd_w(dev, b, l, s, f, hd, r.data_ptr(), None if tf is None else tf.data_ptr(),
+                                     hseq.data_ptr(), dg.data_ptr(), fused.data_ptr(), ws.data_ptr(), _stream(r)))
+        _inst.end(tok)
+        # rows of `fused`: r | z | (W_hn h + b_hn) | (W_in x + b_in); columns: h (hd) | x, tf (1 + f) | 1
+        rr, zz, hn, inn = fused[0:hd], fused[hd:2 * hd], fused[2 * hd:3 * hd], fused[3 * hd:4 * hd]
+        kb = hd + 1 + f
+        dw_hh = torch.cat([rr[:, :hd], zz[:, :hd], hn[:, :hd]], dim=0)
+        dw_ih = torch.cat([rr[:, hd:kb], zz[:, hd:kb], inn[:, hd:kb]], dim=0)
+        db_ih = torch.cat([rr[:, kb], zz[:, kb], inn[:, kb]], dim=0)
+        db_hh = torch.cat([rr[:, kb], zz[:, kb], hn[:, kb]], dim=0)
+        return None, None, dw_ih, dw_hh, db_ih, db_hh
+
+
+def gru_encode(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
+    """Differentiable (wrt the parameters) shared sensor GRU: (B,L,S) [+ (B,L,F)] -> (B,S,64)."""
+    _check_act(r.contiguous(), "r")
+    return _GruEncoder.apply(r, tf, w_ih, w_hh, b_ih, b_hh)
