@@ -17,9 +17,9 @@ One STEP = one pass of the hot path over one batch of B windows:
                embeddings (reference detector.py:178-218 + autograd), with the
                sensor embeddings h_s already resident in HBM.  At N > 1 the step also averages the
                gradients with one flat-bucket NCCL all-reduce (data parallel over windows).
-  * `e2e`    : the call a user makes -- LeakDetector.forward(residual, tfeat) (includes the cuDNN GRU
-               encoder over L = 288), cross-entropy, backward -- with residual/tfeat copied from pinned
-               host memory and the loss read back to the host inside the timed region.
+  * `e2e`    : the call a user makes -- LeakDetector.forward(residual, tfeat) (includes the sensor GRU
+               encoder over L = 288, csrc/gru.cu), cross-entropy, backward -- with residual/tfeat copied from
+               pinned host memory and the loss read back to the host inside the timed region.
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 L2: every step writes and re-reads ~5 GB of activations (693 MB per (B,N,64) tensor), far above
 the 126 MB L2, so nothing survives between steps.
@@ -320,7 +320,8 @@ def run_ours(args) -> None:
     with ClockSampler(local) as clk:
         ms_stack, launches, ksum = timed(stack_step, args.steps, args.warmup, timing_kernels=True)
     clocks = clk.result()
-    ms_e2e, _, _ = timed(e2e_step, max(1, min(args.steps, args.e2e_steps)), max(3, min(args.warmup, 3)))
+    ms_e2e, launches_e2e, ksum_e2e = timed(e2e_step, max(1, min(args.steps, args.e2e_steps)), max(3, min(args.warmup, 3)),
+                                            timing_kernels=True)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
     value = args.batch * world * args.steps / (ms_stack * 1e-3)
@@ -343,6 +344,11 @@ def run_ours(args) -> None:
         "pipe_head_fwd": ("tensor", head_flops), "pipe_head_bwd_dx": ("tensor", head_flops),
         "pipe_head_bwd_w": ("tensor", head_flops),
     }
+    # e2e-only kernels (sensor GRU encoder): fp32-equivalent flops of the fused [h|x|tf|1] x [4H, 96] step GEMM
+    q_seq = args.batch * SENSORS
+    model_of["gru_fwd"] = ("tensor", 2.0 * q_seq * args.l_det * 256 * 75)
+    model_of["gru_bwd_dg"] = ("tensor", 2.0 * q_seq * args.l_det * 192 * 64)
+    model_of["gru_bwd_w"] = ("tensor", 2.0 * q_seq * args.l_det * 256 * 75)
     traffic = {}
     tpath = REPO / "profiles" / "ncu_traffic.json"
     if tpath.exists():
@@ -381,10 +387,11 @@ def run_ours(args) -> None:
             "roofline": roof, "roofline_aggregation": agg, "roofline_all": roofs, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "scope": "LeakDetector.forward(residual, tfeat) incl. cuDNN GRU over L + CE + backward, "
+                    "scope": "LeakDetector.forward(residual, tfeat) incl. the sensor GRU encoder over L + CE + backward, "
                              "pinned-host inputs copied H2D and loss copied D2H every step"},
             "gpu_launches": launches, "clocks": clocks,
             "kernels": {k: {"count": v["count"], "mean_ms": round(v["mean_ms"], 4)} for k, v in ksum.items()},
+            "kernels_e2e": {k: {"count": v["count"], "mean_ms": round(v["mean_ms"], 4)} for k, v in ksum_e2e.items()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
