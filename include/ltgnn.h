@@ -173,9 +173,10 @@ int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D
  * Sequence q = b*S + s has input [r[b,t,s], tf[b,t,0..F)] at step t (the reference's cat([rr, tf]) order);
  * weights in torch.nn.GRU layout (gate order r, z, n): w_ih [3H, 1+F], w_hh [3H, H], b_ih, b_hh [3H].  H = 64.
  * gru_fwd:    h_last [B*S, H] = hidden state after step L-1 (h_0 = 0).  For training also pass
- *             hseq [L, B*S, H] (every state) and gates [L, B*S, 4, H] (r, z, n, W_hn h + b_hn); NULL otherwise.
+ *             hseq (every state, logical [L*Qp, H]) and gates (r, z, n, W_hn h + b_hn; logical [L*Qp, 4H]),
+ *             Qp = B*S rounded up to 128, both in the kernels' blocked-32 layout [rows/32][W/4][32][4]; NULL otherwise.
  *             State lives in tensor memory; recurrent + input GEMM fused on tcgen05 (3xTF32).
- * gru_bwd_dg: back-propagation through time given dh_last [B*S, H]: writes dG [L, B*S, 4, H], the gradient wrt
+ * gru_bwd_dg: back-propagation through time given dh_last [B*S, H]: writes dG (blocked-32, [L*Qp, 4H]), the gradient wrt
  *             the four pre-activation groups (r, z, W_hn h + b_hn, W_in x + b_in).
  * gru_bwd_w:  dBfused [4H, 96] = sum_(t,q) dG^T [h_{t-1} | x | tf | 1 | 0]: columns 0..H-1 are d w_hh, H..H+F
  *             d w_ih, H+F+1 the bias gradients (rows: r, z, hn-part, in-part).  ws: ltgnn_gru_ws_floats() floats.

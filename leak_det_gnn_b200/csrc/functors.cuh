@@ -60,6 +60,7 @@ struct StoreEpilogue {
 
 // ---- plain row-major operands, optionally two matrices stacked side by side to fill the 128 accumulator rows
 struct StackedRows {
+    static constexpr bool kRowFast = false;
     const float4* a;  // [M, wa4]
     const float4* b;  // [M, wb4] (columns wa4.. of the stacked operand) or nullptr
     int wa4, wb4;
@@ -73,6 +74,7 @@ struct StackedRows {
 
 // [a | 1 | 0 ...]: operand rows followed by a ones column (its product column is the column sum of the other operand)
 struct RowsThenOne {
+    static constexpr bool kRowFast = false;
     const float4* a;  // [M, wa4]
     int wa4;
     __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {

@@ -44,15 +44,27 @@ struct GruParams {
     const float* b_ih;   // [3H]
     const float* b_hh;   // [3H]
     float* h_last;       // [Q, H]
-    float* hseq;         // [L, Q, H] or nullptr
-    float* gates;        // [L, Q, 4, H] (r, z, n, W_hn h + b_hn) or nullptr: saved for the backward
+    float* hseq;         // blocked-32 [L * Qp, H] or nullptr
+    float* gates;        // blocked-32 [L * Qp, 4H] (r | z | n | W_hn h + b_hn) or nullptr: saved for the backward
     uint32_t Q;          // B * S sequences
+    uint32_t Qp;         // Q rounded up to a multiple of 128
     int L, S, F;
     uint64_t magic_s;    // fastdiv constant of S (S >= 2), 0 when S == 1
 };
 
-__device__ __forceinline__ float sigmoidf_fast(float v) { return __frcp_rn(1.f + __expf(-v)); }
-__device__ __forceinline__ float tanhf_fast(float v) { return 2.f * __frcp_rn(1.f + __expf(-2.f * v)) - 1.f; }
+__device__ __forceinline__ float rcp_approx(float v) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float sigmoidf_fast(float v) { return rcp_approx(1.f + __expf(-v)); }
+__device__ __forceinline__ float tanhf_fast(float v) { return fmaf(2.f, rcp_approx(1.f + __expf(-2.f * v)), -1.f); }
+
+// "Blocked-32" layout of the tensors saved between the GRU kernels ([rows, W] logical, rows = t * Qp + q with
+// Qp = Q rounded up to 128): element (row, 4*f4 .. 4*f4+3) lives at float4 index ((row / 32) * W/4 + f4) * 32 + row % 32.
+// A thread owns one row, so the 32 lanes of a warp read / write 512 contiguous bytes per instruction instead of
+// 32 segments 1 KB apart (row-major cost ~10 000 LSU wavefronts per step and was the whole runtime).
+__device__ __forceinline__ size_t b32(size_t row, int f4, int w4) { return ((row >> 5) * w4 + f4) * 32 + (row & 31); }
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
     asm volatile(
@@ -194,23 +206,27 @@ gru_fwd_kernel(const GruParams p) {
                         zz[j] = z;
                         in[j] = n;
                     }
-                    if (p.gates && valid) {
-                        float* gp = p.gates + ((static_cast<size_t>(t) * p.Q + q) * 4) * H + j0 + c;
+                    if (p.gates) {
+                        float4* g4 = reinterpret_cast<float4*>(p.gates);
+                        const size_t row = static_cast<size_t>(t) * p.Qp + q;
+                        const int f0 = (j0 + c) >> 2;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            reinterpret_cast<float4*>(gp)[j] = make_float4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
-                            reinterpret_cast<float4*>(gp + H)[j] = make_float4(zz[4 * j], zz[4 * j + 1], zz[4 * j + 2], zz[4 * j + 3]);
-                            reinterpret_cast<float4*>(gp + 2 * H)[j] = make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
-                            reinterpret_cast<float4*>(gp + 3 * H)[j] = make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
+                            stg_stream(g4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]));
+                            stg_stream(g4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(zz[4 * j], zz[4 * j + 1], zz[4 * j + 2], zz[4 * j + 3]));
+                            stg_stream(g4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]));
+                            stg_stream(g4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]));
                         }
                     }
                     tmem_st16(tmem + lane_off + kAhiCol + j0 + c, hi);
                     tmem_st16(tmem + lane_off + kAloCol + j0 + c, lo);
                 }
-                if (p.hseq && valid) {
-                    float4* dst = reinterpret_cast<float4*>(p.hseq + (static_cast<size_t>(t) * p.Q + q) * H + j0);
+                if (p.hseq) {
+                    float4* h4 = reinterpret_cast<float4*>(p.hseq);
+                    const size_t row = static_cast<size_t>(t) * p.Qp + q;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                    for (int j = 0; j < 8; ++j)
+                        stg_stream(h4 + b32(row, (j0 >> 2) + j, H / 4), make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
                 }
                 if (t + 1 < p.L) {
                     if (half == 0) store_aux(t + 1);
@@ -275,11 +291,11 @@ constexpr uint32_t kB_acc = 0, kB_hi = H, kB_lo = H + KB;  // TMEM: acc 64 | dG 
 
 struct GruBwdParams {
     const float* w_hh;   // [3H, H]
-    const float* gates;  // [L, Q, 4, H]
-    const float* hseq;   // [L, Q, H]
+    const float* gates;  // blocked-32 [L * Qp, 4H]
+    const float* hseq;   // blocked-32 [L * Qp, H]
     const float* dh_last;  // [Q, H]
-    float* dG;           // [L, Q, 4, H]
-    uint32_t Q;
+    float* dG;           // blocked-32 [L * Qp, 4H]
+    uint32_t Q, Qp;
     int L;
 };
 
@@ -332,10 +348,10 @@ gru_bwd_kernel(const GruBwdParams p) {
                 }
             }
             for (int t = p.L - 1; t >= 0; --t) {
-                const size_t row = static_cast<size_t>(t) * p.Q + (valid ? q : 0);
-                const float4* gp = reinterpret_cast<const float4*>(p.gates + row * 4 * H + j0);
-                const float4* hp = t > 0 ? reinterpret_cast<const float4*>(p.hseq + (row - p.Q) * H + j0) : nullptr;
-                float4* dgp = reinterpret_cast<float4*>(p.dG + row * 4 * H + j0);
+                const size_t row = static_cast<size_t>(t) * p.Qp + q;  // pad rows (q >= Q) exist in the saved tensors
+                const float4* g4 = reinterpret_cast<const float4*>(p.gates);
+                const float4* h4 = reinterpret_cast<const float4*>(p.hseq);
+                float4* dg4 = reinterpret_cast<float4*>(p.dG);
                 float zkeep[32];
 #pragma unroll
                 for (int c = 0; c < 32; c += 16) {
@@ -343,11 +359,12 @@ gru_bwd_kernel(const GruBwdParams p) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 a = valid ? ldg_stream(gp + (c >> 2) + j) : zero;
-                        const float4 b = valid ? ldg_stream(gp + (H >> 2) + (c >> 2) + j) : zero;
-                        const float4 d = valid ? ldg_stream(gp + (2 * H >> 2) + (c >> 2) + j) : zero;
-                        const float4 e = valid ? ldg_stream(gp + (3 * H >> 2) + (c >> 2) + j) : zero;
-                        const float4 f = (valid && hp) ? ldg_stream(hp + (c >> 2) + j) : zero;
+                        const int f0 = ((j0 + c) >> 2) + j;
+                        const float4 a = valid ? ldg_stream(g4 + b32(row, 0 * (H / 4) + f0, H)) : zero;
+                        const float4 b = valid ? ldg_stream(g4 + b32(row, 1 * (H / 4) + f0, H)) : zero;
+                        const float4 d = valid ? ldg_stream(g4 + b32(row, 2 * (H / 4) + f0, H)) : zero;
+                        const float4 e = valid ? ldg_stream(g4 + b32(row, 3 * (H / 4) + f0, H)) : zero;
+                        const float4 f = (valid && t > 0) ? ldg_stream(h4 + b32(row - p.Qp, f0, H / 4)) : zero;
                         r[4 * j] = a.x; r[4 * j + 1] = a.y; r[4 * j + 2] = a.z; r[4 * j + 3] = a.w;
                         z[4 * j] = b.x; z[4 * j + 1] = b.y; z[4 * j + 2] = b.z; z[4 * j + 3] = b.w;
                         n[4 * j] = d.x; n[4 * j + 1] = d.y; n[4 * j + 2] = d.z; n[4 * j + 3] = d.w;
@@ -365,13 +382,14 @@ gru_bwd_kernel(const GruBwdParams p) {
                         din[j] = dnp;
                         zkeep[c + j] = z[j];
                     }
-                    if (valid) {
+                    {   // pad rows carry zeros (their dh and gates are zero), so the weight-gradient GEMM may read them
+                        const int f0 = (j0 + c) >> 2;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            stg_stream(dgp + (c >> 2) + j, make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]));
-                            stg_stream(dgp + (H >> 2) + (c >> 2) + j, make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]));
-                            stg_stream(dgp + (2 * H >> 2) + (c >> 2) + j, make_float4(dhn[4 * j], dhn[4 * j + 1], dhn[4 * j + 2], dhn[4 * j + 3]));
-                            stg_stream(dgp + (3 * H >> 2) + (c >> 2) + j, make_float4(din[4 * j], din[4 * j + 1], din[4 * j + 2], din[4 * j + 3]));
+                            stg_stream(dg4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]));
+                            stg_stream(dg4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]));
+                            stg_stream(dg4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(dhn[4 * j], dhn[4 * j + 1], dhn[4 * j + 2], dhn[4 * j + 3]));
+                            stg_stream(dg4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(din[4 * j], din[4 * j + 1], din[4 * j + 2], din[4 * j + 3]));
                         }
                     }
                     // A operand of the dh_{t-1} GEMM: columns [g * 64 + j0 + c, +16) for g = r, z, hn
@@ -456,7 +474,8 @@ extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_fwd: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, gates, static_cast<uint32_t>(B * S), L, S, F,
+    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, gates, static_cast<uint32_t>(B * S),
+                static_cast<uint32_t>((B * S + 127) / 128 * 128), L, S, F,
                 S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
     const size_t smem = 1024 + 2ull * NG * KA * 4;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "gru_fwd: %zu B of shared memory", smem);
@@ -482,7 +501,7 @@ extern "C" int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t Hdim, 
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    GruBwdParams p{w_hh, gates, hseq, dh_last, dG, static_cast<uint32_t>(Q), L};
+    GruBwdParams p{w_hh, gates, hseq, dh_last, dG, static_cast<uint32_t>(Q), static_cast<uint32_t>((Q + 127) / 128 * 128), L};
     const size_t smem = 1024 + 2ull * H * KB * 4;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t tiles = (Q + 127) / 128;
@@ -494,27 +513,30 @@ extern "C" int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t Hdim, 
 
 // ---- weight gradients: dBfused[4H, 96] = sum over (t, q) of dG(t, q)^T [h_{t-1}(q) | x | tf | 1 | 0]  (tgrad.cuh)
 namespace {
-struct DgRows {  // 128 of the 256 dG columns of row rho = t * Q + q
-    const float4* dg;  // [L*Q, 64] float4
+struct DgRows {  // 128 of the 256 dG columns of row rho = t * Qp + q (blocked-32 storage)
+    static constexpr bool kRowFast = true;
+    const float4* dg;
     int col4;          // first float4 column (0 or 32)
     __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
-        return ptx::ldg_stream(dg + static_cast<int64_t>(row) * 64 + col4 + c);
+        return ptx::ldg_stream(dg + b32(row, col4 + c, H));
     }
 };
 struct GruInputRows {  // the forward's A operand, rebuilt on the fly
-    const float4* hseq;  // [L*Q, 16] float4
+    static constexpr bool kRowFast = true;
+    const float4* hseq;  // blocked-32 [L * Qp, H]
     const float* r;      // [B, L, S]
     const float* tf;     // [B, L, F]
-    uint32_t Q, S;
+    uint32_t Q, Qp, S;
     int L, F;
-    uint64_t magic_q, magic_s;
+    uint64_t magic_qp, magic_s;
     __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
         if (c < 16) {
-            if (row < Q) return make_float4(0.f, 0.f, 0.f, 0.f);  // t = 0: h_{-1} = 0
-            return ptx::ldg_stream(hseq + static_cast<int64_t>(row - Q) * 16 + c);
+            if (row < Qp) return make_float4(0.f, 0.f, 0.f, 0.f);  // t = 0: h_{-1} = 0
+            return ptx::ldg_stream(hseq + b32(row - Qp, c, H / 4));
         }
-        const uint32_t t = magic_q ? ptx::fastdiv(row, magic_q) : row;
-        const uint32_t q = row - t * Q;
+        const uint32_t t = ptx::fastdiv(row, magic_qp);
+        const uint32_t q = row - t * Qp;
+        if (q >= Q) return make_float4(0.f, 0.f, 0.f, 0.f);     // pad row
         const uint32_t b = magic_s ? ptx::fastdiv(q, magic_s) : q;
         const uint32_t s = q - b * S;
         float v[4];
@@ -549,11 +571,12 @@ extern "C" int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int3
         LTGNN_CUDA_TRY(cudaMemsetAsync(dBfused, 0, sizeof(float) * NG * KA, stream));
         return LTGNN_OK;
     }
-    const int64_t Q = B * S, M = Q * L;
+    const int64_t Q = B * S, Qp = (Q + 127) / 128 * 128, M = Qp * L;
     LTGNN_REQUIRE(M < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_bwd_w: L*B*S=%lld rows exceed the 32-bit row index",
                   static_cast<long long>(M));
-    GruInputRows x{reinterpret_cast<const float4*>(hseq), r, tf, static_cast<uint32_t>(Q), static_cast<uint32_t>(S), L, F,
-                   Q >= 2 ? (~0ull / static_cast<uint64_t>(Q)) + 1 : 0ull, S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
+    GruInputRows x{reinterpret_cast<const float4*>(hseq), r, tf, static_cast<uint32_t>(Q), static_cast<uint32_t>(Qp),
+                   static_cast<uint32_t>(S), L, F, (~0ull / static_cast<uint64_t>(Qp)) + 1,
+                   S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
     for (int half = 0; half < 2; ++half) {
         DgRows g{reinterpret_cast<const float4*>(dG), half * 32};
         int grid = 0;

@@ -13,6 +13,7 @@ namespace {
 
 // ---- pipe head: G = d loss / d pre (from the saved post-activation), X = [feat | 1 | 0...]
 struct HeadDpre {
+    static constexpr bool kRowFast = false;
     const float4* hpost;  // [M][32]
     const float* dlogit;  // [M]
     const float4* w2;     // [32]
@@ -26,6 +27,7 @@ struct HeadDpre {
     }
 };
 struct HeadFeatOnes {
+    static constexpr bool kRowFast = false;
     const float4* x;   // node states [B*N, 16]
     const int2* ends;
     uint32_t P, N;

@@ -105,7 +105,10 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         uint8_t* x_lo = x_hi + x_half;
         // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of both operands, so the
         // row-dependent part of a gather (division, end-node lookup) is done once and all loads go out together
-        const int r = gtid >> 3, q = gtid & 7;
+        // XLoader::kRowFast sources (blocked-32 tensors: 32 consecutive rows of one chunk are contiguous) flip the
+        // mapping: a warp = 32 rows x one chunk (512 contiguous bytes) at the price of 2-way conflicts on the STS
+        const int r = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3);
+        const int q = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
         const int x4 = No / 4;
         uint32_t use = 0;
         for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {

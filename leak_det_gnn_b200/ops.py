@@ -525,7 +525,7 @@ def gru_supported(hidden: int, n_time: int) -> bool:
 
 
 def gru_fwd(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh, save: bool = False):
-    """Raw forward: r (B,L,S), tf (B,L,F) or None -> h_last (B,S,H) [, hseq (L,B*S,H), gates (L,B*S,4,H)]."""
+    """Raw forward: r (B,L,S), tf (B,L,F) or None -> h_last (B,S,H) [, hseq, gates in blocked-32 layout]."""
     _check_act(r, "r")
     b, l, s = r.shape
     f = 0 if tf is None else tf.shape[-1]
@@ -533,8 +533,11 @@ def gru_fwd(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh,
         _check_act(tf, "tf")
     hdim = w_hh.shape[1]
     h_last = torch.empty(b, s, hdim, device=r.device, dtype=torch.float32)
-    hseq = torch.empty(l, b * s, hdim, device=r.device, dtype=torch.float32) if save else None
-    gates = torch.empty(l, b * s, 4, hdim, device=r.device, dtype=torch.float32) if save else None
+    # saved tensors use the kernels' "blocked-32" layout: logical [L * Qp, W] with Qp = B*S rounded up to 128,
+    # stored as [L * Qp / 32, W / 4, 32, 4] (see csrc/gru.cu)
+    qp = (b * s + 127) // 128 * 128
+    hseq = torch.empty(l * qp // 32, hdim // 4, 32, 4, device=r.device, dtype=torch.float32) if save else None
+    gates = torch.empty(l * qp // 32, hdim, 32, 4, device=r.device, dtype=torch.float32) if save else None
     L = _lib.load()
     tok = _inst.begin("gru_fwd")
     _lib.check(L.ltgnn_gru_fwd(_dev_index(r), b, l, s, f, hdim, r.data_ptr(), None if tf is None else tf.data_ptr(),
@@ -597,3 +600,10 @@ def gru_encode(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_
     """Differentiable (wrt the parameters) shared sensor GRU: (B,L,S) [+ (B,L,F)] -> (B,S,64)."""
     _check_act(r.contiguous(), "r")
     return _GruEncoder.apply(r, tf, w_ih, w_hh, b_ih, b_hh)
+
+
+def unblock32(t: torch.Tensor, l: int, q: int) -> torch.Tensor:
+    """Blocked-32 saved tensor [L*Qp/32, W/4, 32, 4] -> logical (L, Q, W) (tests / debugging)."""
+    w = t.shape[1] * 4
+    qp = t.shape[0] * 32 // l
+    return t.permute(0, 2, 1, 3).reshape(l, qp, w)[:, :q, :]
