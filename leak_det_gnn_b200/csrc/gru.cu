@@ -513,13 +513,10 @@ extern "C" int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t Hdim, 
 
 // ---- weight gradients: dBfused[4H, 96] = sum over (t, q) of dG(t, q)^T [h_{t-1}(q) | x | tf | 1 | 0]  (tgrad.cuh)
 namespace {
-struct DgRows {  // 128 of the 256 dG columns of row rho = t * Qp + q (blocked-32 storage)
+struct DgRows {  // the 256 dG columns of row rho = t * Qp + q (blocked-32 storage)
     static constexpr bool kRowFast = true;
     const float4* dg;
-    int col4;          // first float4 column (0 or 32)
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
-        return ptx::ldg_stream(dg + b32(row, col4 + c, H));
-    }
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const { return ptx::ldg_stream(dg + b32(row, c, H)); }
 };
 struct GruInputRows {  // the forward's A operand, rebuilt on the fly
     static constexpr bool kRowFast = true;
@@ -556,7 +553,7 @@ struct GruInputRows {  // the forward's A operand, rebuilt on the fly
 
 extern "C" int64_t ltgnn_gru_ws_floats(int device) {
     const DeviceInfo* di = device_info(device);
-    return di ? static_cast<int64_t>(di->sm_count) * tgrad::kMo * KA : -1;
+    return di ? static_cast<int64_t>(di->sm_count) * NG * KA : -1;
 }
 
 extern "C" int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
@@ -577,13 +574,9 @@ extern "C" int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int3
     GruInputRows x{reinterpret_cast<const float4*>(hseq), r, tf, static_cast<uint32_t>(Q), static_cast<uint32_t>(Qp),
                    static_cast<uint32_t>(S), L, F, (~0ull / static_cast<uint64_t>(Qp)) + 1,
                    S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
-    for (int half = 0; half < 2; ++half) {
-        DgRows g{reinterpret_cast<const float4*>(dG), half * 32};
-        int grid = 0;
-        int rc = tgrad::launch(device, g, x, ws, M, KA, &grid, stream, "gru_bwd_w");
-        if (rc) return rc;
-        rc = tgrad::gather(ws, grid, KA, 0, 128, 0, KA, dBfused + half * 128 * KA, KA, 0, stream);
-        if (rc) return rc;
-    }
-    return LTGNN_OK;
+    DgRows g{reinterpret_cast<const float4*>(dG)};
+    int grid = 0;
+    int rc = tgrad::launch<2>(device, g, x, ws, M, KA, &grid, stream, "gru_bwd_w");  // all 256 rows in one pass over X
+    if (rc) return rc;
+    return tgrad::gather(ws, grid, KA, 0, NG, 0, KA, dBfused, KA, 0, stream, NG);
 }

@@ -58,12 +58,13 @@ __host__ __device__ constexpr uint32_t idesc_tf32_mn(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-__host__ inline size_t stage_bytes(int No) { return 2ull * (kMo + No) * kChunk * 4; }
-__host__ inline size_t smem_bytes(int No) { return 1024 + kGroups * stage_bytes(No); }
+__host__ inline size_t stage_bytes(int No, int mt) { return 2ull * (kMo * mt + No) * kChunk * 4; }
+__host__ inline size_t smem_bytes(int No, int mt) { return 1024 + kGroups * stage_bytes(No, mt); }
 
 // GLoader: float4 operator()(uint32_t row, int c16) for c16 < kMo/4;  XLoader: same for c16 < No/4.
 // Both are only called for row < M.  ws: [gridDim.x][kMo][No].
-template <class GLoader, class XLoader>
+// kMT = 1 or 2 accumulator tiles of 128 rows: operand G has 128 * kMT columns and shares one pass over X.
+template <class GLoader, class XLoader, int kMT>
 __global__ void __launch_bounds__(kThreads, 1)
 tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
@@ -72,7 +73,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t g_half = kMo * kChunk * 4;            // G hi (then G lo)
+    constexpr int kG = kMo * kMT;                        // operand-G columns
+    const uint32_t g_half = kG * kChunk * 4;             // G hi (then G lo)
     const uint32_t x_half = static_cast<uint32_t>(No) * kChunk * 4;
     const uint32_t stage = 2 * (g_half + x_half);
 
@@ -114,15 +116,15 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
             const uint32_t row = ch * kChunk + r;
             const bool valid = row < M;
-            float4 gv[kMo / 32], xv[8];
+            float4 gv[kG / 32], xv[8];
 #pragma unroll
-            for (int j = 0; j < kMo / 32; ++j) gv[j] = valid ? gload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kG / 32; ++j) gv[j] = valid ? gload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
                 xv[j] = (valid && q + 8 * j < x4) ? xload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
 #pragma unroll
-            for (int j = 0; j < kMo / 32; ++j) {
+            for (int j = 0; j < kG / 32; ++j) {
                 float4 hi, lo;
                 split4(gv[j], hi, lo);
                 const uint32_t off = mn_offset(r, q + 8 * j, kChunk);
@@ -157,9 +159,13 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                 const uint32_t xl = mn_desc_lo(base + s * stage + 2 * g_half + x_half);
 #pragma unroll
                 for (uint32_t k = 0; k < kChunk / 8; ++k) {  // 8 rows = 1024 B = 64 descriptor units per K-step
-                    mma_tf32_mn(tmem_base, gl + 64 * k, xh + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
-                    mma_tf32_mn(tmem_base, gh + 64 * k, xl + 64 * k, idesc, 1u);
-                    mma_tf32_mn(tmem_base, gh + 64 * k, xh + 64 * k, idesc, 1u);
+#pragma unroll
+                    for (uint32_t mt = 0; mt < kMT; ++mt) {  // accumulator tile mt <- operand-G columns [128 mt, +128)
+                        const uint32_t go = mt * (4 * kBlockBytes >> 4) + 64 * k, d = tmem_base + mt * No;
+                        mma_tf32_mn(d, gl + go, xh + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
+                        mma_tf32_mn(d, gh + go, xl + 64 * k, idesc, 1u);
+                        mma_tf32_mn(d, gh + go, xh + 64 * k, idesc, 1u);
+                    }
                 }
                 commit(&bar_empty[s]);
                 if (ch + 1 == c_end) commit(&bar_done);
@@ -169,20 +175,24 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     } else {
         // read-out: lane = accumulator row (operand-G column), columns = operand-X columns
         const int q = warp & 3;
-        float* out = ws + (static_cast<size_t>(blockIdx.x) * kMo + q * 32 + lane) * No;
         if (c_begin < c_end) {
             mbar_wait(&bar_done, 0);
             fence_after_sync();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-            for (int c0 = 0; c0 < No; c0 += 16) {
-                float v[16];
-                tmem_ld16(taddr + c0, v);
+        }
+        for (int mt = 0; mt < kMT; ++mt) {
+            float* out = ws + ((static_cast<size_t>(blockIdx.x) * kMT + mt) * kMo + q * 32 + lane) * No;
+            if (c_begin < c_end) {
+                const uint32_t taddr = tmem_base + mt * No + (static_cast<uint32_t>(q * 32) << 16);
+                for (int c0 = 0; c0 < No; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(taddr + c0, v);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    reinterpret_cast<float4*>(out + c0)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j)
+                        reinterpret_cast<float4*>(out + c0)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+            } else {
+                for (int c0 = 0; c0 < No; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-        } else {
-            for (int c0 = 0; c0 < No; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     fence_before_sync();
@@ -193,7 +203,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     }
 }
 
-template <class GLoader, class XLoader>
+// ws: [grid][128 * kMT][No] partial accumulators; `gather` below adds them up (its row index runs over 128 * kMT)
+template <int kMT = 1, class GLoader, class XLoader>
 int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M, int No, int* grid_out,
            cudaStream_t stream, const char* who) {
     LTGNN_REQUIRE(No % 32 == 0 && No > 0 && No <= 256, LTGNN_E_SHAPE, "%s: No=%d must be a multiple of 32, <= 256", who, No);
@@ -202,13 +213,14 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
                   di->cc_minor);
-    const size_t smem = smem_bytes(No);
+    const size_t smem = smem_bytes(No, kMT);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "%s: %zu B of shared memory", who, smem);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    auto kern = tgrad_kernel<GLoader, XLoader>;
+    auto kern = tgrad_kernel<GLoader, XLoader, kMT>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint32_t cols = 32;
-    while (cols < static_cast<uint32_t>(No)) cols <<= 1;
+    while (cols < static_cast<uint32_t>(No) * kMT) cols <<= 1;
+    LTGNN_REQUIRE(cols <= 512, LTGNN_E_SHAPE, "%s: %d accumulator columns exceed tensor memory", who, No * kMT);
     const int grid = di->sm_count;
     kern<<<grid, kThreads, smem, stream>>>(g, x, ws, static_cast<uint32_t>(M), No, cols);
     LTGNN_CUDA_TRY(cudaGetLastError());
@@ -217,21 +229,23 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
 }
 
 // out[r][c] (+)= sum_p ws[p][r][c_src] for a sub-rectangle of the [128][No] accumulator
-static __global__ void gather_partials_kernel(const float* __restrict__ ws, int n_parts, int No, int r0, int rows, int c0,
-                                       int cols, float* __restrict__ out, int ld_out, int accumulate) {
+static __global__ void gather_partials_kernel(const float* __restrict__ ws, int n_parts, int part_rows, int No, int r0,
+                                              int rows, int c0, int cols, float* __restrict__ out, int ld_out,
+                                              int accumulate) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * cols) return;
     const int r = i / cols, c = i - r * cols;
     const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c;
     float t = accumulate ? out[r * ld_out + c] : 0.f;
-    for (int p = 0; p < n_parts; ++p) t += ws[static_cast<size_t>(p) * kMo * No + src];
+    for (int p = 0; p < n_parts; ++p) t += ws[static_cast<size_t>(p) * part_rows * No + src];
     out[r * ld_out + c] = t;
 }
 
 inline int gather(const float* ws, int n_parts, int No, int r0, int rows, int c0, int cols, float* out, int ld_out,
-           int accumulate, cudaStream_t stream) {
+                  int accumulate, cudaStream_t stream, int part_rows = kMo) {
     const int n = rows * cols;
-    gather_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ws, n_parts, No, r0, rows, c0, cols, out, ld_out, accumulate);
+    gather_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ws, n_parts, part_rows, No, r0, rows, c0, cols, out, ld_out,
+                                                                accumulate);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }
