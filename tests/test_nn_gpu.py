@@ -69,3 +69,51 @@ def test_global_mean_pool():
     want = pyg.global_mean_pool(x.cpu().double(), batch.cpu())
     assert rel_err(lnn.global_mean_pool(x, batch), want) <= TOL
     assert rel_err(lnn.global_mean_pool(x, batch, size=5), want) <= TOL
+
+
+def test_gcn_body_large_graph_d128():
+    """BASELINE config 5 shape, scaled down (20k nodes, mean degree ~2.3, hidden 128): the graph does not fit
+    shared memory, so the L2-gather aggregation kernel + tensor-core linears carry the layer.  Forward and all
+    gradients of two GCN layers (conv -> relu) vs the PyG restatement in fp64."""
+    import numpy as np
+    from leak_det_gnn_b200 import ops
+    rng = np.random.default_rng(198)
+    n, bsz, d = 20000, 2, 128
+    par = np.arange(1, n) - 1 - rng.integers(0, np.minimum(np.arange(1, n), 64))
+    extra_u = rng.integers(0, n, 3000)
+    extra_v = np.clip(extra_u + rng.integers(2, 64, 3000), 0, n - 1)
+    src = np.concatenate([np.arange(1, n), par, extra_u, extra_v])
+    dst = np.concatenate([par, np.arange(1, n), extra_v, extra_u])
+    keep = src != dst
+    ei = torch.from_numpy(np.stack([src[keep], dst[keep]]))
+    graph = lnn.PipeGraph(ei, n)
+    assert not ops._staged_ok(graph, d)
+    torch.manual_seed(5)
+    ours = [lnn.GCNConv(d, d).cuda() for _ in range(2)]
+    ref = [pyg.GCNConv(d, d).double() for _ in range(2)]
+    for o, r in zip(ours, ref):
+        r.load_state_dict({k: v.double().cpu() for k, v in o.state_dict().items()})
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(bsz, n, d, generator=gen)
+    dy = torch.randn(bsz, n, d, generator=gen)
+    xo = x.cuda().requires_grad_(True)
+    h = xo
+    masks = []
+    for o in ours:
+        h = torch.relu(o(h, graph))
+        masks.append((h.detach() > 0).reshape(bsz * n, d).cpu().double())
+    h.backward(dy.cuda())
+    xr = x.double().reshape(bsz * n, d).requires_grad_(True)
+    big = batchify_edge_index(ei, n, bsz)
+    hr = xr
+    for r, m in zip(ref, masks):
+        # ReLU with the mask the fp32 forward produced: among 5M pre-activations a handful sit within fp32
+        # rounding of zero and would land on the other side in fp64 -- the backward is defined by the forward
+        # that actually ran
+        hr = r(hr, big) * m
+    hr.backward(dy.double().reshape(bsz * n, d))
+    assert rel_err(h.reshape(bsz * n, d), hr) <= TOL
+    assert rel_err(xo.grad.reshape(bsz * n, d), xr.grad) <= TOL
+    for o, r in zip(ours, ref):
+        assert rel_err(o.lin.weight.grad, r.lin.weight.grad) <= TOL
+        assert rel_err(o.bias.grad, r.bias.grad) <= 5 * TOL
