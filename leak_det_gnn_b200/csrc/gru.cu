@@ -74,9 +74,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         : "memory");
 }
 
-// element (n, k) of the fused operand described in the file header
+// element (n, k) of the fused operand described in the file header.  Rows are ordered in 4 blocks of 64 so that
+// the step GEMM can be issued as 4 independent N = 64 accumulator blocks, block u holding all four gate
+// pre-activations of hidden units [16u, 16u + 16):  n = 64 u + 16 g + jj  <->  gate g, unit 16 u + jj.
 __device__ __forceinline__ float fused_weight(const GruParams& p, int n, int k) {
-    const int g = n / H, j = n - g * H;
+    const int g = (n >> 4) & 3, j = ((n >> 6) << 4) | (n & 15);
     const int fi = 1 + p.F;  // row length of w_ih
     const int kx = H, kb = H + 1 + p.F;  // column of x, column of the constant 1
     if (g < 2) {
@@ -100,7 +102,7 @@ __device__ __forceinline__ float fused_weight(const GruParams& p, int n, int k) 
 __global__ void __launch_bounds__(kThreads, 1)
 gru_fwd_kernel(const GruParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_a, bar_d;
+    __shared__ uint64_t bar_a, bar_d[4];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_hi = smem;
@@ -110,7 +112,7 @@ gru_fwd_kernel(const GruParams p) {
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
         mbar_init(&bar_a, kGateWarps);
-        mbar_init(&bar_d, 1);
+        for (int u = 0; u < 4; ++u) mbar_init(&bar_d[u], 1);
         fence_mbar_init();
     }
     for (int i = tid; i < NG * KA; i += kThreads) {
@@ -130,9 +132,11 @@ gru_fwd_kernel(const GruParams p) {
     uint32_t ph_a = 0, ph_d = 0;  // phases of the two barriers, advanced identically by every role
 
     if (warp < kGateWarps) {
-        const int quad = warp & 3, half = warp >> 2;           // TMEM lane quadrant, hidden-unit half
+        // warp (quad, half): TMEM lanes 32 quad .. +31; accumulator blocks u = half and half + 2, i.e. hidden
+        // units [16 half, +16) and [32 + 16 half, +16).  The tensor core produces the 4 blocks one after the
+        // other, so the sigmoid / tanh work of block u overlaps the MMAs of blocks u+1...
+        const int quad = warp & 3, half = warp >> 2;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const int j0 = half * 32;                              // this thread's hidden units [j0, j0 + 32)
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const uint32_t q = tile * 128 + quad * 32 + lane;  // sequence index = b * S + s
             const bool valid = q < p.Q;
@@ -140,7 +144,7 @@ gru_fwd_kernel(const GruParams p) {
             const uint32_t s = (valid ? q : 0) - b * p.S;
             const float* rp = p.r + static_cast<size_t>(b) * p.L * p.S + s;      // + t * S
             const float* tp = p.tf ? p.tf + static_cast<size_t>(b) * p.L * p.F : nullptr;  // + t * F
-            float h[32];
+            float h[32];  // h[16 pass + jj] = unit 16 (half + 2 pass) + jj
 #pragma unroll
             for (int j = 0; j < 32; ++j) h[j] = 0.f;
 
@@ -149,10 +153,11 @@ gru_fwd_kernel(const GruParams p) {
                 float z16[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) z16[j] = 0.f;
-                tmem_st16(tmem + lane_off + kAhiCol + j0, z16);
-                tmem_st16(tmem + lane_off + kAhiCol + j0 + 16, z16);
-                tmem_st16(tmem + lane_off + kAloCol + j0, z16);
-                tmem_st16(tmem + lane_off + kAloCol + j0 + 16, z16);
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    tmem_st16(tmem + lane_off + kAhiCol + 16 * (half + 2 * pass), z16);
+                    tmem_st16(tmem + lane_off + kAloCol + 16 * (half + 2 * pass), z16);
+                }
             }
             auto store_aux = [&](int t) {  // columns 64..95 of A for step t (half 0 warps only)
                 float a[32], lo[32];
@@ -182,34 +187,34 @@ gru_fwd_kernel(const GruParams p) {
             if (lane == 0) mbar_arrive(&bar_a);
 
             for (int t = 0; t < p.L; ++t) {
-                mbar_wait(&bar_d, ph_d);
-                ph_d ^= 1;
-                fence_after_sync();
+                const size_t row = static_cast<size_t>(t) * p.Qp + q;
+                float hhi[32], hlo[32];
 #pragma unroll
-                for (int c = 0; c < 32; c += 16) {
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int u = half + 2 * pass;
+                    mbar_wait(&bar_d[u], ph_d);
+                    fence_after_sync();
                     float rr[16], zz[16], hn[16], in[16];
-                    tmem_ld16(tmem + lane_off + kAccCol + 0 * H + j0 + c, rr);
-                    tmem_ld16(tmem + lane_off + kAccCol + 1 * H + j0 + c, zz);
-                    tmem_ld16(tmem + lane_off + kAccCol + 2 * H + j0 + c, hn);
-                    tmem_ld16(tmem + lane_off + kAccCol + 3 * H + j0 + c, in);
-                    float hi[16], lo[16];
+                    tmem_ld16(tmem + lane_off + kAccCol + 64 * u + 0, rr);
+                    tmem_ld16(tmem + lane_off + kAccCol + 64 * u + 16, zz);
+                    tmem_ld16(tmem + lane_off + kAccCol + 64 * u + 32, hn);
+                    tmem_ld16(tmem + lane_off + kAccCol + 64 * u + 48, in);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float r = sigmoidf_fast(rr[j]);
                         const float z = sigmoidf_fast(zz[j]);
                         const float n = tanhf_fast(fmaf(r, hn[j], in[j]));
-                        const float hv = fmaf(z, h[c + j] - n, n);  // (1 - z) n + z h
-                        h[c + j] = hv;
-                        hi[j] = tf32_hi(hv);
-                        lo[j] = hv - hi[j];
+                        const float hv = fmaf(z, h[16 * pass + j] - n, n);  // (1 - z) n + z h
+                        h[16 * pass + j] = hv;
+                        hhi[16 * pass + j] = tf32_hi(hv);
+                        hlo[16 * pass + j] = hv - hhi[16 * pass + j];
                         rr[j] = r;
                         zz[j] = z;
                         in[j] = n;
                     }
+                    const int f0 = 4 * u;  // float4 index of unit 16 u within a 64-wide group
                     if (p.gates) {
                         float4* g4 = reinterpret_cast<float4*>(p.gates);
-                        const size_t row = static_cast<size_t>(t) * p.Qp + q;
-                        const int f0 = (j0 + c) >> 2;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             stg_stream(g4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]));
@@ -218,38 +223,53 @@ gru_fwd_kernel(const GruParams p) {
                             stg_stream(g4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]));
                         }
                     }
-                    tmem_st16(tmem + lane_off + kAhiCol + j0 + c, hi);
-                    tmem_st16(tmem + lane_off + kAloCol + j0 + c, lo);
-                }
-                if (p.hseq) {
-                    float4* h4 = reinterpret_cast<float4*>(p.hseq);
-                    const size_t row = static_cast<size_t>(t) * p.Qp + q;
+                    if (p.hseq) {
+                        float4* h4 = reinterpret_cast<float4*>(p.hseq);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        stg_stream(h4 + b32(row, (j0 >> 2) + j, H / 4), make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
+                        for (int j = 0; j < 4; ++j)
+                            stg_stream(h4 + b32(row, f0 + j, H / 4),
+                                       make_float4(h[16 * pass + 4 * j], h[16 * pass + 4 * j + 1], h[16 * pass + 4 * j + 2],
+                                                   h[16 * pass + 4 * j + 3]));
+                    }
                 }
                 if (t + 1 < p.L) {
+                    // A may only be overwritten once every MMA of this step has read it: block 3 commits last
+                    if (half == 0) mbar_wait(&bar_d[3], ph_d);
+                    fence_after_sync();
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        tmem_st16(tmem + lane_off + kAhiCol + 16 * (half + 2 * pass), hhi + 16 * pass);
+                        tmem_st16(tmem + lane_off + kAloCol + 16 * (half + 2 * pass), hlo + 16 * pass);
+                    }
                     if (half == 0) store_aux(t + 1);
                     tmem_wait_st();
                     fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_a);
                 }
+                ph_d ^= 1;
             }
             if (valid) {
-                float4* dst = reinterpret_cast<float4*>(p.h_last + static_cast<size_t>(q) * H + j0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                for (int pass = 0; pass < 2; ++pass) {
+                    float4* dst = reinterpret_cast<float4*>(p.h_last + static_cast<size_t>(q) * H + 16 * (half + 2 * pass));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dst[j] = make_float4(h[16 * pass + 4 * j], h[16 * pass + 4 * j + 1], h[16 * pass + 4 * j + 2],
+                                             h[16 * pass + 4 * j + 3]);
+                }
             }
-            // the tile's last accumulator has been read: the next tile's first A store may proceed only after
-            // every gate warp is past its tcgen05.ld, which the bar_a count of the next arrival guarantees
+            // the next tile's A(0) store must not overtake the last MMAs of this tile
+            if (half == 0) mbar_wait(&bar_d[3], ph_d ^ 1);
             fence_before_sync();
         }
     } else {
         // ------------------------------- MMA issuer -------------------------------
-        const uint32_t idesc = idesc_tf32(128, NG);
+        const uint32_t idesc = idesc_tf32(128, 64);
         const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
-        constexpr uint32_t kg_units = NG * 128u >> 4;  // one 32-column k-atom block of B
+        constexpr uint32_t kg_units = NG * 128u >> 4;   // one 32-column k-atom block of B (256 rows x 128 B)
+        constexpr uint32_t blk_units = 64 * 128u >> 4;  // 64 rows of B inside a k-atom block
+        const uint32_t n_ks = static_cast<uint32_t>(H + p.F + 2 + 7) / 8;  // K-steps that hold data: 10 for F = 9
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             for (int t = 0; t < p.L; ++t) {
                 mbar_wait(&bar_a, ph_a);
@@ -257,13 +277,16 @@ gru_fwd_kernel(const GruParams p) {
                 fence_after_sync();
                 if (elect_one()) {
 #pragma unroll
-                    for (uint32_t ks = 0; ks < KA / 8; ++ks) {
-                        const uint32_t boff = (ks >> 2) * kg_units + 2 * (ks & 3);
-                        mma_tf32_ts(tmem + kAccCol, tmem + kAloCol + 8 * ks, bh + boff, idesc, ks == 0 ? 0u : 1u);
-                        mma_tf32_ts(tmem + kAccCol, tmem + kAhiCol + 8 * ks, bl + boff, idesc, 1u);
-                        mma_tf32_ts(tmem + kAccCol, tmem + kAhiCol + 8 * ks, bh + boff, idesc, 1u);
+                    for (uint32_t u = 0; u < 4; ++u) {
+                        const uint32_t d = tmem + kAccCol + 64 * u;
+                        for (uint32_t ks = 0; ks < n_ks; ++ks) {
+                            const uint32_t boff = (ks >> 2) * kg_units + u * blk_units + 2 * (ks & 3);
+                            mma_tf32_ts(d, tmem + kAloCol + 8 * ks, bh + boff, idesc, ks == 0 ? 0u : 1u);
+                            mma_tf32_ts(d, tmem + kAhiCol + 8 * ks, bl + boff, idesc, 1u);
+                            mma_tf32_ts(d, tmem + kAhiCol + 8 * ks, bh + boff, idesc, 1u);
+                        }
+                        commit(&bar_d[u]);
                     }
-                    commit(&bar_d);
                 }
                 __syncwarp();
             }
