@@ -182,6 +182,15 @@ __device__ __forceinline__ void dropout8(float* v, uint64_t idx8, uint64_t seed,
         v[2 * i + 1] = (w[i] >> 16) >= thresh16 ? v[2 * i + 1] * keep_scale : 0.f;
     }
 }
+// 16-bit-lane variant for a single float4 (same keep probability and scale as dropout8)
+__device__ __forceinline__ void dropout4h(float4& v, uint64_t idx4, uint64_t seed, uint32_t thresh16, float keep_scale) {
+    const uint4 r = philox4x32_7(static_cast<uint32_t>(idx4), static_cast<uint32_t>(idx4 >> 32) ^ 0x2545f491u,
+                                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    v.x = (r.x & 0xffffu) >= thresh16 ? v.x * keep_scale : 0.f;
+    v.y = (r.x >> 16) >= thresh16 ? v.y * keep_scale : 0.f;
+    v.z = (r.y & 0xffffu) >= thresh16 ? v.z * keep_scale : 0.f;
+    v.w = (r.y >> 16) >= thresh16 ? v.w * keep_scale : 0.f;
+}
 // exact floor(x / d) for any 32-bit x: magic = floor((2^64 - 1) / d) + 1 (host side, d >= 2)
 __device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint64_t magic) {
     return static_cast<uint32_t>(__umul64hi(static_cast<uint64_t>(x), magic));

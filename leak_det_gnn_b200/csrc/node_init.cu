@@ -72,7 +72,7 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0) {
             float4 v = sl < 0 ? *reinterpret_cast<const float4*>(base + c * 4)
                               : *reinterpret_cast<const float4*>(sens + sl * D + c * 4);
             if (p.drop_thresh)
-                ptx::dropout4(v, static_cast<uint64_t>(b * p.N * d4 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
+                ptx::dropout4h(v, static_cast<uint64_t>(b * p.N * d4 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
             ptx::stg_stream(out + i, v);
         }
     }
@@ -149,7 +149,9 @@ int check_common(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_
     return LTGNN_OK;
 }
 
-uint32_t thresh_of(float p) { return p > 0.f ? static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0) : 0u; }
+// 16 random bits per element everywhere: keep probability 1 - round(p * 2^16) / 2^16, scale its exact inverse
+uint32_t thresh_of(float p) { return p > 0.f ? static_cast<uint32_t>(static_cast<double>(p) * 65536.0 + 0.5) : 0u; }
+float scale_of(float p) { return 1.f / (1.f - static_cast<float>(thresh_of(p)) / 65536.f); }
 
 }  // namespace
 
@@ -164,7 +166,7 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     LTGNN_REQUIRE(hs && slot && W && bias && X0, LTGNN_E_ARG, "node_init_fwd: null tensor");
     LTGNN_REQUIRE(aligned16(X0), LTGNN_E_ALIGN, "node_init_fwd: X0 must be 16-byte aligned");
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    InitParams p{hs, W, bias, slot, B, N, S, ds, D, thresh_of(drop_p), 1.f / (1.f - drop_p), drop_seed};
+    InitParams p{hs, W, bias, slot, B, N, S, ds, D, thresh_of(drop_p), scale_of(drop_p), drop_seed};
     const size_t smem = sizeof(float) * (static_cast<size_t>(ds + 1) * D + 2 * D + static_cast<size_t>(S) * ds +
                                          static_cast<size_t>(S) * D);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "node_init_fwd: %zu B of shared memory", smem);

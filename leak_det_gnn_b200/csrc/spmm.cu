@@ -43,8 +43,8 @@ struct StagedParams {
     // output epilogue (kEpi): y = dropout(relu(acc + bias))
     const float* bias;
     int32_t relu;
-    uint32_t drop_thresh;  // p * 2^32, 0 = no dropout
-    float keep_scale;      // 1 / (1 - p)
+    uint32_t drop_thresh;  // round(p * 2^16), 0 = no dropout (16 random bits per element)
+    float keep_scale;      // 1 / (1 - drop_thresh / 2^16): exactly unbiased
     uint64_t drop_seed;
     // input gate (kGate): x *= gate > 0 ? gate_scale : 0 before aggregation; column sums of the gated x
     const float* gate;
@@ -128,15 +128,25 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
             // backward of the upstream ReLU(+dropout): its OUTPUT `gate` says which entries were live.
             // Each thread owns column group q for rows tid/8, tid/8 + 64, ...; then all consumers sync.
             const float4* gt = reinterpret_cast<const float4*>(p.gate) + base4;
-            for (int r = threadIdx.x >> 3; r < p.n; r += kConsumerWarps * 4) {
-                const float4 m = ldg_stream(gt + static_cast<int64_t>(r) * p.d4);
-                float4 x = stage[r * 8 + q];
-                x.x = m.x > 0.f ? x.x * p.gate_scale : 0.f;
-                x.y = m.y > 0.f ? x.y * p.gate_scale : 0.f;
-                x.z = m.z > 0.f ? x.z * p.gate_scale : 0.f;
-                x.w = m.w > 0.f ? x.w * p.gate_scale : 0.f;
-                stage[r * 8 + q] = x;
-                csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w;
+            constexpr int kStep = kConsumerWarps * 4;  // rows covered by the consumer threads per pass
+            for (int r0 = threadIdx.x >> 3; r0 < p.n; r0 += 4 * kStep) {
+                float4 m[4];  // 4 gate loads in flight per thread: this pass streams a whole tensor from HBM
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + u * kStep < p.n) m[u] = ldg_stream(gt + static_cast<int64_t>(r0 + u * kStep) * p.d4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = r0 + u * kStep;
+                    if (r < p.n) {
+                        float4 x = stage[r * 8 + q];
+                        x.x = m[u].x > 0.f ? x.x * p.gate_scale : 0.f;
+                        x.y = m[u].y > 0.f ? x.y * p.gate_scale : 0.f;
+                        x.z = m[u].z > 0.f ? x.z * p.gate_scale : 0.f;
+                        x.w = m[u].w > 0.f ? x.w * p.gate_scale : 0.f;
+                        stage[r * 8 + q] = x;
+                        csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w;
+                    }
+                }
             }
             consumer_bar();
         }
@@ -182,11 +192,12 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
                     a0.x = fmaxf(a0.x, 0.f); a0.y = fmaxf(a0.y, 0.f); a0.z = fmaxf(a0.z, 0.f); a0.w = fmaxf(a0.w, 0.f);
                     a1.x = fmaxf(a1.x, 0.f); a1.y = fmaxf(a1.y, 0.f); a1.z = fmaxf(a1.z, 0.f); a1.w = fmaxf(a1.w, 0.f);
                 }
-                if (p.drop_thresh) {
-                    dropout4(a0, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * p.d4), p.drop_seed,
+                if (p.drop_thresh) {  // one Philox call (16 random bits per element) decides both float4
+                    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    dropout8(v, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * p.d4), p.drop_seed,
                              p.drop_thresh, p.keep_scale);
-                    dropout4(a1, static_cast<uint64_t>(base4 + static_cast<int64_t>(r1) * p.d4), p.drop_seed,
-                             p.drop_thresh, p.keep_scale);
+                    a0 = make_float4(v[0], v[1], v[2], v[3]);
+                    a1 = make_float4(v[4], v[5], v[6], v[7]);
                 }
             }
             stg_stream(y + static_cast<int64_t>(r0) * p.d4, a0);
@@ -354,8 +365,8 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
         p.off_stage0 = pl.off_stage0;
         p.bias = f.bias;
         p.relu = f.relu;
-        p.drop_thresh = f.drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(f.drop_p) * 4294967296.0) : 0u;
-        p.keep_scale = 1.f / (1.f - f.drop_p);
+        p.drop_thresh = f.drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(f.drop_p) * 65536.0 + 0.5) : 0u;
+        p.keep_scale = 1.f / (1.f - static_cast<float>(p.drop_thresh) / 65536.f);
         p.drop_seed = f.drop_seed;
         p.gate = f.gate;
         p.gate_scale = f.gate_scale;

@@ -480,7 +480,8 @@ class _GnnBody(torch.autograd.Function):
             del xw
             xs.append(x)
         ctx.save_for_backward(h_s, slot, w0, *conv_params[0::2], *xs)
-        ctx.graph, ctx.n_layers, ctx.scale = graph, n_layers, 1.0 / (1.0 - p)
+        # the kernels draw 16 random bits per element: keep probability 1 - round(p * 2^16) / 2^16
+        ctx.graph, ctx.n_layers, ctx.scale = graph, n_layers, 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
         return xs[-1]
 
     @staticmethod
