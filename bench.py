@@ -317,11 +317,17 @@ def run_ours(args) -> None:
             ms = t.item()
         return ms, inst.launches, inst.summary()
 
-    with ClockSampler(local) as clk:
-        ms_stack, launches, ksum = timed(stack_step, args.steps, args.warmup, timing_kernels=True)
-    clocks = clk.result()
+    # rank 0 alone samples clocks and brackets kernels with events: 8 nvidia-smi pollers + per-kernel events on
+    # every rank measurably slow the host side of an 8-process run
+    if rank == 0:
+        with ClockSampler(local) as clk:
+            ms_stack, launches, ksum = timed(stack_step, args.steps, args.warmup, timing_kernels=True)
+        clocks = clk.result()
+    else:
+        ms_stack, launches, ksum = timed(stack_step, args.steps, args.warmup)
+        clocks = None
     ms_e2e, launches_e2e, ksum_e2e = timed(e2e_step, max(1, min(args.steps, args.e2e_steps)), max(3, min(args.warmup, 3)),
-                                            timing_kernels=True)
+                                            timing_kernels=(rank == 0))
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
 
     value = args.batch * world * args.steps / (ms_stack * 1e-3)
