@@ -141,8 +141,8 @@ int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds,
  * pipe_head_fwd: for every window b and class pipe p with end nodes ends[p] = (u, v):
  *      hidden = dropout(relu(W1 [x_u, x_v, |x_u - x_v|] + b1)),   W1 [H, 3D] (edge_head.mlp.0.weight)
  *      part[b*P + p] = sum over the H hidden units of hidden * w2
- *   so pipe_logit = part + b2 (edge_head.mlp.3).  hpost [B*P, H] (optional) receives `hidden`
- *   for the backward.  X [B,N,D] node states; ends int32 [P,2] on the device.  D = 64, H = 128.
+ *   so pipe_logit = part + b2 (edge_head.mlp.3).  hpost (optional; logical [Mp, H], Mp = B*P rounded up to 128,
+ *   stored blocked-32 as [Mp/32][H/4][32][4]) receives `hidden` for the backward.  X [B,N,D] node states; ends int32 [P,2] on the device.  D = 64, H = 128.
  * pipe_head_bwd_dx: dX[b, u/v, :] += the input gradient of the pipe head given dlogit [B*P]; dX must hold the
  *   gradient arriving from other consumers (ltgnn_mean_pool_bwd_fill, or zeros).  fp32 reductions in L2.
  * mean_pool_fwd / mean_pool_bwd_fill: pooled[b,:] = mean_i X[b,i,:];  dX[b,i,:] = dpooled[b,:] / N.
@@ -160,14 +160,16 @@ int ltgnn_mean_pool_bwd_fill(int device, int64_t B, int32_t N, int32_t D, const 
  * wgrad_tc: same contract as ltgnn_wgrad for Do in {64, 128}, Di a multiple of 32 (<= 256); ~3x faster.
  * pipe_head_bwd_w: dW1 [H, 3D] = dpre^T [x_u, x_v, |x_u - x_v|] and db1 [H] = column sums of dpre, where
  *   dpre[r, j] = dlogit[r] * w2[j] * (hpost[r, j] > 0 ? gate_scale : 0); operands are formed on the fly.
- * ws: ltgnn_tgrad_ws_floats(device, Di) floats (pipe head: No = 224).  Deterministic.
+ *   dw2 [H] = sum_r dlogit[r] * hpost[r, :] (one more streaming pass).  hpost in the blocked-32 layout.
+ * ws: ltgnn_tgrad_ws_floats(device, Di) floats; pipe head: ltgnn_pipe_head_ws_floats(device).  Deterministic.
  */
 int64_t ltgnn_tgrad_ws_floats(int device, int32_t No);
 int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, const float* G, const float* X, float* dW,
                    int accumulate, float* ws, void* stream);
 int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
                           const int32_t* ends, const float* w2, const float* hpost, const float* dlogit,
-                          float gate_scale, float* dW1, float* db1, float* ws, void* stream);
+                          float gate_scale, float* dW1, float* db1, float* dw2, float* ws, void* stream);
+int64_t ltgnn_pipe_head_ws_floats(int device);
 
 /* ---- shared per-sensor GRU encoder (detector.py:28-73) -----------------------
  * Sequence q = b*S + s has input [r[b,t,s], tf[b,t,0..F)] at step t (the reference's cat([rr, tf]) order);

@@ -191,6 +191,11 @@ __device__ __forceinline__ void dropout4h(float4& v, uint64_t idx4, uint64_t see
     v.z = (r.y & 0xffffu) >= thresh16 ? v.z * keep_scale : 0.f;
     v.w = (r.y >> 16) >= thresh16 ? v.w * keep_scale : 0.f;
 }
+// "Blocked-32" layout of row-per-thread tensors ([rows, W] logical): element (row, 4*f4 .. 4*f4+3) lives at float4
+// index ((row / 32) * W/4 + f4) * 32 + row % 32.  A thread owns a row, so the 32 lanes of a warp read / write 512
+// contiguous bytes per instruction instead of 32 segments a row apart (row-major costs 32 LSU wavefronts each).
+__device__ __forceinline__ size_t b32(size_t row, int f4, int w4) { return ((row >> 5) * w4 + f4) * 32 + (row & 31); }
+
 // exact floor(x / d) for any 32-bit x: magic = floor((2^64 - 1) / d) + 1 (host side, d >= 2)
 __device__ __forceinline__ uint32_t fastdiv(uint32_t x, uint64_t magic) {
     return static_cast<uint32_t>(__umul64hi(static_cast<uint64_t>(x), magic));

@@ -60,11 +60,7 @@ __device__ __forceinline__ float rcp_approx(float v) {
 __device__ __forceinline__ float sigmoidf_fast(float v) { return rcp_approx(1.f + __expf(-v)); }
 __device__ __forceinline__ float tanhf_fast(float v) { return fmaf(2.f, rcp_approx(1.f + __expf(-2.f * v)), -1.f); }
 
-// "Blocked-32" layout of the tensors saved between the GRU kernels ([rows, W] logical, rows = t * Qp + q with
-// Qp = Q rounded up to 128): element (row, 4*f4 .. 4*f4+3) lives at float4 index ((row / 32) * W/4 + f4) * 32 + row % 32.
-// A thread owns one row, so the 32 lanes of a warp read / write 512 contiguous bytes per instruction instead of
-// 32 segments 1 KB apart (row-major cost ~10 000 LSU wavefronts per step and was the whole runtime).
-__device__ __forceinline__ size_t b32(size_t row, int f4, int w4) { return ((row >> 5) * w4 + f4) * 32 + (row & 31); }
+// saved tensors use the blocked-32 layout (common.cuh): rows = t * Qp + q with Qp = Q rounded up to 128
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
     asm volatile(

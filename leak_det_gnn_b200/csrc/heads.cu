@@ -86,9 +86,9 @@ struct HeadFwdEpilogue {
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (hpost && valid)
-                    reinterpret_cast<float4*>(hpost + static_cast<int64_t>(row) * H + col)[j] =
-                        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (hpost)  // blocked-32 layout (rows padded to 128 by the caller): coalesced across the warp's rows
+                    ptx::stg_stream(reinterpret_cast<float4*>(hpost) + ptx::b32(row, (col >> 2) + j, H >> 2),
+                                    make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + col) + j);
                 acc = fmaf(v[4 * j + 0], ww.x, acc);
                 acc = fmaf(v[4 * j + 1], ww.y, acc);
@@ -103,17 +103,16 @@ struct HeadFwdEpilogue {
 // ------------------------------------------------------------------ backward (input gradient)
 // A[row, j] = d loss / d pre[row, j] = dlogit[row] * w2[j] * (hpost[row, j] > 0 ? scale : 0)
 struct DpreLoader {
-    const float4* hpost;   // [M][H/4]
+    const float4* hpost;   // blocked-32 [Mp, H]
     const float* dlogit;   // [M]
     const float4* w2;      // [H/4]
     float scale;
     int h4;
     __device__ __forceinline__ void operator()(uint32_t row, int kg, float (&v)[32]) const {
-        const float4* h = hpost + static_cast<int64_t>(row) * h4 + kg * 8;
         const float g = __ldg(dlogit + row) * scale;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 t = ptx::ldg_stream(h + j);
+            const float4 t = ptx::ldg_stream(hpost + ptx::b32(row, kg * 8 + j, h4));  // blocked-32 layout
             const float4 w = __ldg(w2 + kg * 8 + j);
             v[4 * j] = t.x > 0.f ? g * w.x : 0.f;
             v[4 * j + 1] = t.y > 0.f ? g * w.y : 0.f;
@@ -144,29 +143,25 @@ struct HeadBwdEpilogue {
             e = __ldg(ends + (row - b * P));
         }
         const int64_t ru = (static_cast<int64_t>(b) * N + e.x) * D, rv = (static_cast<int64_t>(b) * N + e.y) * D;
-        for (int c0 = 0; c0 < ncols; c0 += 16) {
-            float v[16];
-            pull(c0, v);
+        // columns [0, D) = d/d x_u, [D, 2D) = d/d x_v, [2D, 3D) = d/d |x_u - x_v|: pull the three blocks of a
+        // 16-column chunk together so every end node receives ONE reduction per float4 (32 per row, not 64)
+        for (int c0 = 0; c0 < D; c0 += 16) {
+            float a[16], b[16], c[16];
+            pull(c0, a);
+            pull(D + c0, b);
+            pull(2 * D + c0, c);
             if (!valid) continue;
-            const int gc = var * ncols + c0;
-            const int blk = gc / D, cb = gc - blk * D;
-            if (blk < 2) {
-                float4* dst = reinterpret_cast<float4*>(dx + (blk == 0 ? ru : rv) + cb);
+            const float4* hu = reinterpret_cast<const float4*>(x + ru + c0);
+            const float4* hv = reinterpret_cast<const float4*>(x + rv + c0);
+            float4* du = reinterpret_cast<float4*>(dx + ru + c0);
+            float4* dv = reinterpret_cast<float4*>(dx + rv + c0);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) atomicAdd(dst + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-            } else {
-                const float4* hu = reinterpret_cast<const float4*>(x + ru + cb);
-                const float4* hv = reinterpret_cast<const float4*>(x + rv + cb);
-                float4* du = reinterpret_cast<float4*>(dx + ru + cb);
-                float4* dv = reinterpret_cast<float4*>(dx + rv + cb);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 a = __ldg(hu + j), c = __ldg(hv + j);
-                    const float4 g = make_float4(sgn(a.x - c.x) * v[4 * j], sgn(a.y - c.y) * v[4 * j + 1],
-                                                 sgn(a.z - c.z) * v[4 * j + 2], sgn(a.w - c.w) * v[4 * j + 3]);
-                    atomicAdd(du + j, g);
-                    atomicAdd(dv + j, make_float4(-g.x, -g.y, -g.z, -g.w));
-                }
+            for (int j = 0; j < 4; ++j) {
+                const float4 p = __ldg(hu + j), q = __ldg(hv + j);
+                const float s0 = sgn(p.x - q.x) * c[4 * j], s1 = sgn(p.y - q.y) * c[4 * j + 1];
+                const float s2 = sgn(p.z - q.z) * c[4 * j + 2], s3 = sgn(p.w - q.w) * c[4 * j + 3];
+                atomicAdd(du + j, make_float4(a[4 * j] + s0, a[4 * j + 1] + s1, a[4 * j + 2] + s2, a[4 * j + 3] + s3));
+                atomicAdd(dv + j, make_float4(b[4 * j] - s0, b[4 * j + 1] - s1, b[4 * j + 2] - s2, b[4 * j + 3] - s3));
             }
         }
     }

@@ -13,13 +13,13 @@ namespace {
 
 // ---- pipe head: G = d loss / d pre (from the saved post-activation), X = [feat | 1 | 0...]
 struct HeadDpre {
-    static constexpr bool kRowFast = false;
-    const float4* hpost;  // [M][32]
+    static constexpr bool kRowFast = true;  // hpost is stored blocked-32
+    const float4* hpost;  // blocked-32 [Mp, 128]
     const float* dlogit;  // [M]
     const float4* w2;     // [32]
     float scale;
     __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
-        const float4 h = ptx::ldg_stream(hpost + static_cast<int64_t>(row) * 32 + c);
+        const float4 h = ptx::ldg_stream(hpost + ptx::b32(row, c, 32));
         const float4 w = __ldg(w2 + c);
         const float g = __ldg(dlogit + row) * scale;
         return make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
@@ -46,6 +46,49 @@ struct HeadFeatOnes {
 };
 
 }  // namespace
+
+namespace {
+// dw2[j] = sum_rows dlogit[row] * hpost[row, j]: one streaming pass over the blocked-32 activations.
+// warp w of a CTA owns float4 columns w, w + 8, w + 16, w + 24; lane = row inside a 32-row block.
+__global__ void __launch_bounds__(256)
+head_dw2_kernel(const float4* __restrict__ hpost, const float* __restrict__ dlogit, float* __restrict__ part, uint32_t M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t n_blk = (M + 31) / 32;
+    for (uint32_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+        const uint32_t row = blk * 32 + lane;
+        const float d = row < M ? __ldg(dlogit + row) : 0.f;
+        float4 h[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = ptx::ldg_stream(hpost + (static_cast<size_t>(blk) * 32 + warp + 8 * k) * 32 + lane);
+        if (row >= M) {  // the padding rows of the last block are never written
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            acc[k].x = fmaf(d, h[k].x, acc[k].x); acc[k].y = fmaf(d, h[k].y, acc[k].y);
+            acc[k].z = fmaf(d, h[k].z, acc[k].z); acc[k].w = fmaf(d, h[k].w, acc[k].w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+            acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
+        }
+        if (lane == 0) reinterpret_cast<float4*>(part + static_cast<size_t>(blockIdx.x) * 128)[warp + 8 * k] = acc[k];
+    }
+}
+}  // namespace
+
+extern "C" int64_t ltgnn_pipe_head_ws_floats(int device) {
+    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][224] + dw2 partials [8 sm][128]
+    return di ? static_cast<int64_t>(di->sm_count) * tgrad::kMo * (224 + 8) : -1;
+}
 
 extern "C" int64_t ltgnn_tgrad_ws_floats(int device, int32_t No) {
     const DeviceInfo* di = device_info(device);
@@ -75,18 +118,19 @@ extern "C" int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, con
     return tgrad::gather(ws, grid, Di, 0, Do, 0, Di, dW, Di, accumulate, stream);
 }
 
-// Pipe-head parameter gradients: dW1 [128, 192] and db1 [128].  ws: ltgnn_tgrad_ws_floats(device, 224) floats.
+// Pipe-head parameter gradients: dW1 [128, 192], db1 [128], dw2 [128].  ws: ltgnn_pipe_head_ws_floats(device) floats.
 extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
                                      const int32_t* ends, const float* w2, const float* hpost, const float* dlogit,
-                                     float gate_scale, float* dW1, float* db1, float* ws, void* stream_) {
+                                     float gate_scale, float* dW1, float* db1, float* dw2, float* ws, void* stream_) {
     LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_bwd_w: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
     LTGNN_REQUIRE(D == 64 && H == 128, LTGNN_E_SHAPE, "pipe_head_bwd_w: D=%d H=%d (64 / 128 only)", D, H);
-    LTGNN_REQUIRE(X && ends && w2 && hpost && dlogit && dW1 && db1 && ws, LTGNN_E_ARG, "pipe_head_bwd_w: null tensor");
+    LTGNN_REQUIRE(X && ends && w2 && hpost && dlogit && dW1 && db1 && dw2 && ws, LTGNN_E_ARG, "pipe_head_bwd_w: null tensor");
     LTGNN_REQUIRE(aligned16(X) && aligned16(w2) && aligned16(hpost), LTGNN_E_ALIGN, "pipe_head_bwd_w: alignment");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (B == 0) {
         LTGNN_CUDA_TRY(cudaMemsetAsync(dW1, 0, sizeof(float) * H * 3 * D, stream));
         LTGNN_CUDA_TRY(cudaMemsetAsync(db1, 0, sizeof(float) * H, stream));
+        LTGNN_CUDA_TRY(cudaMemsetAsync(dw2, 0, sizeof(float) * H, stream));
         return LTGNN_OK;
     }
     const int64_t M = B * P;
@@ -99,5 +143,14 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
     if (rc) return rc;
     rc = tgrad::gather(ws, grid, No, 0, H, 0, 3 * D, dW1, 3 * D, 0, stream);
     if (rc) return rc;
-    return tgrad::gather(ws, grid, No, 0, H, 3 * D, 1, db1, 1, 0, stream);
+    rc = tgrad::gather(ws, grid, No, 0, H, 3 * D, 1, db1, 1, 0, stream);
+    if (rc) return rc;
+    const DeviceInfo* di = device_info(device);
+    LTGNN_REQUIRE(di, LTGNN_E_CUDA, "pipe_head_bwd_w: device %d", device);
+    float* part = ws + static_cast<size_t>(di->sm_count) * tgrad::kMo * No;  // [8 sm][128]
+    const int n_blk = static_cast<int>((M + 31) / 32);
+    const int grid2 = n_blk < 8 * di->sm_count ? n_blk : 8 * di->sm_count;
+    head_dw2_kernel<<<grid2, 256, 0, stream>>>(reinterpret_cast<const float4*>(hpost), dlogit, part, static_cast<uint32_t>(M));
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return reduce_parts(part, H, dw2, grid2, H, 0, stream);
 }

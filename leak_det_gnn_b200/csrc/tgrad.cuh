@@ -105,38 +105,39 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         uint8_t* g_lo = g_hi + g_half;
         uint8_t* x_hi = g_lo + g_half;
         uint8_t* x_lo = x_hi + x_half;
-        // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of both operands, so the
+        // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of an operand, so the
         // row-dependent part of a gather (division, end-node lookup) is done once and all loads go out together
-        // XLoader::kRowFast sources (blocked-32 tensors: 32 consecutive rows of one chunk are contiguous) flip the
-        // mapping: a warp = 32 rows x one chunk (512 contiguous bytes) at the price of 2-way conflicts on the STS
-        const int r = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3);
-        const int q = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
+        // kRowFast sources (blocked-32 tensors: 32 consecutive rows of one chunk are contiguous) flip the mapping:
+        // a warp = 32 rows x one chunk (512 contiguous bytes) at the price of 2-way conflicts on the STS.  The two
+        // operands choose independently.
+        const int rg = GLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qg = GLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
+        const int rx = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qx = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
         const int x4 = No / 4;
         uint32_t use = 0;
         for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
-            const uint32_t row = ch * kChunk + r;
-            const bool valid = row < M;
+            const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
             float4 gv[kG / 32], xv[8];
 #pragma unroll
-            for (int j = 0; j < kG / 32; ++j) gv[j] = valid ? gload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kG / 32; ++j)
+                gv[j] = row_g < M ? gload(row_g, qg + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-                xv[j] = (valid && q + 8 * j < x4) ? xload(row, q + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[j] = (row_x < M && qx + 8 * j < x4) ? xload(row_x, qx + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
 #pragma unroll
             for (int j = 0; j < kG / 32; ++j) {
                 float4 hi, lo;
                 split4(gv[j], hi, lo);
-                const uint32_t off = mn_offset(r, q + 8 * j, kChunk);
+                const uint32_t off = mn_offset(rg, qg + 8 * j, kChunk);
                 *reinterpret_cast<float4*>(g_hi + off) = hi;
                 *reinterpret_cast<float4*>(g_lo + off) = lo;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (q + 8 * j < x4) {
+                if (qx + 8 * j < x4) {
                     float4 hi, lo;
                     split4(xv[j], hi, lo);
-                    const uint32_t off = mn_offset(r, q + 8 * j, kChunk);
+                    const uint32_t off = mn_offset(rx, qx + 8 * j, kChunk);
                     *reinterpret_cast<float4*>(x_hi + off) = hi;
                     *reinterpret_cast<float4*>(x_lo + off) = lo;
                 }

@@ -393,7 +393,9 @@ class _Heads(torch.autograd.Function):
         p = float(drop_p) if training else 0.0
         need_grad = any(ctx.needs_input_grad)
         part = torch.empty(1, b, p_cnt, device=x.device, dtype=torch.float32)
-        hpost = torch.empty(b * p_cnt, h, device=x.device, dtype=torch.float32) if need_grad else None
+        # saved hidden activations, blocked-32 layout [Mp/32, H/4, 32, 4] with Mp = B*P rounded up to 128 (csrc/common.cuh)
+        mp = (b * p_cnt + 127) // 128 * 128
+        hpost = torch.empty(mp // 32, h // 4, 32, 4, device=x.device, dtype=torch.float32) if need_grad else None
         w2v = w2.reshape(-1).contiguous()
         tok = _inst.begin("pipe_head_fwd")
         _lib.check(L.ltgnn_pipe_head_fwd(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), w1.data_ptr(),
@@ -431,16 +433,16 @@ class _Heads(torch.autograd.Function):
                                             w2v.data_ptr(), hpost.data_ptr(), dlogit.data_ptr(), ctx.scale,
                                             dx.data_ptr(), _stream(x)))
         _inst.end(tok)
-        # parameter gradients: dW1 / db1 on tensor cores with operands formed on the fly; dw2 is one GEMV
+        # parameter gradients: dW1 / db1 on tensor cores with operands formed on the fly; dw2 one streaming pass
         dw1 = torch.empty_like(w1)
         db1 = torch.empty(h, device=x.device, dtype=torch.float32)
-        ws = torch.empty(int(L.ltgnn_tgrad_ws_floats(dev, 224)), device=x.device, dtype=torch.float32)
+        dw2 = torch.empty(1, h, device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(L.ltgnn_pipe_head_ws_floats(dev)), device=x.device, dtype=torch.float32)
         tok = _inst.begin("pipe_head_bwd_w")
         _lib.check(L.ltgnn_pipe_head_bwd_w(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), w2v.data_ptr(),
                                            hpost.data_ptr(), dlogit.data_ptr(), ctx.scale, dw1.data_ptr(),
-                                           db1.data_ptr(), ws.data_ptr(), _stream(x)))
+                                           db1.data_ptr(), dw2.data_ptr(), ws.data_ptr(), _stream(x)))
         _inst.end(tok)
-        dw2 = torch.mv(hpost.t(), dlogit).view(1, h)
         return dx, None, dw1, db1, dw2, None, None
 
 
