@@ -22,55 +22,23 @@ namespace {
 constexpr int kD = 64;        // node width supported by the fused head
 constexpr int kD4 = kD / 4;
 
-// one row = one class pipe of one window; K values [32 kg, 32 kg + 32) of [x_u | x_v | |x_u - x_v|]
-struct PipeFeatLoader {
-    const float4* x;   // node states [B*N, kD4]
-    const int2* ends;  // [P] (u, v)
-    uint32_t P, N;
-    uint64_t magic;    // fastdiv constant of P (P >= 2), 0 when P == 1
-    __device__ __forceinline__ void operator()(uint32_t row, int kg, float (&v)[32]) const {
-        const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
-        const int2 e = __ldg(ends + (row - b * P));
-        const int seg = kg >> 1, half = kg & 1;  // uniform across the CTA for a ring stage
-        const float4* xb = x + static_cast<int64_t>(b) * N * kD4 + half * 8;
-        const float4* pu = xb + e.x * kD4;
-        const float4* pv = xb + e.y * kD4;
-        if (seg < 2) {
-            const float4* src = seg == 0 ? pu : pv;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 t = __ldg(src + j);
-                v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 a = __ldg(pu + j), c = __ldg(pv + j);
-                v[4 * j] = fabsf(a.x - c.x); v[4 * j + 1] = fabsf(a.y - c.y);
-                v[4 * j + 2] = fabsf(a.z - c.z); v[4 * j + 3] = fabsf(a.w - c.w);
-            }
-        }
-    }
-};
-
-// hidden = dropout(relu(acc + b1)); part[row] = sum over the hidden units of hidden * w2
+// hidden = dropout(relu(acc + b1)) for hidden units [c_begin, c_end) of one pipe row; returns their share of
+// the logit, sum of hidden * w2
 struct HeadFwdEpilogue {
     const float* b1;   // [H]
     const float* w2;   // [H]
-    float* part;       // [nvar][M]
-    float* hpost;      // [M][H] saved post-activation, or nullptr (inference)
-    int64_t M;
-    int H, nh;         // hidden units in total / per variant
+    float* part;       // [M]
+    float* hpost;      // blocked-32 [Mp, H] saved post-activation, or nullptr (inference)
+    int H;
     uint32_t drop_thresh16;  // round(p * 2^16), 0 = no dropout
     float keep_scale;        // 1 / (1 - drop_thresh16 / 2^16)
     uint64_t drop_seed;
     template <class Pull>
-    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int var, Pull&& pull) const {
+    __device__ __forceinline__ float operator()(uint32_t row, int c_begin, int c_end, Pull&& pull) const {
         float acc = 0.f;
-        for (int c0 = 0; c0 < nh; c0 += 16) {
+        for (int col = c_begin; col < c_end; col += 16) {
             float v[16];
-            pull(c0, v);
-            const int col = var * nh + c0;
+            pull(col, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col) + j);
@@ -96,9 +64,197 @@ struct HeadFwdEpilogue {
                 acc = fmaf(v[4 * j + 3], ww.w, acc);
             }
         }
-        if (valid) part[static_cast<int64_t>(var) * M + row] = acc;
+        return acc;
     }
 };
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ forward kernel
+// The generic tensor-memory skeleton (rowgemm_ts.cuh) lets every loader thread fetch its own row, which for
+// gathered node states means 32 different 128-byte lines per load instruction: ncu showed the L1 data pipe
+// (l1tex lsu wavefronts) at 70 % of peak and the tensor pipe at 29 %.  Here a warp fetches the rows
+// cooperatively -- 8 lanes read the 128 B of one row, 4 rows per instruction, every line used in full -- and
+// turns them into the row-per-thread form tcgen05.st needs through a 4 KB XOR-swizzled shared-memory patch
+// (conflict-free both ways).  Each end-node row is fetched once per tile and reused for the |h_u - h_v| block.
+//
+//   warps 0-7   LOADERS   group g = warp / 4 owns feature columns [32 g, 32 g + 32) of every tile and emits
+//                         three A stages: h_u, h_v, |h_u - h_v|  (K blocks 2 seg + g of W1)
+//   warp  8     MMA       elected lane, 3xTF32, A from tensor memory, W1 resident in shared memory (192 KB)
+//   warps 9-16  EPILOGUE  tcgen05.ld + bias / ReLU / dropout / w2 dot, double-buffered accumulators; two warps
+//                         per TMEM lane quadrant, 64 hidden units each (the Philox chains are latency-bound)
+namespace hf {
+using namespace ltgnn::ptx;
+using namespace ltgnn::umma;
+constexpr int kLdWarps = 8, kMmaWarp = 8, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;
+constexpr int kK = 192, kN = 128, kStages = 4, kStageCols = 64;
+constexpr uint32_t kScrBytes = 4096;
+
+// lane l ends with the 8 float4 of patch row l; g[k] holds chunk (l & 7) of patch row 4 k + (l >> 3)
+__device__ __forceinline__ void transpose_in(uint8_t* scr, const float4 (&g)[8], float (&v)[32], int lane) {
+    const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = 4 * k + sub;
+        *reinterpret_cast<float4*>(scr + r * 128 + ((ch ^ (r & 7)) << 4)) = g[k];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = *reinterpret_cast<const float4*>(scr + lane * 128 + ((j ^ (lane & 7)) << 4));
+        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends, uint32_t P, uint32_t N, uint64_t magic,
+                     const HeadFwdEpilogue epilogue, const float* __restrict__ W1, uint32_t M) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float part_s[2][128];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_hi = smem;
+    uint8_t* b_lo = b_hi + kN * kK * 4;
+    uint8_t* scratch = b_lo + kN * kK * 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bar_full[s], 4);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tfull[a], 1);
+            mbar_init(&bar_tempty[a], kEpWarps);
+        }
+        fence_mbar_init();
+    }
+    rowgemm_ts::fill_b(b_hi, b_lo, W1, kK, 0, kK, kN, tid, kThreads);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t acc_base = tmem_base, a_base = tmem_base + 2 * kN;
+    const uint32_t n_tiles = (M + 127) / 128;
+
+    if (warp < kLdWarps) {
+        const int grp = warp >> 2, quad = warp & 3;
+        uint8_t* scr = scratch + warp * kScrBytes;
+        const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const int sub = lane >> 3, ch = lane & 7;
+        uint32_t t = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t row = tile * 128 + quad * 32 + lane;
+            uint32_t iu = 0, iv = 0;  // node rows of the two ends (pad rows read node row 0; their results are unused)
+            if (row < M) {
+                const uint32_t b = magic ? fastdiv(row, magic) : row;
+                const int2 e = __ldg(ends + (row - b * P));
+                iu = b * N + e.x;
+                iv = b * N + e.y;
+            }
+            float4 gu[8], gv[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
+                gu[k] = __ldg(x + static_cast<size_t>(ru) * kD4 + grp * 8 + ch);
+                gv[k] = __ldg(x + static_cast<size_t>(rv) * kD4 + grp * 8 + ch);
+            }
+            // emit one A stage: split 32 values into TF32 hi / lo and store them to this thread's TMEM lane
+            auto emit = [&](int seg, auto&& value) {
+                const uint32_t stage = 6 * t + 3 * grp + seg, slot = stage & 3;
+                mbar_wait(&bar_empty[slot], ((stage >> 2) & 1) ^ 1);  // slot consumed by the tensor core
+                fence_after_sync();
+                const uint32_t st_addr = lane_base + slot * kStageCols;
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = value(c + j);
+                        hi[j] = tf32_hi(a);
+                        lo[j] = a - hi[j];
+                    }
+                    tmem_st8(st_addr + c, hi);
+                    tmem_st8(st_addr + 32 + c, lo);
+                }
+                rowgemm_ts::tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[slot]);
+            };
+            float u[32], v[32];
+            transpose_in(scr, gu, u, lane);
+            emit(0, [&](int j) { return u[j]; });   // h_v still in flight
+            transpose_in(scr, gv, v, lane);
+            emit(1, [&](int j) { return v[j]; });
+            emit(2, [&](int j) { return fabsf(u[j] - v[j]); });
+        }
+    } else if (warp == kMmaWarp) {
+        const uint32_t idesc = idesc_tf32(128, kN);
+        const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
+        constexpr uint32_t kg_units = static_cast<uint32_t>(kN) * 128u >> 4;
+        uint32_t t = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t a = t & 1;
+            mbar_wait(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
+            const uint32_t d = acc_base + a * kN;
+#pragma unroll 1
+            for (uint32_t s = 0; s < 6; ++s) {
+                const uint32_t stage = 6 * t + s, slot = stage & 3;
+                const uint32_t kg = s < 3 ? 2 * s : 2 * (s - 3) + 1;  // K block of W1 this stage multiplies
+                mbar_wait(&bar_full[slot], (stage >> 2) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = a_base + slot * kStageCols, a_lo = a_hi + 32;
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) {
+                        const uint32_t boff = kg * kg_units + 2 * k;
+                        rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (s == 0 && k == 0) ? 0u : 1u);
+                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
+                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
+                    }
+                    commit(&bar_empty[slot]);
+                    if (s == 5) commit(&bar_tfull[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
+        uint32_t t = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t a = t & 1;
+            mbar_wait(&bar_tfull[a], (t >> 1) & 1);
+            fence_after_sync();
+            const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16);
+            const uint32_t row = tile * 128 + q * 32 + lane;
+            const float acc = epilogue(row, half * (kN / 2), (half + 1) * (kN / 2),
+                                       [&](int c0, float (&v)[16]) { tmem_ld16(taddr + c0, v); });
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[a]);
+            // the two warps of a quadrant add their halves of the logit in a fixed order
+            if (half == 1) part_s[a][q * 32 + lane] = acc;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+            if (half == 0 && row < M) epilogue.part[row] = acc + part_s[a][q * 32 + lane];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+}  // namespace hf
 
 // ------------------------------------------------------------------ backward (input gradient)
 // A[row, j] = d loss / d pre[row, j] = dlogit[row] * w2[j] * (hpost[row, j] > 0 ? scale : 0)
@@ -124,48 +280,194 @@ struct DpreLoader {
 
 __device__ __forceinline__ float sgn(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
 
-// dfeat[row, 0:3D] is scattered back to the two end nodes: +u for the h_u block, +v for the h_v block,
-// +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0).  Several pipes share a node, so the
-// adds are fp32 reductions in L2 (red.global.add.v4.f32) -- like the reference's index_add_ in autograd.
-struct HeadBwdEpilogue {
-    float* dx;          // [B*N, D], pre-filled with the mean-pool gradient
-    const float* x;     // node states (for the sign of h_u - h_v)
-    const int2* ends;
-    uint32_t P, N;
-    int D, ncols;       // ncols = feature-gradient columns per variant
-    uint64_t magic;
-    template <class Pull>
-    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int var, Pull&& pull) const {
-        uint32_t b = 0;
-        int2 e = make_int2(0, 0);
-        if (valid) {
-            b = magic ? ptx::fastdiv(row, magic) : row;
-            e = __ldg(ends + (row - b * P));
-        }
-        const int64_t ru = (static_cast<int64_t>(b) * N + e.x) * D, rv = (static_cast<int64_t>(b) * N + e.y) * D;
-        // columns [0, D) = d/d x_u, [D, 2D) = d/d x_v, [2D, 3D) = d/d |x_u - x_v|: pull the three blocks of a
-        // 16-column chunk together so every end node receives ONE reduction per float4 (32 per row, not 64)
-        for (int c0 = 0; c0 < D; c0 += 16) {
-            float a[16], b[16], c[16];
-            pull(c0, a);
-            pull(D + c0, b);
-            pull(2 * D + c0, c);
-            if (!valid) continue;
-            const float4* hu = reinterpret_cast<const float4*>(x + ru + c0);
-            const float4* hv = reinterpret_cast<const float4*>(x + rv + c0);
-            float4* du = reinterpret_cast<float4*>(dx + ru + c0);
-            float4* dv = reinterpret_cast<float4*>(dx + rv + c0);
+// dfeat[row, 0:3D] = dpre[row, :] W1 is scattered back to the two end nodes: +u for the h_u block, +v for the
+// h_v block, +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0).  Several pipes share a node,
+// so the adds are fp32 reductions in L2 (red.global.add.v4.f32) -- like the reference's index_add_ in autograd.
+//
+// Same warp roles as the forward kernel.  The epilogue warps (two per TMEM lane quadrant, 32 of the 64 node
+// features each) turn the row-per-thread accumulator blocks into 128-byte row segments through the swizzled
+// shared-memory patch, so that the node-state reads for the sign and the reductions touch 4 full lines per
+// instruction instead of 32 partial ones, and every end node receives one reduction per 128 B.
+namespace hb {
+using namespace ltgnn::ptx;
+using namespace ltgnn::umma;
+constexpr int kLdWarps = 8, kMmaWarp = 8, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;
+constexpr int kK = 128, kN = 192, kStages = 2, kStageCols = 64;
+constexpr uint32_t kScrBytes = 4096;
+
+// inverse of hf::transpose_in: lane l holds the 8 float4 of patch row l; afterwards g[k] holds chunk (l & 7)
+// of patch row 4 k + (l >> 3)
+__device__ __forceinline__ void transpose_out(uint8_t* scr, const float (&v)[32], float4 (&g)[8], int lane) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float4 p = __ldg(hu + j), q = __ldg(hv + j);
-                const float s0 = sgn(p.x - q.x) * c[4 * j], s1 = sgn(p.y - q.y) * c[4 * j + 1];
-                const float s2 = sgn(p.z - q.z) * c[4 * j + 2], s3 = sgn(p.w - q.w) * c[4 * j + 3];
-                atomicAdd(du + j, make_float4(a[4 * j] + s0, a[4 * j + 1] + s1, a[4 * j + 2] + s2, a[4 * j + 3] + s3));
-                atomicAdd(dv + j, make_float4(b[4 * j] - s0, b[4 * j + 1] - s1, b[4 * j + 2] - s2, b[4 * j + 3] - s3));
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(scr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int sub = lane >> 3, ch = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int r = 4 * k + sub;
+        g[k] = *reinterpret_cast<const float4*>(scr + r * 128 + ((ch ^ (r & 7)) << 4));
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, float4* __restrict__ dx,
+                        const int2* __restrict__ ends, uint32_t P, uint32_t N, uint64_t magic,
+                        const float* __restrict__ W1, uint32_t M) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_hi = smem;  // B[n = feature column (192)][k = hidden unit (128)] = W1[k][n]
+    uint8_t* b_lo = b_hi + kN * kK * 4;
+    uint8_t* scratch = b_lo + kN * kK * 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bar_full[s], 4);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_tfull[a], 1);
+            mbar_init(&bar_tempty[a], kEpWarps);
+        }
+        fence_mbar_init();
+    }
+    rowgemm_ts::fill_b(b_hi, b_lo, W1, kN, 1, kK, kN, tid, kThreads);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t acc_base = tmem_base, a_base = tmem_base + 2 * kN;
+    const uint32_t n_tiles = (M + 127) / 128;
+
+    if (warp < kLdWarps) {
+        // group g = warp / 4 fills stage slot g with hidden units [32 g, +32) and [64 + 32 g, +32) of every tile
+        const int grp = warp >> 2, quad = warp & 3;
+        const uint32_t st_addr = a_base + grp * kStageCols + (static_cast<uint32_t>(quad * 32) << 16);
+        uint32_t use = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t row = tile * 128 + quad * 32 + lane;
+#pragma unroll 1
+            for (int kg = grp; kg < 4; kg += 2, ++use) {
+                float v[32];
+                if (row < M) {
+                    loader(row, kg, v);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
+                mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hi[j] = tf32_hi(v[c + j]);
+                        lo[j] = v[c + j] - hi[j];
+                    }
+                    tmem_st8(st_addr + c, hi);
+                    tmem_st8(st_addr + 32 + c, lo);
+                }
+                rowgemm_ts::tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[grp]);
             }
         }
+    } else if (warp == kMmaWarp) {
+        const uint32_t idesc = idesc_tf32(128, kN);
+        const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
+        constexpr uint32_t kg_units = static_cast<uint32_t>(kN) * 128u >> 4;
+        uint32_t t = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t a = t & 1;
+            mbar_wait(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
+            const uint32_t d = acc_base + a * kN;
+#pragma unroll 1
+            for (uint32_t kg = 0; kg < 4; ++kg) {
+                const uint32_t stage = 4 * t + kg, slot = stage & 1;
+                mbar_wait(&bar_full[slot], (stage >> 1) & 1);
+                fence_after_sync();
+                if (elect_one()) {
+                    const uint32_t a_hi = a_base + slot * kStageCols, a_lo = a_hi + 32;
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k) {
+                        const uint32_t boff = kg * kg_units + 2 * k;
+                        rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (kg == 0 && k == 0) ? 0u : 1u);
+                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
+                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
+                    }
+                    commit(&bar_empty[slot]);
+                    if (kg == 3) commit(&bar_tfull[a]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
+        uint8_t* scr = scratch + (warp - kMmaWarp - 1) * kScrBytes;
+        const int sub = lane >> 3, ch = lane & 7;
+        uint32_t t = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const uint32_t a = t & 1;
+            const uint32_t row0 = tile * 128 + q * 32;
+            uint32_t iu = 0, iv = 0;
+            if (row0 + lane < M) {
+                const uint32_t b = magic ? fastdiv(row0 + lane, magic) : row0 + lane;
+                const int2 e = __ldg(ends + (row0 + lane - b * P));
+                iu = b * N + e.x;
+                iv = b * N + e.y;
+            }
+            mbar_wait(&bar_tfull[a], (t >> 1) & 1);
+            fence_after_sync();
+            const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16) + 32 * half;
+            auto pull32 = [&](uint32_t col, float4 (&g)[8]) {
+                float v[32];
+                tmem_ld16(taddr + col, v);
+                tmem_ld16(taddr + col + 16, v + 16);
+                transpose_out(scr, v, g, lane);
+            };
+            float4 gc[8], ga[8];
+            pull32(2 * kD, gc);  // d / d |x_u - x_v|, turned into +-sign below
+            uint32_t ou[8], ov[8];  // float4 offsets into x / dx (B * N * 16 < 2^32, checked by the caller)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
+                ou[k] = ru * kD4 + half * 8 + ch;
+                ov[k] = rv * kD4 + half * 8 + ch;
+                const float4 p = __ldg(x + ou[k]), r = __ldg(x + ov[k]);
+                gc[k].x *= sgn(p.x - r.x); gc[k].y *= sgn(p.y - r.y); gc[k].z *= sgn(p.z - r.z); gc[k].w *= sgn(p.w - r.w);
+            }
+            pull32(0, ga);       // d / d x_u
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (row0 + 4 * k + sub < M)
+                    atomicAdd(dx + ou[k], make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
+            pull32(kD, ga);      // d / d x_v
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (row0 + 4 * k + sub < M)
+                    atomicAdd(dx + ov[k], make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+        }
     }
-};
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+}  // namespace hb
 
 // ------------------------------------------------------------------ mean pool and its adjoint
 __global__ void __launch_bounds__(256)
@@ -232,12 +534,25 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
                   "pipe_head_fwd: 16-byte alignment required");
     const int64_t M = B * P;
     LTGNN_REQUIRE(M < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*P too large");
-    PipeFeatLoader ld{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends),
-                      static_cast<uint32_t>(P), static_cast<uint32_t>(N), magic_of(P)};
     const uint32_t t16 = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
-    HeadFwdEpilogue ep{b1, w2, part, hpost, M, H, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
-    return rowgemm_ts::launch(device, ld, ep, W1, 3 * D, 0, M, 3 * D, H, static_cast<cudaStream_t>(stream_),
-                              "pipe_head_fwd");
+    HeadFwdEpilogue ep{b1, w2, part, hpost, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_fwd: device is sm_%d%d, need sm_100", di->cc_major,
+                  di->cc_minor);
+    LTGNN_REQUIRE(B * N < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*N too large");
+    const size_t smem = 1024 + 2ull * hf::kN * hf::kK * 4 + hf::kLdWarps * hf::kScrBytes;
+    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_fwd: %zu B of shared memory", smem);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(hf::pipe_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    const int64_t tiles = (M + 127) / 128;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    hf::pipe_head_fwd_kernel<<<grid, hf::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
+        reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
+        static_cast<uint32_t>(N), magic_of(P), ep, W1, static_cast<uint32_t>(M));
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
 }
 
 extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
@@ -252,10 +567,23 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
                   "pipe_head_bwd_dx: 16-byte alignment required");
     const int64_t M = B * P;
     DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, H / 4};
-    HeadBwdEpilogue ep{dX, X, reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P), static_cast<uint32_t>(N),
-                       D, 3 * D, magic_of(P)};
-    return rowgemm_ts::launch(device, ld, ep, W1, 3 * D, 1, M, H, 3 * D, static_cast<cudaStream_t>(stream_),
-                              "pipe_head_bwd_dx");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_bwd_dx: device is sm_%d%d, need sm_100",
+                  di->cc_major, di->cc_minor);
+    LTGNN_REQUIRE(M < (1ll << 31) && B * N < (1ll << 28), LTGNN_E_SHAPE, "pipe_head_bwd_dx: B*P or B*N too large");
+    const size_t smem = 1024 + 2ull * hb::kN * hb::kK * 4 + hb::kEpWarps * hb::kScrBytes;
+    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_bwd_dx: %zu B of shared memory", smem);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(hb::pipe_head_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    const int64_t tiles = (M + 127) / 128;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    hb::pipe_head_bwd_dx_kernel<<<grid, hb::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
+        ld, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(ends),
+        static_cast<uint32_t>(P), static_cast<uint32_t>(N), magic_of(P), W1, static_cast<uint32_t>(M));
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
 }
 
 extern "C" int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, const float* X, float* pooled,
