@@ -116,6 +116,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
+// Same for waits that are NOT on the critical path (a producer running ahead of its consumer): the explicit
+// suspend-time hint (ns) keeps the warp asleep longer per probe, so its polling does not take issue slots
+// from the warps the SM is actually waiting for.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+            : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();
+    }
+}
 
 // 3-D tiled TMA load global -> shared, completion on an mbarrier (coordinates innermost first)
 __device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
@@ -180,6 +198,18 @@ __device__ __forceinline__ void dropout8(float* v, uint64_t idx8, uint64_t seed,
     for (int i = 0; i < 4; ++i) {
         v[2 * i] = (w[i] & 0xffffu) >= thresh16 ? v[2 * i] * keep_scale : 0.f;
         v[2 * i + 1] = (w[i] >> 16) >= thresh16 ? v[2 * i + 1] * keep_scale : 0.f;
+    }
+}
+// Same keep / drop decisions as dropout8 without the rescale (the caller folded 1 / (1 - p) into the producer of v).
+// thresh_hi = thresh16 << 16: the high half of a word is compared in place, the low half after one shift.
+__device__ __forceinline__ void dropout8_mask(float* v, uint64_t idx8, uint64_t seed, uint32_t thresh_hi) {
+    const uint4 r = philox4x32_7(static_cast<uint32_t>(idx8), static_cast<uint32_t>(idx8 >> 32) ^ 0x5bd1e995u,
+                                 static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = (w[i] << 16) >= thresh_hi ? v[2 * i] : 0.f;
+        v[2 * i + 1] = w[i] >= thresh_hi ? v[2 * i + 1] : 0.f;
     }
 }
 // 16-bit-lane variant for a single float4 (same keep probability and scale as dropout8)

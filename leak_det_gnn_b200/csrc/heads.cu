@@ -23,7 +23,8 @@ constexpr int kD = 64;        // node width supported by the fused head
 constexpr int kD4 = kD / 4;
 
 // hidden = dropout(relu(acc + b1)) for hidden units [c_begin, c_end) of one pipe row; returns their share of
-// the logit, sum of hidden * w2
+// the logit, sum of hidden * w2.  The inverted-dropout scale 1 / (1 - p) is folded into W1 and b1 by the kernel
+// (relu commutes with a positive scale), so a kept unit costs add, max, compare, select, fma.
 struct HeadFwdEpilogue {
     const float* b1;   // [H]
     const float* w2;   // [H]
@@ -36,32 +37,37 @@ struct HeadFwdEpilogue {
     template <class Pull>
     __device__ __forceinline__ float operator()(uint32_t row, int c_begin, int c_end, Pull&& pull) const {
         float acc = 0.f;
+        const uint32_t thresh_hi = drop_thresh16 << 16;
         for (int col = c_begin; col < c_end; col += 16) {
+            float4 bb[4], ww[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {  // issued before the tcgen05.ld wait
+                bb[j] = __ldg(reinterpret_cast<const float4*>(b1 + col) + j);
+                ww[j] = __ldg(reinterpret_cast<const float4*>(w2 + col) + j);
+            }
             float v[16];
             pull(col, v);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(b1 + col) + j);
-                v[4 * j + 0] = fmaxf(v[4 * j + 0] + bb.x, 0.f);
-                v[4 * j + 1] = fmaxf(v[4 * j + 1] + bb.y, 0.f);
-                v[4 * j + 2] = fmaxf(v[4 * j + 2] + bb.z, 0.f);
-                v[4 * j + 3] = fmaxf(v[4 * j + 3] + bb.w, 0.f);
+                v[4 * j + 0] = fmaxf(fmaf(bb[j].x, keep_scale, v[4 * j + 0]), 0.f);
+                v[4 * j + 1] = fmaxf(fmaf(bb[j].y, keep_scale, v[4 * j + 1]), 0.f);
+                v[4 * j + 2] = fmaxf(fmaf(bb[j].z, keep_scale, v[4 * j + 2]), 0.f);
+                v[4 * j + 3] = fmaxf(fmaf(bb[j].w, keep_scale, v[4 * j + 3]), 0.f);
             }
             if (drop_thresh16) {
                 const uint64_t i8 = static_cast<uint64_t>(row) * (H >> 3) + (col >> 3);
-                ptx::dropout8(v, i8, drop_seed, drop_thresh16, keep_scale);
-                ptx::dropout8(v + 8, i8 + 1, drop_seed, drop_thresh16, keep_scale);
+                ptx::dropout8_mask(v, i8, drop_seed, thresh_hi);
+                ptx::dropout8_mask(v + 8, i8 + 1, drop_seed, thresh_hi);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (hpost)  // blocked-32 layout (rows padded to 128 by the caller): coalesced across the warp's rows
                     ptx::stg_stream(reinterpret_cast<float4*>(hpost) + ptx::b32(row, (col >> 2) + j, H >> 2),
                                     make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(w2 + col) + j);
-                acc = fmaf(v[4 * j + 0], ww.x, acc);
-                acc = fmaf(v[4 * j + 1], ww.y, acc);
-                acc = fmaf(v[4 * j + 2], ww.z, acc);
-                acc = fmaf(v[4 * j + 3], ww.w, acc);
+                acc = fmaf(v[4 * j + 0], ww[j].x, acc);
+                acc = fmaf(v[4 * j + 1], ww[j].y, acc);
+                acc = fmaf(v[4 * j + 2], ww[j].z, acc);
+                acc = fmaf(v[4 * j + 3], ww[j].w, acc);
             }
         }
         return acc;
@@ -94,20 +100,43 @@ constexpr int kLdWarps = 8, kMmaWarp = 8, kEpWarps = 8, kThreads = (kLdWarps + 1
 constexpr int kK = 192, kN = 128, kStages = 4, kStageCols = 64;
 constexpr uint32_t kScrBytes = 4096;
 
-// lane l ends with the 8 float4 of patch row l; g[k] holds chunk (l & 7) of patch row 4 k + (l >> 3)
-__device__ __forceinline__ void transpose_in(uint8_t* scr, const float4 (&g)[8], float (&v)[32], int lane) {
-    const int sub = lane >> 3, ch = lane & 7;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int r = 4 * k + sub;
-        *reinterpret_cast<float4*>(scr + r * 128 + ((ch ^ (r & 7)) << 4)) = g[k];
+// A 32-row x 128-byte patch, 16-byte chunk c of row r stored at chunk c ^ (r & 7): conflict-free for both access
+// patterns below.  "Coalesced" form: g[k] = chunk (l & 7) of patch row 4 k + (l >> 3).  "Row" form: lane l holds
+// the 8 chunks of patch row l.  Addresses are 2 + 1 registers (row 4 k + sub has (r & 7) = sub or sub + 4).
+struct Patch {
+    uint8_t* w0;  // coalesced-form address for even k (+ 512 k)
+    uint8_t* w1;  // ... for odd k
+    uint8_t* rd;  // row-form address of chunk 0; chunk j sits at rd ^ (j << 4)
+    __device__ __forceinline__ Patch(uint8_t* scr, int lane) {
+        const int sub = lane >> 3, ch = lane & 7;
+        w0 = scr + sub * 128 + ((ch ^ sub) << 4);
+        w1 = scr + sub * 128 + ((ch ^ sub ^ 4) << 4);
+        rd = scr + lane * 128 + ((lane & 7) << 4);
     }
+    __device__ __forceinline__ float4* co(int k) const { return reinterpret_cast<float4*>(((k & 1) ? w1 : w0) + k * 512); }
+    __device__ __forceinline__ float4* row(int j) const {
+        return reinterpret_cast<float4*>(reinterpret_cast<uintptr_t>(rd) ^ static_cast<uintptr_t>(j << 4));
+    }
+};
+// coalesced form -> row form
+__device__ __forceinline__ void transpose_in(const Patch& pt, const float4 (&g)[8], float (&v)[32]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) *pt.co(k) = g[k];
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const float4 t = *reinterpret_cast<const float4*>(scr + lane * 128 + ((j ^ (lane & 7)) << 4));
+        const float4 t = *pt.row(j);
         v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
+    __syncwarp();
+}
+// row form -> coalesced form
+__device__ __forceinline__ void transpose_out(const Patch& pt, const float (&v)[32], float4 (&g)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *pt.row(j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = *pt.co(k);
     __syncwarp();
 }
 
@@ -136,7 +165,7 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
         }
         fence_mbar_init();
     }
-    rowgemm_ts::fill_b(b_hi, b_lo, W1, kK, 0, kK, kN, tid, kThreads);
+    rowgemm_ts::fill_b(b_hi, b_lo, W1, kK, 0, kK, kN, tid, kThreads, epilogue.keep_scale);
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -144,14 +173,19 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t acc_base = tmem_base, a_base = tmem_base + 2 * kN;
     const uint32_t n_tiles = (M + 127) / 128;
+    // each CTA owns a contiguous range of tiles: consecutive tiles share a window, so its node states are fetched
+    // from HBM once and the CTA's reads / writes / reductions stay local
+    const uint32_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_begin = min(blockIdx.x * per_cta, n_tiles), t_end = min(t_begin + per_cta, n_tiles);
 
     if (warp < kLdWarps) {
         const int grp = warp >> 2, quad = warp & 3;
-        uint8_t* scr = scratch + warp * kScrBytes;
+        const Patch patch(scratch + warp * kScrBytes, lane);
+        const uint32_t n_win = magic ? fastdiv(M, magic) : M;  // windows in the batch
         const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int sub = lane >> 3, ch = lane & 7;
         uint32_t t = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
             const uint32_t row = tile * 128 + quad * 32 + lane;
             uint32_t iu = 0, iv = 0;  // node rows of the two ends (pad rows read node row 0; their results are unused)
             if (row < M) {
@@ -167,10 +201,16 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
                 gu[k] = __ldg(x + static_cast<size_t>(ru) * kD4 + grp * 8 + ch);
                 gv[k] = __ldg(x + static_cast<size_t>(rv) * kD4 + grp * 8 + ch);
             }
+            {   // the ~6 tiles of a window pull the node states of the NEXT window into L2, a slice per tile
+                const uint32_t r0 = tile * 128, b0 = magic ? fastdiv(r0, magic) : r0;
+                const uint32_t line = ((r0 - b0 * P) >> 7) * (kLdWarps * 32) + warp * 32 + lane;  // 128-byte lines
+                if (line < 2 * N && b0 + 1 < n_win)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (static_cast<size_t>(b0 + 1) * N * kD4 + line * 8)));
+            }
             // emit one A stage: split 32 values into TF32 hi / lo and store them to this thread's TMEM lane
             auto emit = [&](int seg, auto&& value) {
                 const uint32_t stage = 6 * t + 3 * grp + seg, slot = stage & 3;
-                mbar_wait(&bar_empty[slot], ((stage >> 2) & 1) ^ 1);  // slot consumed by the tensor core
+                mbar_wait_relaxed(&bar_empty[slot], ((stage >> 2) & 1) ^ 1);  // slot consumed by the tensor core
                 fence_after_sync();
                 const uint32_t st_addr = lane_base + slot * kStageCols;
 #pragma unroll
@@ -191,9 +231,9 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
                 if (lane == 0) mbar_arrive(&bar_full[slot]);
             };
             float u[32], v[32];
-            transpose_in(scr, gu, u, lane);
+            transpose_in(patch, gu, u);
             emit(0, [&](int j) { return u[j]; });   // h_v still in flight
-            transpose_in(scr, gv, v, lane);
+            transpose_in(patch, gv, v);
             emit(1, [&](int j) { return v[j]; });
             emit(2, [&](int j) { return fabsf(u[j] - v[j]); });
         }
@@ -202,15 +242,15 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
         const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
         constexpr uint32_t kg_units = static_cast<uint32_t>(kN) * 128u >> 4;
         uint32_t t = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
             const uint32_t a = t & 1;
-            mbar_wait(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
             const uint32_t d = acc_base + a * kN;
 #pragma unroll 1
             for (uint32_t s = 0; s < 6; ++s) {
                 const uint32_t stage = 6 * t + s, slot = stage & 3;
                 const uint32_t kg = s < 3 ? 2 * s : 2 * (s - 3) + 1;  // K block of W1 this stage multiplies
-                mbar_wait(&bar_full[slot], (stage >> 2) & 1);
+                mbar_wait_relaxed(&bar_full[slot], (stage >> 2) & 1);
                 fence_after_sync();
                 if (elect_one()) {
                     const uint32_t a_hi = a_base + slot * kStageCols, a_lo = a_hi + 32;
@@ -230,9 +270,9 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
     } else {
         const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
         uint32_t t = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
             const uint32_t a = t & 1;
-            mbar_wait(&bar_tfull[a], (t >> 1) & 1);
+            mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
             fence_after_sync();
             const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16);
             const uint32_t row = tile * 128 + q * 32 + lane;
@@ -291,26 +331,9 @@ __device__ __forceinline__ float sgn(float d) { return (d > 0.f) ? 1.f : ((d < 0
 namespace hb {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
-constexpr int kLdWarps = 8, kMmaWarp = 8, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;
+constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;  // 13 warps: 128 regs
 constexpr int kK = 128, kN = 192, kStages = 2, kStageCols = 64;
 constexpr uint32_t kScrBytes = 4096;
-
-// inverse of hf::transpose_in: lane l holds the 8 float4 of patch row l; afterwards g[k] holds chunk (l & 7)
-// of patch row 4 k + (l >> 3)
-__device__ __forceinline__ void transpose_out(uint8_t* scr, const float (&v)[32], float4 (&g)[8], int lane) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(scr + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-    const int sub = lane >> 3, ch = lane & 7;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int r = 4 * k + sub;
-        g[k] = *reinterpret_cast<const float4*>(scr + r * 128 + ((ch ^ (r & 7)) << 4));
-    }
-    __syncwarp();
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, float4* __restrict__ dx,
@@ -345,55 +368,86 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t acc_base = tmem_base, a_base = tmem_base + 2 * kN;
     const uint32_t n_tiles = (M + 127) / 128;
+    // each CTA owns a contiguous range of tiles: consecutive tiles share a window, so its node states are fetched
+    // from HBM once and the CTA's reads / writes / reductions stay local
+    const uint32_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+    const uint32_t t_begin = min(blockIdx.x * per_cta, n_tiles), t_end = min(t_begin + per_cta, n_tiles);
 
     if (warp < kLdWarps) {
-        // group g = warp / 4 fills stage slot g with hidden units [32 g, +32) and [64 + 32 g, +32) of every tile
-        const int grp = warp >> 2, quad = warp & 3;
-        const uint32_t st_addr = a_base + grp * kStageCols + (static_cast<uint32_t>(quad * 32) << 16);
-        uint32_t use = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // The four loader warps (thread = pipe row = TMEM lane) emit the four 32-wide K blocks of every tile into the
+        // two A slots in turn.  The saved activations come from HBM (~1.5 us away): the 8 loads of the NEXT block
+        // are issued before the current one is split and stored.
+        const int quad = warp & 3;
+        const uint32_t st_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const float4* w2 = loader.w2;
+        uint32_t stage = 0;
+        uint32_t tile = t_begin;
+        int kg = 0;
+        float4 raw[8];
+        float g = 0.f;
+        auto fetch = [&]() {  // pad rows exist in the blocked-32 tensor; their g is 0
             const uint32_t row = tile * 128 + quad * 32 + lane;
-#pragma unroll 1
-            for (int kg = grp; kg < 4; kg += 2, ++use) {
-                float v[32];
-                if (row < M) {
-                    loader(row, kg, v);
-                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
-                }
-                mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
-                fence_after_sync();
+            for (int j = 0; j < 8; ++j) raw[j] = ldg_stream(loader.hpost + b32(row, kg * 8 + j, kK / 4));
+            if (kg == 0) g = row < M ? __ldg(loader.dlogit + row) * loader.scale : 0.f;
+            // one register stage cannot cover HBM latency: pull the same block of the next tile into L2 now
+            if (tile + 1 < t_end) {
+                const uint32_t nrow = row + 128;
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    float hi[8], lo[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        hi[j] = tf32_hi(v[c + j]);
-                        lo[j] = v[c + j] - hi[j];
-                    }
-                    tmem_st8(st_addr + c, hi);
-                    tmem_st8(st_addr + 32 + c, lo);
-                }
-                rowgemm_ts::tmem_wait_st();
-                fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_full[grp]);
+                for (int j = 0; j < 8; ++j)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(loader.hpost + b32(nrow, kg * 8 + j, kK / 4)));
             }
+        };
+        if (tile < t_end) fetch();
+        while (tile < t_end) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = __ldg(w2 + kg * 8 + j);
+                v[4 * j] = raw[j].x > 0.f ? g * w.x : 0.f;
+                v[4 * j + 1] = raw[j].y > 0.f ? g * w.y : 0.f;
+                v[4 * j + 2] = raw[j].z > 0.f ? g * w.z : 0.f;
+                v[4 * j + 3] = raw[j].w > 0.f ? g * w.w : 0.f;
+            }
+            if (++kg == 4) {
+                kg = 0;
+                ++tile;
+            }
+            if (tile < t_end) fetch();
+            const uint32_t slot = stage & 1;
+            mbar_wait_relaxed(&bar_empty[slot], ((stage >> 1) & 1) ^ 1);
+            ++stage;
+            fence_after_sync();
+            const uint32_t st_addr = st_base + slot * kStageCols;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    hi[j] = tf32_hi(v[c + j]);
+                    lo[j] = v[c + j] - hi[j];
+                }
+                tmem_st8(st_addr + c, hi);
+                tmem_st8(st_addr + 32 + c, lo);
+            }
+            rowgemm_ts::tmem_wait_st();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_full[slot]);
         }
     } else if (warp == kMmaWarp) {
         const uint32_t idesc = idesc_tf32(128, kN);
         const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
         constexpr uint32_t kg_units = static_cast<uint32_t>(kN) * 128u >> 4;
         uint32_t t = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
             const uint32_t a = t & 1;
-            mbar_wait(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
             const uint32_t d = acc_base + a * kN;
 #pragma unroll 1
             for (uint32_t kg = 0; kg < 4; ++kg) {
                 const uint32_t stage = 4 * t + kg, slot = stage & 1;
-                mbar_wait(&bar_full[slot], (stage >> 1) & 1);
+                mbar_wait_relaxed(&bar_full[slot], (stage >> 1) & 1);
                 fence_after_sync();
                 if (elect_one()) {
                     const uint32_t a_hi = a_base + slot * kStageCols, a_lo = a_hi + 32;
@@ -412,10 +466,10 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
         }
     } else {
         const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
-        uint8_t* scr = scratch + (warp - kMmaWarp - 1) * kScrBytes;
+        const hf::Patch patch(scratch + (warp - kMmaWarp - 1) * kScrBytes, lane);
         const int sub = lane >> 3, ch = lane & 7;
         uint32_t t = 0;
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
             const uint32_t a = t & 1;
             const uint32_t row0 = tile * 128 + q * 32;
             uint32_t iu = 0, iv = 0;
@@ -425,39 +479,56 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
                 iu = b * N + e.x;
                 iv = b * N + e.y;
             }
-            mbar_wait(&bar_tfull[a], (t >> 1) & 1);
+            // sign(h_u - h_v) of this lane's 8 row segments, packed as two bit masks (bit 4 k + component): the
+            // node states do not depend on the accumulator, so their latency is paid before the wait
+            uint32_t pos = 0, neg = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
+                const float4 p = __ldg(x + ru * kD4 + half * 8 + ch), r = __ldg(x + rv * kD4 + half * 8 + ch);
+                const float d[4] = {p.x - r.x, p.y - r.y, p.z - r.z, p.w - r.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    pos |= (d[i] > 0.f ? 1u : 0u) << (4 * k + i);
+                    neg |= (d[i] < 0.f ? 1u : 0u) << (4 * k + i);
+                }
+            }
+            mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
             fence_after_sync();
             const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16) + 32 * half;
             auto pull32 = [&](uint32_t col, float4 (&g)[8]) {
                 float v[32];
                 tmem_ld16(taddr + col, v);
                 tmem_ld16(taddr + col + 16, v + 16);
-                transpose_out(scr, v, g, lane);
+                hf::transpose_out(patch, v, g);
             };
+            auto signed_c = [&](float c, int bit) { return (pos >> bit) & 1u ? c : ((neg >> bit) & 1u ? -c : 0.f); };
             float4 gc[8], ga[8];
-            pull32(2 * kD, gc);  // d / d |x_u - x_v|, turned into +-sign below
-            uint32_t ou[8], ov[8];  // float4 offsets into x / dx (B * N * 16 < 2^32, checked by the caller)
+            pull32(2 * kD, gc);  // d / d |x_u - x_v|  ->  +- sign
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
-                ou[k] = ru * kD4 + half * 8 + ch;
-                ov[k] = rv * kD4 + half * 8 + ch;
-                const float4 p = __ldg(x + ou[k]), r = __ldg(x + ov[k]);
-                gc[k].x *= sgn(p.x - r.x); gc[k].y *= sgn(p.y - r.y); gc[k].z *= sgn(p.z - r.z); gc[k].w *= sgn(p.w - r.w);
+                gc[k].x = signed_c(gc[k].x, 4 * k); gc[k].y = signed_c(gc[k].y, 4 * k + 1);
+                gc[k].z = signed_c(gc[k].z, 4 * k + 2); gc[k].w = signed_c(gc[k].w, 4 * k + 3);
             }
             pull32(0, ga);       // d / d x_u
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub);
                 if (row0 + 4 * k + sub < M)
-                    atomicAdd(dx + ou[k], make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
+                    atomicAdd(dx + ru * kD4 + half * 8 + ch,
+                              make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
+            }
             pull32(kD, ga);      // d / d x_v
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
                 if (row0 + 4 * k + sub < M)
-                    atomicAdd(dx + ov[k], make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+                    atomicAdd(dx + rv * kD4 + half * 8 + ch,
+                              make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+            }
         }
     }
     fence_before_sync();

@@ -58,13 +58,15 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 
 // B[n][k] = W[n * ldw + k] (transposed = 0) or W[k * ldw + n] (transposed = 1); resident, K-major SW128, hi/lo
 __device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const float* __restrict__ W, int ldw, int transposed, int K,
-                              int N, int tid, int nthreads) {
+                              int N, int tid, int nthreads, float scale = 1.f) {
     if (!transposed) {
         const int k4 = K >> 2;
         for (int i = tid; i < N * k4; i += nthreads) {
             const int r = i / k4, c = i - r * k4;
             float4 hi, lo;
-            split4(__ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(r) * ldw) + c), hi, lo);
+            float4 w = __ldg(reinterpret_cast<const float4*>(W + static_cast<size_t>(r) * ldw) + c);
+            w.x *= scale; w.y *= scale; w.z *= scale; w.w *= scale;
+            split4(w, hi, lo);
             const uint32_t off = sw128_offset(r, c, N);
             *reinterpret_cast<float4*>(b_hi + off) = hi;
             *reinterpret_cast<float4*>(b_lo + off) = lo;
@@ -72,7 +74,7 @@ __device__ inline void fill_b(uint8_t* b_hi, uint8_t* b_lo, const float* __restr
     } else {
         for (int i = tid; i < N * K; i += nthreads) {
             const int k = i / N, n = i - k * N;
-            const float w = __ldg(W + static_cast<size_t>(k) * ldw + n);
+            const float w = __ldg(W + static_cast<size_t>(k) * ldw + n) * scale;
             const float hi = tf32_hi(w), lo = w - hi;
             const uint32_t off = sw128_offset(n, k >> 2, N) + (k & 3) * 4;
             *reinterpret_cast<float*>(b_hi + off) = hi;
