@@ -56,24 +56,36 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0) {
         const float* hsb = p.hs + b * p.S * p.ds;
         for (int i = tid; i < p.S * p.ds; i += kThreads) hs[i] = __ldg(hsb + i);
         __syncthreads();
-        for (int i = tid; i < p.S * D; i += kThreads) {
-            const int s = i / D, j = i - s * D;
-            float acc = 0.f;
+        for (int i = tid; i < p.S * d4; i += kThreads) {  // thread = (sensor row, 4 output columns)
+            const int s = i / d4, j = (i - s * d4) * 4;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             const float* h = hs + s * p.ds;
 #pragma unroll 8
-            for (int k = 0; k < p.ds; ++k) acc = fmaf(h[k], Wt[k * D + j], acc);
-            sens[i] = fmaxf(acc + cst[j], 0.f);
+            for (int k = 0; k < p.ds; ++k) {
+                const float4 w = *reinterpret_cast<const float4*>(Wt + k * D + j);
+                const float hk = h[k];
+                acc.x = fmaf(hk, w.x, acc.x); acc.y = fmaf(hk, w.y, acc.y);
+                acc.z = fmaf(hk, w.z, acc.z); acc.w = fmaf(hk, w.w, acc.w);
+            }
+            const float4 cj = *reinterpret_cast<const float4*>(cst + j);
+            *reinterpret_cast<float4*>(sens + s * D + j) = make_float4(fmaxf(acc.x + cj.x, 0.f), fmaxf(acc.y + cj.y, 0.f),
+                                                                       fmaxf(acc.z + cj.z, 0.f), fmaxf(acc.w + cj.w, 0.f));
         }
         __syncthreads();
         float4* out = reinterpret_cast<float4*>(X0) + b * p.N * d4;
-        for (int i = tid; i < p.N * d4; i += kThreads) {
-            const int r = i / d4, c = i - r * d4;
+        const int d8 = d4 >> 1;  // a thread writes 8 consecutive features: one Philox call decides all of them
+        const int c = (tid % d8) * 2, rstep = kThreads / d8;  // kThreads % d8 == 0: a thread keeps its column group
+        for (int r = tid / d8; r < p.N; r += rstep) {
+            const int i = r * d8 + (c >> 1);
             const int sl = __ldg(p.slot + r);
-            float4 v = sl < 0 ? *reinterpret_cast<const float4*>(base + c * 4)
-                              : *reinterpret_cast<const float4*>(sens + sl * D + c * 4);
+            const float4* src = reinterpret_cast<const float4*>(sl < 0 ? base + c * 4 : sens + sl * D + c * 4);
+            float v[8];
+            *reinterpret_cast<float4*>(v) = src[0];
+            *reinterpret_cast<float4*>(v + 4) = src[1];
             if (p.drop_thresh)
-                ptx::dropout4h(v, static_cast<uint64_t>(b * p.N * d4 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
-            ptx::stg_stream(out + i, v);
+                ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
+            ptx::stg_stream(out + 2 * i, *reinterpret_cast<const float4*>(v));
+            ptx::stg_stream(out + 2 * i + 1, *reinterpret_cast<const float4*>(v + 4));
         }
     }
 }
@@ -162,6 +174,7 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     int rc = check_common(device, B, N, S, ds, D, &di, "node_init_fwd");
     if (rc) return rc;
     LTGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LTGNN_E_ARG, "node_init_fwd: dropout p=%f", drop_p);
+    LTGNN_REQUIRE(D % 8 == 0, LTGNN_E_SHAPE, "node_init_fwd: D=%d must be a multiple of 8", D);
     if (B == 0) return LTGNN_OK;
     LTGNN_REQUIRE(hs && slot && W && bias && X0, LTGNN_E_ARG, "node_init_fwd: null tensor");
     LTGNN_REQUIRE(aligned16(X0), LTGNN_E_ALIGN, "node_init_fwd: X0 must be 16-byte aligned");
@@ -172,7 +185,7 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "node_init_fwd: %zu B of shared memory", smem);
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(node_init_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    const int64_t cap = static_cast<int64_t>(di->sm_count) * 4;
+    const int64_t cap = static_cast<int64_t>(di->sm_count) * 6;
     const int grid = static_cast<int>(B < cap ? B : cap);
     node_init_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p, X0);
     LTGNN_CUDA_TRY(cudaGetLastError());
