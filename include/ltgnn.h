@@ -92,11 +92,17 @@ int ltgnn_spmm(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float
  *                (GCNConv's `out + bias`, F.relu, nn.Dropout: detector.py:199-201).  Dropout is
  *                inverted dropout from a counter-based Philox stream keyed by drop_seed:
  *                statistically equivalent to torch's, not bit-identical.
+ *   1-bit gates: live_out (optional, with the output epilogue) receives one bit per element of Y,
+ *                word [b][D/32][N]: bit 8 c + q of word (b, s, i) = (Y[b, i, 32 s + 4 q + c] > 0), c < 4, q < 8
+ *                (the order in which a warp vote delivers them).  live_in (instead of
+ *                `gate`) feeds such a tensor to the input gate: the backward then streams 1/32 of the
+ *                bytes of the float gate.  Graphs up to 1024 nodes.
  */
 int64_t ltgnn_spmm_ws_floats(ltgnn_graph_t g);
 int ltgnn_spmm_fused(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y,
                      const float* bias, int relu, float drop_p, uint64_t drop_seed, const float* gate,
-                     float gate_scale, float* colsum, float* ws, void* stream);
+                     float gate_scale, float* colsum, float* ws, uint32_t* live_out, const uint32_t* live_in,
+                     void* stream);
 
 /* ---- dense row-wise layer on tensor cores --------------------------------------------------
  * Y[M,N] = gate( act( X[M,K] op(W) + bias[N] ) )
@@ -128,14 +134,17 @@ int ltgnn_wgrad(int device, int64_t M, int32_t Do, int32_t Di, const float* G, c
  *      slot int32[N] on the device.  Never builds the zero-padded (B,N,ds+1) tensor.
  * bwd: gate = (X0 > 0) * gate_scale applied to dX0; dhs [B,S,ds], dW [D, ds+1], dbias [D].
  *      ws: ltgnn_node_init_ws_floats() floats, 16-byte aligned.  Deterministic.
+ *      live_out (fwd, optional, D % 32 == 0) / live_in (bwd, instead of X0): the gate as 1 bit per element,
+ *      word [b][D/32][N] as in ltgnn_spmm_fused.
  */
 int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
                         const int32_t* slot, const float* W, const float* bias, float drop_p, uint64_t drop_seed,
-                        float* X0, void* stream);
+                        float* X0, uint32_t* live_out, void* stream);
 int64_t ltgnn_node_init_ws_floats(int device, int64_t B, int32_t S, int32_t ds, int32_t D);
 int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
-                        const int32_t* slot, const float* W, const float* dX0, const float* X0, float gate_scale,
-                        float* dhs, float* dW, float* dbias, float* ws, void* stream);
+                        const int32_t* slot, const float* W, const float* dX0, const float* X0,
+                        const uint32_t* live_in, float gate_scale, float* dhs, float* dW, float* dbias, float* ws,
+                        void* stream);
 
 /* ---- read-out heads (detector.py:76-102, 204-216) ---------------------------------------------
  * pipe_head_fwd: for every window b and class pipe p with end nodes ends[p] = (u, v):

@@ -30,7 +30,7 @@ struct InitParams {
 
 // ---------------------------------------- forward ----------------------------------------
 __global__ void __launch_bounds__(kThreads)
-node_init_fwd_kernel(const InitParams p, float* __restrict__ X0) {
+node_init_fwd_kernel(const InitParams p, float* __restrict__ X0, uint32_t* __restrict__ live_out) {
     extern __shared__ __align__(16) float sm[];
     const int ds1 = p.ds + 1, D = p.D, d4 = D >> 2;
     float* Wt = sm;                   // [ds+1][D]  transposed weight
@@ -86,6 +86,20 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0) {
                 ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
             ptx::stg_stream(out + 2 * i, *reinterpret_cast<const float4*>(v));
             ptx::stg_stream(out + 2 * i + 1, *reinterpret_cast<const float4*>(v + 4));
+            if (live_out) {
+                // 1-bit form of x0 > 0 for the backward: the 4 threads of a 32-feature slice (same row, so they run
+                // this loop together) assemble one word, layout [b][D/32][N]
+                // bit 8 c + q <-> element 4 q + c of the slice (see ltgnn_spmm_fused); this thread holds q = 2 t, 2 t + 1
+                uint32_t w = 0;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    w |= ((v[cc] > 0.f ? 1u : 0u) << (8 * cc)) | ((v[4 + cc] > 0.f ? 1u : 0u) << (8 * cc + 1));
+                w <<= 2 * (tid & 3);
+                const uint32_t grp = 0xfu << (tid & 28);
+                w |= __shfl_xor_sync(grp, w, 1);
+                w |= __shfl_xor_sync(grp, w, 2);
+                if ((tid & 3) == 0) live_out[(b * (D >> 5) + (c >> 3)) * p.N + r] = w;
+            }
         }
     }
 }
@@ -97,10 +111,12 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0) {
 //     skeleton, both over the B*S sensor rows only.
 
 // colsum partial layout: part[cta][D]
+// kBits: the gate comes as 1 bit per element (`live`, layout [b][D/32][N]) instead of the float tensor X0
+template <bool kBits>
 __global__ void __launch_bounds__(kThreads)
-gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X0, const int32_t* __restrict__ slot,
-                    float gate_scale, float4* __restrict__ dz, float* __restrict__ part, int64_t B, int N, int S,
-                    int d4) {
+gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X0, const uint32_t* __restrict__ live,
+                    const int32_t* __restrict__ slot, float gate_scale, float4* __restrict__ dz,
+                    float* __restrict__ part, int64_t B, int N, int S, int d4) {
     __shared__ float4 red[kThreads];
     const int tid = threadIdx.x;
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // kThreads % d4 == 0: a thread keeps its column group
@@ -111,22 +127,35 @@ gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X
         float4* dzb = dz + b * S * d4;
         for (int i0 = tid; i0 < n4; i0 += 4 * kThreads) {
             float4 g[4], x[4];
+            uint32_t m[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * kThreads;
                 if (i < n4) {
                     g[u] = ptx::ldg_stream(gb + i);
-                    x[u] = ptx::ldg_stream(xb + i);
+                    if (kBits) {
+                        const int r = i / d4, c = i - r * d4;
+                        m[u] = __ldg(live + (b * (d4 >> 3) + (c >> 3)) * N + r) >> (c & 7);
+                    } else {
+                        x[u] = ptx::ldg_stream(xb + i);
+                    }
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = i0 + u * kThreads;
                 if (i < n4) {
-                    g[u].x = x[u].x > 0.f ? g[u].x * gate_scale : 0.f;
-                    g[u].y = x[u].y > 0.f ? g[u].y * gate_scale : 0.f;
-                    g[u].z = x[u].z > 0.f ? g[u].z * gate_scale : 0.f;
-                    g[u].w = x[u].w > 0.f ? g[u].w * gate_scale : 0.f;
+                    if (kBits) {
+                        g[u].x = (m[u] & 0x1u) ? g[u].x * gate_scale : 0.f;
+                        g[u].y = (m[u] & 0x100u) ? g[u].y * gate_scale : 0.f;
+                        g[u].z = (m[u] & 0x10000u) ? g[u].z * gate_scale : 0.f;
+                        g[u].w = (m[u] & 0x1000000u) ? g[u].w * gate_scale : 0.f;
+                    } else {
+                        g[u].x = x[u].x > 0.f ? g[u].x * gate_scale : 0.f;
+                        g[u].y = x[u].y > 0.f ? g[u].y * gate_scale : 0.f;
+                        g[u].z = x[u].z > 0.f ? g[u].z * gate_scale : 0.f;
+                        g[u].w = x[u].w > 0.f ? g[u].w * gate_scale : 0.f;
+                    }
                     csum.x += g[u].x; csum.y += g[u].y; csum.z += g[u].z; csum.w += g[u].w;
                     const int r = i / d4, c = i - r * d4;
                     const int sl = __ldg(slot + r);
@@ -169,7 +198,7 @@ float scale_of(float p) { return 1.f / (1.f - static_cast<float>(thresh_of(p)) /
 
 extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
                                    const int32_t* slot, const float* W, const float* bias, float drop_p,
-                                   uint64_t drop_seed, float* X0, void* stream_) {
+                                   uint64_t drop_seed, float* X0, uint32_t* live_out, void* stream_) {
     const DeviceInfo* di;
     int rc = check_common(device, B, N, S, ds, D, &di, "node_init_fwd");
     if (rc) return rc;
@@ -187,7 +216,8 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
                                         static_cast<int>(smem)));
     const int64_t cap = static_cast<int64_t>(di->sm_count) * 6;
     const int grid = static_cast<int>(B < cap ? B : cap);
-    node_init_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p, X0);
+    LTGNN_REQUIRE(!live_out || D % 32 == 0, LTGNN_E_SHAPE, "node_init_fwd: live_out needs D %% 32 == 0 (D=%d)", D);
+    node_init_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p, X0, live_out);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }
@@ -205,13 +235,15 @@ extern "C" int64_t ltgnn_node_init_ws_floats(int device, int64_t B, int32_t S, i
 
 extern "C" int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds, int32_t D, const float* hs,
                                    const int32_t* slot, const float* W, const float* dX0, const float* X0,
-                                   float gate_scale, float* dhs, float* dW, float* dbias, float* ws, void* stream_) {
+                                   const uint32_t* live_in, float gate_scale, float* dhs, float* dW, float* dbias,
+                                   float* ws, void* stream_) {
     const DeviceInfo* di;
     int rc = check_common(device, B, N, S, ds, D, &di, "node_init_bwd");
     if (rc) return rc;
     LTGNN_REQUIRE(D == 64 || D == 128, LTGNN_E_SHAPE, "node_init_bwd: D=%d must be 64 or 128", D);
     LTGNN_REQUIRE(ds % 32 == 0 && ds <= 224, LTGNN_E_SHAPE, "node_init_bwd: ds=%d must be a multiple of 32", ds);
-    LTGNN_REQUIRE(hs && slot && W && dX0 && X0 && dhs && dW && dbias && ws, LTGNN_E_ARG, "node_init_bwd: null tensor");
+    LTGNN_REQUIRE(hs && slot && W && dX0 && (X0 || live_in) && dhs && dW && dbias && ws, LTGNN_E_ARG,
+                  "node_init_bwd: null tensor");
     LTGNN_REQUIRE(aligned16(dX0) && aligned16(X0) && aligned16(ws) && aligned16(hs) && aligned16(dhs), LTGNN_E_ALIGN,
                   "node_init_bwd: 16-byte alignment required");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -228,9 +260,14 @@ extern "C" int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, 
 
     // (1) streaming pass
     const int64_t g1 = B < stream_ctas(di) ? B : stream_ctas(di);
-    gate_extract_kernel<<<static_cast<int>(g1), kThreads, 0, stream>>>(
-        reinterpret_cast<const float4*>(dX0), reinterpret_cast<const float4*>(X0), slot, gate_scale,
-        reinterpret_cast<float4*>(dz), cpart, B, N, S, d4);
+    if (live_in)  // 1 bit per element instead of the float activations: half the bytes of this pass
+        gate_extract_kernel<true><<<static_cast<int>(g1), kThreads, 0, stream>>>(
+            reinterpret_cast<const float4*>(dX0), nullptr, live_in, slot, gate_scale, reinterpret_cast<float4*>(dz),
+            cpart, B, N, S, d4);
+    else
+        gate_extract_kernel<false><<<static_cast<int>(g1), kThreads, 0, stream>>>(
+            reinterpret_cast<const float4*>(dX0), reinterpret_cast<const float4*>(X0), nullptr, slot, gate_scale,
+            reinterpret_cast<float4*>(dz), cpart, B, N, S, d4);
     LTGNN_CUDA_TRY(cudaGetLastError());
     rc = reduce_parts(cpart, D, dbias, static_cast<int>(g1), D, 0, stream);
     if (rc) return rc;

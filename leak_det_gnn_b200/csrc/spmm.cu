@@ -27,10 +27,11 @@ namespace {
 
 constexpr int kSliceFloats = 32;  // 128 B of each node row per work unit
 constexpr int kSliceBytes = kSliceFloats * 4;
-constexpr int kConsumerWarps = 16;
+constexpr int kConsumerWarps = 24;
 constexpr int kStagedThreads = (kConsumerWarps + 1) * 32;  // + 1 producer warp
 constexpr int kMaxStages = 4;
 constexpr int kRowsPerPass = kConsumerWarps * 4;  // 8 lanes per row, 4 rows per warp
+constexpr int kMaxGateRows = 11;  // rows per thread in the gate pass: graphs up to 1056 nodes
 
 struct StagedParams {
     const int32_t* rowptr;
@@ -50,6 +51,9 @@ struct StagedParams {
     const float* gate;
     float gate_scale;
     float* colsum_ws;  // [gridDim.x][32] per-CTA partial column sums, or nullptr
+    // 1-bit-per-element form of the gate: word (b, slice, node), bit 8 c + q <-> element (b, node, 32 slice + 4 q + c)
+    uint32_t* live_out;       // written by the output epilogue (kEpi), or nullptr
+    const uint32_t* live_in;  // read by the input gate (kGate) instead of `gate`, or nullptr
 };
 
 __device__ __forceinline__ void fma2(float4& acc, float w, const float4& x) {
@@ -117,14 +121,38 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
     for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
+        const int64_t b = u / p.n_slices;
+        const int sl = static_cast<int>(u - b * p.n_slices);
+        constexpr int kStepG = kConsumerWarps * 4;  // rows covered by the consumer threads per gate pass
+        uint32_t live[kMaxGateRows];
+        if (kGate && p.live_in) {
+            // this thread's rows of the 1-bit gate: 4 bytes per row, all in flight before the stage is even waited for
+            const uint32_t* lw = p.live_in + static_cast<size_t>(u) * p.n + (threadIdx.x >> 3);
+#pragma unroll
+            for (int k = 0; k < kMaxGateRows; ++k) live[k] = (threadIdx.x >> 3) + k * kStepG < p.n ? __ldg(lw + k * kStepG) : 0u;
+        }
         mbar_wait(full + s, ph);
         float4* stage = reinterpret_cast<float4*>(s_stage + static_cast<size_t>(s) * p.stage_bytes);
         const float4* xs = stage + q;
-        const int64_t b = u / p.n_slices;
-        const int sl = static_cast<int>(u - b * p.n_slices);
         const int64_t base4 = (b * p.n) * p.d4 + sl * (kSliceFloats / 4) + q;  // float4 index of (b, row 0, this lane)
 
-        if (kGate) {
+        if (kGate && p.live_in) {
+#pragma unroll
+            for (int k = 0; k < kMaxGateRows; ++k) {
+                const int r = (threadIdx.x >> 3) + k * kStepG;
+                if (r < p.n) {
+                    const uint32_t m = live[k] >> q;  // bit 8 c of m <-> component c of this lane's float4
+                    float4 x = stage[r * 8 + q];
+                    x.x = (m & 0x1u) ? x.x * p.gate_scale : 0.f;
+                    x.y = (m & 0x100u) ? x.y * p.gate_scale : 0.f;
+                    x.z = (m & 0x10000u) ? x.z * p.gate_scale : 0.f;
+                    x.w = (m & 0x1000000u) ? x.w * p.gate_scale : 0.f;
+                    stage[r * 8 + q] = x;
+                    csum.x += x.x; csum.y += x.y; csum.z += x.z; csum.w += x.w;
+                }
+            }
+            consumer_bar();
+        } else if (kGate) {
             // backward of the upstream ReLU(+dropout): its OUTPUT `gate` says which entries were live.
             // Each thread owns column group q for rows tid/8, tid/8 + 64, ...; then all consumers sync.
             const float4* gt = reinterpret_cast<const float4*>(p.gate) + base4;
@@ -156,11 +184,14 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
         if (kEpi && p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias) + sl * (kSliceFloats / 4) + q);
 
         // two rows in flight per lane group for memory-level parallelism on the LDS chain
-        for (int r0 = warp * 4 + g; r0 < p.n; r0 += 2 * kRowsPerPass) {
-            const int r1 = r0 + kRowsPerPass;
-            int k0 = s_rowptr[r0];
-            const int e0 = s_rowptr[r0 + 1];
-            int k1 = 0, e1 = 0;
+        // (the trip count is warp-uniform so that the epilogue may use warp votes)
+        for (int rb = warp * 4; rb < p.n; rb += 2 * kRowsPerPass) {
+            const int r0 = rb + g, r1 = r0 + kRowsPerPass;
+            int k0 = 0, e0 = 0, k1 = 0, e1 = 0;
+            if (r0 < p.n) {
+                k0 = s_rowptr[r0];
+                e0 = s_rowptr[r0 + 1];
+            }
             if (r1 < p.n) {
                 k1 = s_rowptr[r1];
                 e1 = s_rowptr[r1 + 1];
@@ -200,8 +231,22 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
                     a1 = make_float4(v[4], v[5], v[6], v[7]);
                 }
             }
-            stg_stream(y + static_cast<int64_t>(r0) * p.d4, a0);
+            if (r0 < p.n) stg_stream(y + static_cast<int64_t>(r0) * p.d4, a0);
             if (r1 < p.n) stg_stream(y + static_cast<int64_t>(r1) * p.d4, a1);
+            if (kEpi && p.live_out) {
+                // 1-bit record of y > 0: one vote per float4 component, then byte g of each vote (the 8 lanes of
+                // this row) forms the row's word: bit 8 c + q  <->  element 4 q + c of the 32-feature slice
+                const uint32_t sel = static_cast<uint32_t>(g) | (static_cast<uint32_t>(4 + g) << 4);
+                const uint32_t x0 = __ballot_sync(0xffffffffu, a0.x > 0.f), y0 = __ballot_sync(0xffffffffu, a0.y > 0.f);
+                const uint32_t z0 = __ballot_sync(0xffffffffu, a0.z > 0.f), w0 = __ballot_sync(0xffffffffu, a0.w > 0.f);
+                const uint32_t x1 = __ballot_sync(0xffffffffu, a1.x > 0.f), y1 = __ballot_sync(0xffffffffu, a1.y > 0.f);
+                const uint32_t z1 = __ballot_sync(0xffffffffu, a1.z > 0.f), w1 = __ballot_sync(0xffffffffu, a1.w > 0.f);
+                if (q == 0) {
+                    uint32_t* lw = p.live_out + static_cast<size_t>(u) * p.n;
+                    if (r0 < p.n) lw[r0] = __byte_perm(__byte_perm(x0, y0, sel), __byte_perm(z0, w0, sel), 0x5410);
+                    if (r1 < p.n) lw[r1] = __byte_perm(__byte_perm(x1, y1, sel), __byte_perm(z1, w1, sel), 0x5410);
+                }
+            }
         }
         if (kGate) fence_proxy_async_smem();  // our generic-proxy writes to the stage precede the next TMA fill
         __syncwarp();
@@ -302,6 +347,8 @@ struct FusedArgs {
     float gate_scale = 1.f;
     float* colsum = nullptr;
     float* ws = nullptr;
+    uint32_t* live_out = nullptr;
+    const uint32_t* live_in = nullptr;
 };
 
 int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y, int algo,
@@ -313,7 +360,9 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
     LTGNN_REQUIRE(B < (1ll << 31), LTGNN_E_SHAPE, "%s: B too large", who);
     LTGNN_REQUIRE(f.drop_p >= 0.f && f.drop_p < 1.f, LTGNN_E_ARG, "%s: dropout p=%f not in [0,1)", who, f.drop_p);
     const bool epi = f.bias || f.relu || f.drop_p > 0.f;
-    const bool gated = f.gate != nullptr;
+    const bool gated = f.gate != nullptr || f.live_in != nullptr;
+    LTGNN_REQUIRE(!(f.gate && f.live_in), LTGNN_E_ARG, "%s: pass the gate as floats or as bits, not both", who);
+    LTGNN_REQUIRE(!f.live_out || epi, LTGNN_E_ARG, "%s: live_out needs the output epilogue", who);
     LTGNN_REQUIRE(!f.colsum || (gated && f.ws), LTGNN_E_ARG, "%s: colsum needs gate and workspace", who);
     if (B == 0) {
         if (f.colsum) LTGNN_CUDA_TRY(cudaMemsetAsync(f.colsum, 0, sizeof(float) * D, stream));
@@ -371,6 +420,10 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
         p.gate = f.gate;
         p.gate_scale = f.gate_scale;
         p.colsum_ws = f.colsum ? f.ws : nullptr;
+        p.live_out = f.live_out;
+        p.live_in = f.live_in;
+        LTGNN_REQUIRE(!f.live_in || g->n <= kMaxGateRows * kConsumerWarps * 4, LTGNN_E_SHAPE,
+                      "%s: the 1-bit gate supports graphs up to %d nodes", who, kMaxGateRows * kConsumerWarps * 4);
         // a CTA must keep one feature slice for its whole life when it accumulates column sums
         int64_t grid = p.n_units < g->sm_count ? p.n_units : g->sm_count;
         grid -= grid % p.n_slices;
@@ -416,8 +469,11 @@ extern "C" int64_t ltgnn_spmm_ws_floats(ltgnn_graph_t g) { return g ? static_cas
 
 extern "C" int ltgnn_spmm_fused(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float* X, float* Y,
                                 const float* bias, int relu, float drop_p, uint64_t drop_seed, const float* gate,
-                                float gate_scale, float* colsum, float* ws, void* stream_) {
+                                float gate_scale, float* colsum, float* ws, uint32_t* live_out, const uint32_t* live_in,
+                                void* stream_) {
     FusedArgs f;
+    f.live_out = live_out;
+    f.live_in = live_in;
     f.bias = bias;
     f.relu = relu;
     f.drop_p = drop_p;

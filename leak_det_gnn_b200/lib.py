@@ -29,16 +29,17 @@ SIGNATURES = {
     "ltgnn_spmm": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_int, c_void_p]),
     "ltgnn_spmm_ws_floats": (c_int64, [c_void_p]),
     "ltgnn_spmm_fused": (c_int, [c_void_p, c_int, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_float,
-                                 c_uint64, c_void_p, c_float, c_void_p, c_void_p, c_void_p]),
+                                 c_uint64, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ltgnn_linear": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                              c_float, c_void_p, c_void_p]),
     "ltgnn_wgrad_ws_floats": (c_int64, [c_int, c_int32, c_int32]),
     "ltgnn_wgrad": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "ltgnn_node_init_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_float, c_uint64, c_void_p, c_void_p]),
+                                    c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p]),
     "ltgnn_node_init_ws_floats": (c_int64, [c_int, c_int64, c_int32, c_int32, c_int32]),
     "ltgnn_node_init_bwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     "ltgnn_pipe_head_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p]),
     "ltgnn_pipe_head_bwd_dx": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,

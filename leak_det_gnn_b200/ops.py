@@ -154,11 +154,27 @@ def new_dropout_seed() -> int:
     return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
 
 
+def new_live_mask(b: int, n: int, d: int, device) -> torch.Tensor:
+    """Storage for the 1-bit-per-element record of ``activation > 0`` the fused kernels write in the forward and
+    gate with in the backward: word (b, s, i), bit 8 c + q <-> element (b, i, 32 s + 4 q + c)."""
+    return torch.empty(b, d // 32, n, device=device, dtype=torch.int32)
+
+
+def unpack_live_mask(live: torch.Tensor) -> torch.Tensor:
+    """(B, D/32, N) int32 -> bool (B, N, D); for tests and debugging."""
+    e = torch.arange(32, device=live.device, dtype=torch.int32)
+    bits = (live.unsqueeze(-1) >> (8 * (e % 4) + e // 4)) & 1  # (B, S, N, 32): element e of a slice is bit 8 (e % 4) + e // 4
+    return bits.permute(0, 2, 1, 3).reshape(live.shape[0], live.shape[2], -1).bool()
+
+
 def spmm_fused(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, bias: Optional[torch.Tensor] = None,
                relu: bool = False, drop_p: float = 0.0, drop_seed: int = 0, gate: Optional[torch.Tensor] = None,
-               gate_scale: float = 1.0, want_colsum: bool = False):
+               gate_scale: float = 1.0, want_colsum: bool = False, live_out: Optional[torch.Tensor] = None,
+               live_in: Optional[torch.Tensor] = None):
     """Raw fused aggregation (see ltgnn_spmm_fused): ``dropout(relu(A (x * gatemask) + bias))``.
-    Returns ``y`` or ``(y, colsum)`` when ``want_colsum`` (column sums of the gated input)."""
+    Returns ``y`` or ``(y, colsum)`` when ``want_colsum`` (column sums of the gated input).
+    ``live_out`` / ``live_in``: int32 (B, D/32, N) tensors holding ``y > 0`` / the gate as one bit per element
+    (see :func:`new_live_mask`)."""
     _check_act(x, "x")
     n, d = graph.num_nodes, x.shape[-1]
     if x.numel() % (n * d) != 0:
@@ -170,12 +186,16 @@ def spmm_fused(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, bias:
             raise ValueError("gate must have the shape of x")
     if bias is not None:
         _check_act(bias, "bias")
+    for lv, nm in ((live_out, "live_out"), (live_in, "live_in")):
+        if lv is not None and (lv.dtype != torch.int32 or not lv.is_cuda or not lv.is_contiguous()
+                               or tuple(lv.shape) != (b, d // 32, n)):
+            raise ValueError(f"{nm} must be a contiguous int32 CUDA tensor of shape {(b, d // 32, n)}")
     y = torch.empty_like(x)
     L = _lib.load()
     h = graph.handle(x.device)
     colsum = ws = None
     if want_colsum:
-        if gate is None:
+        if gate is None and live_in is None:
             raise ValueError("want_colsum needs a gate")
         colsum = torch.empty(d, device=x.device, dtype=torch.float32)
         ws = torch.empty(int(L.ltgnn_spmm_ws_floats(h)), device=x.device, dtype=torch.float32)
@@ -184,7 +204,9 @@ def spmm_fused(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, bias:
                                   None if bias is None else bias.data_ptr(), int(relu), float(drop_p),
                                   int(drop_seed) & (2**64 - 1), None if gate is None else gate.data_ptr(),
                                   float(gate_scale), None if colsum is None else colsum.data_ptr(),
-                                  None if ws is None else ws.data_ptr(), _stream(x)))
+                                  None if ws is None else ws.data_ptr(),
+                                  None if live_out is None else live_out.data_ptr(),
+                                  None if live_in is None else live_in.data_ptr(), _stream(x)))
     _inst.end(tok)
     return (y, colsum) if want_colsum else y
 
@@ -255,8 +277,9 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return dw
 
 
-def node_init_fwd(h_s, slot, num_nodes, weight, bias, drop_p=0.0, drop_seed=0):
-    """Raw node-feature initialisation (see ltgnn_node_init_fwd).  h_s (B,S,ds) -> (B,N,D)."""
+def node_init_fwd(h_s, slot, num_nodes, weight, bias, drop_p=0.0, drop_seed=0, live_out=None):
+    """Raw node-feature initialisation (see ltgnn_node_init_fwd).  h_s (B,S,ds) -> (B,N,D).
+    ``live_out``: optional int32 (B, D/32, N) tensor that receives ``x0 > 0`` as one bit per element."""
     _check_act(h_s, "h_s")
     _check_act(weight, "weight")
     _check_act(bias, "bias")
@@ -267,13 +290,14 @@ def node_init_fwd(h_s, slot, num_nodes, weight, bias, drop_p=0.0, drop_seed=0):
     tok = _inst.begin("node_init_fwd")
     _lib.check(L.ltgnn_node_init_fwd(_dev_index(h_s), b, num_nodes, s, ds, d, h_s.data_ptr(), slot.data_ptr(),
                                      weight.data_ptr(), bias.data_ptr(), float(drop_p), int(drop_seed) & (2**64 - 1),
-                                     x0.data_ptr(), _stream(h_s)))
+                                     x0.data_ptr(), None if live_out is None else live_out.data_ptr(), _stream(h_s)))
     _inst.end(tok)
     return x0
 
 
-def node_init_bwd(h_s, slot, weight, dx0, x0, gate_scale):
-    """Raw backward of node_init: returns (dh_s, dW, dbias); dx0 is gated by (x0 > 0) * gate_scale."""
+def node_init_bwd(h_s, slot, weight, dx0, x0, gate_scale, live=None):
+    """Raw backward of node_init: returns (dh_s, dW, dbias); dx0 is gated by (x0 > 0) * gate_scale.
+    ``live``: the gate as one bit per element (from node_init_fwd's ``live_out``); x0 is then not read."""
     for t, nm in ((h_s, "h_s"), (weight, "weight"), (dx0, "dx0"), (x0, "x0")):
         _check_act(t, nm)
     b, s, ds = h_s.shape
@@ -294,8 +318,9 @@ def node_init_bwd(h_s, slot, weight, dx0, x0, gate_scale):
     ws = torch.empty(int(L.ltgnn_node_init_ws_floats(dev, b, s, ds, d)), device=h_s.device, dtype=torch.float32)
     tok = _inst.begin("node_init_bwd")
     _lib.check(L.ltgnn_node_init_bwd(dev, b, n, s, ds, d, h_s.data_ptr(), slot.data_ptr(), weight.data_ptr(),
-                                     dx0.data_ptr(), x0.data_ptr(), float(gate_scale), dhs.data_ptr(), dw.data_ptr(),
-                                     db.data_ptr(), ws.data_ptr(), _stream(h_s)))
+                                     dx0.data_ptr(), x0.data_ptr(), None if live is None else live.data_ptr(),
+                                     float(gate_scale), dhs.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                     _stream(h_s)))
     _inst.end(tok)
     return dhs, dw, db
 
@@ -468,19 +493,30 @@ class _GnnBody(torch.autograd.Function):
         n = graph.num_nodes
         p = float(drop_p) if training else 0.0
         n_layers = len(conv_params) // 2
-        x = node_init_fwd(h_s, slot, n, w0, b0, p, new_dropout_seed() if p > 0 else 0)
+        need_grad = any(ctx.needs_input_grad)
+        bsz = h_s.shape[0]
+
+        def live_for(d):  # 1-bit record of (x > 0) for the backward gates: 1/32 of the bytes of x
+            return new_live_mask(bsz, n, d, h_s.device) if need_grad and d % 32 == 0 and n <= 1024 else None
+
+        lives = [live_for(w0.shape[0])]
+        x = node_init_fwd(h_s, slot, n, w0, b0, p, new_dropout_seed() if p > 0 else 0, live_out=lives[0])
         xs = [x]
         for l in range(n_layers):
             w, b = conv_params[2 * l], conv_params[2 * l + 1]
             xw = _linear_any(x, w)
             if _staged_ok(graph, xw.shape[-1]):
-                x = spmm_fused(graph, xw, bias=b, relu=True, drop_p=p, drop_seed=new_dropout_seed() if p > 0 else 0)
+                lives.append(live_for(xw.shape[-1]))
+                x = spmm_fused(graph, xw, bias=b, relu=True, drop_p=p, drop_seed=new_dropout_seed() if p > 0 else 0,
+                               live_out=lives[-1])
             else:  # graph too large for shared memory: L2-gather kernel + elementwise tail
+                lives.append(None)
                 x = torch.relu_(spmm(graph, xw).add_(b))
                 if p > 0:
                     x = torch.nn.functional.dropout(x, p, True)
             del xw
             xs.append(x)
+        ctx.lives = lives
         ctx.save_for_backward(h_s, slot, w0, *conv_params[0::2], *xs)
         # the kernels draw 16 random bits per element: keep probability 1 - round(p * 2^16) / 2^16
         ctx.graph, ctx.n_layers, ctx.scale = graph, n_layers, 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
@@ -499,7 +535,9 @@ class _GnnBody(torch.autograd.Function):
         for l in range(L_ - 1, -1, -1):
             x_out, x_in, w = xs[l + 1], xs[l], ws_[l]
             if _staged_ok(graph, g.shape[-1]):
-                gz, db = spmm_fused(graph, g, transpose=True, gate=x_out, gate_scale=scale, want_colsum=True)
+                live = ctx.lives[l + 1]
+                gz, db = spmm_fused(graph, g, transpose=True, gate=x_out if live is None else None, live_in=live,
+                                    gate_scale=scale, want_colsum=True)
             else:
                 dz = torch.where(x_out > 0, g * scale, torch.zeros((), device=g.device))
                 db = dz.sum(dim=(0, 1))
@@ -509,7 +547,7 @@ class _GnnBody(torch.autograd.Function):
             grads[2 * l + 1] = db
             g = _linear_any(gz, w, transposed=True)
             del gz
-        dhs, dw0, db0 = node_init_bwd(h_s, slot, w0, g, xs[0], scale)
+        dhs, dw0, db0 = node_init_bwd(h_s, slot, w0, g, xs[0], scale, live=ctx.lives[0])
         return (dhs, None, None, None, None, dw0, db0, *grads)
 
 

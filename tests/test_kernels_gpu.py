@@ -150,3 +150,26 @@ def test_heads_dropout_train_mode():
     # backward uses the saved post-dropout activations: d/dw2 = sum dlogit * hidden
     part.sum().backward()
     assert w2.grad.shape == (1, 128) and torch.isfinite(w2.grad).all()
+
+
+@pytest.mark.parametrize("bsz,n,s,ds,d", [(7, 661, 29, 64, 64), (3, 785, 33, 64, 128), (2, 40, 5, 32, 64)])
+def test_node_init_live_mask(bsz, n, s, ds, d):
+    """node_init's 1-bit record of x0 > 0 gates the backward exactly like x0 itself."""
+    gen = torch.Generator().manual_seed(11)
+    idx = torch.randperm(n, generator=gen)[:s]
+    slot = torch.full((n,), -1, dtype=torch.int32)
+    slot[idx] = torch.arange(s, dtype=torch.int32)
+    slot = slot.cuda()
+    h_s = torch.randn(bsz, s, ds, generator=gen).cuda()
+    w = (torch.randn(d, ds + 1, generator=gen) * 0.2).cuda()
+    b = (torch.randn(d, generator=gen) * 0.2).cuda()
+    live = ops.new_live_mask(bsz, n, d, h_s.device)
+    live.fill_(-1)
+    x0 = ops.node_init_fwd(h_s, slot, n, w, b, 0.2, 321, live_out=live)
+    assert torch.equal(x0, ops.node_init_fwd(h_s, slot, n, w, b, 0.2, 321))
+    assert torch.equal(ops.unpack_live_mask(live), x0 > 0)
+    dx0 = torch.randn(bsz, n, d, generator=gen).cuda()
+    want = ops.node_init_bwd(h_s, slot, w, dx0, x0, 1.25)
+    got = ops.node_init_bwd(h_s, slot, w, dx0, x0, 1.25, live=live)
+    for a, c in zip(got, want):
+        assert torch.equal(a, c)

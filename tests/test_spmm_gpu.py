@@ -148,6 +148,28 @@ def test_spmm_fused_epilogue_and_gate_bit_exact(graph_golden, net, b, d):
     assert torch.equal(got, got2) and torch.equal(colsum, colsum2)
 
 
+@pytest.mark.parametrize("net,b,d", [("LTA", 5, 64), ("LT", 3, 64), ("LTA", 9, 128), ("LTA", 2, 32)])
+def test_spmm_fused_live_mask_bit_exact(graph_golden, net, b, d):
+    """The 1-bit gate (live_out / live_in) is the same gate as the float activations it was derived from."""
+    from leak_det_gnn_b200.ops import new_live_mask, spmm_fused, unpack_live_mask
+    pg = _graph(graph_golden, net)
+    n = pg.num_nodes
+    gen = torch.Generator().manual_seed(5 + b)
+    x = torch.randn(b, n, d, generator=gen).cuda()
+    bias = torch.randn(d, generator=gen).cuda()
+    live = new_live_mask(b, n, d, x.device)
+    live.fill_(-1)  # every word must be overwritten
+    y = spmm_fused(pg, x, bias=bias, relu=True, drop_p=0.25, drop_seed=99, live_out=live)
+    assert torch.equal(y, spmm_fused(pg, x, bias=bias, relu=True, drop_p=0.25, drop_seed=99))
+    assert torch.equal(unpack_live_mask(live), y > 0)
+    g = torch.randn(b, n, d, generator=gen).cuda()
+    want, want_cs = spmm_fused(pg, g, transpose=True, gate=y, gate_scale=4.0 / 3.0, want_colsum=True)
+    got, got_cs = spmm_fused(pg, g, transpose=True, live_in=live, gate_scale=4.0 / 3.0, want_colsum=True)
+    assert torch.equal(got, want) and torch.equal(got_cs, want_cs)
+    with pytest.raises(Exception):
+        spmm_fused(pg, g, transpose=True, gate=y, live_in=live)
+
+
 def test_spmm_fused_dropout_statistics(graph_golden):
     from leak_det_gnn_b200.ops import spmm_fused
     pg = _graph(graph_golden, "LTA")
