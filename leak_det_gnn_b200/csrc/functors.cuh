@@ -2,6 +2,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "patch.cuh"
 
 namespace ltgnn {
 namespace functors {
@@ -16,6 +17,8 @@ struct RowLoader {
 
 // bias -> ReLU -> optional gate: y *= (gate[row, col] > 0) ? gate_scale : 0
 // (the gate is the output of an upstream ReLU(+dropout): its positivity IS that layer's backward mask)
+// The accumulator arrives row-per-thread; 32-column blocks go through the warp's transposition patch so that the
+// stores (and gate loads) are 128-byte row segments, 4 rows per instruction, instead of 32 scattered 16-byte pieces.
 struct StoreEpilogue {
     float* y;
     const float* bias;
@@ -24,8 +27,43 @@ struct StoreEpilogue {
     int n;
     int relu;
     template <class Pull>
-    __device__ __forceinline__ void operator()(uint32_t row, bool valid, int /*var*/, Pull&& pull) const {
-        for (int c0 = 0; c0 < n; c0 += 16) {
+    __device__ __forceinline__ void operator()(uint32_t row, uint32_t M, int /*var*/, Pull&& pull, const patch::Patch& pt,
+                                               int lane) const {
+        const bool valid = row < M;
+        const uint32_t row0 = row - lane;  // first row of this warp's 32
+        const int sub = lane >> 3, ch = lane & 7;
+        int c0 = 0;
+        for (; c0 + 32 <= n; c0 += 32) {
+            float v[32];
+            pull(c0, v);
+            pull(c0 + 16, v + 16);
+            if (bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + c0 + j);
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            float4 g[8];
+            patch::transpose_out(pt, v, g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t r = row0 + 4 * k + sub;
+                if (r < M) {
+                    const size_t o = static_cast<size_t>(r) * n + c0 + 4 * ch;
+                    if (gate) {
+                        const float4 m = ptx::ldg_stream(reinterpret_cast<const float4*>(gate + o));
+                        g[k].x = m.x > 0.f ? g[k].x * gate_scale : 0.f;
+                        g[k].y = m.y > 0.f ? g[k].y * gate_scale : 0.f;
+                        g[k].z = m.z > 0.f ? g[k].z * gate_scale : 0.f;
+                        g[k].w = m.w > 0.f ? g[k].w * gate_scale : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(y + o) = g[k];
+                }
+            }
+        }
+        for (; c0 < n; c0 += 16) {  // a trailing 16-column block keeps the row-per-thread form
             float v[16];
             pull(c0, v);
             if (valid) chunk(row, c0, v);

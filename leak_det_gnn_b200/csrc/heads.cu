@@ -12,6 +12,7 @@
 // Both GEMMs run on the tensor-memory-operand skeleton (rowgemm_ts.cuh): the loaders keep one pipe row per
 // thread, split it into TF32 hi/lo in registers and tcgen05.st it into TMEM, so shared memory only holds the
 // whole weight W1 (192 KB as hi + lo) and every tile is produced exactly once.
+#include "patch.cuh"
 #include "rowgemm_ts.cuh"
 
 using namespace ltgnn;
@@ -100,46 +101,6 @@ constexpr int kLdWarps = 8, kMmaWarp = 8, kEpWarps = 8, kThreads = (kLdWarps + 1
 constexpr int kK = 192, kN = 128, kStages = 4, kStageCols = 64;
 constexpr uint32_t kScrBytes = 4096;
 
-// A 32-row x 128-byte patch, 16-byte chunk c of row r stored at chunk c ^ (r & 7): conflict-free for both access
-// patterns below.  "Coalesced" form: g[k] = chunk (l & 7) of patch row 4 k + (l >> 3).  "Row" form: lane l holds
-// the 8 chunks of patch row l.  Addresses are 2 + 1 registers (row 4 k + sub has (r & 7) = sub or sub + 4).
-struct Patch {
-    uint8_t* w0;  // coalesced-form address for even k (+ 512 k)
-    uint8_t* w1;  // ... for odd k
-    uint8_t* rd;  // row-form address of chunk 0; chunk j sits at rd ^ (j << 4)
-    __device__ __forceinline__ Patch(uint8_t* scr, int lane) {
-        const int sub = lane >> 3, ch = lane & 7;
-        w0 = scr + sub * 128 + ((ch ^ sub) << 4);
-        w1 = scr + sub * 128 + ((ch ^ sub ^ 4) << 4);
-        rd = scr + lane * 128 + ((lane & 7) << 4);
-    }
-    __device__ __forceinline__ float4* co(int k) const { return reinterpret_cast<float4*>(((k & 1) ? w1 : w0) + k * 512); }
-    __device__ __forceinline__ float4* row(int j) const {
-        return reinterpret_cast<float4*>(reinterpret_cast<uintptr_t>(rd) ^ static_cast<uintptr_t>(j << 4));
-    }
-};
-// coalesced form -> row form
-__device__ __forceinline__ void transpose_in(const Patch& pt, const float4 (&g)[8], float (&v)[32]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) *pt.co(k) = g[k];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float4 t = *pt.row(j);
-        v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-    }
-    __syncwarp();
-}
-// row form -> coalesced form
-__device__ __forceinline__ void transpose_out(const Patch& pt, const float (&v)[32], float4 (&g)[8]) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) *pt.row(j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] = *pt.co(k);
-    __syncwarp();
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends, uint32_t P, uint32_t N, uint64_t magic,
                      const HeadFwdEpilogue epilogue, const float* __restrict__ W1, uint32_t M) {
@@ -180,7 +141,7 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
 
     if (warp < kLdWarps) {
         const int grp = warp >> 2, quad = warp & 3;
-        const Patch patch(scratch + warp * kScrBytes, lane);
+        const patch::Patch patch(scratch + warp * kScrBytes, lane);
         const uint32_t n_win = magic ? fastdiv(M, magic) : M;  // windows in the batch
         const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int sub = lane >> 3, ch = lane & 7;
@@ -231,9 +192,9 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
                 if (lane == 0) mbar_arrive(&bar_full[slot]);
             };
             float u[32], v[32];
-            transpose_in(patch, gu, u);
+            patch::transpose_in(patch, gu, u);
             emit(0, [&](int j) { return u[j]; });   // h_v still in flight
-            transpose_in(patch, gv, v);
+            patch::transpose_in(patch, gv, v);
             emit(1, [&](int j) { return v[j]; });
             emit(2, [&](int j) { return fabsf(u[j] - v[j]); });
         }
@@ -466,7 +427,7 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
         }
     } else {
         const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
-        const hf::Patch patch(scratch + (warp - kMmaWarp - 1) * kScrBytes, lane);
+        const patch::Patch patch(scratch + (warp - kMmaWarp - 1) * kScrBytes, lane);
         const int sub = lane >> 3, ch = lane & 7;
         uint32_t t = 0;
         for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
@@ -500,7 +461,7 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
                 float v[32];
                 tmem_ld16(taddr + col, v);
                 tmem_ld16(taddr + col + 16, v + 16);
-                hf::transpose_out(patch, v, g);
+                patch::transpose_out(patch, v, g);
             };
             auto signed_c = [&](float c, int bit) { return (pos >> bit) & 1u ? c : ((neg >> bit) & 1u ? -c : 0.f); };
             float4 gc[8], ga[8];

@@ -9,12 +9,14 @@
 //   warp  16    MMA      one elected lane issues the tcgen05.mma chain into one of two TMEM accumulators and
 //                        commits to the "stage free" and "accumulator full" mbarriers
 //   warps 17-20 EPILOGUE tcgen05.ld their 32 TMEM lanes (lane = tile row) 16 columns at a time inside an
-//                        `Epilogue` functor (bias, activation, masks, reductions, stores), release the accumulator
+//                        `Epilogue` functor (bias, activation, masks, reductions, stores), release the accumulator;
+//                        each warp owns a transposition patch (patch.cuh) so that its stores can be coalesced
 //
 // B (the weight, N x K) is split once per CTA and stays resident in shared memory.
 // All hand-offs are mbarriers; no __syncthreads after the prologue.
 #pragma once
 
+#include "patch.cuh"
 #include "umma.cuh"
 
 namespace ltgnn {
@@ -36,7 +38,9 @@ constexpr uint32_t kStageBytes = 2u * kTileM * kKG * 4;  // hi block + lo block 
 // The A ring has 4 stages (2 when the resident B leaves no room).  Each stage is owned by its own group of
 // loader warps, so the global loads / gathers of up to 4 stages are in flight at once -- the loaders are
 // latency-bound, and this is what keeps the tensor pipe and HBM busy.
-__host__ inline size_t smem_bytes(int K, int N, int stages) { return 1024 + static_cast<size_t>(stages) * kStageBytes + 2ull * N * K * 4; }
+__host__ inline size_t smem_bytes(int K, int N, int stages) {
+    return 1024 + static_cast<size_t>(stages) * kStageBytes + 2ull * N * K * 4 + kEpiWarps * patch::kPatchBytes;
+}
 __host__ inline int pick_stages(int K, int N, size_t limit, int prefer = 4) {
     if (prefer == 3 && smem_bytes(K, N, 3) <= limit) return 3;
     if (smem_bytes(K, N, 4) <= limit) return 4;
@@ -97,6 +101,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
     constexpr uint32_t a_half = kTileM * kKG * 4;  // hi block, then lo block
     uint8_t* b_hi = smem + n_stages * kStageBytes;
     uint8_t* b_lo = b_hi + N * K * 4;
+    uint8_t* scratch = b_lo + N * K * 4;  // one transposition patch per epilogue warp
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warps_per_group = n_stages >= 3 ? 4 : 8;  // 3 stages: warps 12-15 idle
@@ -193,6 +198,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
     } else {
         // ------------------------------- epilogue -------------------------------
         const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const patch::Patch pt(scratch + (warp - kEpiWarp0) * patch::kPatchBytes, lane);
         uint32_t t = 0;
         for (uint32_t tile = tile0; tile < n_tiles; tile += tile_step, ++t) {
             const int a = t & 1;
@@ -203,7 +209,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
             const uint32_t row = tile * kTileM + q * 32 + lane;
             // the epilogue pulls 16-column chunks itself (tcgen05.ld is warp-collective: every lane must pull
             // every chunk, valid row or not) and may keep per-row state across chunks
-            epilogue(row, row < M, var, [&](int c0, float (&v)[16]) { tmem_ld16(taddr + c0, v); });
+            epilogue(row, M, var, [&](int c0, float* v) { tmem_ld16(taddr + c0, v); }, pt, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);

@@ -113,7 +113,9 @@ extern "C" int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, con
     StackedRows g{reinterpret_cast<const float4*>(G), nullptr, Do / 4, 0};
     StackedRows x{reinterpret_cast<const float4*>(X), nullptr, Di / 4, 0};
     int grid = 0;
-    int rc = tgrad::launch(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc");
+    // the GCN shape (64 x 64) takes the narrow variant: half of operand G is never stored, loads are pipelined
+    int rc = (Do == 64 && Di == 64) ? tgrad::launch<1, 2, 2>(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc")
+                                    : tgrad::launch(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc");
     if (rc) return rc;
     return tgrad::gather(ws, grid, Di, 0, Do, 0, Di, dW, Di, accumulate, stream);
 }
@@ -139,7 +141,7 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
                    static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
     const int No = 224;  // 192 feature columns + a ones column (-> db1) padded to a whole 32-column block
     int grid = 0;
-    int rc = tgrad::launch(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
+    int rc = tgrad::launch<1, 4, 7>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
     if (rc) return rc;
     rc = tgrad::gather(ws, grid, No, 0, H, 0, 3 * D, dW1, 3 * D, 0, stream);
     if (rc) return rc;

@@ -64,7 +64,11 @@ __host__ inline size_t smem_bytes(int No, int mt) { return 1024 + kGroups * stag
 // GLoader: float4 operator()(uint32_t row, int c16) for c16 < kMo/4;  XLoader: same for c16 < No/4.
 // Both are only called for row < M.  ws: [gridDim.x][kMo][No].
 // kMT = 1 or 2 accumulator tiles of 128 rows: operand G has 128 * kMT columns and shares one pass over X.
-template <class GLoader, class XLoader, int kMT>
+// kGJ / kXJ: 16-byte chunks a loader thread fetches per row of G / X (chunks q, q + 8, ...).  The default covers
+// every operand; a narrow operand (kGJ < 4 kMT: G columns beyond 32 kGJ are zero and are written once at start;
+// kXJ = No / 32) needs few registers per stage, and then the loads of the NEXT chunk are issued before the current
+// one is stored (kPipe) -- twice the bytes in flight for the skinny, HBM-bound weight gradients.
+template <class GLoader, class XLoader, int kMT, int kGJ = 4 * kMT, int kXJ = 8>
 __global__ void __launch_bounds__(kThreads, 1)
 tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols) {
     extern __shared__ uint8_t smem_raw[];
@@ -86,6 +90,13 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         }
         mbar_init(&bar_done, 1);
         fence_mbar_init();
+    }
+    if (kGJ < 4 * kMT) {  // operand-G columns the loaders never write: zero in every stage, hi and lo
+        for (uint32_t i = tid; i < kGroups * 2 * (g_half / 16); i += kThreads) {
+            const uint32_t st = i / (2 * (g_half / 16)), r = i - st * 2 * (g_half / 16);
+            *reinterpret_cast<float4*>(smem + st * stage + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        fence_proxy_async_smem();
     }
     fence_before_sync();
     __syncthreads();
@@ -113,30 +124,43 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         const int rg = GLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qg = GLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
         const int rx = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qx = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
         const int x4 = No / 4;
-        uint32_t use = 0;
-        for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
+        constexpr bool kPipe = (kGJ + kXJ) <= 6;
+        float4 gv[kGJ], xv[kXJ];
+        auto fetch = [&](uint32_t ch, float4 (&gd)[kGJ], float4 (&xd)[kXJ]) {
             const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
-            float4 gv[kG / 32], xv[8];
 #pragma unroll
-            for (int j = 0; j < kG / 32; ++j)
-                gv[j] = row_g < M ? gload(row_g, qg + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kGJ; ++j) gd[j] = row_g < M ? gload(row_g, qg + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                xv[j] = (row_x < M && qx + 8 * j < x4) ? xload(row_x, qx + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kXJ; ++j)
+                xd[j] = (row_x < M && qx + 8 * j < x4) ? xload(row_x, qx + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        uint32_t use = 0;
+        if (kPipe && c_begin + grp < c_end) fetch(c_begin + grp, gv, xv);
+        for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
+            float4 gc[kGJ], xc[kXJ];
+            if (kPipe) {
+#pragma unroll
+                for (int j = 0; j < kGJ; ++j) gc[j] = gv[j];
+#pragma unroll
+                for (int j = 0; j < kXJ; ++j) xc[j] = xv[j];
+                if (ch + kGroups < c_end) fetch(ch + kGroups, gv, xv);  // in flight while this chunk is stored
+            } else {
+                fetch(ch, gc, xc);
+            }
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
 #pragma unroll
-            for (int j = 0; j < kG / 32; ++j) {
+            for (int j = 0; j < kGJ; ++j) {
                 float4 hi, lo;
-                split4(gv[j], hi, lo);
+                split4(gc[j], hi, lo);
                 const uint32_t off = mn_offset(rg, qg + 8 * j, kChunk);
                 *reinterpret_cast<float4*>(g_hi + off) = hi;
                 *reinterpret_cast<float4*>(g_lo + off) = lo;
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < kXJ; ++j) {
                 if (qx + 8 * j < x4) {
                     float4 hi, lo;
-                    split4(xv[j], hi, lo);
+                    split4(xc[j], hi, lo);
                     const uint32_t off = mn_offset(rx, qx + 8 * j, kChunk);
                     *reinterpret_cast<float4*>(x_hi + off) = hi;
                     *reinterpret_cast<float4*>(x_lo + off) = lo;
@@ -205,9 +229,10 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
 }
 
 // ws: [grid][128 * kMT][No] partial accumulators; `gather` below adds them up (its row index runs over 128 * kMT)
-template <int kMT = 1, class GLoader, class XLoader>
+template <int kMT = 1, int kGJ = 4 * kMT, int kXJ = 8, class GLoader, class XLoader>
 int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M, int No, int* grid_out,
            cudaStream_t stream, const char* who) {
+    LTGNN_REQUIRE(No <= 32 * kXJ, LTGNN_E_SHAPE, "%s: No=%d exceeds this variant's %d columns", who, No, 32 * kXJ);
     LTGNN_REQUIRE(No % 32 == 0 && No > 0 && No <= 256, LTGNN_E_SHAPE, "%s: No=%d must be a multiple of 32, <= 256", who, No);
     LTGNN_REQUIRE(M > 0 && M < (1ll << 31) - kChunk, LTGNN_E_SHAPE, "%s: M=%lld", who, static_cast<long long>(M));
     const DeviceInfo* di = device_info(device);
@@ -217,7 +242,7 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     const size_t smem = smem_bytes(No, kMT);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "%s: %zu B of shared memory", who, smem);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    auto kern = tgrad_kernel<GLoader, XLoader, kMT>;
+    auto kern = tgrad_kernel<GLoader, XLoader, kMT, kGJ, kXJ>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint32_t cols = 32;
     while (cols < static_cast<uint32_t>(No) * kMT) cols <<= 1;

@@ -221,7 +221,8 @@ _SMEM_LIMIT = 232448  # sm_100: 227 KB opt-in dynamic shared memory per block
 def _linear_tc_ok(k: int, n: int) -> bool:
     if k % 32 or n % 16 or not (0 < k <= 256) or not (0 < n <= 256):
         return False
-    return 1024 + 2 * 32768 + 2 * n * k * 4 <= _SMEM_LIMIT  # >= 2 ring stages next to the resident weight
+    # >= 2 ring stages and the 4 epilogue transposition patches next to the resident weight
+    return 1024 + 2 * 32768 + 4 * 4096 + 2 * n * k * 4 <= _SMEM_LIMIT
 
 
 def _wgrad_ok(do: int, di: int) -> bool:
