@@ -372,10 +372,11 @@ def run_ours(args) -> None:
     # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
     model_of = {
         "spmm_fwd": ("hbm", 2 * unit_b), "spmm_bwd": ("hbm", 2 * unit_b),
-        "spmm_fused_fwd": ("hbm", 2 * unit_b),            # read XW, write X_l
-        "spmm_fused_bwd": ("hbm", 3 * unit_b),            # read dX_l, read X_l (gate), write G
+        "spmm_fused_fwd": ("hbm", 2 * unit_b + unit_b // 32),   # read XW, write X_l and its 1-bit live mask
+        "spmm_fused_bwd": ("hbm", 2 * unit_b + unit_b // 32),   # read dX_l and the live mask of X_l (gate), write G
         "linear_tc": ("hbm", 2 * unit_b), "wgrad_tc": ("hbm", 2 * unit_b), "wgrad": ("hbm", 2 * unit_b),
-        "node_init_fwd": ("hbm", unit_b), "node_init_bwd": ("hbm", 2 * unit_b),
+        "node_init_fwd": ("hbm", unit_b + unit_b // 32),          # write X_0 and its live mask
+        "node_init_bwd": ("hbm", unit_b + unit_b // 32),          # read dX_0 and the live mask (sensor rows: 4 %)
         "mean_pool_fwd": ("hbm", unit_b), "mean_pool_bwd": ("hbm", unit_b),
         "pipe_head_fwd": ("tensor", head_flops), "pipe_head_bwd_dx": ("tensor", head_flops),
         "pipe_head_bwd_w": ("tensor", head_flops),

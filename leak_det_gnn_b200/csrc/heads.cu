@@ -142,7 +142,6 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
     if (warp < kLdWarps) {
         const int grp = warp >> 2, quad = warp & 3;
         const patch::Patch patch(scratch + warp * kScrBytes, lane);
-        const uint32_t n_win = magic ? fastdiv(M, magic) : M;  // windows in the batch
         const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int sub = lane >> 3, ch = lane & 7;
         uint32_t t = 0;
@@ -161,12 +160,6 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
                 const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
                 gu[k] = __ldg(x + static_cast<size_t>(ru) * kD4 + grp * 8 + ch);
                 gv[k] = __ldg(x + static_cast<size_t>(rv) * kD4 + grp * 8 + ch);
-            }
-            {   // the ~6 tiles of a window pull the node states of the NEXT window into L2, a slice per tile
-                const uint32_t r0 = tile * 128, b0 = magic ? fastdiv(r0, magic) : r0;
-                const uint32_t line = ((r0 - b0 * P) >> 7) * (kLdWarps * 32) + warp * 32 + lane;  // 128-byte lines
-                if (line < 2 * N && b0 + 1 < n_win)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(x + (static_cast<size_t>(b0 + 1) * N * kD4 + line * 8)));
             }
             // emit one A stage: split 32 values into TF32 hi / lo and store them to this thread's TMEM lane
             auto emit = [&](int seg, auto&& value) {

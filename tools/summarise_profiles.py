@@ -14,6 +14,9 @@ launch_csv, rep, tag = sys.argv[1], sys.argv[2], sys.argv[3]
 
 
 def short(name):
+    for k in ("pipe_head_fwd_kernel", "pipe_head_bwd_dx_kernel", "head_dw2_kernel"):
+        if k in name:
+            return k
     if "rowgemm_ts_kernel" in name:
         return "rowgemm_ts<" + ("PipeFeatLoader,HeadFwdEpilogue" if "PipeFeat" in name else "DpreLoader,HeadBwdEpilogue") + ">"
     if "rowgemm_kernel" in name:
@@ -21,7 +24,7 @@ def short(name):
     if "tgrad_kernel" in name:
         return "tgrad<" + ("HeadDpre,HeadFeatOnes" if "HeadDpre" in name else "DgRows,GruInputRows" if "DgRows" in name
                            else "StackedRows,RowsThenOne" if "RowsThenOne" in name else "StackedRows") + ">"
-    m = re.search(r"spmm_staged_kernel<\(bool\)(\d), \(bool\)(\d)>", name)
+    m = re.search(r"spmm_staged_kernel<(?:\(bool\))?(\d), (?:\(bool\))?(\d)>", name)
     if m:
         return f"spmm_staged_kernel<epi={m.group(1)},gate={m.group(2)}>"
     if "spmm_staged" in name:
@@ -85,17 +88,19 @@ want = [w for w in want if w in hdr]
 name_map = {"spmm_staged_kernel<epi=1,gate=0>": "spmm_fused_fwd", "spmm_staged_kernel<epi=0,gate=1>": "spmm_fused_bwd",
             "rowgemm<RowLoader,StoreEpilogue>": "linear_tc", "rowgemm_ts<PipeFeatLoader,HeadFwdEpilogue>": "pipe_head_fwd",
             "rowgemm_ts<DpreLoader,HeadBwdEpilogue>": "pipe_head_bwd_dx", "tgrad<StackedRows>": "wgrad_tc",
-            "tgrad<HeadDpre,HeadFeatOnes>": "pipe_head_bwd_w", "node_init_fwd_kernel": "node_init_fwd",
+            "tgrad<HeadDpre,HeadFeatOnes>": "pipe_head_bwd_w", "head_dw2_kernel": "pipe_head_bwd_w",
+            "pipe_head_fwd_kernel": "pipe_head_fwd", "pipe_head_bwd_dx_kernel": "pipe_head_bwd_dx",
+            "node_init_fwd_kernel": "node_init_fwd",
             "gate_extract_kernel": "node_init_bwd(gate_extract)", "mean_pool_kernel": "mean_pool_fwd",
             "pool_bwd_fill_kernel": "mean_pool_bwd"}
 table = [["kernel"] + want]
-traffic = collections.defaultdict(list)
+traffic = collections.defaultdict(lambda: collections.defaultdict(list))  # op -> kernel -> bytes per launch
 mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
 for r in rows[2:]:
     s = short(r[hdr.index("Kernel Name")])
     table.append([s] + [r[hdr.index(w)] for w in want])
-    if s in name_map:
-        traffic[name_map[s]].append((float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")])) * mult)
+    if s in name_map and float(r[hdr.index("gpu__time_duration.sum")]) * {"us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "ns": 1e-3, "nsecond": 1e-3}.get(units[hdr.index("gpu__time_duration.sum")], 1) > 60:
+        traffic[name_map[s]][s].append((float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")])) * mult)
 with open(REPO / "profiles" / f"{tag}_kernels_ncu_full.csv", "w", newline="") as f:
     w = csv.writer(f)
     w.writerow([f"# ncu --set full --clock-control none; one GNN-stack fwd+bwd at B=4096, L-TOWN-A, D=64, P=764 (tools/prof_step.py 4096 2); units "
@@ -103,8 +108,8 @@ with open(REPO / "profiles" / f"{tag}_kernels_ncu_full.csv", "w", newline="") as
     w.writerows(table)
 tpath = REPO / "profiles" / "ncu_traffic.json"
 t = json.loads(tpath.read_text()) if tpath.exists() else {"B4096_P764": {}}
-for k, v in traffic.items():
-    t["B4096_P764"][k.split("(")[0]] = sum(v) / len(v)
+for k, per_kernel in traffic.items():  # an op's traffic = sum over its kernels of the mean bytes per launch
+    t["B4096_P764"][k.split("(")[0]] = sum(sum(v) / len(v) for v in per_kernel.values())
 tpath.write_text(json.dumps(t, indent=1))
 for row in table[1:]:
     print(row[:6])
