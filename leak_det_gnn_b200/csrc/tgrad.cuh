@@ -15,6 +15,8 @@
 //   warps 17-20 final read-out
 #pragma once
 
+#include <type_traits>
+
 #include "umma.cuh"
 
 namespace ltgnn {
@@ -125,14 +127,56 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         const int rx = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qx = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
         const int x4 = No / 4;
         constexpr bool kPipe = (kGJ + kXJ) <= 6;
+        // chunk j of a thread: q, q + 8, ... for the 8-threads-per-row mapping; for kRowFast sources the warp owns
+        // PAIRS of neighbouring chunks (2 q, 2 q + 1, 2 q + 16, ...) so that the store below can be conflict-free
+        static_assert(!GLoader::kRowFast || kGJ % 2 == 0, "kRowFast operands need an even chunk count");
+        static_assert(!XLoader::kRowFast || kXJ % 2 == 0, "kRowFast operands need an even chunk count");
+        auto cg = [&](int j) { return GLoader::kRowFast ? 2 * qg + (j & 1) + 16 * (j >> 1) : qg + 8 * j; };
+        auto cx = [&](int j) { return XLoader::kRowFast ? 2 * qx + (j & 1) + 16 * (j >> 1) : qx + 8 * j; };
         float4 gv[kGJ], xv[kXJ];
         auto fetch = [&](uint32_t ch, float4 (&gd)[kGJ], float4 (&xd)[kXJ]) {
             const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
 #pragma unroll
-            for (int j = 0; j < kGJ; ++j) gd[j] = row_g < M ? gload(row_g, qg + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kGJ; ++j) gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < kXJ; ++j)
-                xd[j] = (row_x < M && qx + 8 * j < x4) ? xload(row_x, qx + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xd[j] = (row_x < M && cx(j) < x4) ? xload(row_x, cx(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        // store one operand's chunks (hi and lo).  kRowFast: the 32 lanes of a warp hold 32 rows of the SAME chunk,
+        // whose swizzled offsets share only 4 bank groups (2-way conflicts on every quarter-warp).  Lanes whose row
+        // has bit 2 set therefore store the two chunks of a pair in the opposite order: a quarter-warp then covers
+        // both parities x 4 swizzle phases = all 8 bank groups.
+        auto store = [&](auto fast, const auto& v, int nj, int r, auto cj, int climit, uint8_t* hi_base, uint8_t* lo_base) {
+            if constexpr (decltype(fast)::value) {
+                const bool swap = (r >> 2) & 1;
+#pragma unroll
+                for (int j = 0; j < nj; j += 2) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const bool second = swap != (h == 1);
+                        const float4 val = second ? v[j + 1] : v[j];
+                        const int c = cj(j) + (second ? 1 : 0);
+                        if (c < climit) {
+                            float4 hi, lo;
+                            split4(val, hi, lo);
+                            const uint32_t off = mn_offset(r, c, kChunk);
+                            *reinterpret_cast<float4*>(hi_base + off) = hi;
+                            *reinterpret_cast<float4*>(lo_base + off) = lo;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < nj; ++j) {
+                    if (cj(j) < climit) {
+                        float4 hi, lo;
+                        split4(v[j], hi, lo);
+                        const uint32_t off = mn_offset(r, cj(j), kChunk);
+                        *reinterpret_cast<float4*>(hi_base + off) = hi;
+                        *reinterpret_cast<float4*>(lo_base + off) = lo;
+                    }
+                }
+            }
         };
         uint32_t use = 0;
         if (kPipe && c_begin + grp < c_end) fetch(c_begin + grp, gv, xv);
@@ -148,24 +192,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                 fetch(ch, gc, xc);
             }
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
-#pragma unroll
-            for (int j = 0; j < kGJ; ++j) {
-                float4 hi, lo;
-                split4(gc[j], hi, lo);
-                const uint32_t off = mn_offset(rg, qg + 8 * j, kChunk);
-                *reinterpret_cast<float4*>(g_hi + off) = hi;
-                *reinterpret_cast<float4*>(g_lo + off) = lo;
-            }
-#pragma unroll
-            for (int j = 0; j < kXJ; ++j) {
-                if (qx + 8 * j < x4) {
-                    float4 hi, lo;
-                    split4(xc[j], hi, lo);
-                    const uint32_t off = mn_offset(rx, qx + 8 * j, kChunk);
-                    *reinterpret_cast<float4*>(x_hi + off) = hi;
-                    *reinterpret_cast<float4*>(x_lo + off) = lo;
-                }
-            }
+            store(std::integral_constant<bool, GLoader::kRowFast>{}, gc, kGJ, rg, cg, kG / 4, g_hi, g_lo);
+            store(std::integral_constant<bool, XLoader::kRowFast>{}, xc, kXJ, rx, cx, x4, x_hi, x_lo);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[grp]);
