@@ -32,6 +32,7 @@ constexpr int H = 64;            // hidden size supported by this kernel
 constexpr int KA = 96;           // augmented K: h(64) | x | tf(F <= 29) | 1 | pad
 constexpr int NG = 4 * H;        // 256 accumulator columns
 constexpr int kGateWarps = 8;
+constexpr int kAuxIn = 31;       // x + up to 30 time features, held in registers one step ahead
 constexpr int kMmaWarp = kGateWarps;
 constexpr int kThreads = (kGateWarps + 1) * 32;
 constexpr uint32_t kAccCol = 0, kAhiCol = NG, kAloCol = NG + KA;  // TMEM column map (448 of 512 used)
@@ -155,16 +156,24 @@ gru_fwd_kernel(const GruParams p) {
                     tmem_st16(tmem + lane_off + kAloCol + 16 * (half + 2 * pass), z16);
                 }
             }
-            auto store_aux = [&](int t) {  // columns 64..95 of A for step t (half 0 warps only)
+            // columns 64..95 of A for step t (half 0 warps only).  The inputs do not depend on the recurrence: they
+            // are fetched one step ahead (load_aux at the top of step t - 1) so that their L2 / HBM latency is not
+            // paid between the last gate and the next MMA.
+            float xin[kAuxIn];
+            auto load_aux = [&](int t) {
+#pragma unroll
+                for (int j = 0; j < kAuxIn; ++j) xin[j] = 0.f;
+                if (valid && t < p.L) {
+                    xin[0] = __ldg(rp + static_cast<size_t>(t) * p.S);
+#pragma unroll
+                    for (int j = 1; j < kAuxIn; ++j)  // compile-time register indices
+                        if (j <= p.F) xin[j] = __ldg(tp + static_cast<size_t>(t) * p.F + (j - 1));
+                }
+            };
+            auto store_aux = [&]() {
                 float a[32], lo[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = 0.f;
-                if (valid && t < p.L) {
-                    a[0] = __ldg(rp + static_cast<size_t>(t) * p.S);
-#pragma unroll
-                    for (int j = 1; j < 31; ++j)  // compile-time register indices; F <= 30
-                        if (j <= p.F) a[j] = __ldg(tp + static_cast<size_t>(t) * p.F + (j - 1));
-                }
+                for (int j = 0; j < 32; ++j) a[j] = j < kAuxIn ? xin[j] : 0.f;
                 // the constant-one column sits right after the time features
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -176,7 +185,10 @@ gru_fwd_kernel(const GruParams p) {
                 rowgemm_ts::tmem_st32(tmem + lane_off + kAhiCol + H, a);
                 rowgemm_ts::tmem_st32(tmem + lane_off + kAloCol + H, lo);
             };
-            if (half == 0) store_aux(0);
+            if (half == 0) {
+                load_aux(0);
+                store_aux();
+            }
             tmem_wait_st();
             fence_before_sync();
             __syncwarp();
@@ -184,6 +196,7 @@ gru_fwd_kernel(const GruParams p) {
 
             for (int t = 0; t < p.L; ++t) {
                 const size_t row = static_cast<size_t>(t) * p.Qp + q;
+                if (half == 0) load_aux(t + 1);  // in flight while this step's MMAs and gates run
                 float hhi[32], hlo[32];
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
@@ -237,7 +250,7 @@ gru_fwd_kernel(const GruParams p) {
                         tmem_st16(tmem + lane_off + kAhiCol + 16 * (half + 2 * pass), hhi + 16 * pass);
                         tmem_st16(tmem + lane_off + kAloCol + 16 * (half + 2 * pass), hlo + 16 * pass);
                     }
-                    if (half == 0) store_aux(t + 1);
+                    if (half == 0) store_aux();
                     tmem_wait_st();
                     fence_before_sync();
                     __syncwarp();
@@ -483,7 +496,7 @@ extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_
     LTGNN_REQUIRE(B >= 0 && L > 0 && S > 0 && F >= 0, LTGNN_E_ARG, "gru_fwd: B=%lld L=%d S=%d F=%d",
                   static_cast<long long>(B), L, S, F);
     LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_fwd: hidden size %d not supported (64 only)", Hdim);
-    LTGNN_REQUIRE(H + 1 + F + 1 <= KA, LTGNN_E_SHAPE, "gru_fwd: %d time features do not fit the fused operand", F);
+    LTGNN_REQUIRE(H + 1 + F + 1 <= KA && 1 + F <= kAuxIn, LTGNN_E_SHAPE, "gru_fwd: %d time features do not fit the fused operand", F);
     LTGNN_REQUIRE(B * S < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_fwd: too many sequences");
     if (B == 0) return LTGNN_OK;
     LTGNN_REQUIRE(r && w_ih && w_hh && b_ih && b_hh && h_last && (tf || F == 0), LTGNN_E_ARG, "gru_fwd: null tensor");
