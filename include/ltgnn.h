@@ -197,6 +197,14 @@ int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_
                   float* hseq, float* gates, void* stream);
 int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t H, const float* w_hh, const float* gates,
                      const float* hseq, const float* dh_last, float* dG, void* stream);
+/* Recompute form of the BPTT: the forward saves only hseq (pass gates = NULL to gru_fwd), the gates are rebuilt per step
+ * from h_{t-1} on the tensor cores.  gru_inproj: P [B*L, 3H] = W_ih[:, 1:] tf + b_ih (+ b_hh for the r and z rows), the
+ * part of the pre-activations the S sensors of a window share.  gru_bwd_dg_rc: same dG as gru_bwd_dg. */
+int ltgnn_gru_inproj(int device, int64_t B, int32_t L, int32_t F, int32_t H, const float* tf, const float* w_ih,
+                     const float* b_ih, const float* b_hh, float* P, void* stream);
+int ltgnn_gru_bwd_dg_rc(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t H, const float* r,
+                        const float* w_ih, const float* w_hh, const float* b_hh, const float* P, const float* hseq,
+                        const float* dh_last, float* dG, void* stream);
 int64_t ltgnn_gru_ws_floats(int device);
 int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t H, const float* r, const float* tf,
                     const float* hseq, const float* dG, float* dBfused, float* ws, void* stream);

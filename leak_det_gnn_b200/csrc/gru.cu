@@ -488,6 +488,296 @@ gru_bwd_kernel(const GruBwdParams p) {
     }
 }
 
+
+// =====================================================================================================
+// backward through time WITHOUT saved gates ("recompute" form).  The forward then saves only the states
+// (8.75 GB at B*S = 118 784, L = 288 instead of 43.8 GB), and the BPTT kernel reads 8.75 GB instead of 43.8 GB.
+// Per step t and tile of 128 sequences:
+//   pre[r | z | hn] = h_{t-1} W_hh^T                       tcgen05, A = h_{t-1} (hi / lo) in TMEM, 192 columns
+//   r, z = sigma(pre + P + w_x x_t),  hn = pre + b_hn,  n = tanh(P_in + w_xn x_t + r hn)
+//       P[b, t, :] = W_ih[:, 1:] tf_t + b_ih (+ b_hh for r, z) is shared by the S sensors of a window and comes from a
+//       small pre-pass (gru_inproj_kernel, 0.9 GB); w_x = W_ih[:, 0] and b_hn live in shared memory
+//   dG(t) as in gru_bwd_kernel -> HBM;  dh_{t-1} = dh z + [dr | dz | dhn] W_hh      (second tcgen05 round trip)
+// Tensor memory (448 columns): dh accumulator 64 | pre-activations 192, reused for dG lo | h_{t-1} hi+lo 128, reused
+// (192) for dG hi.  Every reuse is by the thread that owned the columns, after the MMA that read them has committed.
+// =====================================================================================================
+constexpr uint32_t kR_accDh = 0, kR_accR = H, kR_a = H + KB;  // 64 | 192 | 192
+
+struct GruBwdRcParams {
+    const float* w_hh;     // [3H, H]
+    const float* w_ih;     // [3H, 1 + F]
+    const float* b_hh;     // [3H]
+    const float* P;        // [B * L, 3H] input projections (r | z | in)
+    const float* r;        // [B, L, S] inputs
+    const float* hseq;     // blocked-32 [L * Qp, H]
+    const float* dh_last;  // [Q, H]
+    float* dG;             // blocked-32 [L * Qp, 4H]
+    uint32_t Q, Qp;
+    int L, S, F;
+    uint64_t magic_s;
+};
+
+// P[(b L + t), n] = b_ih[n] (+ b_hh[n] for the r and z rows) + sum_f W_ih[n, 1 + f] tf[b, t, f]
+__global__ void __launch_bounds__(KB)
+gru_inproj_kernel(const float* __restrict__ tf, const float* __restrict__ w_ih, const float* __restrict__ b_ih,
+                  const float* __restrict__ b_hh, float* __restrict__ P, int64_t rows, int F) {
+    // thread n keeps its weight row and bias in registers and walks the (b, t) rows: coalesced 768-byte stores
+    const int n = threadIdx.x, fi = 1 + F;
+    float w[kAuxIn];
+#pragma unroll
+    for (int f = 0; f < kAuxIn - 1; ++f) w[f] = f < F ? __ldg(w_ih + n * fi + 1 + f) : 0.f;
+    const float bias = __ldg(b_ih + n) + (n < 2 * H ? __ldg(b_hh + n) : 0.f);
+    for (int64_t row0 = static_cast<int64_t>(blockIdx.x) * 4; row0 < rows; row0 += static_cast<int64_t>(gridDim.x) * 4) {
+        float acc[4];  // four rows in flight: the loop is a chain of dependent-latency loads otherwise
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            acc[u] = bias;
+            if (row0 + u < rows) {
+#pragma unroll
+                for (int f = 0; f < kAuxIn - 1; ++f)
+                    if (f < F) acc[u] = fmaf(w[f], __ldg(tf + (row0 + u) * F + f), acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (row0 + u < rows) P[(row0 + u) * KB + n] = acc[u];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gru_bwd_rc_kernel(const GruBwdRcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_a1, bar_a2, bar_r, bar_d;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float4 wx_s[KB / 4], bhn_s[H / 4];  // W_ih[:, 0] (r | z | n rows), b_hh of the n rows
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b1_hi = smem;                  // B1[n = gate row (192)][k = h column (64)] = w_hh[n][k], K-major SW128
+    uint8_t* b1_lo = b1_hi + KB * H * 4;
+    uint8_t* b2_hi = b1_lo + KB * H * 4;    // B2[n = h column (64)][k = gate row (192)] = w_hh[k][n], K-major SW128
+    uint8_t* b2_lo = b2_hi + H * KB * 4;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        mbar_init(&bar_a1, kGateWarps);
+        mbar_init(&bar_a2, kGateWarps);
+        mbar_init(&bar_r, 1);
+        mbar_init(&bar_d, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < KB * H; i += kThreads) {
+        const int k = i / H, n = i - k * H;  // w_hh[k][n]: k = gate row, n = h column
+        const float w = __ldg(p.w_hh + i);
+        const float hi = tf32_hi(w), lo = w - hi;
+        const uint32_t o2 = sw128_offset(n, k >> 2, H) + (k & 3) * 4;
+        *reinterpret_cast<float*>(b2_hi + o2) = hi;
+        *reinterpret_cast<float*>(b2_lo + o2) = lo;
+        const uint32_t o1 = sw128_offset(k, n >> 2, KB) + (n & 3) * 4;
+        *reinterpret_cast<float*>(b1_hi + o1) = hi;
+        *reinterpret_cast<float*>(b1_lo + o1) = lo;
+    }
+    if (tid < KB) reinterpret_cast<float*>(wx_s)[tid] = __ldg(p.w_ih + tid * (1 + p.F));
+    if (tid < H) reinterpret_cast<float*>(bhn_s)[tid] = __ldg(p.b_hh + 2 * H + tid);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t n_tiles = (p.Q + 127) / 128;
+    uint32_t ph = 0;  // one phase bit serves all four barriers: each completes exactly once per step
+
+    if (warp < kGateWarps) {
+        const int quad = warp & 3, half = warp >> 2;
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int j0 = half * 32;
+        const float4* h4 = reinterpret_cast<const float4*>(p.hseq);
+        float4* dg4 = reinterpret_cast<float4*>(p.dG);
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t q = tile * 128 + quad * 32 + lane;
+            const bool valid = q < p.Q;
+            const uint32_t b = p.magic_s ? fastdiv(valid ? q : 0, p.magic_s) : (valid ? q : 0);
+            const uint32_t sidx = (valid ? q : 0) - b * p.S;
+            const float* xr = p.r + static_cast<size_t>(b) * p.L * p.S + sidx;          // + t * S
+            const float4* Pb = reinterpret_cast<const float4*>(p.P) + static_cast<size_t>(b) * p.L * (KB / 4);  // + t * 48
+            float dh[32], hm[32];
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.dh_last + static_cast<size_t>(valid ? q : 0) * H + j0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dh[4 * j] = v.x; dh[4 * j + 1] = v.y; dh[4 * j + 2] = v.z; dh[4 * j + 3] = v.w;
+                }
+            }
+            auto load_h = [&](int t) {  // h_{t-1}[j0 .. j0 + 32): zero for t = 0 and for pad rows
+                const size_t prow = static_cast<size_t>(t > 0 ? t - 1 : 0) * p.Qp + q;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = (valid && t > 0) ? ldg_stream(h4 + b32(prow, (j0 >> 2) + j, H / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    hm[4 * j] = v.x; hm[4 * j + 1] = v.y; hm[4 * j + 2] = v.z; hm[4 * j + 3] = v.w;
+                }
+            };
+            load_h(p.L - 1);
+            for (int t = p.L - 1; t >= 0; --t) {
+                const size_t row = static_cast<size_t>(t) * p.Qp + q;
+                // Nothing below depends on the recurrence except dh, so everything streamed is requested early:
+                //  * the three 128-byte lines of P this thread reads after the first GEMM go to L1 now (the lanes of
+                //    a window ask for the same lines; first touch would otherwise pay HBM latency inside the step);
+                //  * the states the NEXT step's load_h fetches go to L2 now, one lane per 128-byte line.
+                {
+                    const float4* Pn = Pb + static_cast<size_t>(t) * (KB / 4) + (j0 >> 2);
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) asm volatile("prefetch.global.L1 [%0];" ::"l"(Pn + g * (H / 4)));
+                    if (t > 1 && valid && (lane & 7) == 0) {
+                        const size_t prow = static_cast<size_t>(t - 2) * p.Qp + q;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(h4 + b32(prow, (j0 >> 2) + j, H / 4)));
+                    }
+                }
+                // ---- A = h_{t-1} (hi | lo), this thread's 32 of the 64 columns
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { hi[j] = tf32_hi(hm[c + j]); lo[j] = hm[c + j] - hi[j]; }
+                    tmem_st16(tmem + lane_off + kR_a + j0 + c, hi);
+                    tmem_st16(tmem + lane_off + kR_a + H + j0 + c, lo);
+                }
+                tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a1);
+                const float x = valid ? __ldg(xr + static_cast<size_t>(t) * p.S) : 0.f;
+                const float4* Pt = Pb + static_cast<size_t>(t) * (KB / 4);
+                mbar_wait(&bar_r, ph);
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    const int f0 = (j0 + c) >> 2;  // float4 index of this chunk inside a 64-wide group
+                    float r[16], z[16], n[16], hn[16];
+                    auto gate_in = [&](int g, float (&out)[16]) {  // P + w_x x for gate group g (0 r, 1 z, 2 n)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 pp = __ldg(Pt + g * (H / 4) + f0 + j), ww = wx_s[g * (H / 4) + f0 + j];
+                            out[4 * j] = fmaf(ww.x, x, pp.x); out[4 * j + 1] = fmaf(ww.y, x, pp.y);
+                            out[4 * j + 2] = fmaf(ww.z, x, pp.z); out[4 * j + 3] = fmaf(ww.w, x, pp.w);
+                        }
+                    };
+                    {
+                        float pre[16];
+                        gate_in(0, r);
+                        tmem_ld16(tmem + lane_off + kR_accR + 0 * H + j0 + c, pre);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) r[j] = sigmoidf_fast(pre[j] + r[j]);
+                        gate_in(1, z);
+                        tmem_ld16(tmem + lane_off + kR_accR + 1 * H + j0 + c, pre);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) z[j] = sigmoidf_fast(pre[j] + z[j]);
+                        gate_in(2, n);
+                        tmem_ld16(tmem + lane_off + kR_accR + 2 * H + j0 + c, hn);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 bb = bhn_s[f0 + j];
+                            hn[4 * j] += bb.x; hn[4 * j + 1] += bb.y; hn[4 * j + 2] += bb.z; hn[4 * j + 3] += bb.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) n[j] = tanhf_fast(fmaf(r[j], hn[j], n[j]));
+                    }
+                    float dr[16], dz[16], dhn[16], din[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float g = dh[c + j];
+                        const float dnp = g * (1.f - z[j]) * (1.f - n[j] * n[j]);
+                        dz[j] = g * (hm[c + j] - n[j]) * z[j] * (1.f - z[j]);
+                        dr[j] = dnp * hn[j] * r[j] * (1.f - r[j]);
+                        dhn[j] = dnp * r[j];
+                        din[j] = dnp;
+                        dh[c + j] = g * z[j];  // the accumulator of the second GEMM is added after the wait below
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {  // pad rows carry zeros (their dh is zero)
+                        stg_stream(dg4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]));
+                        stg_stream(dg4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]));
+                        stg_stream(dg4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(dhn[4 * j], dhn[4 * j + 1], dhn[4 * j + 2], dhn[4 * j + 3]));
+                        stg_stream(dg4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(din[4 * j], din[4 * j + 1], din[4 * j + 2], din[4 * j + 3]));
+                    }
+                    // A of the second GEMM: hi over the (consumed) h_{t-1} columns, lo over the (consumed) pre-activations
+                    float lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float v = dr[j]; dr[j] = tf32_hi(v); lo[j] = v - dr[j]; }
+                    tmem_st16(tmem + lane_off + kR_a + 0 * H + j0 + c, dr);
+                    tmem_st16(tmem + lane_off + kR_accR + 0 * H + j0 + c, lo);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float v = dz[j]; dz[j] = tf32_hi(v); lo[j] = v - dz[j]; }
+                    tmem_st16(tmem + lane_off + kR_a + 1 * H + j0 + c, dz);
+                    tmem_st16(tmem + lane_off + kR_accR + 1 * H + j0 + c, lo);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { const float v = dhn[j]; dhn[j] = tf32_hi(v); lo[j] = v - dhn[j]; }
+                    tmem_st16(tmem + lane_off + kR_a + 2 * H + j0 + c, dhn);
+                    tmem_st16(tmem + lane_off + kR_accR + 2 * H + j0 + c, lo);
+                }
+                tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a2);
+                if (t > 0) load_h(t - 1);  // h_{t-2}: in flight while the second GEMM runs
+                mbar_wait(&bar_d, ph);
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    float acc[16];
+                    tmem_ld16(tmem + lane_off + kR_accDh + j0 + c, acc);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dh[c + j] += acc[j];
+                }
+                fence_before_sync();
+                ph ^= 1;
+            }
+        }
+    } else {
+        const uint32_t idesc1 = idesc_tf32(128, KB), idesc2 = idesc_tf32(128, H);
+        const uint32_t b1h = desc_lo(smem_u32(b1_hi)), b1l = desc_lo(smem_u32(b1_lo));
+        const uint32_t b2h = desc_lo(smem_u32(b2_hi)), b2l = desc_lo(smem_u32(b2_lo));
+        constexpr uint32_t kg1 = KB * 128u >> 4, kg2 = H * 128u >> 4;  // one 32-column k-atom block of B1 / B2
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int t = 0; t < p.L; ++t) {
+                mbar_wait(&bar_a1, ph);
+                fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < H / 8; ++ks) {
+                        const uint32_t boff = (ks >> 2) * kg1 + 2 * (ks & 3);
+                        mma_tf32_ts(tmem + kR_accR, tmem + kR_a + H + 8 * ks, b1h + boff, idesc1, ks == 0 ? 0u : 1u);
+                        mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1l + boff, idesc1, 1u);
+                        mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1h + boff, idesc1, 1u);
+                    }
+                    commit(&bar_r);
+                }
+                __syncwarp();
+                mbar_wait(&bar_a2, ph);
+                fence_after_sync();
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t ks = 0; ks < KB / 8; ++ks) {
+                        const uint32_t boff = (ks >> 2) * kg2 + 2 * (ks & 3);
+                        mma_tf32_ts(tmem + kR_accDh, tmem + kR_accR + 8 * ks, b2h + boff, idesc2, ks == 0 ? 0u : 1u);
+                        mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2l + boff, idesc2, 1u);
+                        mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2h + boff, idesc2, 1u);
+                    }
+                    commit(&bar_d);
+                }
+                __syncwarp();
+                ph ^= 1;
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 }  // namespace
 
 extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
@@ -539,6 +829,56 @@ extern "C" int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t Hdim, 
     const int64_t tiles = (Q + 127) / 128;
     const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
     gru_bwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_gru_inproj(int device, int64_t B, int32_t L, int32_t F, int32_t Hdim, const float* tf,
+                                const float* w_ih, const float* b_ih, const float* b_hh, float* P, void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && L > 0 && F >= 0, LTGNN_E_ARG, "gru_inproj: B=%lld L=%d F=%d", static_cast<long long>(B), L, F);
+    LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_inproj: hidden size %d not supported (64 only)", Hdim);
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(w_ih && b_ih && b_hh && P && (tf || F == 0), LTGNN_E_ARG, "gru_inproj: null tensor");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    const int64_t rows = B * L;
+    LTGNN_REQUIRE(F < kAuxIn, LTGNN_E_SHAPE, "gru_inproj: %d time features not supported", F);
+    int64_t blocks = (rows + 3) / 4;
+    const int64_t cap = static_cast<int64_t>(di->sm_count) * 10;
+    if (blocks > cap) blocks = cap;
+    gru_inproj_kernel<<<static_cast<int>(blocks), KB, 0, static_cast<cudaStream_t>(stream_)>>>(tf, w_ih, b_ih, b_hh, P,
+                                                                                                rows, F);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_gru_bwd_dg_rc(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
+                                   const float* w_ih, const float* w_hh, const float* b_hh, const float* P,
+                                   const float* hseq, const float* dh_last, float* dG, void* stream_) {
+    LTGNN_REQUIRE(B >= 0 && L > 0 && S > 0 && F >= 0, LTGNN_E_ARG, "gru_bwd_dg_rc: B=%lld L=%d S=%d F=%d",
+                  static_cast<long long>(B), L, S, F);
+    LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_bwd_dg_rc: hidden size %d not supported (64 only)", Hdim);
+    LTGNN_REQUIRE(B * S < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_bwd_dg_rc: too many sequences");
+    if (B == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(r && w_ih && w_hh && b_hh && P && hseq && dh_last && dG, LTGNN_E_ARG, "gru_bwd_dg_rc: null tensor");
+    LTGNN_REQUIRE(aligned16(P) && aligned16(hseq) && aligned16(dh_last) && aligned16(dG), LTGNN_E_ALIGN,
+                  "gru_bwd_dg_rc: 16-byte alignment required");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg_rc: device is sm_%d%d, need sm_100", di->cc_major,
+                  di->cc_minor);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    const int64_t Q = B * S;
+    GruBwdRcParams p{w_hh, w_ih, b_hh, P, r, hseq, dh_last, dG, static_cast<uint32_t>(Q),
+                     static_cast<uint32_t>((Q + 127) / 128 * 128), L, S, F,
+                     S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
+    const size_t smem = 1024 + 4ull * H * KB * 4;
+    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "gru_bwd_dg_rc: %zu B of shared memory", smem);
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_bwd_rc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles = (Q + 127) / 128;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    gru_bwd_rc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }
