@@ -4,14 +4,14 @@
 //              feat = [h_u, h_v, |h_u - h_v|] -> Linear(3D, H) -> ReLU -> Dropout -> Linear(H, 1)
 //              The reference gathers h_u / h_v into (B, P, D) tensors, concatenates a (B, P, 3D) feature
 //              tensor (2.4 GB at B = 4096, P = 764) and runs cuBLAS on it.  Here the features are formed
-//              on the fly by the loader warps of the tcgen05 row-GEMM (rowgemm.cuh) straight from the
-//              L2-resident node states; the hidden layer never leaves the SM in the forward except as the
-//              saved post-activation the backward needs.
+//              on the fly by the loader warps straight from the node states; the hidden layer never leaves
+//              the SM in the forward except as the saved post-activation the backward needs.
 //   mean pool  (models/detector.py:214-215, PyG global_mean_pool over equal-sized graphs).
 //
-// Both GEMMs run on the tensor-memory-operand skeleton (rowgemm_ts.cuh): the loaders keep one pipe row per
-// thread, split it into TF32 hi/lo in registers and tcgen05.st it into TMEM, so shared memory only holds the
-// whole weight W1 (192 KB as hi + lo) and every tile is produced exactly once.
+// Both head GEMMs keep the A operand in tensor memory (building blocks: rowgemm_ts.cuh): a thread owns one pipe
+// row (= TMEM lane), splits it into TF32 hi/lo in registers and tcgen05.st's it, so shared memory only holds the
+// whole weight W1 (192 KB as hi + lo) and every tile is produced exactly once.  Global memory is always touched
+// in 128-byte row segments; the switch to / from the row-per-thread form goes through patch.cuh.
 #include "patch.cuh"
 #include "rowgemm_ts.cuh"
 
@@ -257,19 +257,6 @@ struct DpreLoader {
     const float* dlogit;   // [M]
     const float4* w2;      // [H/4]
     float scale;
-    int h4;
-    __device__ __forceinline__ void operator()(uint32_t row, int kg, float (&v)[32]) const {
-        const float g = __ldg(dlogit + row) * scale;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 t = ptx::ldg_stream(hpost + ptx::b32(row, kg * 8 + j, h4));  // blocked-32 layout
-            const float4 w = __ldg(w2 + kg * 8 + j);
-            v[4 * j] = t.x > 0.f ? g * w.x : 0.f;
-            v[4 * j + 1] = t.y > 0.f ? g * w.y : 0.f;
-            v[4 * j + 2] = t.z > 0.f ? g * w.z : 0.f;
-            v[4 * j + 3] = t.w > 0.f ? g * w.w : 0.f;
-        }
-    }
 };
 
 __device__ __forceinline__ float sgn(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
@@ -591,7 +578,7 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
     LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(w2) && aligned16(hpost) && aligned16(dX), LTGNN_E_ALIGN,
                   "pipe_head_bwd_dx: 16-byte alignment required");
     const int64_t M = B * P;
-    DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, H / 4};
+    DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale};
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_bwd_dx: device is sm_%d%d, need sm_100",
