@@ -121,30 +121,29 @@ gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X
     const int tid = threadIdx.x;
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // kThreads % d4 == 0: a thread keeps its column group
     const int n4 = N * d4;
+    const int c = tid % d4, rstep = kThreads / d4;  // a thread keeps its float4 column: no division in the loop
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        const float4* gb = dX0 + b * n4;
-        const float4* xb = X0 + b * n4;
-        float4* dzb = dz + b * S * d4;
-        for (int i0 = tid; i0 < n4; i0 += 4 * kThreads) {
+        const float4* gb = dX0 + b * n4 + c;
+        const float4* xb = kBits ? nullptr : X0 + b * n4 + c;
+        const uint32_t* lw = kBits ? live + (b * (d4 >> 3) + (c >> 3)) * N : nullptr;
+        float4* dzb = dz + b * S * d4 + c;
+        for (int r0 = tid / d4; r0 < N; r0 += 4 * rstep) {
             float4 g[4], x[4];
             uint32_t m[4];
+            int sl[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kThreads;
-                if (i < n4) {
-                    g[u] = ptx::ldg_stream(gb + i);
-                    if (kBits) {
-                        const int r = i / d4, c = i - r * d4;
-                        m[u] = __ldg(live + (b * (d4 >> 3) + (c >> 3)) * N + r) >> (c & 7);
-                    } else {
-                        x[u] = ptx::ldg_stream(xb + i);
-                    }
+                const int r = r0 + u * rstep;
+                if (r < N) {
+                    g[u] = ptx::ldg_stream(gb + r * d4);
+                    if (kBits) m[u] = __ldg(lw + r) >> (c & 7);
+                    else x[u] = ptx::ldg_stream(xb + r * d4);
+                    sl[u] = __ldg(slot + r);
                 }
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int i = i0 + u * kThreads;
-                if (i < n4) {
+                if (r0 + u * rstep < N) {
                     if (kBits) {
                         g[u].x = (m[u] & 0x1u) ? g[u].x * gate_scale : 0.f;
                         g[u].y = (m[u] & 0x100u) ? g[u].y * gate_scale : 0.f;
@@ -157,9 +156,7 @@ gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X
                         g[u].w = x[u].w > 0.f ? g[u].w * gate_scale : 0.f;
                     }
                     csum.x += g[u].x; csum.y += g[u].y; csum.z += g[u].z; csum.w += g[u].w;
-                    const int r = i / d4, c = i - r * d4;
-                    const int sl = __ldg(slot + r);
-                    if (sl >= 0) dzb[sl * d4 + c] = g[u];
+                    if (sl[u] >= 0) dzb[sl[u] * d4] = g[u];
                 }
             }
         }

@@ -282,24 +282,39 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     return LTGNN_OK;
 }
 
-// out[r][c] (+)= sum_p ws[p][r][c_src] for a sub-rectangle of the [128][No] accumulator
-static __global__ void gather_partials_kernel(const float* __restrict__ ws, int n_parts, int part_rows, int No, int r0,
-                                              int rows, int c0, int cols, float* __restrict__ out, int ld_out,
-                                              int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    const int r = i / cols, c = i - r * cols;
-    const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c;
-    float t = accumulate ? out[r * ld_out + c] : 0.f;
-    for (int p = 0; p < n_parts; ++p) t += ws[static_cast<size_t>(p) * part_rows * No + src];
-    out[r * ld_out + c] = t;
+// out[r][c] (+)= sum_p ws[p][r][c_src] for a sub-rectangle of the [128][No] accumulator.  The partials of one output
+// are summed by kGatherY threads (thread y takes p = y, y + kGatherY, ...: independent loads in flight instead of one
+// chain of ~150 dependent-latency loads) and combined in a fixed order: deterministic.
+constexpr int kGatherX = 64, kGatherY = 8;
+static __global__ void __launch_bounds__(kGatherX * kGatherY)
+gather_partials_kernel(const float* __restrict__ ws, int n_parts, int part_rows, int No, int r0, int rows, int c0, int cols,
+                       float* __restrict__ out, int ld_out, int accumulate) {
+    __shared__ float red[kGatherY][kGatherX];
+    const int x = threadIdx.x % kGatherX, y = threadIdx.x / kGatherX;
+    const int i = blockIdx.x * kGatherX + x;
+    float t = 0.f;
+    int r = 0, c = 0;
+    if (i < rows * cols) {
+        r = i / cols;
+        c = i - r * cols;
+        const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c, stride = static_cast<size_t>(part_rows) * No;
+        for (int p = y; p < n_parts; p += kGatherY) t += ws[p * stride + src];
+    }
+    red[y][x] = t;
+    __syncthreads();
+    if (y == 0 && i < rows * cols) {
+        float s = accumulate ? out[r * ld_out + c] : 0.f;
+#pragma unroll
+        for (int k = 0; k < kGatherY; ++k) s += red[k][x];
+        out[r * ld_out + c] = s;
+    }
 }
 
 inline int gather(const float* ws, int n_parts, int No, int r0, int rows, int c0, int cols, float* out, int ld_out,
                   int accumulate, cudaStream_t stream, int part_rows = kMo) {
     const int n = rows * cols;
-    gather_partials_kernel<<<(n + 127) / 128, 128, 0, stream>>>(ws, n_parts, part_rows, No, r0, rows, c0, cols, out, ld_out,
-                                                                accumulate);
+    gather_partials_kernel<<<(n + kGatherX - 1) / kGatherX, kGatherX * kGatherY, 0, stream>>>(
+        ws, n_parts, part_rows, No, r0, rows, c0, cols, out, ld_out, accumulate);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }
