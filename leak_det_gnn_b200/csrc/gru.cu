@@ -46,7 +46,8 @@ struct GruParams {
     const float* b_hh;   // [3H]
     float* h_last;       // [Q, H]
     float* hseq;         // blocked-32 [L * Qp, H] or nullptr
-    float* gates;        // blocked-32 [L * Qp, 4H] (r | z | n | W_hn h + b_hn) or nullptr: saved for the backward
+    float* gates;        // blocked-32 [L * Qp, 4H] (r | z | n | W_hn h + b_hn), or 3H without the last group, or nullptr
+    int gates_w4;        // float4 per saved gates row: 64 (four groups) or 48 (r | z | n: hn is rebuilt by the backward)
     uint32_t Q;          // B * S sequences
     uint32_t Qp;         // Q rounded up to a multiple of 128
     int L, S, F;
@@ -69,6 +70,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
           "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15])
         : "memory");
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3])
+                 : "memory");
 }
 
 // element (n, k) of the fused operand described in the file header.  Rows are ordered in 4 blocks of 64 so that
@@ -224,12 +231,14 @@ gru_fwd_kernel(const GruParams p) {
                     const int f0 = 4 * u;  // float4 index of unit 16 u within a 64-wide group
                     if (p.gates) {
                         float4* g4 = reinterpret_cast<float4*>(p.gates);
+                        const int w4 = p.gates_w4;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            stg_stream(g4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]));
-                            stg_stream(g4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(zz[4 * j], zz[4 * j + 1], zz[4 * j + 2], zz[4 * j + 3]));
-                            stg_stream(g4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]));
-                            stg_stream(g4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]));
+                            stg_stream(g4 + b32(row, 0 * (H / 4) + f0 + j, w4), make_float4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]));
+                            stg_stream(g4 + b32(row, 1 * (H / 4) + f0 + j, w4), make_float4(zz[4 * j], zz[4 * j + 1], zz[4 * j + 2], zz[4 * j + 3]));
+                            stg_stream(g4 + b32(row, 2 * (H / 4) + f0 + j, w4), make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]));
+                            if (w4 == H)
+                                stg_stream(g4 + b32(row, 3 * (H / 4) + f0 + j, w4), make_float4(hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]));
                         }
                     }
                     if (p.hseq) {
@@ -544,7 +553,229 @@ gru_inproj_kernel(const float* __restrict__ tf, const float* __restrict__ w_ih, 
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+// =====================================================================================================
+// backward through time with r | z | n saved and hn = W_hn h_{t-1} + b_hn rebuilt per step (one extra 64-column
+// tcgen05 GEMM, no transcendental): the forward writes and the BPTT reads 8.75 GB less than with four saved
+// groups, at the price of a second MMA round trip that stays under the HBM time of the step.
+// Tensor memory as in gru_bwd_rc_kernel (the 64 hn columns sit at the start of the dG-lo region).
+// =====================================================================================================
+constexpr int kDg3W4 = 3 * H / 4;  // float4 per row of the saved r | z | n
+constexpr int kGateWarpsHn = 16, kThreadsHn = kGateWarpsHn * 32;  // 4 gate warps per scheduler hide the loads
+struct GruBwdHnParams {
+    const float* w_hh;     // [3H, H]
+    const float* b_hh;     // [3H]
+    const float* gates;    // blocked-32 [L * Qp, 3H]: r | z | n
+    const float* hseq;     // blocked-32 [L * Qp, H]
+    const float* dh_last;  // [Q, H]
+    float* dG;             // blocked-32 [L * Qp, 4H]
+    uint32_t Q, Qp;
+    int L;
+};
+
+__global__ void __launch_bounds__(kThreadsHn, 1)
+gru_bwd_hn_kernel(const GruBwdHnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_a1, bar_a2, bar_r, bar_d;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float4 bhn_s[H / 4];  // b_hh of the n rows
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b1_hi = smem;                  // B1[n = unit (64)][k = h column (64)] = w_hh[2H + n][k], K-major SW128
+    uint8_t* b1_lo = b1_hi + H * H * 4;
+    uint8_t* b2_hi = b1_lo + H * H * 4;     // B2[n = h column (64)][k = gate row (192)] = w_hh[k][n], K-major SW128
+    uint8_t* b2_lo = b2_hi + H * KB * 4;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        mbar_init(&bar_a1, kGateWarpsHn);
+        mbar_init(&bar_a2, kGateWarpsHn);
+        mbar_init(&bar_r, 1);
+        mbar_init(&bar_d, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < KB * H; i += kThreadsHn) {
+        const int k = i / H, n = i - k * H;  // w_hh[k][n]: k = gate row, n = h column
+        const float w = __ldg(p.w_hh + i);
+        const float hi = tf32_hi(w), lo = w - hi;
+        const uint32_t o2 = sw128_offset(n, k >> 2, H) + (k & 3) * 4;
+        *reinterpret_cast<float*>(b2_hi + o2) = hi;
+        *reinterpret_cast<float*>(b2_lo + o2) = lo;
+        if (k >= 2 * H) {
+            const uint32_t o1 = sw128_offset(k - 2 * H, n >> 2, H) + (n & 3) * 4;
+            *reinterpret_cast<float*>(b1_hi + o1) = hi;
+            *reinterpret_cast<float*>(b1_lo + o1) = lo;
+        }
+    }
+    if (tid < H) reinterpret_cast<float*>(bhn_s)[tid] = __ldg(p.b_hh + 2 * H + tid);
+    fence_proxy_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t n_tiles = (p.Q + 127) / 128;
+    uint32_t ph = 0;  // one phase bit serves all four barriers: each completes exactly once per step
+
+    {
+        // 16 gate warps: thread = one sequence (TMEM lane) x 16 hidden units [16 part, +16).  Warp 0 also issues the
+        // two GEMMs of a step (it would only wait for them otherwise): 16 warps = 4 per scheduler, 128 registers each.
+        const uint32_t idesc1 = idesc_tf32(128, H), idesc2 = idesc_tf32(128, H);
+        const uint32_t b1h = desc_lo(smem_u32(b1_hi)), b1l = desc_lo(smem_u32(b1_lo));
+        const uint32_t b2h = desc_lo(smem_u32(b2_hi)), b2l = desc_lo(smem_u32(b2_lo));
+        constexpr uint32_t kg1 = H * 128u >> 4, kg2 = H * 128u >> 4;  // one 32-column k-atom block of B1 / B2
+        const int quad = warp & 3, part = warp >> 2;
+        const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+        const int j0 = part * 16;
+        const float4* h4 = reinterpret_cast<const float4*>(p.hseq);
+        float4* dg4 = reinterpret_cast<float4*>(p.dG);
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t q = tile * 128 + quad * 32 + lane;
+            const bool valid = q < p.Q;
+            const float4* g4 = reinterpret_cast<const float4*>(p.gates);
+            float dh[16], hm[16];
+            {
+                const float4* src = reinterpret_cast<const float4*>(p.dh_last + static_cast<size_t>(valid ? q : 0) * H + j0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dh[4 * j] = v.x; dh[4 * j + 1] = v.y; dh[4 * j + 2] = v.z; dh[4 * j + 3] = v.w;
+                }
+            }
+            auto load_h = [&](int t) {  // h_{t-1}[j0 .. j0 + 16): zero for t = 0 and for pad rows
+                const size_t prow = static_cast<size_t>(t > 0 ? t - 1 : 0) * p.Qp + q;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = (valid && t > 0) ? ldg_stream(h4 + b32(prow, (j0 >> 2) + j, H / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    hm[4 * j] = v.x; hm[4 * j + 1] = v.y; hm[4 * j + 2] = v.z; hm[4 * j + 3] = v.w;
+                }
+            };
+            load_h(p.L - 1);
+            for (int t = p.L - 1; t >= 0; --t) {
+                const size_t row = static_cast<size_t>(t) * p.Qp + q;
+                // ---- A = h_{t-1} (hi | lo), this thread's 16 of the 64 columns
+#pragma unroll
+                for (int c = 0; c < 16; c += 16) {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) { hi[j] = tf32_hi(hm[c + j]); lo[j] = hm[c + j] - hi[j]; }
+                    tmem_st16(tmem + lane_off + kR_a + j0 + c, hi);
+                    tmem_st16(tmem + lane_off + kR_a + H + j0 + c, lo);
+                }
+                tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a1);
+                {
+                    const int f0 = j0 >> 2;  // float4 index of this thread's units inside a 64-wide group
+                    // saved r | z | n: requested before the first GEMM is waited for
+                    float4 r4[4], z4[4], n4[4];
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        r4[j] = valid ? ldg_stream(g4 + b32(row, 0 * (H / 4) + f0 + j, kDg3W4)) : zero;
+                        z4[j] = valid ? ldg_stream(g4 + b32(row, 1 * (H / 4) + f0 + j, kDg3W4)) : zero;
+                        n4[j] = valid ? ldg_stream(g4 + b32(row, 2 * (H / 4) + f0 + j, kDg3W4)) : zero;
+                    }
+                    if (warp == 0) {  // hn pre-activations = h_{t-1} W_hn^T
+                        mbar_wait(&bar_a1, ph);
+                        fence_after_sync();
+                        if (elect_one()) {
+#pragma unroll
+                            for (uint32_t ks = 0; ks < H / 8; ++ks) {
+                                const uint32_t boff = (ks >> 2) * kg1 + 2 * (ks & 3);
+                                mma_tf32_ts(tmem + kR_accR, tmem + kR_a + H + 8 * ks, b1h + boff, idesc1, ks == 0 ? 0u : 1u);
+                                mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1l + boff, idesc1, 1u);
+                                mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1h + boff, idesc1, 1u);
+                            }
+                            commit(&bar_r);
+                        }
+                        __syncwarp();
+                    }
+                    mbar_wait(&bar_r, ph);
+                    fence_after_sync();
+                    float hn[16];
+                    tmem_ld16(tmem + lane_off + kR_accR + j0, hn);
+                    // four units at a time: dG to HBM, its hi / lo to tensor memory (hi over the consumed h_{t-1}
+                    // columns, lo over the consumed hn columns), so that no 16-wide temporaries stay live
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = bhn_s[f0 + j];
+                        const float rr[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w}, zz[4] = {z4[j].x, z4[j].y, z4[j].z, z4[j].w};
+                        const float nn[4] = {n4[j].x, n4[j].y, n4[j].z, n4[j].w}, bh[4] = {bb.x, bb.y, bb.z, bb.w};
+                        float dr[4], dz[4], dhn[4], din[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float g = dh[4 * j + e], hv = hn[4 * j + e] + bh[e];
+                            const float dnp = g * (1.f - zz[e]) * (1.f - nn[e] * nn[e]);
+                            dz[e] = g * (hm[4 * j + e] - nn[e]) * zz[e] * (1.f - zz[e]);
+                            dr[e] = dnp * hv * rr[e] * (1.f - rr[e]);
+                            dhn[e] = dnp * rr[e];
+                            din[e] = dnp;
+                            dh[4 * j + e] = g * zz[e];  // the accumulator of the second GEMM is added after the wait below
+                        }
+                        // pad rows carry zeros (their dh is zero)
+                        stg_stream(dg4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(dr[0], dr[1], dr[2], dr[3]));
+                        stg_stream(dg4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(dz[0], dz[1], dz[2], dz[3]));
+                        stg_stream(dg4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(dhn[0], dhn[1], dhn[2], dhn[3]));
+                        stg_stream(dg4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(din[0], din[1], din[2], din[3]));
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dr[e]); lo[e] = dr[e] - hi[e]; }
+                        tmem_st4(tmem + lane_off + kR_a + 0 * H + j0 + 4 * j, hi);
+                        tmem_st4(tmem + lane_off + kR_accR + 0 * H + j0 + 4 * j, lo);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dz[e]); lo[e] = dz[e] - hi[e]; }
+                        tmem_st4(tmem + lane_off + kR_a + 1 * H + j0 + 4 * j, hi);
+                        tmem_st4(tmem + lane_off + kR_accR + 1 * H + j0 + 4 * j, lo);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dhn[e]); lo[e] = dhn[e] - hi[e]; }
+                        tmem_st4(tmem + lane_off + kR_a + 2 * H + j0 + 4 * j, hi);
+                        tmem_st4(tmem + lane_off + kR_accR + 2 * H + j0 + 4 * j, lo);
+                    }
+                }
+                tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_a2);
+                if (t > 0) load_h(t - 1);  // h_{t-2}: in flight while the second GEMM runs
+                if (warp == 0) {  // dh_{t-1} += [dr | dz | dhn] W_hh
+                    mbar_wait(&bar_a2, ph);
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (uint32_t ks = 0; ks < KB / 8; ++ks) {
+                            const uint32_t boff = (ks >> 2) * kg2 + 2 * (ks & 3);
+                            mma_tf32_ts(tmem + kR_accDh, tmem + kR_accR + 8 * ks, b2h + boff, idesc2, ks == 0 ? 0u : 1u);
+                            mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2l + boff, idesc2, 1u);
+                            mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2h + boff, idesc2, 1u);
+                        }
+                        commit(&bar_d);
+                    }
+                    __syncwarp();
+                }
+                mbar_wait(&bar_d, ph);
+                fence_after_sync();
+#pragma unroll
+                for (int c = 0; c < 16; c += 16) {
+                    float acc[16];
+                    tmem_ld16(tmem + lane_off + kR_accDh + j0 + c, acc);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) dh[c + j] += acc[j];
+                }
+                fence_before_sync();
+                ph ^= 1;
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        fence_after_sync();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+
+__global__ void __launch_bounds__(kThreadsHn, 1)
 gru_bwd_rc_kernel(const GruBwdRcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_a1, bar_a2, bar_r, bar_d;
@@ -557,15 +788,15 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
     uint8_t* b2_lo = b2_hi + H * KB * 4;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        mbar_init(&bar_a1, kGateWarps);
-        mbar_init(&bar_a2, kGateWarps);
+        mbar_init(&bar_a1, kGateWarpsHn);
+        mbar_init(&bar_a2, kGateWarpsHn);
         mbar_init(&bar_r, 1);
         mbar_init(&bar_d, 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < KB * H; i += kThreads) {
+    for (int i = tid; i < KB * H; i += kThreadsHn) {
         const int k = i / H, n = i - k * H;  // w_hh[k][n]: k = gate row, n = h column
         const float w = __ldg(p.w_hh + i);
         const float hi = tf32_hi(w), lo = w - hi;
@@ -586,10 +817,16 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
     const uint32_t n_tiles = (p.Q + 127) / 128;
     uint32_t ph = 0;  // one phase bit serves all four barriers: each completes exactly once per step
 
-    if (warp < kGateWarps) {
-        const int quad = warp & 3, half = warp >> 2;
+    {
+        // 16 gate warps: thread = one sequence (TMEM lane) x 16 hidden units [16 part, +16).  Warp 0 also issues the
+        // two GEMMs of a step (it would only wait for them otherwise): 16 warps = 4 per scheduler, 128 registers each.
+        const uint32_t idesc1 = idesc_tf32(128, KB), idesc2 = idesc_tf32(128, H);
+        const uint32_t b1h = desc_lo(smem_u32(b1_hi)), b1l = desc_lo(smem_u32(b1_lo));
+        const uint32_t b2h = desc_lo(smem_u32(b2_hi)), b2l = desc_lo(smem_u32(b2_lo));
+        constexpr uint32_t kg1 = KB * 128u >> 4, kg2 = H * 128u >> 4;  // one 32-column k-atom block of B1 / B2
+        const int quad = warp & 3, part = warp >> 2;
         const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-        const int j0 = half * 32;
+        const int j0 = part * 16;
         const float4* h4 = reinterpret_cast<const float4*>(p.hseq);
         float4* dg4 = reinterpret_cast<float4*>(p.dG);
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -599,19 +836,19 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
             const uint32_t sidx = (valid ? q : 0) - b * p.S;
             const float* xr = p.r + static_cast<size_t>(b) * p.L * p.S + sidx;          // + t * S
             const float4* Pb = reinterpret_cast<const float4*>(p.P) + static_cast<size_t>(b) * p.L * (KB / 4);  // + t * 48
-            float dh[32], hm[32];
+            float dh[16], hm[16];
             {
                 const float4* src = reinterpret_cast<const float4*>(p.dh_last + static_cast<size_t>(valid ? q : 0) * H + j0);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float4 v = valid ? __ldg(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     dh[4 * j] = v.x; dh[4 * j + 1] = v.y; dh[4 * j + 2] = v.z; dh[4 * j + 3] = v.w;
                 }
             }
-            auto load_h = [&](int t) {  // h_{t-1}[j0 .. j0 + 32): zero for t = 0 and for pad rows
+            auto load_h = [&](int t) {  // h_{t-1}[j0 .. j0 + 16): zero for t = 0 and for pad rows
                 const size_t prow = static_cast<size_t>(t > 0 ? t - 1 : 0) * p.Qp + q;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float4 v = (valid && t > 0) ? ldg_stream(h4 + b32(prow, (j0 >> 2) + j, H / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     hm[4 * j] = v.x; hm[4 * j + 1] = v.y; hm[4 * j + 2] = v.z; hm[4 * j + 3] = v.w;
                 }
@@ -619,23 +856,10 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
             load_h(p.L - 1);
             for (int t = p.L - 1; t >= 0; --t) {
                 const size_t row = static_cast<size_t>(t) * p.Qp + q;
-                // Nothing below depends on the recurrence except dh, so everything streamed is requested early:
-                //  * the three 128-byte lines of P this thread reads after the first GEMM go to L1 now (the lanes of
-                //    a window ask for the same lines; first touch would otherwise pay HBM latency inside the step);
-                //  * the states the NEXT step's load_h fetches go to L2 now, one lane per 128-byte line.
-                {
-                    const float4* Pn = Pb + static_cast<size_t>(t) * (KB / 4) + (j0 >> 2);
+                const float x = valid ? __ldg(xr + static_cast<size_t>(t) * p.S) : 0.f;
+                // ---- A = h_{t-1} (hi | lo), this thread's 16 of the 64 columns
 #pragma unroll
-                    for (int g = 0; g < 3; ++g) asm volatile("prefetch.global.L1 [%0];" ::"l"(Pn + g * (H / 4)));
-                    if (t > 1 && valid && (lane & 7) == 0) {
-                        const size_t prow = static_cast<size_t>(t - 2) * p.Qp + q;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(h4 + b32(prow, (j0 >> 2) + j, H / 4)));
-                    }
-                }
-                // ---- A = h_{t-1} (hi | lo), this thread's 32 of the 64 columns
-#pragma unroll
-                for (int c = 0; c < 32; c += 16) {
+                for (int c = 0; c < 16; c += 16) {
                     float hi[16], lo[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { hi[j] = tf32_hi(hm[c + j]); lo[j] = hm[c + j] - hi[j]; }
@@ -646,84 +870,112 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_a1);
-                const float x = valid ? __ldg(xr + static_cast<size_t>(t) * p.S) : 0.f;
-                const float4* Pt = Pb + static_cast<size_t>(t) * (KB / 4);
-                mbar_wait(&bar_r, ph);
-                fence_after_sync();
-#pragma unroll
-                for (int c = 0; c < 32; c += 16) {
-                    const int f0 = (j0 + c) >> 2;  // float4 index of this chunk inside a 64-wide group
-                    float r[16], z[16], n[16], hn[16];
-                    auto gate_in = [&](int g, float (&out)[16]) {  // P + w_x x for gate group g (0 r, 1 z, 2 n)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float4 pp = __ldg(Pt + g * (H / 4) + f0 + j), ww = wx_s[g * (H / 4) + f0 + j];
-                            out[4 * j] = fmaf(ww.x, x, pp.x); out[4 * j + 1] = fmaf(ww.y, x, pp.y);
-                            out[4 * j + 2] = fmaf(ww.z, x, pp.z); out[4 * j + 3] = fmaf(ww.w, x, pp.w);
-                        }
-                    };
+                {
+                    const int f0 = j0 >> 2;  // float4 index of this thread's units inside a 64-wide group
+                    // P + w_x x_t for the r | z | n pre-activations: requested before the first GEMM is waited for (the
+                    // S sensors of a window read the same P lines: L1 hits after the first toucher)
+                    float4 r4[4], z4[4], n4[4];
                     {
-                        float pre[16];
-                        gate_in(0, r);
-                        tmem_ld16(tmem + lane_off + kR_accR + 0 * H + j0 + c, pre);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) r[j] = sigmoidf_fast(pre[j] + r[j]);
-                        gate_in(1, z);
-                        tmem_ld16(tmem + lane_off + kR_accR + 1 * H + j0 + c, pre);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) z[j] = sigmoidf_fast(pre[j] + z[j]);
-                        gate_in(2, n);
-                        tmem_ld16(tmem + lane_off + kR_accR + 2 * H + j0 + c, hn);
+                        const float4* Pt = Pb + static_cast<size_t>(t) * (KB / 4) + f0;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const float4 bb = bhn_s[f0 + j];
-                            hn[4 * j] += bb.x; hn[4 * j + 1] += bb.y; hn[4 * j + 2] += bb.z; hn[4 * j + 3] += bb.w;
+                            const float4 pr = __ldg(Pt + j), pz = __ldg(Pt + H / 4 + j), pn = __ldg(Pt + 2 * (H / 4) + j);
+                            const float4 wr = wx_s[f0 + j], wz = wx_s[H / 4 + f0 + j], wn = wx_s[2 * (H / 4) + f0 + j];
+                            r4[j] = make_float4(fmaf(wr.x, x, pr.x), fmaf(wr.y, x, pr.y), fmaf(wr.z, x, pr.z), fmaf(wr.w, x, pr.w));
+                            z4[j] = make_float4(fmaf(wz.x, x, pz.x), fmaf(wz.y, x, pz.y), fmaf(wz.z, x, pz.z), fmaf(wz.w, x, pz.w));
+                            n4[j] = make_float4(fmaf(wn.x, x, pn.x), fmaf(wn.y, x, pn.y), fmaf(wn.z, x, pn.z), fmaf(wn.w, x, pn.w));
                         }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) n[j] = tanhf_fast(fmaf(r[j], hn[j], n[j]));
                     }
-                    float dr[16], dz[16], dhn[16], din[16];
+                    if (warp == 0) {  // r | z | hn pre-activations = h_{t-1} W_hh^T
+                        mbar_wait(&bar_a1, ph);
+                        fence_after_sync();
+                        if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float g = dh[c + j];
-                        const float dnp = g * (1.f - z[j]) * (1.f - n[j] * n[j]);
-                        dz[j] = g * (hm[c + j] - n[j]) * z[j] * (1.f - z[j]);
-                        dr[j] = dnp * hn[j] * r[j] * (1.f - r[j]);
-                        dhn[j] = dnp * r[j];
-                        din[j] = dnp;
-                        dh[c + j] = g * z[j];  // the accumulator of the second GEMM is added after the wait below
+                            for (uint32_t ks = 0; ks < H / 8; ++ks) {
+                                const uint32_t boff = (ks >> 2) * kg1 + 2 * (ks & 3);
+                                mma_tf32_ts(tmem + kR_accR, tmem + kR_a + H + 8 * ks, b1h + boff, idesc1, ks == 0 ? 0u : 1u);
+                                mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1l + boff, idesc1, 1u);
+                                mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1h + boff, idesc1, 1u);
+                            }
+                            commit(&bar_r);
+                        }
+                        __syncwarp();
                     }
+                    mbar_wait(&bar_r, ph);
+                    fence_after_sync();
+                    float ar[16], az[16], hn[16];
+                    tmem_ld16(tmem + lane_off + kR_accR + 0 * H + j0, ar);
+                    tmem_ld16(tmem + lane_off + kR_accR + 1 * H + j0, az);
+                    tmem_ld16(tmem + lane_off + kR_accR + 2 * H + j0, hn);
+                    // four units at a time: gates, dG to HBM, its hi / lo to tensor memory (hi over the consumed
+                    // h_{t-1} columns, lo over the consumed pre-activation columns)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {  // pad rows carry zeros (their dh is zero)
-                        stg_stream(dg4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(dr[4 * j], dr[4 * j + 1], dr[4 * j + 2], dr[4 * j + 3]));
-                        stg_stream(dg4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(dz[4 * j], dz[4 * j + 1], dz[4 * j + 2], dz[4 * j + 3]));
-                        stg_stream(dg4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(dhn[4 * j], dhn[4 * j + 1], dhn[4 * j + 2], dhn[4 * j + 3]));
-                        stg_stream(dg4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(din[4 * j], din[4 * j + 1], din[4 * j + 2], din[4 * j + 3]));
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bb = bhn_s[f0 + j];
+                        const float ir[4] = {r4[j].x, r4[j].y, r4[j].z, r4[j].w}, iz[4] = {z4[j].x, z4[j].y, z4[j].z, z4[j].w};
+                        const float in[4] = {n4[j].x, n4[j].y, n4[j].z, n4[j].w}, bh[4] = {bb.x, bb.y, bb.z, bb.w};
+                        float rr[4], zz[4], nn[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            rr[e] = sigmoidf_fast(ar[4 * j + e] + ir[e]);
+                            zz[e] = sigmoidf_fast(az[4 * j + e] + iz[e]);
+                            nn[e] = tanhf_fast(fmaf(rr[e], hn[4 * j + e] + bh[e], in[e]));
+                        }
+                        float dr[4], dz[4], dhn[4], din[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float g = dh[4 * j + e], hv = hn[4 * j + e] + bh[e];
+                            const float dnp = g * (1.f - zz[e]) * (1.f - nn[e] * nn[e]);
+                            dz[e] = g * (hm[4 * j + e] - nn[e]) * zz[e] * (1.f - zz[e]);
+                            dr[e] = dnp * hv * rr[e] * (1.f - rr[e]);
+                            dhn[e] = dnp * rr[e];
+                            din[e] = dnp;
+                            dh[4 * j + e] = g * zz[e];  // the accumulator of the second GEMM is added after the wait below
+                        }
+                        // pad rows carry zeros (their dh is zero)
+                        stg_stream(dg4 + b32(row, 0 * (H / 4) + f0 + j, H), make_float4(dr[0], dr[1], dr[2], dr[3]));
+                        stg_stream(dg4 + b32(row, 1 * (H / 4) + f0 + j, H), make_float4(dz[0], dz[1], dz[2], dz[3]));
+                        stg_stream(dg4 + b32(row, 2 * (H / 4) + f0 + j, H), make_float4(dhn[0], dhn[1], dhn[2], dhn[3]));
+                        stg_stream(dg4 + b32(row, 3 * (H / 4) + f0 + j, H), make_float4(din[0], din[1], din[2], din[3]));
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dr[e]); lo[e] = dr[e] - hi[e]; }
+                        tmem_st4(tmem + lane_off + kR_a + 0 * H + j0 + 4 * j, hi);
+                        tmem_st4(tmem + lane_off + kR_accR + 0 * H + j0 + 4 * j, lo);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dz[e]); lo[e] = dz[e] - hi[e]; }
+                        tmem_st4(tmem + lane_off + kR_a + 1 * H + j0 + 4 * j, hi);
+                        tmem_st4(tmem + lane_off + kR_accR + 1 * H + j0 + 4 * j, lo);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { hi[e] = tf32_hi(dhn[e]); lo[e] = dhn[e] - hi[e]; }
+                        tmem_st4(tmem + lane_off + kR_a + 2 * H + j0 + 4 * j, hi);
+                        tmem_st4(tmem + lane_off + kR_accR + 2 * H + j0 + 4 * j, lo);
                     }
-                    // A of the second GEMM: hi over the (consumed) h_{t-1} columns, lo over the (consumed) pre-activations
-                    float lo[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { const float v = dr[j]; dr[j] = tf32_hi(v); lo[j] = v - dr[j]; }
-                    tmem_st16(tmem + lane_off + kR_a + 0 * H + j0 + c, dr);
-                    tmem_st16(tmem + lane_off + kR_accR + 0 * H + j0 + c, lo);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { const float v = dz[j]; dz[j] = tf32_hi(v); lo[j] = v - dz[j]; }
-                    tmem_st16(tmem + lane_off + kR_a + 1 * H + j0 + c, dz);
-                    tmem_st16(tmem + lane_off + kR_accR + 1 * H + j0 + c, lo);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { const float v = dhn[j]; dhn[j] = tf32_hi(v); lo[j] = v - dhn[j]; }
-                    tmem_st16(tmem + lane_off + kR_a + 2 * H + j0 + c, dhn);
-                    tmem_st16(tmem + lane_off + kR_accR + 2 * H + j0 + c, lo);
                 }
                 tmem_wait_st();
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_a2);
                 if (t > 0) load_h(t - 1);  // h_{t-2}: in flight while the second GEMM runs
+                if (warp == 0) {  // dh_{t-1} += [dr | dz | dhn] W_hh
+                    mbar_wait(&bar_a2, ph);
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (uint32_t ks = 0; ks < KB / 8; ++ks) {
+                            const uint32_t boff = (ks >> 2) * kg2 + 2 * (ks & 3);
+                            mma_tf32_ts(tmem + kR_accDh, tmem + kR_accR + 8 * ks, b2h + boff, idesc2, ks == 0 ? 0u : 1u);
+                            mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2l + boff, idesc2, 1u);
+                            mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2h + boff, idesc2, 1u);
+                        }
+                        commit(&bar_d);
+                    }
+                    __syncwarp();
+                }
                 mbar_wait(&bar_d, ph);
                 fence_after_sync();
 #pragma unroll
-                for (int c = 0; c < 32; c += 16) {
+                for (int c = 0; c < 16; c += 16) {
                     float acc[16];
                     tmem_ld16(tmem + lane_off + kR_accDh + j0 + c, acc);
 #pragma unroll
@@ -733,46 +985,10 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
                 ph ^= 1;
             }
         }
-    } else {
-        const uint32_t idesc1 = idesc_tf32(128, KB), idesc2 = idesc_tf32(128, H);
-        const uint32_t b1h = desc_lo(smem_u32(b1_hi)), b1l = desc_lo(smem_u32(b1_lo));
-        const uint32_t b2h = desc_lo(smem_u32(b2_hi)), b2l = desc_lo(smem_u32(b2_lo));
-        constexpr uint32_t kg1 = KB * 128u >> 4, kg2 = H * 128u >> 4;  // one 32-column k-atom block of B1 / B2
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int t = 0; t < p.L; ++t) {
-                mbar_wait(&bar_a1, ph);
-                fence_after_sync();
-                if (elect_one()) {
-#pragma unroll
-                    for (uint32_t ks = 0; ks < H / 8; ++ks) {
-                        const uint32_t boff = (ks >> 2) * kg1 + 2 * (ks & 3);
-                        mma_tf32_ts(tmem + kR_accR, tmem + kR_a + H + 8 * ks, b1h + boff, idesc1, ks == 0 ? 0u : 1u);
-                        mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1l + boff, idesc1, 1u);
-                        mma_tf32_ts(tmem + kR_accR, tmem + kR_a + 8 * ks, b1h + boff, idesc1, 1u);
-                    }
-                    commit(&bar_r);
-                }
-                __syncwarp();
-                mbar_wait(&bar_a2, ph);
-                fence_after_sync();
-                if (elect_one()) {
-#pragma unroll
-                    for (uint32_t ks = 0; ks < KB / 8; ++ks) {
-                        const uint32_t boff = (ks >> 2) * kg2 + 2 * (ks & 3);
-                        mma_tf32_ts(tmem + kR_accDh, tmem + kR_accR + 8 * ks, b2h + boff, idesc2, ks == 0 ? 0u : 1u);
-                        mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2l + boff, idesc2, 1u);
-                        mma_tf32_ts(tmem + kR_accDh, tmem + kR_a + 8 * ks, b2h + boff, idesc2, 1u);
-                    }
-                    commit(&bar_d);
-                }
-                __syncwarp();
-                ph ^= 1;
-            }
-        }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == kMmaWarp) {
+    if (warp == 0) {
         fence_after_sync();
         tmem_dealloc(tmem, 512);
     }
@@ -782,7 +998,7 @@ gru_bwd_rc_kernel(const GruBwdRcParams p) {
 
 extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_t F, int32_t Hdim, const float* r,
                              const float* tf, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                             float* h_last, float* hseq, float* gates, void* stream_) {
+                             float* h_last, float* hseq, float* gates, int32_t save_hn, void* stream_) {
     LTGNN_REQUIRE(B >= 0 && L > 0 && S > 0 && F >= 0, LTGNN_E_ARG, "gru_fwd: B=%lld L=%d S=%d F=%d",
                   static_cast<long long>(B), L, S, F);
     LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_fwd: hidden size %d not supported (64 only)", Hdim);
@@ -796,7 +1012,8 @@ extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_fwd: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
     LTGNN_CUDA_TRY(cudaSetDevice(device));
-    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, gates, static_cast<uint32_t>(B * S),
+    GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, gates, save_hn ? H : 3 * H / 4,
+                static_cast<uint32_t>(B * S),
                 static_cast<uint32_t>((B * S + 127) / 128 * 128), L, S, F,
                 S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
     const size_t smem = 1024 + 2ull * NG * KA * 4;
@@ -878,7 +1095,33 @@ extern "C" int ltgnn_gru_bwd_dg_rc(int device, int64_t B, int32_t L, int32_t S, 
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_bwd_rc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t tiles = (Q + 127) / 128;
     const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
-    gru_bwd_rc_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    gru_bwd_rc_kernel<<<grid, kThreadsHn, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}
+
+extern "C" int ltgnn_gru_bwd_dg_hn(int device, int64_t Q, int32_t L, int32_t Hdim, const float* w_hh, const float* b_hh,
+                                   const float* gates3, const float* hseq, const float* dh_last, float* dG,
+                                   void* stream_) {
+    LTGNN_REQUIRE(Q >= 0 && L > 0, LTGNN_E_ARG, "gru_bwd_dg_hn: Q=%lld L=%d", static_cast<long long>(Q), L);
+    LTGNN_REQUIRE(Hdim == H, LTGNN_E_SHAPE, "gru_bwd_dg_hn: hidden size %d not supported (64 only)", Hdim);
+    LTGNN_REQUIRE(Q < (1ll << 31) - 128, LTGNN_E_SHAPE, "gru_bwd_dg_hn: too many sequences");
+    if (Q == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(w_hh && b_hh && gates3 && hseq && dh_last && dG, LTGNN_E_ARG, "gru_bwd_dg_hn: null tensor");
+    LTGNN_REQUIRE(aligned16(gates3) && aligned16(hseq) && aligned16(dh_last) && aligned16(dG), LTGNN_E_ALIGN,
+                  "gru_bwd_dg_hn: 16-byte alignment required");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg_hn: device is sm_%d%d, need sm_100", di->cc_major,
+                  di->cc_minor);
+    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    GruBwdHnParams p{w_hh, b_hh, gates3, hseq, dh_last, dG, static_cast<uint32_t>(Q),
+                     static_cast<uint32_t>((Q + 127) / 128 * 128), L};
+    const size_t smem = 1024 + 2ull * H * H * 4 + 2ull * H * KB * 4;
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_bwd_hn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles = (Q + 127) / 128;
+    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    gru_bwd_hn_kernel<<<grid, kThreadsHn, smem, static_cast<cudaStream_t>(stream_)>>>(p);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

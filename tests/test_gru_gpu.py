@@ -35,11 +35,11 @@ def test_gru_forward(b, l, s, f):
     assert torch.equal(h2, h_last)
 
 
-@pytest.mark.parametrize("recompute", [True, False])
+@pytest.mark.parametrize("mode", ["hn", "saved", "all"])
 @pytest.mark.parametrize("b,l,s,f", [(2, 5, 3, 2), (3, 36, 29, 9), (7, 20, 29, 9), (2, 100, 29, 9), (9, 8, 11, 0)])
-def test_gru_backward(b, l, s, f, recompute, monkeypatch):
-    """Both BPTT forms -- gates rebuilt from the saved states (default) and gates saved by the forward."""
-    monkeypatch.setattr(ops, "GRU_RECOMPUTE", recompute)
+def test_gru_backward(b, l, s, f, mode, monkeypatch):
+    """The three BPTT forms: hn rebuilt (default), all four gate groups saved, every gate rebuilt from the states."""
+    monkeypatch.setattr(ops, "GRU_BPTT", mode)
     torch.manual_seed(7 * b + l)
     gru = torch.nn.GRU(input_size=1 + f, hidden_size=64, num_layers=1, batch_first=True).double()
     r = torch.randn(b, l, s)
