@@ -386,7 +386,7 @@ def run_ours(args) -> None:
     # e2e-only kernels (sensor GRU encoder): fp32-equivalent flops of the fused [h|x|tf|1] x [4H, 96] step GEMM
     q_seq = args.batch * SENSORS
     model_of["gru_fwd"] = ("tensor", 2.0 * q_seq * args.l_det * 256 * 75)
-    model_of["gru_bwd_dg"] = ("tensor", 2.0 * q_seq * args.l_det * 192 * 64)
+    model_of["gru_bwd_dg"] = ("tensor", 2.0 * q_seq * args.l_det * (192 * 64 + 64 * 64))  # dh GEMM + rebuilt hn
     model_of["gru_bwd_w"] = ("tensor", 2.0 * q_seq * args.l_det * 256 * 75)
     traffic = {}
     tpath = REPO / "profiles" / "ncu_traffic.json"
