@@ -50,3 +50,26 @@ def test_fails_loudly_without_gpu(graph_golden):
     assert "cuda" in L.last_error().lower()
     with pytest.raises(L.LtgnnError):
         L.check(rc)
+
+
+def test_live_mask_and_blocked32_layouts_documented_in_the_header():
+    """Host-side mirrors of the two device layouts the C ABI documents (include/ltgnn.h): the 1-bit gate word
+    (bit 8c+q <-> element 4q+c of a 32-feature slice) and the blocked-32 row layout [rows/32][W/4][32][4]."""
+    from leak_det_gnn_b200 import ops
+    gen = torch.Generator().manual_seed(0)
+    b, n, d = 2, 37, 64
+    y = torch.randn(b, n, d, generator=gen).relu()
+    words = torch.zeros(b, d // 32, n, dtype=torch.int64)
+    for s in range(d // 32):
+        for e in range(32):
+            q, c = divmod(e, 4)
+            words[:, s, :] |= (y[:, :, 32 * s + e] > 0).long() << (8 * c + q)
+    words = torch.where(words >= 2**31, words - 2**32, words).to(torch.int32)  # bit 31 lives in the sign
+    assert torch.equal(ops.unpack_live_mask(words), y > 0)
+
+    l, q_, w = 3, 70, 64
+    qp = (q_ + 127) // 128 * 128
+    logical = torch.randn(l, qp, w, generator=gen)
+    rows = logical.reshape(l * qp, w)
+    blocked = rows.reshape(l * qp // 32, 32, w // 4, 4).permute(0, 2, 1, 3).contiguous()
+    assert torch.equal(ops.unblock32(blocked, l, q_), logical[:, :q_])
