@@ -28,15 +28,15 @@ struct StoreEpilogue {
     int relu;
     template <class Pull>
     __device__ __forceinline__ void operator()(uint32_t row, uint32_t M, int /*var*/, Pull&& pull, const patch::Patch& pt,
-                                               int lane) const {
+                                               int lane, int c_first = 0, int c_stride = 32) const {
+        // (c_first, c_stride): the 32-column blocks this warp handles when several warps share the rows
         const bool valid = row < M;
         const uint32_t row0 = row - lane;  // first row of this warp's 32
         const int sub = lane >> 3, ch = lane & 7;
-        int c0 = 0;
-        for (; c0 + 32 <= n; c0 += 32) {
+        int c0 = c_first;
+        for (; c0 + 32 <= n; c0 += c_stride) {
             float v[32];
-            pull(c0, v);
-            pull(c0 + 16, v + 16);
+            pull(c0, v, 32);
             if (bias) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += __ldg(bias + c0 + j);
@@ -63,9 +63,10 @@ struct StoreEpilogue {
                 }
             }
         }
-        for (; c0 < n; c0 += 16) {  // a trailing 16-column block keeps the row-per-thread form
+        if (c_first != 0) return;
+        for (c0 = n & ~31; c0 < n; c0 += 16) {  // a trailing 16-column block keeps the row-per-thread form
             float v[16];
-            pull(c0, v);
+            pull(c0, v, 16);
             if (valid) chunk(row, c0, v);
         }
     }

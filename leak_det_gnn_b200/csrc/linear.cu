@@ -21,14 +21,16 @@ namespace {
 // the HBM peak with no other unit saturated.  Here the A operand goes to TENSOR memory: loader warps fetch rows
 // cooperatively (8 lanes = 128 bytes of one row), transpose them to the row-per-thread form through a patch, split and
 // tcgen05.st them; the MMA reads only the resident weight from shared memory.
-//   warps 0-7   LOADERS   group g = warp / 4 fills the A slots of the units (tile, 32-column K block) with unit % 2 == g
-//   warp  8     MMA       elected lane, 3xTF32
-//   warps 9-12  EPILOGUE  StoreEpilogue (bias / ReLU / gate, coalesced stores through the patch)
+//   warps 0-3   LOADERS   fill the A slots of the units (tile, 32-column K block) in order
+//   warp  4     MMA       elected lane, 3xTF32
+//   warps 5-12  EPILOGUE  StoreEpilogue (bias / ReLU / gate, coalesced stores through the patch); two warps per TMEM
+//                         lane quadrant share the 32-column blocks -- a device-side timeline showed the epilogue, not
+//                         the loads or the MMAs, setting the pace (3 300 clocks per tile with 4 warps)
 // ---------------------------------------------------------------------------------------------------------
 namespace lt {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
-constexpr int kLdWarps = 8, kMmaWarp = 8, kEpWarps = 4, kThreads = (kLdWarps + 1 + kEpWarps) * 32;
+constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;  // 13 warps: 128 regs
 constexpr int kSlots = 4, kSlotCols = 64;
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -40,7 +42,7 @@ linear_ts_kernel(const float4* __restrict__ X, const StoreEpilogue epilogue, con
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_hi = smem;
     uint8_t* b_lo = b_hi + N * K * 4;
-    uint8_t* scratch = b_lo + N * K * 4;  // 8 loader rings of `depth` patches, then 4 epilogue patches
+    uint8_t* scratch = b_lo + N * K * 4;  // 4 loader rings of `depth` patches, then 8 epilogue patches
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_kg = K >> 5, k4 = K >> 2;
 
@@ -70,9 +72,9 @@ linear_ts_kernel(const float4* __restrict__ X, const StoreEpilogue epilogue, con
 
     if (warp < kLdWarps) {
         // Each loader warp owns a ring of `depth` patches that cp.async fills straight from global memory (no
-        // registers in between): 8 warps x depth x 4 KB of loads are in flight per SM, which is what an HBM stream at
+        // registers in between): 4 warps x depth x 4 KB of loads are in flight per SM, which is what an HBM stream at
         // ~2 us of loaded latency needs (32 KB of register-staged loads capped this kernel at 73 % of the HBM peak).
-        const int grp = warp >> 2, quad = warp & 3;
+        const int quad = warp & 3;
         uint8_t* ring = scratch + static_cast<size_t>(warp) * depth * patch::kPatchBytes;
         const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int sub = lane >> 3, ch = lane & 7;
@@ -93,12 +95,11 @@ linear_ts_kernel(const float4* __restrict__ X, const StoreEpilogue epilogue, con
             }
             asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group keeps the wait count uniform)
         };
-        for (int d = 0; d < depth; ++d) fetch(grp + 2 * d, d);
-        uint32_t i = 0;
-        for (uint32_t unit = grp; unit < n_units; unit += 2, ++i) {
-            const int slot_p = static_cast<int>(i % depth);
-            if (depth == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
-            else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        for (int d = 0; d < depth; ++d) fetch(d, d);
+        for (uint32_t unit = 0; unit < n_units; ++unit) {
+            const int slot_p = static_cast<int>(unit % depth);
+            if (depth == 8) asm volatile("cp.async.wait_group 7;" ::: "memory");
+            else asm volatile("cp.async.wait_group 3;" ::: "memory");
             __syncwarp();
             float v[32];
             {
@@ -110,7 +111,7 @@ linear_ts_kernel(const float4* __restrict__ X, const StoreEpilogue epilogue, con
                 }
             }
             __syncwarp();
-            fetch(unit + 2 * depth, slot_p);  // refill the patch just read
+            fetch(unit + depth, slot_p);  // refill the patch just read
             const uint32_t slot = unit & 3;
             mbar_wait_relaxed(&bar_empty[slot], ((unit >> 2) & 1) ^ 1);
             fence_after_sync();
@@ -165,7 +166,7 @@ linear_ts_kernel(const float4* __restrict__ X, const StoreEpilogue epilogue, con
             }
         }
     } else {
-        const int q = warp & 3;  // TMEM lane quadrant = warp % 4
+        const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
         const patch::Patch pt(scratch + (kLdWarps * depth + warp - kMmaWarp - 1) * patch::kPatchBytes, lane);
         for (uint32_t t = 0; t < t_end - t_begin; ++t) {
             const uint32_t a = t & 1;
@@ -173,7 +174,7 @@ linear_ts_kernel(const float4* __restrict__ X, const StoreEpilogue epilogue, con
             fence_after_sync();
             const uint32_t taddr = acc_base + a * 128 + (static_cast<uint32_t>(q * 32) << 16);
             const uint32_t row = (t_begin + t) * 128 + q * 32 + lane;
-            epilogue(row, M, 0, [&](int c0, float* v) { tmem_ld16(taddr + c0, v); }, pt, lane);
+            epilogue(row, M, 0, [&](int c0, float* v, int w) { if (w == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v); }, pt, lane, 32 * half, 64);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);
@@ -206,7 +207,7 @@ extern "C" int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const f
         LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "linear: device is sm_%d%d, need sm_100", di->cc_major,
                       di->cc_minor);
         const size_t wbytes = 2ull * N * K * 4;
-        const int depth = 1024 + wbytes + (lt::kLdWarps * 4 + lt::kEpWarps) * patch::kPatchBytes <= static_cast<size_t>(di->smem_optin) ? 4 : 2;
+        const int depth = 1024 + wbytes + (lt::kLdWarps * 8 + lt::kEpWarps) * patch::kPatchBytes <= static_cast<size_t>(di->smem_optin) ? 8 : 4;
         const size_t smem = 1024 + wbytes + (lt::kLdWarps * depth + lt::kEpWarps) * patch::kPatchBytes;
         LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "linear: %zu B of shared memory", smem);
         LTGNN_CUDA_TRY(cudaSetDevice(device));

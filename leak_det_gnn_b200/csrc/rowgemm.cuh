@@ -209,7 +209,7 @@ rowgemm_kernel(const Loader loader, const Epilogue epilogue, const BSpec bspec, 
             const uint32_t row = tile * kTileM + q * 32 + lane;
             // the epilogue pulls 16-column chunks itself (tcgen05.ld is warp-collective: every lane must pull
             // every chunk, valid row or not) and may keep per-row state across chunks
-            epilogue(row, M, var, [&](int c0, float* v) { tmem_ld16(taddr + c0, v); }, pt, lane);
+            epilogue(row, M, var, [&](int c0, float* v, int w) { if (w == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v); }, pt, lane);
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);
