@@ -439,8 +439,7 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
             const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16) + 32 * half;
             auto pull32 = [&](uint32_t col, float4 (&g)[8]) {
                 float v[32];
-                tmem_ld16(taddr + col, v);
-                tmem_ld16(taddr + col + 16, v + 16);
+                tmem_ld32(taddr + col, v);
                 patch::transpose_out(patch, v, g);
             };
             auto signed_c = [&](float c, int bit) { return (pos >> bit) & 1u ? c : ((neg >> bit) & 1u ? -c : 0.f); };
