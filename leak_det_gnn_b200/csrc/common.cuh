@@ -34,6 +34,28 @@ int fail(int code, const char* fmt, ...);  // records the thread-local message, 
         if (!(cond)) return ::ltgnn::fail(code, __VA_ARGS__); \
     } while (0)
 
+// Every entry point runs on the device its tensors live on and leaves the caller's current device untouched
+// (torch keeps its own notion of the current device; a stray cudaSetDevice would redirect later allocations).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev != device) {
+            e = cudaSetDevice(device);
+            switched = (e == cudaSuccess);
+        }
+        return e;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define LTGNN_USE_DEVICE(dev)           \
+    ::ltgnn::DeviceGuard dev_guard__;   \
+    LTGNN_CUDA_TRY(dev_guard__.enter(dev))
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // cuTensorMapEncodeTiled resolved through the runtime (no -lcuda link dependency)

@@ -147,7 +147,7 @@ extern "C" int ltgnn_graph_create(int device, int32_t n_nodes, int32_t nnz, cons
     rc = check_csr(n_nodes, nnz, t_rowptr, t_col, "A_hat^T", &g.max_row_len[1]);
     if (rc) return rc;
 
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int32_t* rp[2] = {rowptr, t_rowptr};
     const int32_t* cc[2] = {col, t_col};
     const float* vv[2] = {val, t_val};
@@ -158,12 +158,19 @@ extern "C" int ltgnn_graph_create(int device, int32_t n_nodes, int32_t nnz, cons
             memcpy(&bits, &vv[t][k], 4);
             packed[k] = make_int2(cc[t][k], bits);
         }
-        LTGNN_CUDA_TRY(cudaMalloc(&g.rowptr[t], sizeof(int32_t) * (static_cast<size_t>(n_nodes) + 1)));
-        LTGNN_CUDA_TRY(cudaMalloc(&g.colval[t], sizeof(int2) * (static_cast<size_t>(nnz) + 1)));
-        LTGNN_CUDA_TRY(cudaMemcpy(g.rowptr[t], rp[t], sizeof(int32_t) * (static_cast<size_t>(n_nodes) + 1),
-                                  cudaMemcpyHostToDevice));
-        LTGNN_CUDA_TRY(cudaMemcpy(g.colval[t], packed.data(), sizeof(int2) * static_cast<size_t>(nnz),
-                                  cudaMemcpyHostToDevice));
+        cudaError_t e = cudaMalloc(&g.rowptr[t], sizeof(int32_t) * (static_cast<size_t>(n_nodes) + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&g.colval[t], sizeof(int2) * (static_cast<size_t>(nnz) + 1));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(g.rowptr[t], rp[t], sizeof(int32_t) * (static_cast<size_t>(n_nodes) + 1), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(g.colval[t], packed.data(), sizeof(int2) * static_cast<size_t>(nnz), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {  // release whatever was allocated before the failure
+            for (int u = 0; u < 2; ++u) {
+                cudaFree(g.rowptr[u]);
+                cudaFree(g.colval[u]);
+            }
+            return fail(LTGNN_E_CUDA, "graph_create: %s", cudaGetErrorString(e));
+        }
     }
     *out = new ltgnn_graph(g);
     return LTGNN_OK;
@@ -171,7 +178,8 @@ extern "C" int ltgnn_graph_create(int device, int32_t n_nodes, int32_t nnz, cons
 
 extern "C" int ltgnn_graph_destroy(ltgnn_graph_t g) {
     if (!g) return LTGNN_OK;
-    cudaSetDevice(g->device);
+    DeviceGuard guard;
+    guard.enter(g->device);
     for (int t = 0; t < 2; ++t) {
         cudaFree(g->rowptr[t]);
         cudaFree(g->colval[t]);

@@ -1011,7 +1011,7 @@ extern "C" int ltgnn_gru_fwd(int device, int64_t B, int32_t L, int32_t S, int32_
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_fwd: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     GruParams p{r, F ? tf : nullptr, w_ih, w_hh, b_ih, b_hh, h_last, hseq, gates, save_hn ? H : 3 * H / 4,
                 static_cast<uint32_t>(B * S),
                 static_cast<uint32_t>((B * S + 127) / 128 * 128), L, S, F,
@@ -1039,7 +1039,7 @@ extern "C" int ltgnn_gru_bwd_dg(int device, int64_t Q, int32_t L, int32_t Hdim, 
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     GruBwdParams p{w_hh, gates, hseq, dh_last, dG, static_cast<uint32_t>(Q), static_cast<uint32_t>((Q + 127) / 128 * 128), L};
     const size_t smem = 1024 + 2ull * H * KB * 4;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1058,7 +1058,7 @@ extern "C" int ltgnn_gru_inproj(int device, int64_t B, int32_t L, int32_t F, int
     LTGNN_REQUIRE(w_ih && b_ih && b_hh && P && (tf || F == 0), LTGNN_E_ARG, "gru_inproj: null tensor");
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int64_t rows = B * L;
     LTGNN_REQUIRE(F < kAuxIn, LTGNN_E_SHAPE, "gru_inproj: %d time features not supported", F);
     int64_t blocks = (rows + 3) / 4;
@@ -1085,7 +1085,7 @@ extern "C" int ltgnn_gru_bwd_dg_rc(int device, int64_t B, int32_t L, int32_t S, 
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg_rc: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int64_t Q = B * S;
     GruBwdRcParams p{w_hh, w_ih, b_hh, P, r, hseq, dh_last, dG, static_cast<uint32_t>(Q),
                      static_cast<uint32_t>((Q + 127) / 128 * 128), L, S, F,
@@ -1114,7 +1114,7 @@ extern "C" int ltgnn_gru_bwd_dg_hn(int device, int64_t Q, int32_t L, int32_t Hdi
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "gru_bwd_dg_hn: device is sm_%d%d, need sm_100", di->cc_major,
                   di->cc_minor);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     GruBwdHnParams p{w_hh, b_hh, gates3, hseq, dh_last, dG, static_cast<uint32_t>(Q),
                      static_cast<uint32_t>((Q + 127) / 128 * 128), L};
     const size_t smem = 1024 + 2ull * H * H * 4 + 2ull * H * KB * 4;

@@ -554,7 +554,7 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
     LTGNN_REQUIRE(B * N < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*N too large");
     const size_t smem = 1024 + 2ull * hf::kN * hf::kK * 4 + hf::kLdWarps * hf::kScrBytes;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_fwd: %zu B of shared memory", smem);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(hf::pipe_head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     const int64_t tiles = (M + 127) / 128;
@@ -585,7 +585,7 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
     LTGNN_REQUIRE(M < (1ll << 31) && B * N < (1ll << 28), LTGNN_E_SHAPE, "pipe_head_bwd_dx: B*P or B*N too large");
     const size_t smem = 1024 + 2ull * hb::kN * hb::kK * 4 + hb::kEpWarps * hb::kScrBytes;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_bwd_dx: %zu B of shared memory", smem);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(hb::pipe_head_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     const int64_t tiles = (M + 127) / 128;
@@ -606,7 +606,7 @@ extern "C" int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, 
     LTGNN_REQUIRE(aligned16(X) && aligned16(pooled), LTGNN_E_ALIGN, "mean_pool_fwd: 16-byte alignment required");
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int64_t cap = static_cast<int64_t>(di->sm_count) * 8;
     mean_pool_kernel<<<static_cast<int>(B < cap ? B : cap), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
         reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(pooled), B, N, D / 4);
@@ -623,7 +623,7 @@ extern "C" int ltgnn_mean_pool_bwd_fill(int device, int64_t B, int32_t N, int32_
     LTGNN_REQUIRE(aligned16(dpooled) && aligned16(dX), LTGNN_E_ALIGN, "mean_pool_bwd_fill: 16-byte alignment required");
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int64_t total4 = B * N * (D / 4);
     int64_t blocks = (total4 + 255) / 256;
     const int64_t cap = static_cast<int64_t>(di->sm_count) * 16;

@@ -210,7 +210,7 @@ extern "C" int ltgnn_linear(int device, int64_t M, int32_t K, int32_t N, const f
         const int depth = 1024 + wbytes + (lt::kLdWarps * 8 + lt::kEpWarps) * patch::kPatchBytes <= static_cast<size_t>(di->smem_optin) ? 8 : 4;
         const size_t smem = 1024 + wbytes + (lt::kLdWarps * depth + lt::kEpWarps) * patch::kPatchBytes;
         LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "linear: %zu B of shared memory", smem);
-        LTGNN_CUDA_TRY(cudaSetDevice(device));
+        LTGNN_USE_DEVICE(device);
         LTGNN_CUDA_TRY(cudaFuncSetAttribute(lt::linear_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
         const int64_t tiles = (M + 127) / 128;

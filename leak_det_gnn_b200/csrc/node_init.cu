@@ -204,7 +204,7 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     if (B == 0) return LTGNN_OK;
     LTGNN_REQUIRE(hs && slot && W && bias && X0, LTGNN_E_ARG, "node_init_fwd: null tensor");
     LTGNN_REQUIRE(aligned16(X0), LTGNN_E_ALIGN, "node_init_fwd: X0 must be 16-byte aligned");
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     InitParams p{hs, W, bias, slot, B, N, S, ds, D, thresh_of(drop_p), scale_of(drop_p), drop_seed};
     const size_t smem = sizeof(float) * (static_cast<size_t>(ds + 1) * D + 2 * D + static_cast<size_t>(S) * ds +
                                          static_cast<size_t>(S) * D);
@@ -244,7 +244,7 @@ extern "C" int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, 
     LTGNN_REQUIRE(aligned16(dX0) && aligned16(X0) && aligned16(ws) && aligned16(hs) && aligned16(dhs), LTGNN_E_ALIGN,
                   "node_init_bwd: 16-byte alignment required");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int n_w = D * (ds + 1), d4 = D / 4;
     if (B == 0) {
         LTGNN_CUDA_TRY(cudaMemsetAsync(dW, 0, sizeof(float) * n_w, stream));

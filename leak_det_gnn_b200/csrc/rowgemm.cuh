@@ -239,7 +239,7 @@ int launch(int device, const Loader& loader, const Epilogue& epilogue, const BSp
     LTGNN_REQUIRE(M < (1ll << 31) - kTileM, LTGNN_E_SHAPE, "%s: M=%lld rows exceed the 32-bit row index", who,
                   static_cast<long long>(M));
     const size_t smem = smem_bytes(K, N, stages);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     auto kern = rowgemm_kernel<Loader, Epilogue>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t tiles = (M + kTileM - 1) / kTileM;

@@ -372,7 +372,7 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
     LTGNN_REQUIRE(X != Y, LTGNN_E_ARG, "%s: X and Y must not alias", who);
     LTGNN_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(f.bias) && aligned16(f.gate), LTGNN_E_ALIGN,
                   "%s: tensors must be 16-byte aligned", who);
-    LTGNN_CUDA_TRY(cudaSetDevice(g->device));
+    LTGNN_USE_DEVICE(g->device);
 
     const StagedPlan pl = plan_staged(g, D);
     const bool fused = epi || gated;

@@ -269,7 +269,7 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
                   di->cc_minor);
     const size_t smem = smem_bytes(No, kMT);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "%s: %zu B of shared memory", who, smem);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     auto kern = tgrad_kernel<GLoader, XLoader, kMT, kGJ, kXJ>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint32_t cols = 32;

@@ -132,7 +132,7 @@ extern "C" int ltgnn_wgrad(int device, int64_t M, int32_t Do, int32_t Di, const 
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "wgrad: device is sm_%d%d, need sm_100", di->cc_major, di->cc_minor);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    LTGNN_CUDA_TRY(cudaSetDevice(device));
+    LTGNN_USE_DEVICE(device);
     const int n = Do * Di;
     size_t smem = 2ull * kChunkRows * (Do + Di) * 4;
     if (smem < static_cast<size_t>(n) * 4) smem = static_cast<size_t>(n) * 4;

@@ -47,7 +47,8 @@ class SharedSensorGRUEncoder(nn.Module):
         if self.use_time and tfeat is None:
             raise ValueError("tfeat required when use_time=True")
         g = self.gru
-        if (self.use_native and r.is_cuda and g.num_layers == 1 and
+        wants_input_grad = torch.is_grad_enabled() and (r.requires_grad or (tfeat is not None and tfeat.requires_grad))
+        if (self.use_native and r.is_cuda and g.num_layers == 1 and not wants_input_grad and
                 ops.gru_supported(self.hidden_size, tfeat.shape[-1] if self.use_time else 0)):
             # persistent tcgen05 kernel: state in tensor memory, no per-timestep launches (csrc/gru.cu)
             return ops.gru_encode(r, tfeat if self.use_time else None, g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0,

@@ -8,13 +8,13 @@ zero).  ``forward`` accepts
 * ``conv(x, graph)`` with ``graph`` a :class:`~leak_det_gnn_b200.ops.PipeGraph` and ``x`` of
   shape (B, N, D) or (B*N, D): the fast path -- batch is a dense leading dimension;
 * ``conv(x, edge_index)`` with a ``(2, E)`` int64 tensor, PyG's own signature: the graph over
-  ``x.size(0)`` nodes is normalised on the host once per distinct ``edge_index`` tensor
-  (cached on its storage pointer/version) and then runs the same kernels as one big window.
+  ``x.size(0)`` nodes is normalised on the host once per distinct ``edge_index`` content
+  (the cache keeps its own copy and compares contents) and then runs the same kernels as one big window.
 """
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional, Tuple, Union
+from typing import List, Optional, Tuple, Union
 
 import torch
 import torch.nn as nn
@@ -40,16 +40,21 @@ class _GlorotLinear(nn.Module):
             self.weight.uniform_(-bound, bound)
 
 
-_EDGE_CACHE: Dict[Tuple[int, int, int, int], PipeGraph] = {}
+# PyG-signature path: one normalised graph per distinct ``edge_index`` CONTENT.  The entry keeps its own copy of the
+# index tensor (the caller's may be freed and its storage recycled for a different graph of the same size), and a hit is
+# confirmed by comparing contents, never by address.
+_EDGE_CACHE: List[Tuple[torch.Tensor, int, PipeGraph]] = []
 
 
 def _graph_from_edge_index(edge_index: torch.Tensor, num_nodes: int) -> PipeGraph:
-    key = (edge_index.data_ptr(), edge_index._version, edge_index.size(1), num_nodes)
-    g = _EDGE_CACHE.get(key)
-    if g is None:
-        if len(_EDGE_CACHE) > 8:
-            _EDGE_CACHE.clear()
-        g = _EDGE_CACHE[key] = PipeGraph(edge_index, num_nodes)
+    for kept, n, g in _EDGE_CACHE:
+        if n == num_nodes and kept.shape == edge_index.shape and kept.device == edge_index.device \
+                and torch.equal(kept, edge_index):
+            return g
+    if len(_EDGE_CACHE) >= 8:
+        _EDGE_CACHE.pop(0)
+    g = PipeGraph(edge_index, num_nodes)
+    _EDGE_CACHE.append((edge_index.detach().clone(), num_nodes, g))
     return g
 
 

@@ -20,6 +20,12 @@ from .graph import GCNCsr, build_gcn_csr
 __all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported", "gru_encode", "gru_supported"]
 
 
+# Test hook: when set to a dict, the autograd nodes drop the masks they saved into it (``lives``: the 1-bit ReLU-and-
+# dropout records of x_0..x_L; ``head_live``: the same for the pipe head's hidden layer), so that a test can replay a
+# train-mode step with exactly these masks in the fp64 oracle.  Never set by the product.
+DEBUG_CAPTURE: Optional[dict] = None
+
+
 def _ptr(a: np.ndarray) -> ctypes.c_void_p:
     return a.ctypes.data_as(ctypes.c_void_p)
 
@@ -432,6 +438,8 @@ class _Heads(torch.autograd.Function):
         tok = _inst.begin("mean_pool_fwd")
         _lib.check(L.ltgnn_mean_pool_fwd(dev, b, n, d, x.data_ptr(), pooled.data_ptr(), _stream(x)))
         _inst.end(tok)
+        if DEBUG_CAPTURE is not None and hpost is not None:
+            DEBUG_CAPTURE["head_live"] = unblock32(hpost, 1, b * p_cnt)[0] != 0   # (B*P, H) bool
         if need_grad:
             ctx.save_for_backward(x, ends, w1, w2v, hpost)
         # the kernel draws 16 random bits per hidden unit: its keep probability is 1 - round(p * 2^16) / 2^16
@@ -518,6 +526,8 @@ class _GnnBody(torch.autograd.Function):
             del xw
             xs.append(x)
         ctx.lives = lives
+        if DEBUG_CAPTURE is not None:
+            DEBUG_CAPTURE["lives"] = lives
         ctx.save_for_backward(h_s, slot, w0, *conv_params[0::2], *xs)
         # the kernels draw 16 random bits per element: keep probability 1 - round(p * 2^16) / 2^16
         ctx.graph, ctx.n_layers, ctx.scale = graph, n_layers, 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
@@ -620,6 +630,7 @@ class _GruEncoder(torch.autograd.Function):
             else:
                 ctx.save_for_backward(r, tf, params[1], params[3], hseq, gates)
         else:
+            ctx.mode = None  # nothing requires a gradient: backward is never reached
             h_last = gru_fwd(r, tf, *params)
         return h_last
 
@@ -681,6 +692,9 @@ class _GruEncoder(torch.autograd.Function):
 def gru_encode(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_hh) -> torch.Tensor:
     """Differentiable (wrt the parameters) shared sensor GRU: (B,L,S) [+ (B,L,F)] -> (B,S,64)."""
     _check_act(r.contiguous(), "r")
+    if r.requires_grad or (tf is not None and tf.requires_grad):
+        raise ValueError("gru_encode: gradients with respect to the inputs are not implemented by the native GRU "
+                         "(the reference never asks for them); use the cuDNN route (use_native = False)")
     return _GruEncoder.apply(r, tf, w_ih, w_hh, b_ih, b_hh)
 
 

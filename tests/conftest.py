@@ -58,3 +58,18 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     b = b.detach().double().cpu()
     denom = b.abs().max().item()
     return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
+
+
+def parity_log(tag: str, report: dict) -> None:
+    """Per-tensor error report of a parity comparison: printed (pytest -s / -rP) and appended to
+    gpurun_out/parity_report.jsonl so that the margins against the stated tolerances are on record."""
+    import json
+    line = json.dumps({"case": tag, "errors": report})
+    print(line)
+    out = REPO / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        with open(out / "parity_report.jsonl", "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass

@@ -1,0 +1,266 @@
+"""Parity at bench-scale tile counts: every persistent kernel is driven through MORE THAN TWO tiles per CTA
+(148 SMs) and compared with fp64 -- the second and later iterations of the `tile += gridDim.x` / contiguous-range
+loops (tensor-memory accumulator reuse, mbarrier phase continuation, ring wrap-around) are what bench.py times.
+
+Also here: the whole detector at the reference's training batch (B = 128, train_detector.py:142; BASELINE config 2)
+and at B = 512 against the oracle built on the fly, and one TRAIN-MODE step whose dropout masks are captured from
+the kernels and replayed in the fp64 oracle, so that gate_scale / keep_scale are checked end to end.
+
+Every comparison appends its per-tensor errors to gpurun_out/parity_report.jsonl (conftest.parity_log).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, TOPO, parity_log, rel_err
+from leak_det_gnn_b200 import ops
+from leak_det_gnn_b200.models import LeakDetector
+from oracle import pyg_restatement as pyg
+from oracle.detector_oracle import OracleLeakDetector
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+SM = 148
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def _head_ref(x, ends, w1, b1, w2, b2):
+    h_u, h_v = x[:, ends[:, 0], :], x[:, ends[:, 1], :]
+    feat = torch.cat([h_u, h_v, (h_u - h_v).abs()], dim=-1)
+    hid = torch.relu(torch.nn.functional.linear(feat, w1, b1))
+    return torch.nn.functional.linear(hid, w2, b2).squeeze(-1), x.mean(dim=1)
+
+
+@pytest.mark.parametrize("bsz,n,p", [(64, 661, 764), (256, 661, 764), (130, 785, 905)])
+def test_heads_many_tiles_per_cta(bsz, n, p):
+    """382 / 1528 / 920 row tiles of 128 pipe rows: 3 / 11 / 7 tiles per CTA through pipe_head_fwd, pipe_head_bwd_dx
+    and the tgrad<HeadDpre> weight gradient (reference detector.py:76-88,204-211)."""
+    assert (bsz * p + 127) // 128 > 2 * SM
+    gen = torch.Generator().manual_seed(bsz + p)
+    x = torch.randn(bsz, n, 64, generator=gen).relu()
+    ends = torch.randint(0, n, (p, 2), generator=gen)
+    ends[0, 1] = ends[0, 0]
+    w1 = torch.randn(128, 192, generator=gen) * 0.1
+    b1 = torch.randn(128, generator=gen) * 0.1
+    w2 = torch.randn(1, 128, generator=gen) * 0.2
+    b2 = torch.randn(1, generator=gen)
+    dlog = torch.randn(bsz, p, generator=gen)
+    dpool = torch.randn(bsz, 64, generator=gen)
+
+    t = [v.double().requires_grad_(True) for v in (x, w1, b1, w2, b2)]
+    lr, pr = _head_ref(t[0], ends, *t[1:])
+    ((lr * dlog.double()).sum() + (pr * dpool.double()).sum()).backward()
+
+    o = [v.cuda().requires_grad_(True) for v in (x, w1, b1, w2)]
+    b2c = b2.cuda().requires_grad_(True)
+    part, pooled = ops.heads(o[0], ends.to(torch.int32).cuda(), o[1], o[2], o[3], 0.1, False)
+    logits = part.sum(0) + b2c
+    ((logits * dlog.cuda()).sum() + (pooled * dpool.cuda()).sum()).backward()
+    rep = {"logits": rel_err(logits, lr), "pooled": rel_err(pooled, pr), "dx": rel_err(o[0].grad, t[0].grad),
+           "dw1": rel_err(o[1].grad, t[1].grad), "db1": rel_err(o[2].grad, t[2].grad),
+           "dw2": rel_err(o[3].grad, t[3].grad), "db2": rel_err(b2c.grad, t[4].grad)}
+    parity_log(f"heads_many_tiles B={bsz} N={n} P={p}", rep)
+    assert all(v <= TOL for v in rep.values()), rep
+
+
+# ------------------------------------------------------------------------------------------------ GRU
+def _gru_ref(r, tf, gru):
+    b, l, s = r.shape
+    seq = r.transpose(1, 2).reshape(b * s, l, 1)
+    if tf is not None:
+        seq = torch.cat([seq, tf.unsqueeze(1).expand(b, s, l, tf.shape[-1]).reshape(b * s, l, -1)], dim=-1)
+    return gru(seq)[0]
+
+
+GRU_NAMES = ("weight_ih_l0", "weight_hh_l0", "bias_ih_l0", "bias_hh_l0")
+
+
+def test_gru_forward_many_tiles_per_cta():
+    """40 600 sequences = 318 tiles of 128: the persistent forward kernel runs 2-3 tiles per CTA (detector.py:60-73)."""
+    b, l, s, f = 1400, 8, 29, 9
+    assert (b * s + 127) // 128 > 2 * SM
+    torch.manual_seed(11)
+    gru = torch.nn.GRU(input_size=1 + f, hidden_size=64, num_layers=1, batch_first=True).double()
+    r, tf = torch.randn(b, l, s), torch.randn(b, l, f)
+    out = _gru_ref(r.double(), tf.double(), gru)
+    w = [getattr(gru, n).detach().float().cuda() for n in GRU_NAMES]
+    h_last, hseq, _ = ops.gru_fwd(r.cuda(), tf.cuda(), *w, save=True)
+    hseq = ops.unblock32(hseq, l, b * s)
+    rep = {"hseq": rel_err(hseq.permute(1, 0, 2), out), "h_last": rel_err(h_last.reshape(b * s, 64), out[:, -1, :])}
+    parity_log(f"gru_fwd_many_tiles B={b} L={l}", rep)
+    assert all(v <= 2e-5 for v in rep.values()), rep
+
+
+@pytest.mark.parametrize("mode", ["hn", "saved", "all"])
+def test_gru_backward_many_tiles_per_cta(mode, monkeypatch):
+    """The three BPTT forms + the weight-gradient pass at 318 sequence tiles (> 2 per CTA)."""
+    monkeypatch.setattr(ops, "GRU_BPTT", mode)
+    b, l, s, f = 1400, 8, 29, 9
+    torch.manual_seed(12)
+    gru = torch.nn.GRU(input_size=1 + f, hidden_size=64, num_layers=1, batch_first=True).double()
+    r, tf = torch.randn(b, l, s), torch.randn(b, l, f)
+    dh = torch.randn(b * s, 64)
+    out = _gru_ref(r.double(), tf.double(), gru)
+    (out[:, -1, :] * dh.double()).sum().backward()
+    w = [getattr(gru, n).detach().float().cuda().requires_grad_(True) for n in GRU_NAMES]
+    h = ops.gru_encode(r.cuda(), tf.cuda(), *w)
+    (h.reshape(b * s, 64) * dh.cuda()).sum().backward()
+    rep = {n: rel_err(p.grad, getattr(gru, n).grad) for n, p in zip(GRU_NAMES, w)}
+    parity_log(f"gru_bwd_many_tiles mode={mode} B={b} L={l}", rep)
+    assert all(v <= 5e-5 for v in rep.values()), rep
+
+
+# ------------------------------------------------------------------------------------------------ whole detector
+def _fixture(net):
+    z = np.load(GOLDEN / f"graph_{net}.npz")
+    return {k: z[k] for k in z.files}
+
+
+def _models(net, n_pipes, seed=42):
+    """(drop-in on cuda, oracle fp32, oracle fp64) sharing one seeded state_dict; conv biases perturbed (PyG zero-inits)."""
+    g = _fixture(net)
+    pipe_ids = [str(p) for p in g["pipe_ids"]][:n_pipes]
+    sensors = [str(s) for s in g["sensor_node_ids"]]
+    torch.manual_seed(seed)
+    ours = LeakDetector(TOPO[net], sensors, pipe_ids, sensor_hidden=64, node_hidden=64, gnn_layers=2, dropout=0.1)
+    gen = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for conv in ours.convs:
+            conv.bias.copy_(0.05 * torch.randn(conv.bias.shape, generator=gen))
+    state = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+
+    def oracle(dtype):
+        m = OracleLeakDetector(len(g["node_names"]), torch.from_numpy(g["edge_index"]),
+                               torch.from_numpy(g["pipe_ends"][:n_pipes]), g["sensor_node_idx"].tolist(), 64, 64, 2, 0.1,
+                               True).to(dtype)
+        m.load_state_dict({k: v.to(dtype) for k, v in state.items()}, strict=True)
+        return m
+
+    return ours.cuda(), oracle(torch.float32), oracle(torch.float64), g
+
+
+def _inputs(bsz, l_det, n_classes, seed=198):
+    gen = torch.Generator().manual_seed(seed)
+    residual = torch.randn(bsz, l_det, 29, generator=gen)
+    tfeat = torch.randn(bsz, l_det, 9, generator=gen)
+    label = torch.randint(0, n_classes, (bsz,), generator=gen)
+    return residual, tfeat, label
+
+
+def _compare(tag, ours, o32, o64, residual, tfeat, label, tol_gru=5e-5, slack=3.0):
+    """eval-mode forward + CE + backward of the three models; returns the per-tensor report {name: (ours, ref32)}."""
+    ours.eval()
+    o32.eval()
+    o64.eval()
+    lo = ours(residual.cuda(), tfeat.cuda())
+    torch.nn.functional.cross_entropy(lo, label.cuda()).backward()
+    l32 = o32(residual, tfeat)
+    torch.nn.functional.cross_entropy(l32, label).backward()
+    l64 = o64(residual.double(), tfeat.double())
+    torch.nn.functional.cross_entropy(l64, label).backward()
+    rep = {"logits": (rel_err(lo, l64), rel_err(l32, l64))}
+    g32 = dict(o32.named_parameters())
+    g64 = dict(o64.named_parameters())
+    for name, p in ours.named_parameters():
+        rep[name] = (rel_err(p.grad, g64[name].grad), rel_err(g32[name].grad, g64[name].grad))
+    parity_log(tag, {k: {"ours": a, "oracle_fp32": b} for k, (a, b) in rep.items()})
+    for name, (a, b) in rep.items():
+        tol = tol_gru if name.startswith("sensor_encoder.") else TOL
+        assert a <= max(tol, slack * b), (name, a, b)
+    return rep
+
+
+@pytest.mark.parametrize("net,bsz,n_pipes", [("LTA", 128, 764), ("LTA", 128, 2), ("LTA", 512, 764), ("LT", 256, 905)])
+def test_detector_training_batch_vs_oracle(net, bsz, n_pipes):
+    """BASELINE config 2 (B = 128, l_det = 36, P = 2 and P = 764), B = 512 and config 4's per-GPU batch on full L-TOWN:
+    logits and all 18 gradients of LeakDetector.forward + CE vs the fp64 oracle (reference detector.py:170-218,
+    train_detector.py:310-314)."""
+    ours, o32, o64, _ = _models(net, n_pipes)
+    residual, tfeat, label = _inputs(bsz, 36, n_pipes + 1)
+    rep = _compare(f"detector {net} B={bsz} P={n_pipes}", ours, o32, o64, residual, tfeat, label)
+    assert len(rep) == 19
+
+
+# ------------------------------------------------------------------------------------------------ train mode
+def _replay_train_fp64(o64, h_s, masks, head_live, noleak_keep, scale, n_nodes):
+    """fp64 restatement of detector.py:178-218 in TRAIN mode with the dropout decisions the kernels took:
+    every `dropout(relu(pre))` becomes `pre * live * scale`, live = (pre > 0 and kept) as recorded by the forward."""
+    b = h_s.shape[0]
+    n = n_nodes
+    h0 = torch.zeros(b, n, h_s.shape[-1], dtype=torch.float64)
+    h0 = h0.index_copy(1, o64.sensor_node_idx, h_s)
+    mask = torch.zeros(n, 1, dtype=torch.float64)
+    mask[o64.sensor_node_idx, 0] = 1.0
+    x = o64.sensor_to_node(torch.cat([h0, mask.unsqueeze(0).expand(b, -1, -1)], dim=-1)) * masks[0] * scale
+    x = x.reshape(b * n, -1)
+    e = o64.edge_index_single.size(1)
+    edge_index = o64.edge_index_single.repeat(1, b) + (torch.arange(b).repeat_interleave(e) * n).unsqueeze(0)
+    for li, conv in enumerate(o64.convs):
+        x = conv(x, edge_index) * masks[li + 1].reshape(b * n, -1) * scale
+    hn = x.view(b, n, -1)
+    h_u, h_v = hn[:, o64.pipe_ends[:, 0], :], hn[:, o64.pipe_ends[:, 1], :]
+    feat = torch.cat([h_u, h_v, (h_u - h_v).abs()], dim=-1)
+    mlp = o64.edge_head.mlp
+    pipe_logits = mlp[3](mlp[0](feat) * head_live.view(b, -1, head_live.shape[-1]) * scale).squeeze(-1)
+    pooled = pyg.global_mean_pool(x, torch.arange(b).repeat_interleave(n))
+    mlp = o64.noleak_head.mlp
+    noleak = mlp[3](torch.relu(mlp[0](pooled)) * noleak_keep)  # (B, 1); noleak_keep already carries 1 / (1 - p)
+    return torch.cat([pipe_logits, noleak], dim=-1)
+
+
+@pytest.mark.parametrize("bsz,n_pipes", [(64, 764), (9, 2)])
+def test_train_mode_gradients_with_replayed_masks(bsz, n_pipes):
+    """Train mode (dropout 0.1, detector.py:190,201 and the heads' Dropout): the 1-bit live masks of x_0..x_L and of
+    the pipe head's hidden layer are captured from the kernels, torch's mask of the no-leak head by a hook, and the
+    fp64 oracle replays the step with them.  All 18 gradients to 1e-5 (GRU 5e-5)."""
+    ours, _, o64, g = _models("LTA", n_pipes)
+    residual, tfeat, label = _inputs(bsz, 36, n_pipes + 1, seed=7)
+    ours.train()
+    cap = {}
+    keep = {}
+
+    def hook(_m, inp, out):
+        keep["v"] = torch.where(inp[0] != 0, out / inp[0], torch.zeros((), device=out.device)).detach()
+
+    h = ours.noleak_head.mlp[2].register_forward_hook(hook)
+    ops.DEBUG_CAPTURE = cap
+    try:
+        torch.manual_seed(3)
+        lo = ours(residual.cuda(), tfeat.cuda())
+        torch.nn.functional.cross_entropy(lo, label.cuda()).backward()
+    finally:
+        ops.DEBUG_CAPTURE = None
+        h.remove()
+    masks = [ops.unpack_live_mask(m).cpu().double() for m in cap["lives"]]
+    assert 0.02 < 1.0 - masks[1].mean().item() < 0.98  # some units dropped / dead, some alive
+    head_live = cap["head_live"].cpu().double()
+    p_eff = round(0.1 * 65536) / 65536           # the kernels draw 16 random bits per element
+    scale = float(np.float32(1.0) / (np.float32(1.0) - np.float32(p_eff)))
+    o64.train()
+    h_s = o64.sensor_encoder(residual.double(), tfeat.double())
+    l64 = _replay_train_fp64(o64, h_s, masks, head_live, keep["v"].cpu().double(), scale, len(g["node_names"]))
+    torch.nn.functional.cross_entropy(l64, label).backward()
+    rep = {"logits": rel_err(lo, l64)}
+    g64 = dict(o64.named_parameters())
+    for name, p in ours.named_parameters():
+        rep[name] = rel_err(p.grad, g64[name].grad)
+    parity_log(f"train_mode_replay B={bsz} P={n_pipes}", rep)
+    for name, v in rep.items():
+        assert v <= (5e-5 if name.startswith("sensor_encoder.") else TOL), (name, v, rep)
+
+
+def test_backward_is_bitwise_reproducible():
+    """north_star: backward is a deterministic gather.  Two identical train-mode steps (same torch seed) give
+    bit-identical gradients for every parameter and for the sensor embeddings."""
+    ours, _, _, _ = _models("LTA", 764)
+    residual, tfeat, label = _inputs(96, 36, 765, seed=5)
+    ours.train()
+    runs = []
+    for _ in range(2):
+        ours.zero_grad(set_to_none=True)
+        torch.manual_seed(9)
+        lo = ours(residual.cuda(), tfeat.cuda())
+        torch.nn.functional.cross_entropy(lo, label.cuda()).backward()
+        runs.append({n: p.grad.clone() for n, p in ours.named_parameters()})
+    for n in runs[0]:
+        assert torch.equal(runs[0][n], runs[1][n]), n
