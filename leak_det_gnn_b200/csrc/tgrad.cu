@@ -11,83 +11,92 @@ using namespace ltgnn::functors;
 
 namespace {
 
-// ---- pipe head: G = d loss / d pre (from the saved post-activation), X = [feat | 1 | 0...]
-struct HeadDpre {
+// ---- pipe head.  d pre[row, j] = dlogit[row] * scale * w2[j] * live[row, j] is rank one up to the 0/1 mask, so
+//      dW1[j, :] = w2[j] * sum_rows live[row, j] * (dlogit[row] * scale * feat[row, :]):
+//      G = live (exactly representable: no lo copy, one MMA less per K step), X = F' = dlogit * scale * feat, and the
+//      row scale w2[j] is applied when the CTA partials are added.  The 192 result columns are split over three CTAs
+//      per row range -- h_u, h_v and |h_u - h_v| -- so that every CTA keeps its 128 x 64 totals in registers
+//      (tgrad.cuh, register-total form); the three read the same saved activations at the same time (one from HBM, two
+//      from L2).  d w2 and d b1 ride on the slice-0 CTAs' pass over the activations.
+constexpr int kHeadSlices = 3;
+struct HeadSide {
+    float4 dw2, db1;
+};
+struct HeadLive {
     static constexpr bool kRowFast = true;  // hpost is stored blocked-32
+    static constexpr bool kExact = true;
+    using Side = HeadSide;
     const float4* hpost;  // blocked-32 [Mp, 128]
     const float* dlogit;  // [M]
     const float4* w2;     // [32]
     float scale;
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
+    float* side_part;     // [2 * gridDim.x][256]: d w2 | d b1, one partial per (CTA, loader group)
+    __device__ __forceinline__ float4 load(uint32_t row, int c, Side& side) const {
         const float4 h = ptx::ldg_stream(hpost + ptx::b32(row, c, 32));
-        const float4 w = __ldg(w2 + c);
-        const float g = __ldg(dlogit + row) * scale;
-        return make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
-                           h.w > 0.f ? g * w.w : 0.f);
+        const float4 live = make_float4(h.x > 0.f ? 1.f : 0.f, h.y > 0.f ? 1.f : 0.f, h.z > 0.f ? 1.f : 0.f,
+                                        h.w > 0.f ? 1.f : 0.f);
+        if (blockIdx.x % kHeadSlices == 0) {
+            const float4 w = __ldg(w2 + c);
+            const float d = __ldg(dlogit + row), g = d * scale;
+            side.dw2.x = fmaf(d, h.x, side.dw2.x); side.dw2.y = fmaf(d, h.y, side.dw2.y);
+            side.dw2.z = fmaf(d, h.z, side.dw2.z); side.dw2.w = fmaf(d, h.w, side.dw2.w);
+            side.db1.x = fmaf(g * w.x, live.x, side.db1.x); side.db1.y = fmaf(g * w.y, live.y, side.db1.y);
+            side.db1.z = fmaf(g * w.z, live.z, side.db1.z); side.db1.w = fmaf(g * w.w, live.w, side.db1.w);
+        }
+        return live;
+    }
+    // the 32 lanes of a loader warp hold 32 different rows of the same columns: butterfly sum, lane 0 writes
+    __device__ __forceinline__ void finish(Side* side, const int* cols, int n, uint32_t cta, int group, int lane) const {
+        for (int j = 0; j < n; ++j) {
+            float4 t = side[j].dw2, u = side[j].db1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+                t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+                u.x += __shfl_xor_sync(0xffffffffu, u.x, o); u.y += __shfl_xor_sync(0xffffffffu, u.y, o);
+                u.z += __shfl_xor_sync(0xffffffffu, u.z, o); u.w += __shfl_xor_sync(0xffffffffu, u.w, o);
+            }
+            if (lane == 0) {
+                float4* dst = reinterpret_cast<float4*>(side_part + (static_cast<size_t>(cta) * 2 + group) * 256);
+                dst[cols[j]] = t;
+                dst[32 + cols[j]] = u;
+            }
+        }
     }
 };
-struct HeadFeatOnes {
+struct HeadFeatSlice {
     static constexpr bool kRowFast = false;
+    static constexpr int kSlices = kHeadSlices;
     const float4* x;   // node states [B*N, 16]
     const int2* ends;
+    const float* dlogit;
+    float scale;
     uint32_t P, N;
     uint64_t magic;
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
-        if (c >= 48) return make_float4(c == 48 ? 1.f : 0.f, 0.f, 0.f, 0.f);  // column 192 = 1 -> db1
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {  // c < 16: one 64-column slice
         const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
         const int2 e = __ldg(ends + (row - b * P));
-        const int seg = c >> 4, cc = c & 15;
-        const float4* xb = x + static_cast<int64_t>(b) * N * 16 + cc;
-        if (seg == 0) return __ldg(xb + e.x * 16);
-        if (seg == 1) return __ldg(xb + e.y * 16);
-        const float4 a = __ldg(xb + e.x * 16), d = __ldg(xb + e.y * 16);
-        return make_float4(fabsf(a.x - d.x), fabsf(a.y - d.y), fabsf(a.z - d.z), fabsf(a.w - d.w));
+        const float g = __ldg(dlogit + row) * scale;
+        const int slice = blockIdx.x % kHeadSlices;
+        const float4* xb = x + static_cast<int64_t>(b) * N * 16 + c;
+        float4 v;
+        if (slice == 0) {
+            v = __ldg(xb + e.x * 16);
+        } else if (slice == 1) {
+            v = __ldg(xb + e.y * 16);
+        } else {
+            const float4 a = __ldg(xb + e.x * 16), d = __ldg(xb + e.y * 16);
+            v = make_float4(fabsf(a.x - d.x), fabsf(a.y - d.y), fabsf(a.z - d.z), fabsf(a.w - d.w));
+        }
+        return make_float4(g * v.x, g * v.y, g * v.z, g * v.w);
     }
 };
 
-}  // namespace
-
-namespace {
-// dw2[j] = sum_rows dlogit[row] * hpost[row, j]: one streaming pass over the blocked-32 activations.
-// warp w of a CTA owns float4 columns w, w + 8, w + 16, w + 24; lane = row inside a 32-row block.
-__global__ void __launch_bounds__(256)
-head_dw2_kernel(const float4* __restrict__ hpost, const float* __restrict__ dlogit, float* __restrict__ part, uint32_t M) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float4 acc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t n_blk = (M + 31) / 32;
-    for (uint32_t blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
-        const uint32_t row = blk * 32 + lane;
-        const float d = row < M ? __ldg(dlogit + row) : 0.f;
-        float4 h[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = ptx::ldg_stream(hpost + (static_cast<size_t>(blk) * 32 + warp + 8 * k) * 32 + lane);
-        if (row >= M) {  // the padding rows of the last block are never written
-#pragma unroll
-            for (int k = 0; k < 4; ++k) h[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            acc[k].x = fmaf(d, h[k].x, acc[k].x); acc[k].y = fmaf(d, h[k].y, acc[k].y);
-            acc[k].z = fmaf(d, h[k].z, acc[k].z); acc[k].w = fmaf(d, h[k].w, acc[k].w);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o); acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-            acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, o); acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, o);
-        }
-        if (lane == 0) reinterpret_cast<float4*>(part + static_cast<size_t>(blockIdx.x) * 128)[warp + 8 * k] = acc[k];
-    }
-}
 }  // namespace
 
 extern "C" int64_t ltgnn_pipe_head_ws_floats(int device) {
-    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][224] + dw2 partials [8 sm][128]
-    return di ? static_cast<int64_t>(di->sm_count) * tgrad::kMo * (224 + 8) : -1;
+    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][64] + (d w2 | d b1) partials [2 sm][256]
+    return di ? static_cast<int64_t>(di->sm_count) * (tgrad::kMo * 64 + 2 * 256) : -1;
 }
 
 extern "C" int64_t ltgnn_tgrad_ws_floats(int device, int32_t No) {
@@ -101,7 +110,7 @@ extern "C" int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, con
                               int accumulate, float* ws, void* stream_) {
     LTGNN_REQUIRE(M >= 0, LTGNN_E_ARG, "wgrad_tc: M=%lld", static_cast<long long>(M));
     LTGNN_REQUIRE(Do == 64 || Do == 128, LTGNN_E_SHAPE, "wgrad_tc: Do=%d must be 64 or 128", Do);
-    LTGNN_REQUIRE(Di % 32 == 0 && Di > 0 && Di <= 256, LTGNN_E_SHAPE, "wgrad_tc: Di=%d must be a multiple of 32, <= 256", Di);
+    LTGNN_REQUIRE(Di % 32 == 0 && Di > 0 && Di <= 192, LTGNN_E_SHAPE, "wgrad_tc: Di=%d must be a multiple of 32, <= 192", Di);
     LTGNN_REQUIRE(G && X && dW && ws, LTGNN_E_ARG, "wgrad_tc: null tensor");
     LTGNN_REQUIRE(aligned16(G) && aligned16(X), LTGNN_E_ALIGN, "wgrad_tc: G/X must be 16-byte aligned");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -114,7 +123,7 @@ extern "C" int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, con
     StackedRows x{reinterpret_cast<const float4*>(X), nullptr, Di / 4, 0};
     int grid = 0;
     // the GCN shape (64 x 64) takes the narrow variant: half of operand G is never stored, loads are pipelined
-    int rc = (Do == 64 && Di == 64) ? tgrad::launch<1, 2, 2>(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc")
+    int rc = (Do == 64 && Di == 64) ? tgrad::launch<1, 2, 2, -1>(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc")
                                     : tgrad::launch(device, g, x, ws, M, Di, &grid, stream, "wgrad_tc");
     if (rc) return rc;
     return tgrad::gather(ws, grid, Di, 0, Do, 0, Di, dW, Di, accumulate, stream);
@@ -136,23 +145,21 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
         return LTGNN_OK;
     }
     const int64_t M = B * P;
-    HeadDpre g{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale};
-    HeadFeatOnes x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
-                   static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
-    const int No = 224;  // 192 feature columns + a ones column (-> db1) padded to a whole 32-column block
-    int grid = 0;
-    int rc = tgrad::launch<1, 4, 7>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
-    if (rc) return rc;
-    rc = tgrad::gather(ws, grid, No, 0, H, 0, 3 * D, dW1, 3 * D, 0, stream);
-    if (rc) return rc;
-    rc = tgrad::gather(ws, grid, No, 0, H, 3 * D, 1, db1, 1, 0, stream);
-    if (rc) return rc;
     const DeviceInfo* di = device_info(device);
     LTGNN_REQUIRE(di, LTGNN_E_CUDA, "pipe_head_bwd_w: device %d", device);
-    float* part = ws + static_cast<size_t>(di->sm_count) * tgrad::kMo * No;  // [8 sm][128]
-    const int n_blk = static_cast<int>((M + 31) / 32);
-    const int grid2 = n_blk < 8 * di->sm_count ? n_blk : 8 * di->sm_count;
-    head_dw2_kernel<<<grid2, 256, 0, stream>>>(reinterpret_cast<const float4*>(hpost), dlogit, part, static_cast<uint32_t>(M));
-    LTGNN_CUDA_TRY(cudaGetLastError());
-    return reduce_parts(part, H, dw2, grid2, H, 0, stream);
+    const int No = D;  // one 64-column slice of the 192 feature columns per CTA
+    float* part = ws + static_cast<size_t>(di->sm_count) * tgrad::kMo * No;  // [2 sm][256]
+    HeadLive g{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, part};
+    HeadFeatSlice x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), dlogit, gate_scale,
+                    static_cast<uint32_t>(P), static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
+    int grid = 0;
+    int rc = tgrad::launch<1, 4, 2, -1>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
+    if (rc) return rc;
+    for (int sl = 0; sl < kHeadSlices; ++sl) {  // dW1[:, 64 sl : 64 sl + 64] = w2[j] * sum over the row ranges of slice sl
+        rc = tgrad::gather(ws, grid, No, 0, H, 0, No, dW1 + sl * No, 3 * D, 0, stream, tgrad::kMo, sl, kHeadSlices, w2);
+        if (rc) return rc;
+    }
+    rc = reduce_parts(part, 256, dw2, 2 * grid, H, 0, stream);
+    if (rc) return rc;
+    return reduce_parts(part + 128, 256, db1, 2 * grid, H, 0, stream);
 }

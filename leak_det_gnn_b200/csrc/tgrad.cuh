@@ -7,12 +7,21 @@
 // stride offset = one group of 4 rows (512 B).  One tcgen05.mma (kind::tf32, K = 8) consumes 8 rows;
 // 3xTF32 as everywhere.
 //
-// The accumulator (Mo = 128 lanes x No <= 256 columns) stays in tensor memory for the whole life of the CTA;
-// at the end the CTA writes its partial to a workspace and a second kernel adds the partials in a fixed order.
+// Accumulation.  The tensor core adds into its fp32 accumulator with TRUNCATION: a bias of ~2e-8 |acc| per MMA that
+// grows linearly with the number of accumulations.  Measured on this kernel with one accumulator for the CTA's whole
+// row range: 4e-6 after 570 rows per CTA, 1.2e-4 after 18 000 (the B = 4096 bench size); and on the ill-conditioned
+// sums a cross-entropy gradient produces (sum of |terms| ~ 100 x |sum|) 1e-4 already at B = 128, 30 x the error of an
+// fp32 FMA loop.  So the tensor core only ever accumulates the hi*hi products of ONE 32-row chunk (4 MMAs) into a
+// `main` temporary (64-column blocks, 2-4 of them in rotation); the read-out warps add it to the running total with
+// round-to-nearest fp32 adds on the CUDA cores.  The total also lives in tensor memory (tcgen05.ld / add / tcgen05.st),
+// so a flush moves no bytes outside the SM.  The cross products lo*hi + hi*lo are 2^-11 of the sum, their truncation
+// bias is 2^-11 of an already small number, and they accumulate in a persistent `cross` accumulator for the CTA's
+// life.  Error after the change: 2-4e-7 on random operands, 6-9e-6 on the ill-conditioned ones (torch fp32: 2-3e-6).
+// At the end the CTA writes total + cross to a workspace and a second kernel adds the CTA partials in a fixed order.
 //   warps 0-15  loaders, two groups of 8 warps, one ring stage each (rows are produced by functors, so the
 //               "matrices" can be gathers or on-the-fly gradients and never exist in memory)
 //   warp  16    MMA issue (elected lane)
-//   warps 17-20 final read-out
+//   warps 17-20 read-out: one warp per tensor-memory lane quadrant
 #pragma once
 
 #include <type_traits>
@@ -27,11 +36,14 @@ using namespace ltgnn::umma;
 
 constexpr int kMo = 128;        // accumulator rows (operand-G columns); pad / stack operands up to it
 constexpr int kChunk = 32;      // rows per ring stage (4 K-steps)
+constexpr int kReadWarps = 4;    // one per tensor-memory lane quadrant (more warps would cap the loaders below 80 registers)
+constexpr int kMaxBuf = 4;       // `main` temporaries in rotation
 constexpr int kLoaderWarps = 16;
 constexpr int kGroups = 2;
 constexpr int kGroupThreads = kLoaderWarps / kGroups * 32;  // 256
 constexpr int kMmaWarp = kLoaderWarps;
-constexpr int kThreads = (kLoaderWarps + 1 + 4) * 32;
+constexpr int kThreads = (kLoaderWarps + 1 + kReadWarps) * 32;
+constexpr int kThreadsReg = (kLoaderWarps + 1 + 8) * 32;  // register-total form: two read-out warps per quadrant
 constexpr uint32_t kBlockBytes = kChunk * 128;  // one 32-column block of a 32-row chunk = 4 KB
 
 // MN-major SWIZZLE_128B_BASE32B descriptor: LBO = distance between 32-column blocks, SBO = 4 rows = 512 B
@@ -60,6 +72,35 @@ __host__ __device__ constexpr uint32_t idesc_tf32_mn(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// A G loader may carry a per-thread side accumulation over the values it fetches (`using Side = ...`,
+// `load(row, c, Side&)`, `finish(Side*, n, cta, group, warp_in_group, lane)`): the pipe head's d w2 rides on the
+// pass that reads the saved activations anyway.
+template <class T, class = void>
+struct has_side : std::false_type {};
+template <class T>
+struct has_side<T, std::void_t<typename T::Side>> : std::true_type {};
+template <class T, bool = has_side<T>::value>
+struct side_of { struct type {}; };
+template <class T>
+struct side_of<T, true> { using type = typename T::Side; };
+
+// Optional loader traits.  XLoader::kSlices = S: S consecutive CTAs share one row range and each produces its own No
+// columns of the result (the loaders look at blockIdx.x % S themselves) -- a wide result split so that every CTA can keep
+// its totals in registers.  GLoader::kExact: the G values are exactly representable in TF32 (0 / 1 masks), so the lo
+// copy and its MMAs are skipped.
+template <class T, class = void>
+struct slices_of { static constexpr int value = 1; };
+template <class T>
+struct slices_of<T, std::void_t<decltype(T::kSlices)>> { static constexpr int value = T::kSlices; };
+template <class T, class = void>
+struct exact_of { static constexpr bool value = false; };
+template <class T>
+struct exact_of<T, std::void_t<decltype(T::kExact)>> { static constexpr bool value = T::kExact; };
+
+// float4 index of (row, columns 4 c4 .. 4 c4 + 3) inside one [128 x No] partial of the workspace: row-fast, so that a
+// read-out warp (lane = row) touches 512 contiguous bytes per instruction
+__host__ __device__ inline size_t ws_f4(int row, int c4) { return static_cast<size_t>(c4) * kMo + row; }
+
 __host__ inline size_t stage_bytes(int No, int mt) { return 2ull * (kMo * mt + No) * kChunk * 4; }
 __host__ inline size_t smem_bytes(int No, int mt) { return 1024 + kGroups * stage_bytes(No, mt); }
 
@@ -70,11 +111,18 @@ __host__ inline size_t smem_bytes(int No, int mt) { return 1024 + kGroups * stag
 // every operand; a narrow operand (kGJ < 4 kMT: G columns beyond 32 kGJ are zero and are written once at start;
 // kXJ = No / 32) needs few registers per stage, and then the loads of the NEXT chunk are issued before the current
 // one is stored (kPipe) -- twice the bytes in flight for the skinny, HBM-bound weight gradients.
-template <class GLoader, class XLoader, int kMT, int kGJ = 4 * kMT, int kXJ = 8>
-__global__ void __launch_bounds__(kThreads, 1)
-tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols) {
+// kSeg = 0: the accurate form described in the header (per-chunk flush).  kSeg > 0: the cheap form for sums that are not
+// ill-conditioned (the GRU parameter gradients, held to 5e-5): all three products go to one of two full-width
+// accumulators for kSeg chunks, then the read-out warps add it to the CTA's partial in the (L2-resident) workspace.
+// kSeg = -1: the accurate form for narrow results (No <= 64, kMT = 1; the GCN layers): the totals stay in REGISTERS
+// of eight read-out warps (32 columns each), so a flush is one tensor-memory read of `main` -- tensor memory moves
+// 64 B / clock / SM, and the load / add / store of a total that lives there costs three times that.
+template <class GLoader, class XLoader, int kMT, int kGJ = 4 * kMT, int kXJ = 8, int kSeg = 0>
+__global__ void __launch_bounds__(kSeg < 0 ? kThreadsReg : kThreads, 1)
+tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols,
+             int nb, uint32_t nbuf_log2) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kGroups], bar_empty[kGroups], bar_done;
+    __shared__ uint64_t bar_full[kGroups], bar_empty[kGroups], bar_tmp_full[kMaxBuf], bar_tmp_empty[kMaxBuf];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
@@ -90,11 +138,14 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
             mbar_init(&bar_full[s], kLoaderWarps / kGroups);
             mbar_init(&bar_empty[s], 1);
         }
-        mbar_init(&bar_done, 1);
+        for (int a = 0; a < kMaxBuf; ++a) {
+            mbar_init(&bar_tmp_full[a], 1);
+            mbar_init(&bar_tmp_empty[a], kSeg < 0 ? 8 : kReadWarps);
+        }
         fence_mbar_init();
     }
     if (kGJ < 4 * kMT) {  // operand-G columns the loaders never write: zero in every stage, hi and lo
-        for (uint32_t i = tid; i < kGroups * 2 * (g_half / 16); i += kThreads) {
+        for (uint32_t i = tid; i < kGroups * 2 * (g_half / 16); i += blockDim.x) {
             const uint32_t st = i / (2 * (g_half / 16)), r = i - st * 2 * (g_half / 16);
             *reinterpret_cast<float4*>(smem + st * stage + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -104,11 +155,20 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
+    const uint32_t nbuf_mask = (1u << nbuf_log2) - 1;  // 2 or 4 temporaries in rotation
+    // tensor memory: total [kMT][No] | cross [kMT][No] | main [nbuf][nb]   (nb = 64 or 32 columns per block)
+    // (register-total form: cross [No] | main [nbuf][nb])
+    const uint32_t t_cross = kSeg < 0 ? tmem_base : tmem_base + kMT * No;
+    const uint32_t t_tmp = kSeg < 0 ? tmem_base + No : tmem_base + 2 * kMT * No;
 
     // contiguous range of row chunks per CTA
+    constexpr uint32_t kSl = slices_of<XLoader>::value;
+    constexpr bool kExactG = exact_of<GLoader>::value;
+    static_assert(!kExactG || kSeg < 0, "exact-G operands are only handled by the register-total form");
     const uint32_t n_chunks = (M + kChunk - 1) / kChunk;
-    const uint32_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
-    const uint32_t c_begin = blockIdx.x * per;
+    const uint32_t n_ranges = gridDim.x / kSl;
+    const uint32_t per = (n_chunks + n_ranges - 1) / n_ranges;
+    const uint32_t c_begin = (blockIdx.x / kSl) * per;
     const uint32_t c_end = c_begin + per < n_chunks ? c_begin + per : n_chunks;
 
     if (warp < kLoaderWarps) {
@@ -134,10 +194,16 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         auto cg = [&](int j) { return GLoader::kRowFast ? 2 * qg + (j & 1) + 16 * (j >> 1) : qg + 8 * j; };
         auto cx = [&](int j) { return XLoader::kRowFast ? 2 * qx + (j & 1) + 16 * (j >> 1) : qx + 8 * j; };
         float4 gv[kGJ], xv[kXJ];
+        typename side_of<GLoader>::type side[kGJ] = {};
         auto fetch = [&](uint32_t ch, float4 (&gd)[kGJ], float4 (&xd)[kXJ]) {
             const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
 #pragma unroll
-            for (int j = 0; j < kGJ; ++j) gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kGJ; ++j) {
+                if constexpr (has_side<GLoader>::value)
+                    gd[j] = row_g < M ? gload.load(row_g, cg(j), side[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                else
+                    gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int j = 0; j < kXJ; ++j)
                 xd[j] = (row_x < M && cx(j) < x4) ? xload(row_x, cx(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,7 +212,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         // whose swizzled offsets share only 4 bank groups (2-way conflicts on every quarter-warp).  Lanes whose row
         // has bit 2 set therefore store the two chunks of a pair in the opposite order: a quarter-warp then covers
         // both parities x 4 swizzle phases = all 8 bank groups.
-        auto store = [&](auto fast, const auto& v, int nj, int r, auto cj, int climit, uint8_t* hi_base, uint8_t* lo_base) {
+        auto store = [&](auto fast, auto with_lo, const auto& v, int nj, int r, auto cj, int climit, uint8_t* hi_base,
+                         uint8_t* lo_base) {
             if constexpr (decltype(fast)::value) {
                 const bool swap = (r >> 2) & 1;
 #pragma unroll
@@ -161,7 +228,7 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                             split4(val, hi, lo);
                             const uint32_t off = mn_offset(r, c, kChunk);
                             *reinterpret_cast<float4*>(hi_base + off) = hi;
-                            *reinterpret_cast<float4*>(lo_base + off) = lo;
+                            if constexpr (decltype(with_lo)::value) *reinterpret_cast<float4*>(lo_base + off) = lo;
                         }
                     }
                 }
@@ -173,7 +240,7 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                         split4(v[j], hi, lo);
                         const uint32_t off = mn_offset(r, cj(j), kChunk);
                         *reinterpret_cast<float4*>(hi_base + off) = hi;
-                        *reinterpret_cast<float4*>(lo_base + off) = lo;
+                        if constexpr (decltype(with_lo)::value) *reinterpret_cast<float4*>(lo_base + off) = lo;
                     }
                 }
             }
@@ -192,18 +259,67 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                 fetch(ch, gc, xc);
             }
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
-            store(std::integral_constant<bool, GLoader::kRowFast>{}, gc, kGJ, rg, cg, kG / 4, g_hi, g_lo);
-            store(std::integral_constant<bool, XLoader::kRowFast>{}, xc, kXJ, rx, cx, x4, x_hi, x_lo);
+            store(std::integral_constant<bool, GLoader::kRowFast>{}, std::integral_constant<bool, !kExactG>{}, gc, kGJ, rg, cg, kG / 4,
+                  g_hi, g_lo);
+            store(std::integral_constant<bool, XLoader::kRowFast>{}, std::true_type{}, xc, kXJ, rx, cx, x4, x_hi, x_lo);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[grp]);
         }
-    } else if (warp == kMmaWarp) {
+        if constexpr (has_side<GLoader>::value) {
+            static_assert(GLoader::kRowFast, "side accumulation reduces over the lanes = rows of the row-fast mapping");
+            int cols[kGJ];
+#pragma unroll
+            for (int j = 0; j < kGJ; ++j) cols[j] = cg(j);
+            gload.finish(side, cols, kGJ, blockIdx.x, grp, lane);
+        }
+    } else if (warp == kMmaWarp && kSeg < 0) {
+        // register-total form: one block per chunk.  This warp is a single serial instruction stream that every chunk
+        // passes through (an earlier, general version of this loop -- runtime block widths, a division for the rotation
+        // index -- ran 190 instructions per chunk and set the kernel's pace), so everything loop-invariant is hoisted.
+        const uint32_t idesc = idesc_tf32_mn(kMo, No);
+        const uint32_t base = smem_u32(smem);
+        uint32_t gh[kGroups], gl[kGroups], xh[kGroups], xl[kGroups];
+#pragma unroll
+        for (int s = 0; s < kGroups; ++s) {
+            gh[s] = mn_desc_lo(base + s * stage);
+            gl[s] = mn_desc_lo(base + s * stage + g_half);
+            xh[s] = mn_desc_lo(base + s * stage + 2 * g_half);
+            xl[s] = mn_desc_lo(base + s * stage + 2 * g_half + x_half);
+        }
+        const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
+        for (uint32_t n = 0; n < n_local; ++n) {
+            const uint32_t s = n & 1, a = n & nbuf_mask;
+            mbar_wait(&bar_tmp_empty[a], ((n >> nbuf_log2) & 1) ^ 1);  // the read-out drained this temporary
+            mbar_wait(&bar_full[s], (n >> 1) & 1);
+            fence_after_sync();
+            if (elect_one()) {
+                const uint32_t g_h = s ? gh[1] : gh[0], g_l = s ? gl[1] : gl[0], x_h = s ? xh[1] : xh[0], x_l = s ? xl[1] : xl[0];
+                const uint32_t d_main = t_tmp + a * nb;
+#pragma unroll
+                for (uint32_t k = 0; k < kChunk / 8; ++k) {
+                    if constexpr (!kExactG) {
+                        mma_tf32_mn(t_cross, g_l + 64 * k, x_h + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
+                        mma_tf32_mn(t_cross, g_h + 64 * k, x_l + 64 * k, idesc, 1u);
+                    } else {
+                        mma_tf32_mn(t_cross, g_h + 64 * k, x_l + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
+                    }
+                }
+#pragma unroll
+                for (uint32_t k = 0; k < kChunk / 8; ++k) mma_tf32_mn(d_main, g_h + 64 * k, x_h + 64 * k, idesc, k ? 1u : 0u);
+                commit(&bar_tmp_full[a]);
+                commit(&bar_empty[s]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kMmaWarp && kSeg > 0) {
         const uint32_t idesc = idesc_tf32_mn(kMo, No);
         const uint32_t base = smem_u32(smem);
         uint32_t n = 0;
         for (uint32_t ch = c_begin; ch < c_end; ++ch, ++n) {
             const uint32_t s = n % kGroups;
+            const uint32_t seg = n / (kSeg > 0 ? kSeg : 1), in_seg = n % (kSeg > 0 ? kSeg : 1), a = seg & 1;
+            if (in_seg == 0) mbar_wait(&bar_tmp_empty[a], ((seg >> 1) & 1) ^ 1);  // the read-out drained this accumulator
             mbar_wait(&bar_full[s], (n / kGroups) & 1);
             fence_after_sync();
             if (elect_one()) {
@@ -214,37 +330,199 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                 for (uint32_t k = 0; k < kChunk / 8; ++k) {  // 8 rows = 1024 B = 64 descriptor units per K-step
 #pragma unroll
                     for (uint32_t mt = 0; mt < kMT; ++mt) {  // accumulator tile mt <- operand-G columns [128 mt, +128)
-                        const uint32_t go = mt * (4 * kBlockBytes >> 4) + 64 * k, d = tmem_base + mt * No;
-                        mma_tf32_mn(d, gl + go, xh + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
+                        const uint32_t go = mt * (4 * kBlockBytes >> 4) + 64 * k, d = tmem_base + (a * kMT + mt) * No;
+                        mma_tf32_mn(d, gl + go, xh + 64 * k, idesc, (in_seg == 0 && k == 0) ? 0u : 1u);
                         mma_tf32_mn(d, gh + go, xl + 64 * k, idesc, 1u);
                         mma_tf32_mn(d, gh + go, xh + 64 * k, idesc, 1u);
                     }
                 }
                 commit(&bar_empty[s]);
-                if (ch + 1 == c_end) commit(&bar_done);
+                if (in_seg == kSeg - 1 || ch + 1 == c_end) commit(&bar_tmp_full[a]);
             }
             __syncwarp();
         }
-    } else {
-        // read-out: lane = accumulator row (operand-G column), columns = operand-X columns
-        const int q = warp & 3;
-        if (c_begin < c_end) {
-            mbar_wait(&bar_done, 0);
+    } else if (warp == kMmaWarp) {
+        const uint32_t base = smem_u32(smem);
+        uint32_t n = 0, unit = 0;
+        for (uint32_t ch = c_begin; ch < c_end; ++ch, ++n) {
+            const uint32_t s = n % kGroups;
+            mbar_wait(&bar_full[s], (n / kGroups) & 1);
             fence_after_sync();
+            const uint32_t gh = mn_desc_lo(base + s * stage), gl = mn_desc_lo(base + s * stage + g_half);
+            const uint32_t xh = mn_desc_lo(base + s * stage + 2 * g_half);
+            const uint32_t xl = mn_desc_lo(base + s * stage + 2 * g_half + x_half);
+            const uint32_t idesc_full = idesc_tf32_mn(kMo, No);
+#pragma unroll 1
+            for (uint32_t mt = 0; mt < kMT; ++mt) {  // accumulator tile mt <- operand-G columns [128 mt, +128)
+                if (elect_one()) {  // cross products, full width, into the persistent accumulator
+#pragma unroll
+                    for (uint32_t k = 0; k < kChunk / 8; ++k) {  // 8 rows = 1024 B = 64 descriptor units per K-step
+                        const uint32_t go = mt * (4 * kBlockBytes >> 4) + 64 * k;
+                        mma_tf32_mn(t_cross + mt * No, gl + go, xh + 64 * k, idesc_full, (n == 0 && k == 0) ? 0u : 1u);
+                        mma_tf32_mn(t_cross + mt * No, gh + go, xl + 64 * k, idesc_full, 1u);
+                    }
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int c0 = 0; c0 < No; c0 += nb, ++unit) {
+                    const uint32_t a = unit & nbuf_mask;
+                    mbar_wait(&bar_tmp_empty[a], ((unit >> nbuf_log2) & 1) ^ 1);  // the read-out drained this temporary
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const int w = No - c0 < nb ? No - c0 : nb;
+                        const uint32_t idesc = idesc_tf32_mn(kMo, w);
+                        const uint32_t xo = static_cast<uint32_t>(c0 >> 5) * (kBlockBytes >> 4);
+#pragma unroll
+                        for (uint32_t k = 0; k < kChunk / 8; ++k)
+                            mma_tf32_mn(t_tmp + a * nb, gh + mt * (4 * kBlockBytes >> 4) + 64 * k, xh + xo + 64 * k, idesc,
+                                        k == 0 ? 0u : 1u);
+                        commit(&bar_tmp_full[a]);
+                        if (mt + 1 == kMT && c0 + nb >= No) commit(&bar_empty[s]);  // last unit of the chunk: stage free
+                    }
+                    __syncwarp();
+                }
+            }
         }
-        for (int mt = 0; mt < kMT; ++mt) {
-            float* out = ws + ((static_cast<size_t>(blockIdx.x) * kMT + mt) * kMo + q * 32 + lane) * No;
-            if (c_begin < c_end) {
-                const uint32_t taddr = tmem_base + mt * No + (static_cast<uint32_t>(q * 32) << 16);
+    } else if (kSeg < 0) {
+        // read-out, register-total form: warp (q, half) owns columns [32 half, +32) of lane quadrant q
+        const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2, row = q * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
+        float tot[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tot[j] = 0.f;
+        if (32 * half < No) {
+            for (uint32_t n = 0; n < n_local; ++n) {
+                const uint32_t a = n & nbuf_mask;
+                mbar_wait(&bar_tmp_full[a], (n >> nbuf_log2) & 1);
+                fence_after_sync();
+                float m0[16], m1[16];
+                tmem_ld16_nowait(t_tmp + lane_off + a * nb + 32 * half, m0);
+                tmem_ld16_nowait(t_tmp + lane_off + a * nb + 32 * half + 16, m1);
+                tmem_wait_ld();
+                tmem_pin16(m0);
+                tmem_pin16(m1);
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tmp_empty[a]);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    tot[j] += m0[j];
+                    tot[16 + j] += m1[j];
+                }
+            }
+            if (n_local) {  // the last `main` commit also covers every cross MMA issued before it
+                float c0v[16], c1v[16];
+                tmem_ld16(t_cross + lane_off + 32 * half, c0v);
+                tmem_ld16(t_cross + lane_off + 32 * half + 16, c1v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    tot[j] += c0v[j];
+                    tot[16 + j] += c1v[j];
+                }
+            }
+            float4* part = reinterpret_cast<float4*>(ws) + static_cast<size_t>(blockIdx.x) * kMo * (No / 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                part[ws_f4(row, 8 * half + j)] = make_float4(tot[4 * j], tot[4 * j + 1], tot[4 * j + 2], tot[4 * j + 3]);
+        } else {  // No = 32: the second warp of the quadrant only keeps the barrier counts right
+            for (uint32_t n = 0; n < n_local; ++n) {
+                const uint32_t a = n & nbuf_mask;
+                mbar_wait(&bar_tmp_full[a], (n >> nbuf_log2) & 1);
+                if (lane == 0) mbar_arrive(&bar_tmp_empty[a]);
+            }
+        }
+    } else if (kSeg > 0) {
+        // read-out, cheap form: segment 0 overwrites the CTA's partial, later segments add to it (each thread only ever
+        // touches its own entries; row-fast layout: a warp moves 512 contiguous bytes per instruction)
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
+        const uint32_t n_seg = (n_local + (kSeg > 0 ? kSeg : 1) - 1) / (kSeg > 0 ? kSeg : 1);
+        float4* part = reinterpret_cast<float4*>(ws) + static_cast<size_t>(blockIdx.x) * kMT * kMo * (No / 4);
+        for (uint32_t seg = 0; seg < n_seg; ++seg) {
+            const uint32_t a = seg & 1;
+            mbar_wait(&bar_tmp_full[a], (seg >> 1) & 1);
+            fence_after_sync();
+            for (int mt = 0; mt < kMT; ++mt) {
+                float4* out = part + static_cast<size_t>(mt) * kMo * (No / 4);
+                const uint32_t taddr = tmem_base + (a * kMT + mt) * No + (static_cast<uint32_t>(q * 32) << 16);
                 for (int c0 = 0; c0 < No; c0 += 16) {
+                    float4 prev[4];
+                    if (seg) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) prev[j] = out[ws_f4(row, (c0 >> 2) + j)];
+                    }
                     float v[16];
                     tmem_ld16(taddr + c0, v);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        reinterpret_cast<float4*>(out + c0)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) {
+                        float4 t = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (seg) {
+                            t.x += prev[j].x; t.y += prev[j].y; t.z += prev[j].z; t.w += prev[j].w;
+                        }
+                        out[ws_f4(row, (c0 >> 2) + j)] = t;
+                    }
                 }
-            } else {
-                for (int c0 = 0; c0 < No; c0 += 4) *reinterpret_cast<float4*>(out + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tmp_empty[a]);
+        }
+        if (n_seg == 0) {
+            for (int i = 0; i < kMT * (No / 4); ++i) part[static_cast<size_t>(i) * kMo + row] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        // read-out: lane = accumulator row (operand-G column).  total += main per (chunk, tile, block), in fp32 on the CUDA
+        // cores, 16 columns per round (main and total loads in flight together, one wait).
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
+        uint32_t unit = 0;
+        for (uint32_t n = 0; n < n_local; ++n) {
+            for (int mt = 0; mt < kMT; ++mt) {
+                for (int c0 = 0; c0 < No; c0 += nb, ++unit) {
+                    const uint32_t a = unit & nbuf_mask;
+                    mbar_wait(&bar_tmp_full[a], (unit >> nbuf_log2) & 1);
+                    fence_after_sync();
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");  // my stores of the previous chunk
+                    const int w = No - c0 < nb ? No - c0 : nb;
+                    const uint32_t t_total = tmem_base + lane_off + mt * No + c0, t_main = t_tmp + lane_off + a * nb;
+                    for (int p = 0; p < w; p += 16) {
+                        float m0[16], s0[16];
+                        tmem_ld16_nowait(t_main + p, m0);
+                        if (n) tmem_ld16_nowait(t_total + p, s0);
+                        tmem_wait_ld();
+                        tmem_pin16(m0);
+                        if (n) {
+                            tmem_pin16(s0);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) m0[j] += s0[j];
+                        }
+                        tmem_st16(t_total + p, m0);
+                    }
+                    fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_tmp_empty[a]);  // the loads of `main` have completed (wait::ld)
+                }
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // the last `main` commit also covers every cross MMA issued before it
+        float4* part = reinterpret_cast<float4*>(ws) + static_cast<size_t>(blockIdx.x) * kMT * kMo * (No / 4);
+        for (int mt = 0; mt < kMT; ++mt) {
+            float4* out = part + static_cast<size_t>(mt) * kMo * (No / 4);
+            for (int c0 = 0; c0 < No; c0 += 8) {
+                float v[8], vc[8];
+                if (n_local) {
+                    tmem_ld8x2(tmem_base + lane_off + mt * No + c0, t_cross + lane_off + mt * No + c0, v, vc);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] += vc[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                }
+                out[ws_f4(row, c0 >> 2)] = make_float4(v[0], v[1], v[2], v[3]);
+                out[ws_f4(row, (c0 >> 2) + 1)] = make_float4(v[4], v[5], v[6], v[7]);
             }
         }
     }
@@ -257,7 +535,7 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
 }
 
 // ws: [grid][128 * kMT][No] partial accumulators; `gather` below adds them up (its row index runs over 128 * kMT)
-template <int kMT = 1, int kGJ = 4 * kMT, int kXJ = 8, class GLoader, class XLoader>
+template <int kMT = 1, int kGJ = 4 * kMT, int kXJ = 8, int kSeg = 0, class GLoader, class XLoader>
 int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M, int No, int* grid_out,
            cudaStream_t stream, const char* who) {
     LTGNN_REQUIRE(No <= 32 * kXJ, LTGNN_E_SHAPE, "%s: No=%d exceeds this variant's %d columns", who, No, 32 * kXJ);
@@ -270,13 +548,26 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     const size_t smem = smem_bytes(No, kMT);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "%s: %zu B of shared memory", who, smem);
     LTGNN_USE_DEVICE(device);
-    auto kern = tgrad_kernel<GLoader, XLoader, kMT, kGJ, kXJ>;
+    auto kern = tgrad_kernel<GLoader, XLoader, kMT, kGJ, kXJ, kSeg>;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     uint32_t cols = 32;
-    while (cols < static_cast<uint32_t>(No) * kMT) cols <<= 1;
-    LTGNN_REQUIRE(cols <= 512, LTGNN_E_SHAPE, "%s: %d accumulator columns exceed tensor memory", who, No * kMT);
-    const int grid = di->sm_count;
-    kern<<<grid, kThreads, smem, stream>>>(g, x, ws, static_cast<uint32_t>(M), No, cols);
+    // tensor memory: total + cross accumulators (No * kMT columns each) + 2..4 `main` temporaries of 64 (or 32) columns
+    // (kSeg > 0: two full-width accumulators; kSeg < 0: cross + 4 temporaries as wide as the result)
+    static_assert(kSeg >= 0 || kMT == 1, "the register-total form handles one accumulator tile");
+    LTGNN_REQUIRE(kSeg >= 0 || No <= 64, LTGNN_E_SHAPE, "%s: the register-total form needs No <= 64, got %d", who, No);
+    const int left = 512 - 2 * No * kMT;
+    const int nb = kSeg < 0 ? No : (left >= 2 * 64 ? 64 : 32);
+    int nbuf = kSeg > 0 ? 2 : (kSeg < 0 ? kMaxBuf : left / nb);
+    nbuf = nbuf >= 4 ? 4 : nbuf;  // rotation counts are powers of two
+    if (nbuf == 3) nbuf = 2;
+    LTGNN_REQUIRE(nbuf >= 2 && left >= 0, LTGNN_E_SHAPE, "%s: 2 x %d accumulator columns leave no room in tensor memory", who,
+                  No * kMT);
+    const uint32_t need = kSeg > 0 ? 2 * No * kMT : (kSeg < 0 ? No + nbuf * nb : 2 * No * kMT + nbuf * nb);
+    while (cols < need) cols <<= 1;
+    constexpr int kSl = slices_of<XLoader>::value;
+    const int grid = di->sm_count / kSl * kSl;
+    kern<<<grid, kSeg < 0 ? kThreadsReg : kThreads, smem, stream>>>(g, x, ws, static_cast<uint32_t>(M), No, cols, nb,
+                                                                  nbuf == 4 ? 2u : 1u);
     LTGNN_CUDA_TRY(cudaGetLastError());
     *grid_out = grid;
     return LTGNN_OK;
@@ -288,7 +579,8 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
 constexpr int kGatherX = 64, kGatherY = 8;
 static __global__ void __launch_bounds__(kGatherX * kGatherY)
 gather_partials_kernel(const float* __restrict__ ws, int n_parts, int part_rows, int No, int r0, int rows, int c0, int cols,
-                       float* __restrict__ out, int ld_out, int accumulate) {
+                       float* __restrict__ out, int ld_out, int accumulate, int p0, int p_step,
+                       const float* __restrict__ row_scale) {
     __shared__ float red[kGatherY][kGatherX];
     const int x = threadIdx.x % kGatherX, y = threadIdx.x / kGatherX;
     const int i = blockIdx.x * kGatherX + x;
@@ -297,24 +589,31 @@ gather_partials_kernel(const float* __restrict__ ws, int n_parts, int part_rows,
     if (i < rows * cols) {
         r = i / cols;
         c = i - r * cols;
-        const size_t src = static_cast<size_t>(r0 + r) * No + c0 + c, stride = static_cast<size_t>(part_rows) * No;
-        for (int p = y; p < n_parts; p += kGatherY) t += ws[p * stride + src];
+        // partial layout: [part_rows / 128][No / 4][128][4] (ws_f4)
+        const int rr = r0 + r, cc = c0 + c;
+        const size_t src = static_cast<size_t>(rr >> 7) * kMo * No + (ws_f4(rr & 127, cc >> 2) << 2) + (cc & 3);
+        const size_t stride = static_cast<size_t>(part_rows) * No;
+        for (int p = p0 + y * p_step; p < n_parts; p += kGatherY * p_step) t += ws[p * stride + src];
     }
     red[y][x] = t;
     __syncthreads();
     if (y == 0 && i < rows * cols) {
         float s = accumulate ? out[r * ld_out + c] : 0.f;
+        float u = 0.f;
 #pragma unroll
-        for (int k = 0; k < kGatherY; ++k) s += red[k][x];
-        out[r * ld_out + c] = s;
+        for (int k = 0; k < kGatherY; ++k) u += red[k][x];
+        if (row_scale) u *= row_scale[r];
+        out[r * ld_out + c] = s + u;
     }
 }
 
+// parts p0, p0 + p_step, ... < n_parts are summed (sliced results: p_step = number of slices); row_scale[r] multiplies row r
 inline int gather(const float* ws, int n_parts, int No, int r0, int rows, int c0, int cols, float* out, int ld_out,
-                  int accumulate, cudaStream_t stream, int part_rows = kMo) {
+                  int accumulate, cudaStream_t stream, int part_rows = kMo, int p0 = 0, int p_step = 1,
+                  const float* row_scale = nullptr) {
     const int n = rows * cols;
     gather_partials_kernel<<<(n + kGatherX - 1) / kGatherX, kGatherX * kGatherY, 0, stream>>>(
-        ws, n_parts, part_rows, No, r0, rows, c0, cols, out, ld_out, accumulate);
+        ws, n_parts, part_rows, No, r0, rows, c0, cols, out, ld_out, accumulate, p0, p_step, row_scale);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

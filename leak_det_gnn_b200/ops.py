@@ -268,7 +268,7 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     L = _lib.load()
     dev = _dev_index(g)
     dw = torch.empty(do, di, device=g.device, dtype=torch.float32)
-    if do in (64, 128) and di % 32 == 0 and 0 < di <= 256 and m > 0:
+    if do in (64, 128) and di % 32 == 0 and 0 < di <= 192 and m > 0:
         ws = torch.empty(int(L.ltgnn_tgrad_ws_floats(dev, di)), device=g.device, dtype=torch.float32)
         tok = _inst.begin("wgrad_tc")
         _lib.check(L.ltgnn_wgrad_tc(dev, m, do, di, g.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(),
