@@ -104,6 +104,78 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0, uint32_t* __res
     }
 }
 
+// Same result for sensor sets too large to stage (the 100k-node network has 1 000 sensors: 768 KB of embeddings per
+// window): only the transposed weight lives in shared memory, and the thread that owns (row, 8 features) of a sensor row
+// forms its 8 dot products straight from the embeddings in global memory.  Sensor rows are ~1 % of the rows there.
+__global__ void __launch_bounds__(kThreads)
+node_init_fwd_direct_kernel(const InitParams p, float* __restrict__ X0, uint32_t* __restrict__ live_out) {
+    extern __shared__ __align__(16) float sm[];
+    const int ds1 = p.ds + 1, D = p.D, d4 = D >> 2;
+    float* Wt = sm;                   // [ds+1][D]  transposed weight
+    float* base = Wt + ds1 * D;       // [D] relu(bias)
+    float* cst = base + D;            // [D] W[:, ds] + bias
+    const int tid = threadIdx.x;
+    for (int i = tid; i < D * ds1; i += kThreads) {
+        const int j = i / ds1, k = i - j * ds1;
+        Wt[k * D + j] = __ldg(p.W + i);
+    }
+    __syncthreads();
+    for (int j = tid; j < D; j += kThreads) {
+        const float b = __ldg(p.bias + j);
+        base[j] = fmaxf(b, 0.f);
+        cst[j] = Wt[p.ds * D + j] + b;
+    }
+    __syncthreads();
+    const int d8 = d4 >> 1;
+    const int c = (tid % d8) * 2, rstep = kThreads / d8;
+    // work unit = (window, block of rows): the large graphs come with few windows
+    const int rows_per_unit = rstep * 64;
+    const int units_per_b = (p.N + rows_per_unit - 1) / rows_per_unit;
+    for (int64_t u = blockIdx.x; u < p.B * units_per_b; u += gridDim.x) {
+        const int64_t b = u / units_per_b;
+        const int r_lo = static_cast<int>(u - b * units_per_b) * rows_per_unit;
+        const int r_hi = r_lo + rows_per_unit < p.N ? r_lo + rows_per_unit : p.N;
+        float4* out = reinterpret_cast<float4*>(X0) + b * p.N * d4;
+        for (int r = r_lo + tid / d8; r < r_hi; r += rstep) {
+            const int i = r * d8 + (c >> 1);
+            const int sl = __ldg(p.slot + r);
+            float v[8];
+            if (sl < 0) {
+                *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(base + c * 4);
+                *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(base + c * 4 + 4);
+            } else {
+                const float* h = p.hs + (b * p.S + sl) * p.ds;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                for (int k = 0; k < p.ds; ++k) {
+                    const float hk = __ldg(h + k);
+                    const float4 w0 = *reinterpret_cast<const float4*>(Wt + k * D + c * 4);
+                    const float4 w1 = *reinterpret_cast<const float4*>(Wt + k * D + c * 4 + 4);
+                    v[0] = fmaf(hk, w0.x, v[0]); v[1] = fmaf(hk, w0.y, v[1]); v[2] = fmaf(hk, w0.z, v[2]); v[3] = fmaf(hk, w0.w, v[3]);
+                    v[4] = fmaf(hk, w1.x, v[4]); v[5] = fmaf(hk, w1.y, v[5]); v[6] = fmaf(hk, w1.z, v[6]); v[7] = fmaf(hk, w1.w, v[7]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + cst[c * 4 + j], 0.f);
+            }
+            if (p.drop_thresh)
+                ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
+            ptx::stg_stream(out + 2 * i, *reinterpret_cast<const float4*>(v));
+            ptx::stg_stream(out + 2 * i + 1, *reinterpret_cast<const float4*>(v + 4));
+            if (live_out) {  // same word layout as node_init_fwd_kernel
+                uint32_t w = 0;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    w |= ((v[cc] > 0.f ? 1u : 0u) << (8 * cc)) | ((v[4 + cc] > 0.f ? 1u : 0u) << (8 * cc + 1));
+                w <<= 2 * (tid & 3);
+                const uint32_t grp = 0xfu << (tid & 28);
+                w |= __shfl_xor_sync(grp, w, 1);
+                w |= __shfl_xor_sync(grp, w, 2);
+                if ((tid & 3) == 0) live_out[(b * (D >> 5) + (c >> 3)) * p.N + r] = w;
+            }
+        }
+    }
+}
+
 // ---------------------------------------- backward ----------------------------------------
 // (1) one pure streaming kernel over dx0 / x0: gate, per-column sums (-> d bias) and the gated gradient of the S
 //     sensor rows of every window, written compactly to dz [B, S, D] (4 % of the bytes);
@@ -208,12 +280,21 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     InitParams p{hs, W, bias, slot, B, N, S, ds, D, thresh_of(drop_p), scale_of(drop_p), drop_seed};
     const size_t smem = sizeof(float) * (static_cast<size_t>(ds + 1) * D + 2 * D + static_cast<size_t>(S) * ds +
                                          static_cast<size_t>(S) * D);
-    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "node_init_fwd: %zu B of shared memory", smem);
+    LTGNN_REQUIRE(!live_out || D % 32 == 0, LTGNN_E_SHAPE, "node_init_fwd: live_out needs D %% 32 == 0 (D=%d)", D);
+    if (smem > static_cast<size_t>(di->smem_optin)) {  // sensor set too large to stage: rows formed straight from global
+        const size_t smem_d = sizeof(float) * (static_cast<size_t>(ds + 1) * D + 2 * D);
+        LTGNN_REQUIRE(smem_d <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "node_init_fwd: %zu B of shared memory",
+                      smem_d);
+        LTGNN_CUDA_TRY(cudaFuncSetAttribute(node_init_fwd_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem_d)));
+        node_init_fwd_direct_kernel<<<di->sm_count * 4, kThreads, smem_d, static_cast<cudaStream_t>(stream_)>>>(p, X0, live_out);
+        LTGNN_CUDA_TRY(cudaGetLastError());
+        return LTGNN_OK;
+    }
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(node_init_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     const int64_t cap = static_cast<int64_t>(di->sm_count) * 6;
     const int grid = static_cast<int>(B < cap ? B : cap);
-    LTGNN_REQUIRE(!live_out || D % 32 == 0, LTGNN_E_SHAPE, "node_init_fwd: live_out needs D %% 32 == 0 (D=%d)", D);
     node_init_fwd_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p, X0, live_out);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;

@@ -11,21 +11,16 @@ using namespace ltgnn::functors;
 
 namespace {
 
-// ---- pipe head.  d pre[row, j] = dlogit[row] * scale * w2[j] * live[row, j] is rank one up to the 0/1 mask, so
-//      dW1[j, :] = w2[j] * sum_rows live[row, j] * (dlogit[row] * scale * feat[row, :]):
-//      G = live (exactly representable: no lo copy, one MMA less per K step), X = F' = dlogit * scale * feat, and the
-//      row scale w2[j] is applied when the CTA partials are added.  The 192 result columns are split over three CTAs
-//      per row range -- h_u, h_v and |h_u - h_v| -- so that every CTA keeps its 128 x 64 totals in registers
-//      (tgrad.cuh, register-total form); the three read the same saved activations at the same time (one from HBM, two
-//      from L2).  d w2 and d b1 ride on the slice-0 CTAs' pass over the activations.
-constexpr int kHeadSlices = 3;
+// ---- pipe head: G = d loss / d pre (from the saved post-activation), X = feat; d w2 and d b1 ride on the same pass.
+// (Tried and dropped: G = the 0/1 live mask (exact in TF32: no lo copy), X = dlogit * feat, the 192 result columns split
+// over three CTAs per row range so that each keeps its totals in registers -- accurate, but with 6 loads per loader
+// thread the kernel became latency bound: 5.4 ms against 1.7 ms for this form.)
 struct HeadSide {
     float4 dw2, db1;
 };
-struct HeadLive {
+struct HeadDpre {
     static constexpr bool kRowFast = true;  // hpost is stored blocked-32
-    static constexpr bool kExact = true;
-    using Side = HeadSide;
+    using Side = HeadSide;  // this thread's share of d w2 = sum_rows dlogit * hpost and of d b1 = sum_rows d pre
     const float4* hpost;  // blocked-32 [Mp, 128]
     const float* dlogit;  // [M]
     const float4* w2;     // [32]
@@ -33,17 +28,15 @@ struct HeadLive {
     float* side_part;     // [2 * gridDim.x][256]: d w2 | d b1, one partial per (CTA, loader group)
     __device__ __forceinline__ float4 load(uint32_t row, int c, Side& side) const {
         const float4 h = ptx::ldg_stream(hpost + ptx::b32(row, c, 32));
-        const float4 live = make_float4(h.x > 0.f ? 1.f : 0.f, h.y > 0.f ? 1.f : 0.f, h.z > 0.f ? 1.f : 0.f,
-                                        h.w > 0.f ? 1.f : 0.f);
-        if (blockIdx.x % kHeadSlices == 0) {
-            const float4 w = __ldg(w2 + c);
-            const float d = __ldg(dlogit + row), g = d * scale;
-            side.dw2.x = fmaf(d, h.x, side.dw2.x); side.dw2.y = fmaf(d, h.y, side.dw2.y);
-            side.dw2.z = fmaf(d, h.z, side.dw2.z); side.dw2.w = fmaf(d, h.w, side.dw2.w);
-            side.db1.x = fmaf(g * w.x, live.x, side.db1.x); side.db1.y = fmaf(g * w.y, live.y, side.db1.y);
-            side.db1.z = fmaf(g * w.z, live.z, side.db1.z); side.db1.w = fmaf(g * w.w, live.w, side.db1.w);
-        }
-        return live;
+        const float4 w = __ldg(w2 + c);
+        const float d = __ldg(dlogit + row);
+        side.dw2.x = fmaf(d, h.x, side.dw2.x); side.dw2.y = fmaf(d, h.y, side.dw2.y);
+        side.dw2.z = fmaf(d, h.z, side.dw2.z); side.dw2.w = fmaf(d, h.w, side.dw2.w);
+        const float g = d * scale;
+        const float4 dp = make_float4(h.x > 0.f ? g * w.x : 0.f, h.y > 0.f ? g * w.y : 0.f, h.z > 0.f ? g * w.z : 0.f,
+                                      h.w > 0.f ? g * w.w : 0.f);
+        side.db1.x += dp.x; side.db1.y += dp.y; side.db1.z += dp.z; side.db1.w += dp.w;
+        return dp;
     }
     // the 32 lanes of a loader warp hold 32 different rows of the same columns: butterfly sum, lane 0 writes
     __device__ __forceinline__ void finish(Side* side, const int* cols, int n, uint32_t cta, int group, int lane) const {
@@ -64,39 +57,29 @@ struct HeadLive {
         }
     }
 };
-struct HeadFeatSlice {
+struct HeadFeat {
     static constexpr bool kRowFast = false;
-    static constexpr int kSlices = kHeadSlices;
     const float4* x;   // node states [B*N, 16]
     const int2* ends;
-    const float* dlogit;
-    float scale;
     uint32_t P, N;
     uint64_t magic;
-    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {  // c < 16: one 64-column slice
+    __device__ __forceinline__ float4 operator()(uint32_t row, int c) const {
         const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
         const int2 e = __ldg(ends + (row - b * P));
-        const float g = __ldg(dlogit + row) * scale;
-        const int slice = blockIdx.x % kHeadSlices;
-        const float4* xb = x + static_cast<int64_t>(b) * N * 16 + c;
-        float4 v;
-        if (slice == 0) {
-            v = __ldg(xb + e.x * 16);
-        } else if (slice == 1) {
-            v = __ldg(xb + e.y * 16);
-        } else {
-            const float4 a = __ldg(xb + e.x * 16), d = __ldg(xb + e.y * 16);
-            v = make_float4(fabsf(a.x - d.x), fabsf(a.y - d.y), fabsf(a.z - d.z), fabsf(a.w - d.w));
-        }
-        return make_float4(g * v.x, g * v.y, g * v.z, g * v.w);
+        const int seg = c >> 4, cc = c & 15;
+        const float4* xb = x + static_cast<int64_t>(b) * N * 16 + cc;
+        if (seg == 0) return __ldg(xb + e.x * 16);
+        if (seg == 1) return __ldg(xb + e.y * 16);
+        const float4 a = __ldg(xb + e.x * 16), d = __ldg(xb + e.y * 16);
+        return make_float4(fabsf(a.x - d.x), fabsf(a.y - d.y), fabsf(a.z - d.z), fabsf(a.w - d.w));
     }
 };
 
 }  // namespace
 
 extern "C" int64_t ltgnn_pipe_head_ws_floats(int device) {
-    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][64] + (d w2 | d b1) partials [2 sm][256]
-    return di ? static_cast<int64_t>(di->sm_count) * (tgrad::kMo * 64 + 2 * 256) : -1;
+    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][192] + (d w2 | d b1) partials [2 sm][256]
+    return di ? static_cast<int64_t>(di->sm_count) * (tgrad::kMo * 192 + 2 * 256) : -1;
 }
 
 extern "C" int64_t ltgnn_tgrad_ws_floats(int device, int32_t No) {
@@ -147,18 +130,16 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
     const int64_t M = B * P;
     const DeviceInfo* di = device_info(device);
     LTGNN_REQUIRE(di, LTGNN_E_CUDA, "pipe_head_bwd_w: device %d", device);
-    const int No = D;  // one 64-column slice of the 192 feature columns per CTA
+    const int No = 3 * D;  // the 192 feature columns; d b1 and d w2 are accumulated by the loaders on the side
     float* part = ws + static_cast<size_t>(di->sm_count) * tgrad::kMo * No;  // [2 sm][256]
-    HeadLive g{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, part};
-    HeadFeatSlice x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), dlogit, gate_scale,
-                    static_cast<uint32_t>(P), static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
+    HeadDpre g{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale, part};
+    HeadFeat x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
+               static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
     int grid = 0;
-    int rc = tgrad::launch<1, 4, 2, -1>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
+    int rc = tgrad::launch<1, 4, 6>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
     if (rc) return rc;
-    for (int sl = 0; sl < kHeadSlices; ++sl) {  // dW1[:, 64 sl : 64 sl + 64] = w2[j] * sum over the row ranges of slice sl
-        rc = tgrad::gather(ws, grid, No, 0, H, 0, No, dW1 + sl * No, 3 * D, 0, stream, tgrad::kMo, sl, kHeadSlices, w2);
-        if (rc) return rc;
-    }
+    rc = tgrad::gather(ws, grid, No, 0, H, 0, No, dW1, No, 0, stream);
+    if (rc) return rc;
     rc = reduce_parts(part, 256, dw2, 2 * grid, H, 0, stream);
     if (rc) return rc;
     return reduce_parts(part + 128, 256, db1, 2 * grid, H, 0, stream);

@@ -201,8 +201,38 @@ def make_detector_golden(ref_detector, case: str, net: str, pipe_ids, sensors, b
     print(f"[detector] {case}: logits {tuple(logits.shape)} loss={loss.item():.6f} oracle==reference(bitwise)={bit_equal}")
 
 
+def make_residual_golden(ref_utils, n_sensors: int = 29) -> None:
+    """``residual_TCN.pt``: the REFERENCE's ``build_residual_sequence_from_segment`` (models/utils.py:169-216) run with
+    the REFERENCE's ``NormalPredictorTCN`` (models/predictor.py:55-81, imported unmodified; pure torch) on a seeded
+    segment batch -- the pinned oracle of SURVEY 8f rank 1.  Separate RNG streams: existing goldens are unaffected."""
+    import models.predictor as ref_predictor  # noqa: E402  (reference code, unmodified)
+
+    gen = torch.Generator().manual_seed(77)
+    torch.manual_seed(77)
+    model = ref_predictor.NormalPredictorTCN(n_sensors, 9).eval()
+    with torch.no_grad():  # LayerNorm affine / biases away from their trivial init
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=gen))
+    l_pred = l_det = 36
+    noisy = torch.randn(6, l_pred + l_det, n_sensors, generator=gen)
+    tf = torch.from_numpy(np.stack([time_features(l_pred + l_det, 5 * 17 * i) for i in range(6)]))
+    with torch.no_grad():
+        residual = ref_utils.build_residual_sequence_from_segment(model, noisy, tf, l_pred, l_det)
+        y_first = model(noisy[:, :l_pred], tf[:, :l_pred])
+        res64 = ref_utils.build_residual_sequence_from_segment(model.double(), noisy.double(), tf.double(), l_pred, l_det)
+    model.float()
+    torch.save({"state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()}, "noisy_seg": noisy,
+                "time_seg": tf, "l_pred": l_pred, "l_det": l_det, "residual": residual, "residual64": res64,
+                "y_hat_first_window": y_first, "torch_version": str(torch.__version__)}, HERE / "residual_TCN.pt")
+    print(f"[residual] {tuple(residual.shape)} max|r|={residual.abs().max().item():.4f} "
+          f"fp32 vs fp64 {(residual.double() - res64).abs().max().item():.2e}")
+
+
 def main() -> None:
     ref_detector, ref_utils = _import_reference()
+    if "--residual-only" in sys.argv:
+        make_residual_golden(ref_utils)
+        return
     sensors = yaml.safe_load((REF / "configs/sim_LTA.yaml").read_text())["sensors"]["pressure_node_ids"]
     info = make_graph_goldens(ref_utils, sensors)
     lta_pipes = info["LTA"][1]
@@ -219,6 +249,7 @@ def main() -> None:
                          sensor_hidden=64, gnn_layers=2, seed=43)
     make_detector_golden(ref_detector, "LTA_D128_L3", "LTA", lta_pipes[:40], sensors, batch=2, l_det=12,
                          node_hidden=128, sensor_hidden=32, gnn_layers=3, seed=44)
+    make_residual_golden(ref_utils)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "window_graphs_per_sec_fwd_bwd" and d["unit"] == "window-graphs/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0 and "workload" in d["config"]
-    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    # same scopes as the product arm: value = GNN stack from resident sensor embeddings, e2e = the full detector call
+    # (sensor GRU included), so value / value and e2e / e2e ratios are like for like
+    assert 0 < d["e2e"]["value"] <= d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
