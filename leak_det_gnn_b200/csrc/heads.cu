@@ -31,6 +31,8 @@ struct HeadFwdEpilogue {
     const float* w2;   // [H]
     float* part;       // [M]
     float* hpost;      // blocked-32 [Mp, H] saved post-activation, or nullptr (inference)
+    uint32_t* hmask;   // [Mp, H/32] 1 bit per hidden unit: hidden > 0 (ReLU-and-dropout gate of the backward), or nullptr;
+                       // hidden unit j is bit 31 - j % 32 of word j / 32
     int H;
     uint32_t drop_thresh16;  // round(p * 2^16), 0 = no dropout
     float keep_scale;        // 1 / (1 - drop_thresh16 / 2^16)
@@ -39,6 +41,7 @@ struct HeadFwdEpilogue {
     __device__ __forceinline__ float operator()(uint32_t row, int c_begin, int c_end, Pull&& pull) const {
         float acc = 0.f;
         const uint32_t thresh_hi = drop_thresh16 << 16;
+        uint32_t bits = 0;
         for (int col = c_begin; col < c_end; col += 16) {
             float4 bb[4], ww[4];
 #pragma unroll
@@ -59,6 +62,16 @@ struct HeadFwdEpilogue {
                 const uint64_t i8 = static_cast<uint64_t>(row) * (H >> 3) + (col >> 3);
                 ptx::dropout8_mask(v, i8, drop_seed, thresh_hi);
                 ptx::dropout8_mask(v + 8, i8 + 1, drop_seed, thresh_hi);
+            }
+            if (hmask) {
+                // v >= +0 here, so v > 0 <=> its bit pattern u != 0 <=> the top bit of -u is set; one funnel shift moves
+                // that bit into the word: hidden unit j of a 32-unit group ends up at bit 31 - j
+#pragma unroll
+                for (int j = 0; j < 16; ++j) bits = __funnelshift_l(0u - __float_as_uint(v[j]), bits, 1);
+                if ((col & 16) != 0) {  // a 32-unit word is complete
+                    hmask[static_cast<size_t>(row) * (H >> 5) + (col >> 5)] = bits;
+                    bits = 0;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -251,24 +264,28 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
 }  // namespace hf
 
 // ------------------------------------------------------------------ backward (input gradient)
-// A[row, j] = d loss / d pre[row, j] = dlogit[row] * w2[j] * (hpost[row, j] > 0 ? scale : 0)
+// A[row, j] = d loss / d pre[row, j] = dlogit[row] * scale * w2[j] * live[row, j]
 struct DpreLoader {
-    const float4* hpost;   // blocked-32 [Mp, H]
+    const uint4* hmask;    // [Mp] rows of 128 bits: hidden unit j of a row is live <=> bit 31 - j % 32 of word j / 32
     const float* dlogit;   // [M]
-    const float4* w2;      // [H/4]
+    const float* w2;       // [H]
     float scale;
 };
 
 __device__ __forceinline__ float sgn(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
 
-// dfeat[row, 0:3D] = dpre[row, :] W1 is scattered back to the two end nodes: +u for the h_u block, +v for the
-// h_v block, +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0).  Several pipes share a node,
-// so the adds are fp32 reductions in L2 (red.global.add.v4.f32) -- like the reference's index_add_ in autograd.
+// dfeat[row, 0:3D] = dpre[row, :] W1 goes back to the two end nodes: +u for the h_u block, +v for the h_v block,
+// +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0).  Several pipes share a node, and the reference
+// adds them with index_add_ (atomics on a GPU).  Here the sum is a GATHER in a fixed order, so the gradient is
+// bit-reproducible: a CTA works through whole windows; the epilogue warps park the per-pipe rows [du | dv] of the window
+// in a CTA-private scratch (P x 128 floats, reused window after window: it lives in L2) and then walk the node ->
+// incident pipe-end lists: dx[b, i, :] = dpooled[b, :] / N + sum over the pipe ends at node i, written exactly once
+// (the mean-pool gradient rides along: no separate fill pass, no read-modify-write of dx).
 //
 // Same warp roles as the forward kernel.  The epilogue warps (two per TMEM lane quadrant, 32 of the 64 node
 // features each) turn the row-per-thread accumulator blocks into 128-byte row segments through the swizzled
-// shared-memory patch, so that the node-state reads for the sign and the reductions touch 4 full lines per
-// instruction instead of 32 partial ones, and every end node receives one reduction per 128 B.
+// shared-memory patch, so that the node-state reads for the sign and the scratch stores touch 4 full lines per
+// instruction instead of 32 partial ones.
 namespace hb {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
@@ -276,17 +293,20 @@ constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 8, kThreads = (kLdWarps + 1
 constexpr int kK = 128, kN = 192, kStages = 2, kStageCols = 64;
 constexpr uint32_t kScrBytes = 4096;
 
+__device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory"); }
+
 __global__ void __launch_bounds__(kThreads, 1)
 pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, float4* __restrict__ dx,
-                        const int2* __restrict__ ends, uint32_t P, uint32_t N, uint64_t magic,
-                        const float* __restrict__ W1, uint32_t M) {
+                        const int2* __restrict__ ends, const int32_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc,
+                        const int4* __restrict__ inc_ell, const float4* __restrict__ dpooled, float4* __restrict__ scratch, uint32_t P, uint32_t N, uint32_t B,
+                        const float* __restrict__ W1) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_hi = smem;  // B[n = feature column (192)][k = hidden unit (128)] = W1[k][n]
     uint8_t* b_lo = b_hi + kN * kK * 4;
-    uint8_t* scratch = b_lo + kN * kK * 4;
+    uint8_t* scr_patch = b_lo + kN * kK * 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
@@ -308,80 +328,78 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t acc_base = tmem_base, a_base = tmem_base + 2 * kN;
-    const uint32_t n_tiles = (M + 127) / 128;
-    // each CTA owns a contiguous range of tiles: consecutive tiles share a window, so its node states are fetched
-    // from HBM once and the CTA's reads / writes / reductions stay local
-    const uint32_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
-    const uint32_t t_begin = min(blockIdx.x * per_cta, n_tiles), t_end = min(t_begin + per_cta, n_tiles);
+    // each CTA owns a contiguous range of windows; a window is T tiles of 128 pipe rows (the last one padded)
+    const uint32_t T = (P + 127) / 128;
+    const uint32_t per_cta = (B + gridDim.x - 1) / gridDim.x;
+    const uint32_t w_begin = min(blockIdx.x * per_cta, B), w_end = min(w_begin + per_cta, B);
+    const uint32_t n_tiles = (w_end - w_begin) * T;
 
     if (warp < kLdWarps) {
         // The four loader warps (thread = pipe row = TMEM lane) emit the four 32-wide K blocks of every tile into the
-        // two A slots in turn.  The saved activations come from HBM (~1.5 us away): the 8 loads of the NEXT block
-        // are issued before the current one is split and stored.
+        // two A slots in turn.  A row needs 16 bytes of gate bits and one dlogit: fetched one tile ahead.
         const int quad = warp & 3;
         const uint32_t st_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
-        const float4* w2 = loader.w2;
+        const float* w2 = loader.w2;
         uint32_t stage = 0;
-        uint32_t tile = t_begin;
-        int kg = 0;
-        float4 raw[8];
-        float g = 0.f;
-        auto fetch = [&]() {  // pad rows exist in the blocked-32 tensor; their g is 0
-            const uint32_t row = tile * 128 + quad * 32 + lane;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) raw[j] = ldg_stream(loader.hpost + b32(row, kg * 8 + j, kK / 4));
-            if (kg == 0) g = row < M ? __ldg(loader.dlogit + row) * loader.scale : 0.f;
-            // one register stage cannot cover HBM latency: pull the same block of the next tile into L2 now
-            if (tile + 1 < t_end) {
-                const uint32_t nrow = row + 128;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(loader.hpost + b32(nrow, kg * 8 + j, kK / 4)));
+        uint4 m_next = make_uint4(0, 0, 0, 0);
+        float g_next = 0.f;
+        auto fetch = [&](uint32_t t) {
+            const uint32_t w = w_begin + t / T, p = (t % T) * 128 + quad * 32 + lane;
+            if (t < n_tiles && p < P) {
+                const size_t row = static_cast<size_t>(w) * P + p;
+                m_next = __ldg(loader.hmask + row);
+                g_next = __ldg(loader.dlogit + row) * loader.scale;
+            } else {
+                m_next = make_uint4(0, 0, 0, 0);
+                g_next = 0.f;
             }
         };
-        if (tile < t_end) fetch();
-        while (tile < t_end) {
-            float v[32];
+        fetch(0);
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint4 m = m_next;
+            const float g = g_next;
+            fetch(t + 1);
+            const uint32_t words[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll 1
+            for (int kg = 0; kg < 4; ++kg) {
+                // the 32 operand values of this K block are formed BEFORE the slot is waited for
+                const uint32_t bits = words[kg];
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 w = __ldg(w2 + kg * 8 + j);
-                v[4 * j] = raw[j].x > 0.f ? g * w.x : 0.f;
-                v[4 * j + 1] = raw[j].y > 0.f ? g * w.y : 0.f;
-                v[4 * j + 2] = raw[j].z > 0.f ? g * w.z : 0.f;
-                v[4 * j + 3] = raw[j].w > 0.f ? g * w.w : 0.f;
-            }
-            if (++kg == 4) {
-                kg = 0;
-                ++tile;
-            }
-            if (tile < t_end) fetch();
-            const uint32_t slot = stage & 1;
-            mbar_wait_relaxed(&bar_empty[slot], ((stage >> 1) & 1) ^ 1);
-            ++stage;
-            fence_after_sync();
-            const uint32_t st_addr = st_base + slot * kStageCols;
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-                float hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    hi[j] = tf32_hi(v[c + j]);
-                    lo[j] = v[c + j] - hi[j];
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w2) + kg * 8 + j4);
+                    v[4 * j4 + 0] = (bits >> (31 - 4 * j4)) & 1u ? g * wv.x : 0.f;
+                    v[4 * j4 + 1] = (bits >> (30 - 4 * j4)) & 1u ? g * wv.y : 0.f;
+                    v[4 * j4 + 2] = (bits >> (29 - 4 * j4)) & 1u ? g * wv.z : 0.f;
+                    v[4 * j4 + 3] = (bits >> (28 - 4 * j4)) & 1u ? g * wv.w : 0.f;
                 }
-                tmem_st8(st_addr + c, hi);
-                tmem_st8(st_addr + 32 + c, lo);
+                const uint32_t slot = stage & 1;
+                mbar_wait_relaxed(&bar_empty[slot], ((stage >> 1) & 1) ^ 1);
+                ++stage;
+                fence_after_sync();
+                const uint32_t st_addr = st_base + slot * kStageCols;
+#pragma unroll
+                for (int c = 0; c < 32; c += 8) {
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hi[j] = tf32_hi(v[c + j]);
+                        lo[j] = v[c + j] - hi[j];
+                    }
+                    tmem_st8(st_addr + c, hi);
+                    tmem_st8(st_addr + 32 + c, lo);
+                }
+                rowgemm_ts::tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[slot]);
             }
-            rowgemm_ts::tmem_wait_st();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[slot]);
         }
     } else if (warp == kMmaWarp) {
         const uint32_t idesc = idesc_tf32(128, kN);
         const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
         constexpr uint32_t kg_units = static_cast<uint32_t>(kN) * 128u >> 4;
-        uint32_t t = 0;
-        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
+        for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t a = t & 1;
             mbar_wait_relaxed(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
             const uint32_t d = acc_base + a * kN;
@@ -407,18 +425,20 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
         }
     } else {
         const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
-        const patch::Patch patch(scratch + (warp - kMmaWarp - 1) * kScrBytes, lane);
+        const patch::Patch patch(scr_patch + (warp - kMmaWarp - 1) * kScrBytes, lane);
         const int sub = lane >> 3, ch = lane & 7;
-        uint32_t t = 0;
-        for (uint32_t tile = t_begin; tile < t_end; ++tile, ++t) {
+        const int et = (warp - kMmaWarp - 1) * 32 + lane;           // 0..255 among the epilogue threads
+        float4* scr = scratch + static_cast<size_t>(blockIdx.x) * T * 128 * 32;  // [T * 128 rows][du 16 | dv 16] float4
+        const float inv_n = 1.f / static_cast<float>(N);
+        for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t a = t & 1;
-            const uint32_t row0 = tile * 128 + q * 32;
+            const uint32_t w = w_begin + t / T, tt = t % T;
+            const uint32_t p0 = tt * 128 + q * 32;                  // first pipe of this warp's 32 rows
             uint32_t iu = 0, iv = 0;
-            if (row0 + lane < M) {
-                const uint32_t b = magic ? fastdiv(row0 + lane, magic) : row0 + lane;
-                const int2 e = __ldg(ends + (row0 + lane - b * P));
-                iu = b * N + e.x;
-                iv = b * N + e.y;
+            if (p0 + lane < P) {
+                const int2 e = __ldg(ends + p0 + lane);
+                iu = w * N + e.x;
+                iv = w * N + e.y;
             }
             // sign(h_u - h_v) of this lane's 8 row segments, packed as two bit masks (bit 4 k + component): the
             // node states do not depend on the accumulator, so their latency is paid before the wait
@@ -426,8 +446,8 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
-                const float4 p = __ldg(x + ru * kD4 + half * 8 + ch), r = __ldg(x + rv * kD4 + half * 8 + ch);
-                const float d[4] = {p.x - r.x, p.y - r.y, p.z - r.z, p.w - r.w};
+                const float4 pu = __ldg(x + ru * kD4 + half * 8 + ch), pv = __ldg(x + rv * kD4 + half * 8 + ch);
+                const float d[4] = {pu.x - pv.x, pu.y - pv.y, pu.z - pv.z, pu.w - pv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     pos |= (d[i] > 0.f ? 1u : 0u) << (4 * k + i);
@@ -452,22 +472,86 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
             }
             pull32(0, ga);       // d / d x_u
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub);
-                if (row0 + 4 * k + sub < M)
-                    atomicAdd(dx + ru * kD4 + half * 8 + ch,
-                              make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
-            }
+            for (int k = 0; k < 8; ++k)  // rows past P are never read back
+                __stcg(scr + static_cast<size_t>(p0 + 4 * k + sub) * 32 + half * 8 + ch,
+                       make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
             pull32(kD, ga);      // d / d x_v
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
-                if (row0 + 4 * k + sub < M)
-                    atomicAdd(dx + rv * kD4 + half * 8 + ch,
-                              make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+            for (int k = 0; k < 8; ++k)
+                __stcg(scr + static_cast<size_t>(p0 + 4 * k + sub) * 32 + 16 + half * 8 + ch,
+                       make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+            if (tt == T - 1) {
+                // the window is complete: every node gathers its pipe ends in list order (16 threads = the 256 bytes of a node)
+                ep_bar();
+                const int f = et & 15;
+                const float4 pl = dpooled ? __ldg(dpooled + static_cast<size_t>(w) * kD4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inc_ell) {
+                    // fixed-width lists (8 slots per node, -1 = empty): the loads of three nodes go out together -- the
+                    // scratch sits in L2, and a dependent chain per node made this phase longer than the six tiles
+                    constexpr int kNodes = 2, kStep = (kEpWarps * 32) >> 4;
+                    auto load_ent = [&](uint32_t i0, int h4, int4 (&ent)[kNodes]) {
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) {
+                            const uint32_t i = i0 + u * kStep;
+                            ent[u] = i < N ? __ldg(inc_ell + 2 * i + h4) : make_int4(-1, -1, -1, -1);
+                        }
+                    };
+                    auto add_slots = [&](const int4 (&ent)[kNodes], float4 (&acc)[kNodes]) {
+                        float4 c[kNodes][4];
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) {
+                            const int e4[4] = {ent[u].x, ent[u].y, ent[u].z, ent[u].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (e4[k] >= 0) c[u][k] = __ldcg(scr + static_cast<size_t>(e4[k] >> 1) * 32 + (e4[k] & 1) * 16 + f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) {
+                            const int e4[4] = {ent[u].x, ent[u].y, ent[u].z, ent[u].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (e4[k] >= 0) {
+                                    acc[u].x += c[u][k].x; acc[u].y += c[u][k].y; acc[u].z += c[u][k].z; acc[u].w += c[u][k].w;
+                                }
+                        }
+                    };
+                    int4 ent_next[kNodes];
+                    load_ent(et >> 4, 0, ent_next);
+                    for (uint32_t i0 = et >> 4; i0 < N; i0 += kNodes * kStep) {
+                        int4 ent[kNodes], ent_hi[kNodes];
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) ent[u] = ent_next[u];
+                        load_ent(i0, 1, ent_hi);                       // slots 4-7 of this batch (rarely occupied)
+                        load_ent(i0 + kNodes * kStep, 0, ent_next);    // slots 0-3 of the next batch: in flight during the adds
+                        float4 acc[kNodes];
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) acc[u] = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
+                        add_slots(ent, acc);
+                        bool any = false;
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) any = any || ent_hi[u].x >= 0;
+                        if (__any_sync(0xffffffffu, any)) add_slots(ent_hi, acc);
+#pragma unroll
+                        for (int u = 0; u < kNodes; ++u) {
+                            const uint32_t i = i0 + u * kStep;
+                            if (i < N) stg_stream(dx + (static_cast<size_t>(w) * N + i) * kD4 + f, acc[u]);
+                        }
+                    }
+                } else
+                    for (uint32_t i = et >> 4; i < N; i += (kEpWarps * 32) >> 4) {
+                    float4 acc = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
+                    const int e_end = __ldg(inc_ptr + i + 1);
+                    for (int e = __ldg(inc_ptr + i); e < e_end; ++e) {
+                        const int ent = __ldg(inc + e);  // pipe << 1 | end
+                        const float4 c = __ldcg(scr + static_cast<size_t>(ent >> 1) * 32 + (ent & 1) * 16 + f);
+                        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+                    }
+                    stg_stream(dx + (static_cast<size_t>(w) * N + i) * kD4 + f, acc);
+                }
+                ep_bar();  // the next window's rows may overwrite the scratch
             }
         }
     }
@@ -534,19 +618,20 @@ int head_shape_check(int D, int H, const char* who) {
 
 extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
                                    const int32_t* ends, const float* W1, const float* b1, const float* w2,
-                                   float drop_p, uint64_t drop_seed, float* part, float* hpost, void* stream_) {
+                                   float drop_p, uint64_t drop_seed, float* part, float* hpost, uint32_t* hmask,
+                                   void* stream_) {
     LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_fwd: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
     int rc = head_shape_check(D, H, "pipe_head_fwd");
     if (rc) return rc;
     LTGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LTGNN_E_ARG, "pipe_head_fwd: dropout p=%f", drop_p);
     if (B == 0) return LTGNN_OK;
     LTGNN_REQUIRE(X && ends && W1 && b1 && w2 && part, LTGNN_E_ARG, "pipe_head_fwd: null tensor");
-    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(b1) && aligned16(w2) && aligned16(hpost), LTGNN_E_ALIGN,
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(b1) && aligned16(w2) && aligned16(hpost) && aligned16(hmask), LTGNN_E_ALIGN,
                   "pipe_head_fwd: 16-byte alignment required");
     const int64_t M = B * P;
     LTGNN_REQUIRE(M < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*P too large");
     const uint32_t t16 = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
-    HeadFwdEpilogue ep{b1, w2, part, hpost, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
+    HeadFwdEpilogue ep{b1, w2, part, hpost, hmask, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_fwd: device is sm_%d%d, need sm_100", di->cc_major,
@@ -566,33 +651,41 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
     return LTGNN_OK;
 }
 
+extern "C" int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t P) {
+    const DeviceInfo* di = device_info(device);  // per CTA: the window's pipe rows [du | dv], padded to whole tiles
+    return di ? static_cast<int64_t>(di->sm_count) * ((P + 127) / 128) * 128 * 128 : -1;
+}
+
 extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
-                                      const int32_t* ends, const float* W1, const float* w2, const float* hpost,
-                                      const float* dlogit, float gate_scale, float* dX, void* stream_) {
+                                      const int32_t* ends, const int32_t* inc_ptr, const int32_t* inc,
+                                      const int32_t* inc_ell, const float* W1,
+                                      const float* w2, const uint32_t* hmask, const float* dlogit, float gate_scale,
+                                      const float* dpooled, float* ws, float* dX, void* stream_) {
     LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_bwd_dx: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
     int rc = head_shape_check(D, H, "pipe_head_bwd_dx");
     if (rc) return rc;
     if (B == 0) return LTGNN_OK;
-    LTGNN_REQUIRE(X && ends && W1 && w2 && hpost && dlogit && dX, LTGNN_E_ARG, "pipe_head_bwd_dx: null tensor");
-    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(w2) && aligned16(hpost) && aligned16(dX), LTGNN_E_ALIGN,
-                  "pipe_head_bwd_dx: 16-byte alignment required");
-    const int64_t M = B * P;
-    DpreLoader ld{reinterpret_cast<const float4*>(hpost), dlogit, reinterpret_cast<const float4*>(w2), gate_scale};
+    LTGNN_REQUIRE(X && ends && inc_ptr && inc && W1 && w2 && hmask && dlogit && ws && dX, LTGNN_E_ARG,
+                  "pipe_head_bwd_dx: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(hmask) && aligned16(dX) && aligned16(ws) && aligned16(dpooled) &&
+                      aligned16(inc_ell),
+                  LTGNN_E_ALIGN, "pipe_head_bwd_dx: 16-byte alignment required");
+    DpreLoader ld{reinterpret_cast<const uint4*>(hmask), dlogit, w2, gate_scale};
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_bwd_dx: device is sm_%d%d, need sm_100",
                   di->cc_major, di->cc_minor);
-    LTGNN_REQUIRE(M < (1ll << 31) && B * N < (1ll << 28), LTGNN_E_SHAPE, "pipe_head_bwd_dx: B*P or B*N too large");
+    LTGNN_REQUIRE(B * P < (1ll << 31) && B * N < (1ll << 28), LTGNN_E_SHAPE, "pipe_head_bwd_dx: B*P or B*N too large");
     const size_t smem = 1024 + 2ull * hb::kN * hb::kK * 4 + hb::kEpWarps * hb::kScrBytes;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_bwd_dx: %zu B of shared memory", smem);
     LTGNN_USE_DEVICE(device);
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(hb::pipe_head_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    const int64_t tiles = (M + 127) / 128;
-    const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
+    const int grid = static_cast<int>(B < di->sm_count ? B : di->sm_count);
     hb::pipe_head_bwd_dx_kernel<<<grid, hb::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
-        ld, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(ends),
-        static_cast<uint32_t>(P), static_cast<uint32_t>(N), magic_of(P), W1, static_cast<uint32_t>(M));
+        ld, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(ends), inc_ptr,
+        inc, reinterpret_cast<const int4*>(inc_ell), reinterpret_cast<const float4*>(dpooled), reinterpret_cast<float4*>(ws), static_cast<uint32_t>(P),
+        static_cast<uint32_t>(N), static_cast<uint32_t>(B), W1);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

@@ -130,7 +130,8 @@ class LeakDetector(nn.Module):
         if hit is None:
             slot = torch.full((len(self.node_names),), -1, dtype=torch.int32)
             slot[self.sensor_node_idx] = torch.arange(len(self.sensor_node_ids), dtype=torch.int32)
-            hit = (slot.to(device), self.pipe_ends.to(device), self.pipe_ends.to(device=device, dtype=torch.int32))
+            ends32 = self.pipe_ends.to(device=device, dtype=torch.int32)
+            hit = (slot.to(device), self.pipe_ends.to(device), ends32, ops.pipe_incidence(ends32, len(self.node_names)))
             self._dev_cache[key] = hit
         return hit
 
@@ -139,7 +140,7 @@ class LeakDetector(nn.Module):
         message-passing hot path."""
         if not h_s.is_cuda:
             raise ValueError("LeakDetector runs on CUDA only (sm_100a kernels; no CPU fallback)")
-        slot, ends, ends32 = self._index_tensors(h_s.device)
+        slot, ends, ends32, incidence = self._index_tensors(h_s.device)
         conv_params = [t for conv in self.convs for t in (conv.lin.weight, conv.bias)]
         x = ops.gnn_body(h_s, slot, self.pipe_graph, self.dropout.p, self.training, self.sensor_to_node.weight,
                          self.sensor_to_node.bias, conv_params)
@@ -147,7 +148,8 @@ class LeakDetector(nn.Module):
         if ops.heads_supported(x.shape[-1], lin1.out_features):
             # fused pipe head (features formed on the fly, tcgen05) + mean pool; the H -> 1 layer's bias and the
             # tiny no-leak MLP on the pooled (B, D) vector stay in torch
-            part, pooled = ops.heads(x, ends32, lin1.weight, lin1.bias, lin2.weight, self.dropout.p, self.training)
+            part, pooled = ops.heads(x, ends32, lin1.weight, lin1.bias, lin2.weight, self.dropout.p, self.training,
+                                     incidence)
             pipe_logits = part.sum(0) + lin2.bias
         else:
             pipe_logits = self.edge_head(x[:, ends[:, 0], :], x[:, ends[:, 1], :])
