@@ -1191,7 +1191,7 @@ extern "C" int ltgnn_gru_bwd_w(int device, int64_t B, int32_t L, int32_t S, int3
                    S >= 2 ? (~0ull / static_cast<uint64_t>(S)) + 1 : 0ull};
     DgRows g{reinterpret_cast<const float4*>(dG)};
     int grid = 0;
-    int rc = tgrad::launch<2, 8, 4, 8>(device, g, x, ws, M, KA, &grid, stream, "gru_bwd_w");  // all 256 rows in one pass over X
+    int rc = tgrad::launch<2, 8, 4, 16>(device, g, x, ws, M, KA, &grid, stream, "gru_bwd_w");  // all 256 rows in one pass over X
     if (rc) return rc;
     return tgrad::gather(ws, grid, KA, 0, NG, 0, KA, dBfused, KA, 0, stream, NG);
 }

@@ -565,16 +565,21 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
 }  // namespace hb
 
 // ------------------------------------------------------------------ mean pool and its adjoint
+// out[u, :] = scale * sum of rows [r_lo, r_hi) of window b, u = b * units_per_b + block (one unit per window and
+// scale = 1 / N for the L-TOWN sizes; large graphs are split into row blocks and a second call sums the partials)
 __global__ void __launch_bounds__(256)
-mean_pool_kernel(const float4* __restrict__ x, float4* __restrict__ pooled, int64_t B, int N, int d4) {
+mean_pool_kernel(const float4* __restrict__ x, float4* __restrict__ pooled, int64_t B, int N, int d4, int units_per_b,
+                 int rows_per_unit, float inv) {
     __shared__ float4 red[256];
     const int tid = threadIdx.x;
     const int c = tid % d4, r0 = tid / d4, rstep = 256 / d4;
-    const float inv = 1.f / static_cast<float>(N);
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    for (int64_t u = blockIdx.x; u < B * units_per_b; u += gridDim.x) {
+        const int64_t b = u / units_per_b;
+        const int r_lo = static_cast<int>(u - b * units_per_b) * rows_per_unit;
+        const int r_hi = r_lo + rows_per_unit < N ? r_lo + rows_per_unit : N;
         const float4* xb = x + b * N * d4 + c;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = r0; r < N; r += rstep) {
+        for (int r = r_lo + r0; r < r_hi; r += rstep) {
             const float4 v = ptx::ldg_stream(xb + static_cast<int64_t>(r) * d4);
             s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         }
@@ -586,7 +591,7 @@ mean_pool_kernel(const float4* __restrict__ x, float4* __restrict__ pooled, int6
                 const float4 o = red[k];
                 t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
             }
-            pooled[b * d4 + tid] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
+            pooled[u * d4 + tid] = make_float4(t.x * inv, t.y * inv, t.z * inv, t.w * inv);
         }
         __syncthreads();
     }
@@ -701,9 +706,30 @@ extern "C" int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, 
     if (!di) return LTGNN_E_CUDA;
     LTGNN_USE_DEVICE(device);
     const int64_t cap = static_cast<int64_t>(di->sm_count) * 8;
-    mean_pool_kernel<<<static_cast<int>(B < cap ? B : cap), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-        reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(pooled), B, N, D / 4);
-    LTGNN_CUDA_TRY(cudaGetLastError());
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const float inv = 1.f / static_cast<float>(N);
+    int units_per_b = static_cast<int>((cap + B - 1) / B);
+    const int max_units = (N + 2047) / 2048;  // at least 2048 rows per unit
+    if (units_per_b > max_units) units_per_b = max_units;
+    if (units_per_b <= 1) {
+        mean_pool_kernel<<<static_cast<int>(B < cap ? B : cap), 256, 0, stream>>>(
+            reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(pooled), B, N, D / 4, 1, N, inv);
+        LTGNN_CUDA_TRY(cudaGetLastError());
+        return LTGNN_OK;
+    }
+    // few windows over a large graph: partial sums per (window, row block) in a stream-ordered temporary, then the same
+    // kernel over the partials ([B, units_per_b, D] seen as B windows of units_per_b rows); fixed order, no atomics
+    const int rows_per_unit = (N + units_per_b - 1) / units_per_b;
+    const int64_t n_units = B * units_per_b;
+    float4* part = nullptr;
+    LTGNN_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&part), sizeof(float) * n_units * D, stream));
+    mean_pool_kernel<<<static_cast<int>(n_units < cap ? n_units : cap), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(X), part, B, N, D / 4, units_per_b, rows_per_unit, 1.f);
+    mean_pool_kernel<<<static_cast<int>(B < cap ? B : cap), 256, 0, stream>>>(part, reinterpret_cast<float4*>(pooled), B,
+                                                                              units_per_b, D / 4, 1, units_per_b, inv);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(part, stream);
+    LTGNN_CUDA_TRY(e);
     return LTGNN_OK;
 }
 

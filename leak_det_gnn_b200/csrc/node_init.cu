@@ -188,25 +188,30 @@ template <bool kBits>
 __global__ void __launch_bounds__(kThreads)
 gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X0, const uint32_t* __restrict__ live,
                     const int32_t* __restrict__ slot, float gate_scale, float4* __restrict__ dz,
-                    float* __restrict__ part, int64_t B, int N, int S, int d4) {
+                    float* __restrict__ part, int64_t B, int N, int S, int d4, int units_per_b, int rows_per_unit) {
     __shared__ float4 red[kThreads];
     const int tid = threadIdx.x;
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);  // kThreads % d4 == 0: a thread keeps its column group
     const int n4 = N * d4;
     const int c = tid % d4, rstep = kThreads / d4;  // a thread keeps its float4 column: no division in the loop
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    // work unit = (window, block of rows): a large graph comes with few windows, and one CTA per window would leave
+    // most of the machine idle (the 100k-node network: 16 windows)
+    for (int64_t u = blockIdx.x; u < B * units_per_b; u += gridDim.x) {
+        const int64_t b = u / units_per_b;
+        const int r_lo = static_cast<int>(u - b * units_per_b) * rows_per_unit;
+        const int r_hi = r_lo + rows_per_unit < N ? r_lo + rows_per_unit : N;
         const float4* gb = dX0 + b * n4 + c;
         const float4* xb = kBits ? nullptr : X0 + b * n4 + c;
         const uint32_t* lw = kBits ? live + (b * (d4 >> 3) + (c >> 3)) * N : nullptr;
         float4* dzb = dz + b * S * d4 + c;
-        for (int r0 = tid / d4; r0 < N; r0 += 4 * rstep) {
+        for (int r0 = r_lo + tid / d4; r0 < r_hi; r0 += 4 * rstep) {
             float4 g[4], x[4];
             uint32_t m[4];
             int sl[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int r = r0 + u * rstep;
-                if (r < N) {
+                if (r < r_hi) {
                     g[u] = ptx::ldg_stream(gb + r * d4);
                     if (kBits) m[u] = __ldg(lw + r) >> (c & 7);
                     else x[u] = ptx::ldg_stream(xb + r * d4);
@@ -215,7 +220,7 @@ gate_extract_kernel(const float4* __restrict__ dX0, const float4* __restrict__ X
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (r0 + u * rstep < N) {
+                if (r0 + u * rstep < r_hi) {
                     if (kBits) {
                         g[u].x = (m[u] & 0x1u) ? g[u].x * gate_scale : 0.f;
                         g[u].y = (m[u] & 0x100u) ? g[u].y * gate_scale : 0.f;
@@ -337,15 +342,20 @@ extern "C" int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, 
     float* wpart = cpart + static_cast<int64_t>(stream_ctas(di)) * D;
 
     // (1) streaming pass
-    const int64_t g1 = B < stream_ctas(di) ? B : stream_ctas(di);
+    int units_per_b = static_cast<int>((stream_ctas(di) + B - 1) / B);
+    const int max_units = (N + 1023) / 1024;  // at least 1024 rows per unit
+    if (units_per_b > max_units) units_per_b = max_units;
+    const int rows_per_unit = (N + units_per_b - 1) / units_per_b;
+    const int64_t n_units = B * units_per_b;
+    const int64_t g1 = n_units < stream_ctas(di) ? n_units : stream_ctas(di);
     if (live_in)  // 1 bit per element instead of the float activations: half the bytes of this pass
         gate_extract_kernel<true><<<static_cast<int>(g1), kThreads, 0, stream>>>(
             reinterpret_cast<const float4*>(dX0), nullptr, live_in, slot, gate_scale, reinterpret_cast<float4*>(dz),
-            cpart, B, N, S, d4);
+            cpart, B, N, S, d4, units_per_b, rows_per_unit);
     else
         gate_extract_kernel<false><<<static_cast<int>(g1), kThreads, 0, stream>>>(
             reinterpret_cast<const float4*>(dX0), reinterpret_cast<const float4*>(X0), nullptr, slot, gate_scale,
-            reinterpret_cast<float4*>(dz), cpart, B, N, S, d4);
+            reinterpret_cast<float4*>(dz), cpart, B, N, S, d4, units_per_b, rows_per_unit);
     LTGNN_CUDA_TRY(cudaGetLastError());
     rc = reduce_parts(cpart, D, dbias, static_cast<int>(g1), D, 0, stream);
     if (rc) return rc;
