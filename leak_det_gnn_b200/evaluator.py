@@ -114,7 +114,7 @@ class DetectorEvaluator:
                     code = torch.tensor([BUCKETS.index(str(b)) if str(b) in BUCKETS else -1 for b in bl], device=dev)
                     onehot = (code.unsqueeze(1) == torch.arange(len(BUCKETS), device=dev).unsqueeze(0)).to(torch.int64)
                     cols = torch.stack([torch.ones_like(hit1), hit1, hitk, pred_nl], dim=1).to(torch.int64)
-                    b_cnt += onehot.t() @ cols
+                    b_cnt += (onehot.unsqueeze(2) * cols.unsqueeze(1)).sum(0)   # (integer matmul does not exist on CUDA)
                     false_alarm = is_nl & pred_leak
                     acc["pre_fa"] += (false_alarm & (code == BUCKETS.index("pre"))).sum()
                     acc["noleak_fa"] += (false_alarm & (code == BUCKETS.index("noleak"))).sum()
