@@ -146,6 +146,18 @@ int ltgnn_node_init_bwd(int device, int64_t B, int32_t N, int32_t S, int32_t ds,
                         const uint32_t* live_in, float gate_scale, float* dhs, float* dW, float* dbias, float* ws,
                         void* stream);
 
+/* ---- one GCN layer forward as ONE kernel (detector.py:198-201: conv -> relu -> dropout) ---------
+ * Y = dropout(relu(A_hat (X W^T) + bias)) with the dense product on tcgen05 and never written to HBM: the window's
+ * X W^T slice goes from tensor memory to shared memory and is aggregated there.  X [B,N,K], W [D,K] (torch Linear
+ * layout, GCNConv.lin.weight), bias [D] or null, Y [B,N,D]; dropout / live_out as in ltgnn_spmm_fused.  Bit-identical to
+ * ltgnn_linear followed by ltgnn_spmm_fused.  ltgnn_gcn_layer_supported: 1 if the kernel takes (graph, K, D) -- K a
+ * multiple of 32 up to 128, D a multiple of 32, at most 896 nodes, the slice of the graph fits shared memory.
+ */
+int ltgnn_gcn_layer_supported(ltgnn_graph_t g, int32_t K, int32_t D);
+int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_t D, const float* X, const float* W,
+                        const float* bias, int relu, float drop_p, uint64_t drop_seed, float* Y, uint32_t* live_out,
+                        void* stream);
+
 /* ---- read-out heads (detector.py:76-102, 204-216) ---------------------------------------------
  * pipe_head_fwd: for every window b and class pipe p with end nodes ends[p] = (u, v):
  *      hidden = dropout(relu(W1 [x_u, x_v, |x_u - x_v|] + b1)),   W1 [H, 3D] (edge_head.mlp.0.weight)

@@ -284,6 +284,39 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return dw
 
 
+# One kernel per GCN layer forward (csrc/gcn_layer.cu) where the shape allows; False = the two-launch path
+# (ltgnn_linear + ltgnn_spmm_fused), which computes the same bits and stays as the cross-check.
+FUSED_LAYER = True
+
+
+def gcn_layer_supported(graph: PipeGraph, x: torch.Tensor, weight: torch.Tensor) -> bool:
+    return bool(_lib.load().ltgnn_gcn_layer_supported(graph.handle(x.device), int(weight.shape[1]), int(weight.shape[0])))
+
+
+def gcn_layer_fwd(graph: PipeGraph, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  relu: bool = False, drop_p: float = 0.0, drop_seed: int = 0,
+                  live_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw fused layer forward (see ltgnn_gcn_layer_fwd): ``dropout(relu(A_hat (x W^T) + bias))`` in one kernel.
+    x (B, N, K) fp32 CUDA, weight (D, K); returns (B, N, D)."""
+    _check_act(x, "x")
+    _check_act(weight, "weight")
+    n, k, d = graph.num_nodes, x.shape[-1], weight.shape[0]
+    if weight.shape[1] != k or x.numel() % (n * k) != 0:
+        raise ValueError(f"x {tuple(x.shape)} / weight {tuple(weight.shape)} do not fit a {n}-node graph")
+    b = x.numel() // (n * k)
+    if live_out is not None and (live_out.dtype != torch.int32 or tuple(live_out.shape) != (b, d // 32, n)):
+        raise ValueError(f"live_out must be int32 of shape {(b, d // 32, n)}")
+    y = torch.empty(b, n, d, device=x.device, dtype=torch.float32)
+    L = _lib.load()
+    tok = _inst.begin("gcn_layer_fwd")
+    _lib.check(L.ltgnn_gcn_layer_fwd(graph.handle(x.device), b, k, d, x.data_ptr(), weight.data_ptr(),
+                                     None if bias is None else bias.data_ptr(), int(relu), float(drop_p),
+                                     int(drop_seed) & (2**64 - 1), y.data_ptr(),
+                                     None if live_out is None else live_out.data_ptr(), _stream(x)))
+    _inst.end(tok)
+    return y
+
+
 def node_init_fwd(h_s, slot, num_nodes, weight, bias, drop_p=0.0, drop_seed=0, live_out=None):
     """Raw node-feature initialisation (see ltgnn_node_init_fwd).  h_s (B,S,ds) -> (B,N,D).
     ``live_out``: optional int32 (B, D/32, N) tensor that receives ``x0 > 0`` as one bit per element."""
@@ -541,6 +574,12 @@ class _GnnBody(torch.autograd.Function):
         xs = [x]
         for l in range(n_layers):
             w, b = conv_params[2 * l], conv_params[2 * l + 1]
+            if FUSED_LAYER and w.is_contiguous() and gcn_layer_supported(graph, x, w):
+                lives.append(live_for(w.shape[0]))
+                x = gcn_layer_fwd(graph, x, w, bias=b, relu=True, drop_p=p, drop_seed=new_dropout_seed() if p > 0 else 0,
+                                  live_out=lives[-1])
+                xs.append(x)
+                continue
             xw = _linear_any(x, w)
             if _staged_ok(graph, xw.shape[-1]):
                 lives.append(live_for(xw.shape[-1]))
