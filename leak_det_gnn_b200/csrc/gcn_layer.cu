@@ -5,18 +5,22 @@
 // (linear.cu: X W^T written to HBM) and the aggregation (spmm.cu: read back, aggregate, epilogue) as two launches: four
 // activation tensors of traffic per layer.  Here the product X W^T never leaves the SM: two tensors.
 //
-// Work unit = (window b, 32-feature output slice s); a CTA keeps one slice for its life (W[32 s : 32 s + 32, :] resident
-// in shared memory as TF32 hi/lo) and walks over windows.  Per unit:
-//   warps 0-3   LOADERS   stream the window's X rows (cp.async into a ring of transposition patches, 8 lanes = the
-//                         128 bytes of one row), split fp32 -> TF32 hi/lo and tcgen05.st them into A slots in tensor memory
-//   warp  4     MMA       tcgen05.mma kind::tf32, 3xTF32, A from tensor memory, N = 32: tile t of the window (128 node
-//                         rows) accumulates into its own 32 tensor-memory columns -- the whole window's X W^T slice
-//                         (up to 7 x 128 rows) sits in tensor memory when the unit's last MMA commits
-//   warps 5-16  CONSUMERS drain the accumulators into a shared-memory stage [N][32] (XOR-swizzled 16-byte chunks, so
-//                         that both the row-per-lane writes and the 8-lanes-per-row reads are conflict-free), then
-//                         gather neighbour rows from it exactly like spmm_staged_kernel (same CSR order, one mul + one
-//                         add per entry), add the bias, ReLU, Philox dropout, 1-bit live mask, 128-bit streaming stores.
-// The tensor core works on window u + 1 while the consumers aggregate window u: the only serial part is the drain.
+// Work unit = one window; the whole weight (D x K, TF32 hi/lo) is resident in shared memory.  Per window:
+//   warps 0-3   LOADERS   stream the window's X rows ONCE (cp.async into a ring of transposition patches, 8 lanes = the
+//                         128 bytes of one row), split fp32 -> TF32 hi/lo and tcgen05.st them into A slots in tensor
+//                         memory (a slot = 16 K values: what is left of the 512 columns next to the accumulators)
+//   warp  4     MMA       tcgen05.mma kind::tf32, 3xTF32, A from tensor memory, N = D: tile t of the window (128 node
+//                         rows) accumulates into its own D tensor-memory columns -- the window's whole X W^T (up to
+//                         7 x 128 rows x 64) sits in tensor memory when the window's last MMA commits
+//   warps 5-16  CONSUMERS per 32-feature slice: drain that slice of the accumulators into a shared-memory stage
+//                         [N][32] (XOR-swizzled 16-byte chunks: the row-per-lane writes and the 8-lanes-per-row reads
+//                         are both conflict-free), then gather neighbour rows from it exactly like spmm_staged_kernel
+//                         (same CSR order, one mul + one add per entry), add the bias, ReLU, Philox dropout, 1-bit live
+//                         mask, 128-bit streaming stores.
+// The tensor core starts the next window as soon as the last slice is drained, i.e. under that slice's aggregation.
+// (A first version gave every CTA one 32-feature slice and let two CTAs read each window: correct, but the window's rows
+// then cross every SM's load path twice, and with ~64 KB of loads in flight per SM that, not HBM, set the pace -- 0.58 ms
+// per layer, no better than the two launches.)
 // Arithmetic is the unfused path's, operation for operation (same MMA sequence per output element, same summation
 // order, same dropout counter), so the result is BIT-IDENTICAL to ltgnn_linear + ltgnn_spmm_fused -- which stays as the
 // path for shapes this kernel does not take (K > 128, more than 896 nodes, graphs that do not fit shared memory).
@@ -30,9 +34,12 @@ namespace gl {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
 
-constexpr int kLdWarps = 4, kMmaWarp = 4, kCons = 12, kThreads = (kLdWarps + 1 + kCons) * 32;  // 17 warps: 96 registers
-constexpr int kSlots = 4, kSlotCols = 64, kMaxTiles = 7, kSlice = 32;
-constexpr int kRowsPerPass = kCons * 4;  // 8 lanes per row, 4 rows per warp
+constexpr int kLdWarps = 4, kMmaWarp = 4, kCons = 24, kThreads = (kLdWarps + 1 + kCons) * 32;  // 29 warps: 64 registers
+// (12 consumer warps were tried first: the gather is a chain of dependent shared-memory loads per row, and half the warps
+// took twice as long -- 0.55 ms per layer; with 24 the aggregation runs at spmm.cu's pace and the GEMM hides under it)
+constexpr int kMaxSlots = 4, kSlotCols = 32, kMaxTiles = 7, kSlice = 32;  // a slot: 16 K values as hi (16 columns) | lo (16)
+constexpr int kRowsPerPass = kCons * 4;  // 8 lanes per row, 4 rows per warp; rows r and r + 96 share one Philox call, as in
+                                         // spmm.cu: the dropout decisions are the unfused path's bit for bit
 
 struct Params {
     const int32_t* rowptr;
@@ -43,7 +50,7 @@ struct Params {
     const float* bias;    // [Dout] or nullptr
     uint32_t* live_out;   // [B, Dout/32, N] or nullptr
     int64_t B;
-    int32_t n, nnz, K, D, n_slices, T, depth, relu;
+    int32_t n, nnz, K, D, n_slices, T, depth, relu, n_slots;
     uint32_t drop_thresh;
     float keep_scale;
     uint64_t drop_seed;
@@ -62,11 +69,11 @@ __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n
 __global__ void __launch_bounds__(kThreads, 1)
 gcn_layer_fwd_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kSlots], bar_empty[kSlots], bar_acc_full, bar_acc_empty;
+    __shared__ uint64_t bar_full[kMaxSlots], bar_empty[kMaxSlots], bar_acc_full, bar_acc_empty;
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_hi = smem;
-    uint8_t* b_lo = b_hi + kSlice * p.K * 4;
+    uint8_t* b_lo = b_hi + p.D * p.K * 4;
     float4* stage = reinterpret_cast<float4*>(smem + p.off_stage);
     int32_t* s_rowptr = reinterpret_cast<int32_t*>(smem + p.off_rowptr);
     int2* s_colval = reinterpret_cast<int2*>(smem + p.off_colval);
@@ -76,7 +83,7 @@ gcn_layer_fwd_kernel(const Params p) {
 
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
-        for (int s = 0; s < kSlots; ++s) {
+        for (int s = 0; s < kMaxSlots; ++s) {
             mbar_init(&bar_full[s], 4);
             mbar_init(&bar_empty[s], 1);
         }
@@ -84,8 +91,7 @@ gcn_layer_fwd_kernel(const Params p) {
         mbar_init(&bar_acc_empty, kCons);
         fence_mbar_init();
     }
-    const int sl = blockIdx.x % p.n_slices;  // this CTA's output slice for its whole life
-    rowgemm_ts::fill_b(b_hi, b_lo, p.W + static_cast<size_t>(sl) * kSlice * p.K, p.K, 0, p.K, kSlice, tid, kThreads);
+    rowgemm_ts::fill_b(b_hi, b_lo, p.W, p.K, 0, p.K, p.D, tid, kThreads);
     for (int i = tid; i <= p.n; i += kThreads) s_rowptr[i] = __ldg(p.rowptr + i);
     for (int i = tid; i < p.nnz; i += kThreads) s_colval[i] = __ldg(p.colval + i);
     fence_proxy_async_smem();
@@ -93,10 +99,11 @@ gcn_layer_fwd_kernel(const Params p) {
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t acc_base = tmem_base, a_base = tmem_base + 256;  // 7 x 32 accumulator columns, then 4 A slots
-    const int64_t w_first = blockIdx.x / p.n_slices, w_step = gridDim.x / p.n_slices;
+    const uint32_t acc_base = tmem_base, a_base = tmem_base + p.T * p.D;  // T x D accumulator columns, then the A slots
+    const uint32_t slot_mask = p.n_slots - 1, slot_log2 = p.n_slots == 4 ? 2u : 1u;  // 2 or 4 A slots in rotation
+    const int64_t w_first = blockIdx.x, w_step = gridDim.x;
     const uint32_t n_win = w_first < p.B ? static_cast<uint32_t>((p.B - w_first + w_step - 1) / w_step) : 0;
-    const uint32_t per_win = p.T * n_kg;  // A-slot fills per window
+    const uint32_t per_win = p.T * n_kg;  // patch fills (32 K values each = two A slots) per window
 
     if (warp < kLdWarps) {
         // ---------------- loaders: as linear.cu's tensor-memory form, rows = the nodes of this CTA's windows ----------------
@@ -124,69 +131,74 @@ gcn_layer_fwd_kernel(const Params p) {
             asm volatile("cp.async.commit_group;" ::: "memory");  // (an empty group keeps the wait count uniform)
         };
         for (int d = 0; d < depth; ++d) fetch(d, d);
+        uint32_t sf = 0;  // running A-slot fill
         for (uint32_t f = 0; f < n_fills; ++f) {
             const int slot_p = static_cast<int>(f % depth);
             if (depth == 4) asm volatile("cp.async.wait_group 3;" ::: "memory");
             else asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncwarp();
-            float v[32];
-            {
-                const patch::Patch pt(ring + slot_p * patch::kPatchBytes, lane);
+            const patch::Patch pt(ring + slot_p * patch::kPatchBytes, lane);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 t = *pt.row(j);
+            for (int h = 0; h < 2; ++h, ++sf) {  // the patch's 32 K values go out as two 16-value slots
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = *pt.row(4 * h + j);
                     v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
                 }
-            }
-            __syncwarp();
-            fetch(f + depth, slot_p);  // refill the patch just read
-            const uint32_t slot = f & 3;
-            mbar_wait_relaxed(&bar_empty[slot], ((f >> 2) & 1) ^ 1);
-            fence_after_sync();
-            const uint32_t st_addr = lane_base + slot * kSlotCols;
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-                float hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    hi[j] = tf32_hi(v[c + j]);
-                    lo[j] = v[c + j] - hi[j];
+                if (h == 1) {
+                    __syncwarp();
+                    fetch(f + depth, slot_p);  // the patch has been read: refill it
                 }
-                tmem_st8(st_addr + c, hi);
-                tmem_st8(st_addr + 32 + c, lo);
+                const uint32_t slot = sf & slot_mask;
+                mbar_wait_relaxed(&bar_empty[slot], ((sf >> slot_log2) & 1) ^ 1);
+                fence_after_sync();
+                const uint32_t st_addr = lane_base + slot * kSlotCols;
+#pragma unroll
+                for (int c = 0; c < 16; c += 8) {
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        hi[j] = tf32_hi(v[c + j]);
+                        lo[j] = v[c + j] - hi[j];
+                    }
+                    tmem_st8(st_addr + c, hi);
+                    tmem_st8(st_addr + 16 + c, lo);
+                }
+                rowgemm_ts::tmem_wait_st();
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[slot]);
             }
-            rowgemm_ts::tmem_wait_st();
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[slot]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == kMmaWarp) {
-        // ---------------- MMA: tile t of a window -> accumulator columns [32 t, 32 t + 32) ----------------
-        const uint32_t idesc = idesc_tf32(128, kSlice);
+        // ---------------- MMA: tile t of a window -> accumulator columns [D t, D t + D) ----------------
+        const uint32_t idesc = idesc_tf32(128, p.D);
         const uint32_t bh = desc_lo(smem_u32(b_hi)), bl = desc_lo(smem_u32(b_lo));
-        const uint32_t kg_units = static_cast<uint32_t>(kSlice) * 128u >> 4;
-        uint32_t f = 0;
+        const uint32_t kg_units = static_cast<uint32_t>(p.D) * 128u >> 4;
+        uint32_t sf = 0;
         for (uint32_t wi = 0; wi < n_win; ++wi) {
             mbar_wait_relaxed(&bar_acc_empty, (wi & 1) ^ 1);  // the consumers drained the previous window
             fence_after_sync();
             for (int t = 0; t < p.T; ++t) {
-                const uint32_t d = acc_base + t * kSlice;
-                for (int kg = 0; kg < n_kg; ++kg, ++f) {
-                    const uint32_t slot = f & 3;
-                    mbar_wait_relaxed(&bar_full[slot], (f >> 2) & 1);
+                const uint32_t d = acc_base + t * p.D;
+                for (int kh = 0; kh < 2 * n_kg; ++kh, ++sf) {  // 16 K values per slot
+                    const uint32_t slot = sf & slot_mask;
+                    mbar_wait_relaxed(&bar_full[slot], (sf >> slot_log2) & 1);
                     fence_after_sync();
                     if (elect_one()) {
-                        const uint32_t a_hi = a_base + slot * kSlotCols, a_lo = a_hi + 32;
+                        const uint32_t a_hi = a_base + slot * kSlotCols, a_lo = a_hi + 16;
+                        const uint32_t bbase = static_cast<uint32_t>(kh >> 1) * kg_units + 4 * (kh & 1);
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k) {
-                            const uint32_t boff = kg * kg_units + 2 * k;
-                            rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (kg == 0 && k == 0) ? 0u : 1u);
+                        for (uint32_t k = 0; k < 2; ++k) {
+                            const uint32_t boff = bbase + 2 * k;
+                            rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (kh == 0 && k == 0) ? 0u : 1u);
                             rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
                             rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
                         }
                         commit(&bar_empty[slot]);
-                        if (t == p.T - 1 && kg == n_kg - 1) commit(&bar_acc_full);
+                        if (t == p.T - 1 && kh == 2 * n_kg - 1) commit(&bar_acc_full);
                     }
                     __syncwarp();
                 }
@@ -194,18 +206,17 @@ gcn_layer_fwd_kernel(const Params p) {
         }
     } else {
         // ---------------- consumers ----------------
-        const int cw = warp - kMmaWarp - 1;          // 0 .. 11
-        const int q4 = warp & 3, dj = cw >> 2;       // tensor-memory lane quadrant = warp % 4; this warp drains tiles dj, dj + 3, dj + 6
+        const int cw = warp - kMmaWarp - 1;          // 0 .. 23
+        const int q4 = warp & 3, dj = cw >> 2;       // tensor-memory lane quadrant = warp % 4; this warp drains tiles dj, dj + 6
         const int g = lane >> 3, q = lane & 7;       // aggregation: row within the warp's group of 4, float4 of the slice
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias) + sl * (kSlice / 4) + q);
         for (uint32_t wi = 0; wi < n_win; ++wi) {
             const int64_t b = w_first + static_cast<int64_t>(wi) * w_step;
             mbar_wait(&bar_acc_full, wi & 1);
             fence_after_sync();
-            for (int t = dj; t < p.T; t += 3) {
+          for (int sl = 0; sl < p.n_slices; ++sl) {
+            for (int t = dj; t < p.T; t += kCons / 4) {
                 float v[32];
-                tmem_ld32(acc_base + t * kSlice + (static_cast<uint32_t>(q4 * 32) << 16), v);
+                tmem_ld32(acc_base + t * p.D + sl * kSlice + (static_cast<uint32_t>(q4 * 32) << 16), v);
                 const int r = t * 128 + q4 * 32 + lane;
                 if (r < p.n) {
 #pragma unroll
@@ -213,10 +224,14 @@ gcn_layer_fwd_kernel(const Params p) {
                         stage[r * 8 + (c ^ (r & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                 }
             }
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_acc_empty);  // accumulators free: the tensor core starts the next window
+            if (sl == p.n_slices - 1) {  // accumulators free: the tensor core starts the next window
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_acc_empty);
+            }
             cons_bar();                                  // the whole stage is written
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias) + sl * (kSlice / 4) + q);
 
             const int64_t u = b * p.n_slices + sl;       // unit index as in spmm.cu (dropout counter, live-mask row)
             const int64_t base4 = (b * p.n) * d4 + sl * (kSlice / 4) + q;
@@ -283,6 +298,7 @@ gcn_layer_fwd_kernel(const Params p) {
                 }
             }
             cons_bar();  // every consumer is done with the stage: the next drain may overwrite it
+          }
         }
     }
     fence_before_sync();
@@ -300,12 +316,12 @@ inline uint32_t align_up(uint32_t x, uint32_t a) { return (x + a - 1) / a * a; }
 
 // 1 if ltgnn_gcn_layer_fwd takes this (graph, K = Din, D = Dout), else 0 (callers then run ltgnn_linear + ltgnn_spmm_fused)
 extern "C" int ltgnn_gcn_layer_supported(ltgnn_graph_t g, int32_t K, int32_t D) {
-    if (!g || K % 32 || K <= 0 || K > 128 || D % 32 || D <= 0) return 0;
-    if ((g->n + 127) / 128 > gl::kMaxTiles) return 0;
-    const uint32_t fixed = 2u * gl::kSlice * K * 4 + gl::align_up(static_cast<uint32_t>(g->n) * 128, 128) +
-                           gl::align_up(4u * (g->n + 1), 16) + gl::align_up(8u * g->nnz, 128);
-    return 1024 + fixed + gl::kLdWarps * 2 * patch::kPatchBytes <= static_cast<uint32_t>(g->smem_optin) &&
-           g->sm_count >= D / 32;
+    if (!g || K % 32 || K <= 0 || K > 128 || D % 32 || D <= 0 || D > 256) return 0;
+    const int T = (g->n + 127) / 128;
+    if (T > gl::kMaxTiles || T * D + 2 * gl::kSlotCols > 512) return 0;  // accumulators + at least two A slots
+    const uint32_t fixed = gl::align_up(2u * D * K * 4 + gl::align_up(static_cast<uint32_t>(g->n) * 128, 128) +
+                                            gl::align_up(4u * (g->n + 1), 16) + 8u * g->nnz, 1024);
+    return 1024 + fixed + gl::kLdWarps * 2 * patch::kPatchBytes <= static_cast<uint32_t>(g->smem_optin);
 }
 
 extern "C" int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_t D, const float* X, const float* W,
@@ -342,19 +358,17 @@ extern "C" int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_
     p.drop_thresh = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
     p.keep_scale = 1.f / (1.f - static_cast<float>(p.drop_thresh) / 65536.f);
     p.drop_seed = drop_seed;
-    p.off_stage = 2u * gl::kSlice * K * 4;
+    p.n_slots = (512 - p.T * D) / gl::kSlotCols >= gl::kMaxSlots ? gl::kMaxSlots : 2;  // a power of two
+    p.off_stage = 2u * D * K * 4;
     p.off_rowptr = p.off_stage + gl::align_up(static_cast<uint32_t>(g->n) * 128, 128);
     p.off_colval = p.off_rowptr + gl::align_up(4u * (g->n + 1), 16);
-    p.off_ring = p.off_colval + gl::align_up(8u * g->nnz, 128);
+    p.off_ring = gl::align_up(p.off_colval + 8u * g->nnz, 1024);  // patches address chunks by XOR: keep them aligned
     const uint32_t room = static_cast<uint32_t>(g->smem_optin) - 1024 - p.off_ring;
-    p.depth = room >= gl::kLdWarps * 4 * patch::kPatchBytes ? 4 : 2;
+    p.depth = room >= gl::kLdWarps * 4 * patch::kPatchBytes ? 4 : 2;  // 64 KB (or 32 KB) of loads in flight
     const size_t smem = 1024 + p.off_ring + static_cast<size_t>(gl::kLdWarps) * p.depth * patch::kPatchBytes;
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(gl::gcn_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    const int64_t n_units = B * p.n_slices;
-    int64_t grid = n_units < g->sm_count ? n_units : g->sm_count;
-    grid -= grid % p.n_slices;
-    LTGNN_REQUIRE(grid > 0, LTGNN_E_SHAPE, "gcn_layer_fwd: fewer SMs (%d) than feature slices (%d)", g->sm_count, p.n_slices);
+    const int64_t grid = B < g->sm_count ? B : g->sm_count;
     gl::gcn_layer_fwd_kernel<<<static_cast<int>(grid), gl::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
