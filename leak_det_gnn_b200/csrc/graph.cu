@@ -62,6 +62,14 @@ const DeviceInfo* device_info(int device) {
         d.sm_count = prop.multiProcessorCount;
         d.smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
         d.smem_per_sm = static_cast<int>(prop.sharedMemPerMultiprocessor);
+        // the few stream-ordered temporaries (cudaMallocAsync: partial sums of the large-graph paths) come from the
+        // device's default pool; by default it hands memory back to the driver at every synchronisation and the next
+        // allocation takes milliseconds -- keep it cached
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         d.ok = true;
     }
     return &d;

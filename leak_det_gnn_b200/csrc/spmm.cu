@@ -283,9 +283,16 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ ws, float* __rest
     colsum[col] = t;
 }
 
+// kEpi: y = dropout(relu(acc + bias)) as in the STAGED kernel (same Philox counter: the float4 pair (r, r + 96) of a
+// window shares one call there; here a thread owns one float4, so it draws for its own index with dropout4h -- the two
+// paths are statistically, not bitwise, the same stream).  kGate: every neighbour value is gated on the fly by the float
+// gate tensor (the upstream layer's output): x * (gate > 0 ? gate_scale : 0).
+template <bool kEpi, bool kGate>
 __global__ void __launch_bounds__(256)
-spmm_gather_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ colval,
-                   const float4* __restrict__ X, float4* __restrict__ Y, int32_t n, int32_t d4, int64_t total) {
+spmm_gather_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ colval, const float4* __restrict__ X,
+                   float4* __restrict__ Y, int32_t n, int32_t d4, int64_t total, const float4* __restrict__ bias, int relu,
+                   uint32_t drop_thresh, float keep_scale, uint64_t drop_seed, const float4* __restrict__ gate,
+                   float gate_scale) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int64_t row = e / d4;
@@ -293,22 +300,67 @@ spmm_gather_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ 
         const int64_t b = row / n;
         const int r = static_cast<int>(row - b * n);
         const float4* xb = X + b * n * d4 + c4;
+        const float4* gb = kGate ? gate + b * n * d4 + c4 : nullptr;
+        auto fetch = [&](int col) {
+            float4 x = __ldg(xb + static_cast<int64_t>(col) * d4);
+            if (kGate) {
+                const float4 m = __ldg(gb + static_cast<int64_t>(col) * d4);
+                x.x = m.x > 0.f ? x.x * gate_scale : 0.f; x.y = m.y > 0.f ? x.y * gate_scale : 0.f;
+                x.z = m.z > 0.f ? x.z * gate_scale : 0.f; x.w = m.w > 0.f ? x.w * gate_scale : 0.f;
+            }
+            return x;
+        };
         int k = __ldg(rowptr + r);
         const int end = __ldg(rowptr + r + 1);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (; k + 1 < end; k += 2) {
             const int2 c0 = __ldg(colval + k);
             const int2 c1 = __ldg(colval + k + 1);
-            const float4 x0 = __ldg(xb + static_cast<int64_t>(c0.x) * d4);
-            const float4 x1 = __ldg(xb + static_cast<int64_t>(c1.x) * d4);
+            const float4 x0 = fetch(c0.x);
+            const float4 x1 = fetch(c1.x);
             fma2(acc, __int_as_float(c0.y), x0);
             fma2(acc, __int_as_float(c1.y), x1);
         }
         if (k < end) {
             const int2 c0 = __ldg(colval + k);
-            fma2(acc, __int_as_float(c0.y), __ldg(xb + static_cast<int64_t>(c0.x) * d4));
+            fma2(acc, __int_as_float(c0.y), fetch(c0.x));
+        }
+        if (kEpi) {
+            if (bias) {
+                const float4 bb = __ldg(bias + c4);
+                acc.x = __fadd_rn(acc.x, bb.x); acc.y = __fadd_rn(acc.y, bb.y);
+                acc.z = __fadd_rn(acc.z, bb.z); acc.w = __fadd_rn(acc.w, bb.w);
+            }
+            if (relu) {
+                acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            }
+            if (drop_thresh) dropout4h(acc, static_cast<uint64_t>(e), drop_seed, drop_thresh, keep_scale);
         }
         stg_stream(Y + e, acc);
+    }
+}
+
+// colsum[c] = sum over all rows of gate(x): per-CTA partials, fixed order (the d bias of the gather path)
+__global__ void __launch_bounds__(256)
+gated_colsum_kernel(const float4* __restrict__ X, const float4* __restrict__ gate, float gate_scale, int64_t rows, int d4,
+                    float* __restrict__ part) {
+    __shared__ float4 red[256];
+    const int tid = threadIdx.x, c = tid % d4, rstep = 256 / d4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * rstep + tid / d4; r < rows; r += static_cast<int64_t>(gridDim.x) * rstep) {
+        const float4 x = ldg_stream(X + r * d4 + c), m = ldg_stream(gate + r * d4 + c);
+        s.x += m.x > 0.f ? x.x * gate_scale : 0.f; s.y += m.y > 0.f ? x.y * gate_scale : 0.f;
+        s.z += m.z > 0.f ? x.z * gate_scale : 0.f; s.w += m.w > 0.f ? x.w * gate_scale : 0.f;
+    }
+    red[tid] = s;
+    __syncthreads();
+    if (tid < d4) {
+        float4 t = red[tid];
+        for (int k = tid + d4; k < 256; k += d4) {
+            const float4 o = red[k];
+            t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+        }
+        reinterpret_cast<float4*>(part)[static_cast<size_t>(blockIdx.x) * d4 + tid] = t;
     }
 }
 
@@ -376,11 +428,15 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
 
     const StagedPlan pl = plan_staged(g, D);
     const bool fused = epi || gated;
-    const bool want_staged = (algo == LTGNN_SPMM_STAGED) || fused ||
+    const bool want_staged = (algo == LTGNN_SPMM_STAGED) || (fused && pl.ok) ||
                              (algo == LTGNN_SPMM_AUTO && pl.ok && pl.n_stages >= 2);
-    if (algo == LTGNN_SPMM_STAGED || fused)
+    if (algo == LTGNN_SPMM_STAGED)
         LTGNN_REQUIRE(pl.ok, LTGNN_E_SHAPE, "%s: the STAGED kernel needs D %% 32 == 0 and a 32-feature slice of the "
                       "graph (%d rows) to fit shared memory", who, g->n);
+    if (fused && !want_staged) {  // large graphs: the L2-gather kernel carries the same epilogue / gate
+        LTGNN_REQUIRE(!f.live_in && !f.live_out, LTGNN_E_SHAPE, "%s: 1-bit gates need the STAGED kernel (graph too large)", who);
+        LTGNN_REQUIRE(256 % (D / 4) == 0 || !f.colsum, LTGNN_E_SHAPE, "%s: colsum on the gather path needs D/4 | 256", who);
+    }
 
     if (want_staged) {
         PFN_tmapEncodeTiled enc = tmap_encode_fn();
@@ -451,10 +507,33 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
     int64_t blocks = (total + 255) / 256;
     const int64_t cap = static_cast<int64_t>(g->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    spmm_gather_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(
-        g->rowptr[transpose], g->colval[transpose], reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-        g->n, D / 4, total);
-    LTGNN_CUDA_TRY(cudaGetLastError());
+    const uint32_t thresh = f.drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(f.drop_p) * 65536.0 + 0.5) : 0u;
+    const float keep = 1.f / (1.f - static_cast<float>(thresh) / 65536.f);
+    auto launch_g = [&](auto kern) -> int {
+        kern<<<static_cast<int>(blocks), 256, 0, stream>>>(
+            g->rowptr[transpose], g->colval[transpose], reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
+            g->n, D / 4, total, reinterpret_cast<const float4*>(f.bias), f.relu, thresh, keep, f.drop_seed,
+            reinterpret_cast<const float4*>(f.gate), f.gate_scale);
+        LTGNN_CUDA_TRY(cudaGetLastError());
+        return LTGNN_OK;
+    };
+    int rc;
+    if (gated) rc = epi ? launch_g(spmm_gather_kernel<true, true>) : launch_g(spmm_gather_kernel<false, true>);
+    else rc = epi ? launch_g(spmm_gather_kernel<true, false>) : launch_g(spmm_gather_kernel<false, false>);
+    if (rc) return rc;
+    if (f.colsum) {
+        const int n_parts = g->sm_count;  // ws holds sm_count * 32 floats >= n_parts * D only for D <= 32: use our own
+        float* part = nullptr;
+        LTGNN_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&part), sizeof(float) * n_parts * D, stream));
+        gated_colsum_kernel<<<n_parts, 256, 0, stream>>>(reinterpret_cast<const float4*>(X),
+                                                          reinterpret_cast<const float4*>(f.gate), f.gate_scale,
+                                                          B * g->n, D / 4, part);
+        cudaError_t e = cudaGetLastError();
+        int rr = e == cudaSuccess ? reduce_parts(part, D, f.colsum, n_parts, D, 0, stream) : LTGNN_OK;
+        cudaFreeAsync(part, stream);
+        LTGNN_CUDA_TRY(e);
+        return rr;
+    }
     return LTGNN_OK;
 }
 
@@ -482,5 +561,5 @@ extern "C" int ltgnn_spmm_fused(ltgnn_graph_t g, int transpose, int64_t B, int32
     f.gate_scale = gate_scale;
     f.colsum = colsum;
     f.ws = ws;
-    return spmm_impl(g, transpose, B, D, X, Y, LTGNN_SPMM_STAGED, f, static_cast<cudaStream_t>(stream_), "spmm_fused");
+    return spmm_impl(g, transpose, B, D, X, Y, LTGNN_SPMM_AUTO, f, static_cast<cudaStream_t>(stream_), "spmm_fused");
 }

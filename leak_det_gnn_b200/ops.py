@@ -581,15 +581,11 @@ class _GnnBody(torch.autograd.Function):
                 xs.append(x)
                 continue
             xw = _linear_any(x, w)
-            if _staged_ok(graph, xw.shape[-1]):
-                lives.append(live_for(xw.shape[-1]))
-                x = spmm_fused(graph, xw, bias=b, relu=True, drop_p=p, drop_seed=new_dropout_seed() if p > 0 else 0,
-                               live_out=lives[-1])
-            else:  # graph too large for shared memory: L2-gather kernel + elementwise tail
-                lives.append(None)
-                x = torch.relu_(spmm(graph, xw).add_(b))
-                if p > 0:
-                    x = torch.nn.functional.dropout(x, p, True)
+            # graphs that fit shared memory: STAGED kernel + 1-bit live mask; larger ones: the L2-gather kernel with the
+            # same fused epilogue (the backward then gates with the float activations)
+            lives.append(live_for(xw.shape[-1]) if _staged_ok(graph, xw.shape[-1]) else None)
+            x = spmm_fused(graph, xw.view(bsz, n, -1), bias=b, relu=True, drop_p=p,
+                           drop_seed=new_dropout_seed() if p > 0 else 0, live_out=lives[-1])
             del xw
             xs.append(x)
         ctx.lives = lives
@@ -612,15 +608,9 @@ class _GnnBody(torch.autograd.Function):
         grads = [None] * (2 * L_)
         for l in range(L_ - 1, -1, -1):
             x_out, x_in, w = xs[l + 1], xs[l], ws_[l]
-            if _staged_ok(graph, g.shape[-1]):
-                live = ctx.lives[l + 1]
-                gz, db = spmm_fused(graph, g, transpose=True, gate=x_out if live is None else None, live_in=live,
-                                    gate_scale=scale, want_colsum=True)
-            else:
-                dz = torch.where(x_out > 0, g * scale, torch.zeros((), device=g.device))
-                db = dz.sum(dim=(0, 1))
-                gz = spmm(graph, dz, transpose=True)
-                del dz
+            live = ctx.lives[l + 1]
+            gz, db = spmm_fused(graph, g, transpose=True, gate=x_out if live is None else None, live_in=live,
+                                gate_scale=scale, want_colsum=True)
             grads[2 * l] = wgrad(gz, x_in)
             grads[2 * l + 1] = db
             g = _linear_any(gz, w, transposed=True)

@@ -117,3 +117,48 @@ def test_gcn_body_large_graph_d128():
     for o, r in zip(ours, ref):
         assert rel_err(o.lin.weight.grad, r.lin.weight.grad) <= TOL
         assert rel_err(o.bias.grad, r.bias.grad) <= 5 * TOL
+
+
+def test_gnn_body_large_graph_uses_native_epilogues():
+    """The detector body on a graph too large for shared memory (BASELINE config 5 shape, scaled down): node init with
+    more sensors than fit a CTA, then layers on the L2-gather kernel with the bias / ReLU / dropout epilogue and the
+    gated backward inside the kernel -- against the same computation assembled from the operator-level pieces
+    (each checked against fp64 elsewhere).  Forward bit-equal, gradients to fp32 rounding."""
+    import numpy as np
+    from leak_det_gnn_b200 import ops
+    rng = np.random.default_rng(7)
+    n, bsz, d, s_cnt = 12000, 3, 128, 700
+    par = np.arange(1, n) - 1 - rng.integers(0, np.minimum(np.arange(1, n), 64))
+    ei = torch.from_numpy(np.stack([np.concatenate([np.arange(1, n), par]), np.concatenate([par, np.arange(1, n)])]))
+    graph = lnn.PipeGraph(ei, n)
+    assert not ops._staged_ok(graph, d)
+    slot = torch.full((n,), -1, dtype=torch.int32)
+    slot[torch.from_numpy(np.sort(rng.choice(n, s_cnt, replace=False)))] = torch.arange(s_cnt, dtype=torch.int32)
+    slot = slot.cuda()
+    gen = torch.Generator().manual_seed(2)
+    mk = lambda *shape: (torch.randn(*shape, generator=gen) * 0.2).cuda().requires_grad_(True)
+    h_s, w0, b0, w1, b1, w2, b2 = mk(bsz, s_cnt, 64), mk(d, 65), mk(d), mk(d, d), mk(d), mk(d, d), mk(d)
+    dy = torch.randn(bsz, n, d, generator=gen).cuda()
+    y = ops.gnn_body(h_s, slot, graph, 0.0, False, w0, b0, [w1, b1, w2, b2])
+    y.backward(dy)
+    got = [y.detach().clone()] + [t.grad.clone() for t in (h_s, w0, b0, w1, b1, w2, b2)]
+    for t in (h_s, w0, b0, w1, b1, w2, b2):
+        t.grad = None
+    x0 = ops.node_init_fwd(h_s.detach(), slot, n, w0.detach(), b0.detach())
+    x0r = x0.clone().requires_grad_(True)
+    x1 = torch.relu(ops.gcn_conv(x0r, graph, w1, b1))
+    x2 = torch.relu(ops.gcn_conv(x1, graph, w2, b2))
+    x2.backward(dy)
+    dhs, dw0, db0 = ops.node_init_bwd(h_s.detach(), slot, w0.detach(), x0r.grad, x0, 1.0)
+    want = [x2.detach(), dhs, dw0, db0, w1.grad, b1.grad, w2.grad, b2.grad]
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert rel_err(a, b) <= 2e-6, rel_err(a, b)
+    # train mode: the in-kernel dropout is active, unbiased and reproducible
+    torch.manual_seed(4)
+    ya = ops.gnn_body(h_s, slot, graph, 0.1, True, w0, b0, [w1, b1, w2, b2]).detach()
+    torch.manual_seed(4)
+    yb = ops.gnn_body(h_s, slot, graph, 0.1, True, w0, b0, [w1, b1, w2, b2]).detach()
+    assert torch.equal(ya, yb) and not torch.equal(ya, got[0])
+    drop = ((ya == 0) & (got[0] > 0)).float().sum() / (got[0] > 0).float().sum()
+    assert 0.05 < drop.item() < 0.35     # two dropout layers in sequence thin the last activations
