@@ -188,16 +188,19 @@ int ltgnn_mean_pool_bwd_fill(int device, int64_t B, int32_t N, int32_t D, const 
 /* ---- weight gradients on tensor cores (tcgen05, MN-major operands, 3xTF32) ---------------------
  * wgrad_tc: same contract as ltgnn_wgrad for Do in {64, 128}, Di a multiple of 32 (<= 256); ~3x faster.
  * pipe_head_bwd_w: dW1 [H, 3D] = dpre^T [x_u, x_v, |x_u - x_v|] and db1 [H] = column sums of dpre, where
- *   dpre[r, j] = dlogit[r] * w2[j] * (hpost[r, j] > 0 ? gate_scale : 0); operands are formed on the fly.
- *   dw2 [H] = sum_r dlogit[r] * hpost[r, :] (one more streaming pass).  hpost in the blocked-32 layout.
+ *   dpre[r, j] = dlogit[r] * w2[j] * (hidden[r, j] > 0 ? gate_scale : 0), with the gate read as 1 bit per unit from
+ *   hmask (ltgnn_pipe_head_fwd) and the operands formed on the fly; dw2 [H] = sum_r dlogit[r] * hidden[r, :] is
+ *   recovered from the same accumulators (hidden is linear in W1, b1 under the gate), so the forward need not save
+ *   the hidden activations.
  * ws: ltgnn_tgrad_ws_floats(device, Di) floats; pipe head: ltgnn_pipe_head_ws_floats(device).  Deterministic.
  */
 int64_t ltgnn_tgrad_ws_floats(int device, int32_t No);
 int ltgnn_wgrad_tc(int device, int64_t M, int32_t Do, int32_t Di, const float* G, const float* X, float* dW,
                    int accumulate, float* ws, void* stream);
 int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
-                          const int32_t* ends, const float* w2, const float* hpost, const float* dlogit,
-                          float gate_scale, float* dW1, float* db1, float* dw2, float* ws, void* stream);
+                          const int32_t* ends, const float* W1, const float* b1, const float* w2, const uint32_t* hmask,
+                          const float* dlogit, float gate_scale, float* dW1, float* db1, float* dw2, float* ws,
+                          void* stream);
 int64_t ltgnn_pipe_head_ws_floats(int device);
 
 /* ---- shared per-sensor GRU encoder (detector.py:28-73) -----------------------

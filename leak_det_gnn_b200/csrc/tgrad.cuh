@@ -72,9 +72,13 @@ __host__ __device__ constexpr uint32_t idesc_tf32_mn(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// A G loader may carry a per-thread side accumulation over the values it fetches (`using Side = ...`,
-// `load(row, c, Side&)`, `finish(Side*, n, cta, group, warp_in_group, lane)`): the pipe head's d w2 rides on the
-// pass that reads the saved activations anyway.
+// Loaders come in two styles.  Plain: `float4 operator()(row, c)` returns the operand chunk.  Raw: `using Raw = ...;
+// Raw raw(row, c); float aux(row); float4 convert(const Raw&, float aux, int c[, Side&])` -- `raw` / `aux` only LOAD (no
+// arithmetic on the loaded values), `convert` turns them into the operand chunk when the chunk is stored, one pipeline
+// stage later.  With few loads per thread the difference is everything: a fetch that computes on what it loads waits
+// for memory right there, and the prefetch of the next chunk no longer overlaps anything.
+// A raw-style G loader may also carry a per-thread side accumulation (`using Side = ...`, updated in `convert`,
+// written out by `finish(Side*, cols, n, cta, group, lane)`).
 template <class T, class = void>
 struct has_side : std::false_type {};
 template <class T>
@@ -83,6 +87,14 @@ template <class T, bool = has_side<T>::value>
 struct side_of { struct type {}; };
 template <class T>
 struct side_of<T, true> { using type = typename T::Side; };
+template <class T, class = void>
+struct has_raw : std::false_type {};
+template <class T>
+struct has_raw<T, std::void_t<typename T::Raw>> : std::true_type {};
+template <class T, bool = has_raw<T>::value>
+struct raw_of { using type = float4; };
+template <class T>
+struct raw_of<T, true> { using type = typename T::Raw; };
 
 // Optional loader traits.  XLoader::kSlices = S: S consecutive CTAs share one row range and each produces its own No
 // columns of the result (the loaders look at blockIdx.x % S themselves) -- a wide result split so that every CTA can keep
@@ -193,20 +205,30 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         static_assert(!XLoader::kRowFast || kXJ % 2 == 0, "kRowFast operands need an even chunk count");
         auto cg = [&](int j) { return GLoader::kRowFast ? 2 * qg + (j & 1) + 16 * (j >> 1) : qg + 8 * j; };
         auto cx = [&](int j) { return XLoader::kRowFast ? 2 * qx + (j & 1) + 16 * (j >> 1) : qx + 8 * j; };
-        float4 gv[kGJ], xv[kXJ];
+        using GRaw = typename raw_of<GLoader>::type;
+        using XRaw = typename raw_of<XLoader>::type;
+        static_assert(!has_side<GLoader>::value || has_raw<GLoader>::value, "side accumulation needs a raw-style loader");
+        GRaw gv[kGJ];
+        XRaw xv[kXJ];
+        float gaux_v = 0.f, xaux_v = 0.f;
         typename side_of<GLoader>::type side[kGJ] = {};
-        auto fetch = [&](uint32_t ch, float4 (&gd)[kGJ], float4 (&xd)[kXJ]) {
+        // raw-style loaders: rows past M are fetched from row M - 1 and zeroed at convert time -- a select on the loaded
+        // value would be a use of it, and the thread would wait for memory inside the fetch
+        auto fetch = [&](uint32_t ch, GRaw (&gd)[kGJ], XRaw (&xd)[kXJ], float& gaux, float& xaux) {
             const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
+            const uint32_t row_gc = row_g < M ? row_g : M - 1, row_xc = row_x < M ? row_x : M - 1;
 #pragma unroll
             for (int j = 0; j < kGJ; ++j) {
-                if constexpr (has_side<GLoader>::value)
-                    gd[j] = row_g < M ? gload.load(row_g, cg(j), side[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                else
-                    gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (has_raw<GLoader>::value) gd[j] = gload.raw(row_gc, cg(j));
+                else gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            if constexpr (has_raw<GLoader>::value) gaux = gload.aux(row_gc);
 #pragma unroll
-            for (int j = 0; j < kXJ; ++j)
-                xd[j] = (row_x < M && cx(j) < x4) ? xload(row_x, cx(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < kXJ; ++j) {
+                if constexpr (has_raw<XLoader>::value) xd[j] = xload.raw(row_xc, cx(j) < x4 ? cx(j) : 0);
+                else xd[j] = (row_x < M && cx(j) < x4) ? xload(row_x, cx(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if constexpr (has_raw<XLoader>::value) xaux = xload.aux(row_xc);
         };
         // store one operand's chunks (hi and lo).  kRowFast: the 32 lanes of a warp hold 32 rows of the SAME chunk,
         // whose swizzled offsets share only 4 bank groups (2-way conflicts on every quarter-warp).  Lanes whose row
@@ -246,22 +268,42 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
             }
         };
         uint32_t use = 0;
-        if (kPipe && c_begin + grp < c_end) fetch(c_begin + grp, gv, xv);
+        if (kPipe && c_begin + grp < c_end) fetch(c_begin + grp, gv, xv, gaux_v, xaux_v);
         for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
-            float4 gc[kGJ], xc[kXJ];
+            GRaw gc[kGJ];
+            XRaw xc[kXJ];
+            float gaux = 0.f, xaux = 0.f;
             if (kPipe) {
 #pragma unroll
                 for (int j = 0; j < kGJ; ++j) gc[j] = gv[j];
 #pragma unroll
                 for (int j = 0; j < kXJ; ++j) xc[j] = xv[j];
-                if (ch + kGroups < c_end) fetch(ch + kGroups, gv, xv);  // in flight while this chunk is stored
+                gaux = gaux_v;
+                xaux = xaux_v;
+                if (ch + kGroups < c_end) fetch(ch + kGroups, gv, xv, gaux_v, xaux_v);  // in flight while this chunk is stored
             } else {
-                fetch(ch, gc, xc);
+                fetch(ch, gc, xc, gaux, xaux);
+            }
+            float4 gval[kGJ], xval[kXJ];
+            const bool g_ok = ch * kChunk + rg < M, x_ok = ch * kChunk + rx < M;
+            if constexpr (has_raw<GLoader>::value) gaux = g_ok ? gaux : 0.f;   // (a zero aux keeps the side sums clean)
+#pragma unroll
+            for (int j = 0; j < kGJ; ++j) {
+                if constexpr (has_side<GLoader>::value) gval[j] = gload.convert(gc[j], gaux, cg(j), side[j]);
+                else if constexpr (has_raw<GLoader>::value) gval[j] = gload.convert(gc[j], gaux, cg(j));
+                else gval[j] = gc[j];
+                if (has_raw<GLoader>::value && !g_ok) gval[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < kXJ; ++j) {
+                if constexpr (has_raw<XLoader>::value) xval[j] = xload.convert(xc[j], xaux, cx(j));
+                else xval[j] = xc[j];
+                if (has_raw<XLoader>::value && !(x_ok && cx(j) < x4)) xval[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
-            store(std::integral_constant<bool, GLoader::kRowFast>{}, std::integral_constant<bool, !kExactG>{}, gc, kGJ, rg, cg, kG / 4,
-                  g_hi, g_lo);
-            store(std::integral_constant<bool, XLoader::kRowFast>{}, std::true_type{}, xc, kXJ, rx, cx, x4, x_hi, x_lo);
+            store(std::integral_constant<bool, GLoader::kRowFast>{}, std::integral_constant<bool, !kExactG>{}, gval, kGJ, rg, cg,
+                  kG / 4, g_hi, g_lo);
+            store(std::integral_constant<bool, XLoader::kRowFast>{}, std::true_type{}, xval, kXJ, rx, cx, x4, x_hi, x_lo);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_full[grp]);

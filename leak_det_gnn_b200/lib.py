@@ -54,7 +54,8 @@ SIGNATURES = {
     "ltgnn_tgrad_ws_floats": (c_int64, [c_int, c_int32]),
     "ltgnn_wgrad_tc": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "ltgnn_pipe_head_bwd_w": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "ltgnn_pipe_head_ws_floats": (c_int64, [c_int]),
     "ltgnn_gru_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),

@@ -61,6 +61,10 @@ def test_heads_many_tiles_per_cta(bsz, n, p):
         ops.DEBUG_CAPTURE = None
     logits = part.sum(0) + b2c
     ((logits * dlog.cuda()).sum() + (pooled * dpool.cuda()).sum()).backward()
+    # the 1-bit gate the backward kernels read == (saved hidden activation > 0): unit j <-> bit 31 - j % 32 of word j / 32
+    words = cap["head_mask_words"].to(torch.int64) & 0xFFFFFFFF
+    bits = (words.unsqueeze(-1) >> (31 - torch.arange(32, device=words.device))) & 1
+    assert torch.equal(bits.reshape(bsz * p, 128).bool(), cap["head_live"])
 
     t = [v.double().requires_grad_(True) for v in (x, w1, b1, w2, b2)]
     lr, pr = _head_ref(t[0], ends, *t[1:], cap["head_live"].cpu().double().view(bsz, p, 128))
