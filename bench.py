@@ -517,9 +517,59 @@ def run_ours(args, wl: dict) -> None:
                 model(r1, t1)
             le1.record()
             torch.cuda.synchronize()
-        latency = {"b1_forward_ms": le0.elapsed_time(le1) / 50, "calls": 50,
-                   "scope": "LeakDetector.forward at B = 1, eval mode, device inputs (event_evaluator.py:486)"}
+        from leak_det_gnn_b200.event_windows import GraphedDetector
+
+        graphed = GraphedDetector(model, 1, args.l_det)
+        for _ in range(5):
+            graphed(r1, t1)
+        torch.cuda.synchronize()
+        ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ge0.record()
+        for _ in range(200):
+            graphed(r1, t1)
+        ge1.record()
+        torch.cuda.synchronize()
+        latency = {"b1_forward_ms": le0.elapsed_time(le1) / 50, "b1_forward_cuda_graph_ms": ge0.elapsed_time(ge1) / 200,
+                   "calls": 50,
+                   "scope": "LeakDetector.forward at B = 1, eval mode, device inputs (event_evaluator.py:486): eager "
+                            "(one ctypes call per kernel) and replayed as a CUDA graph (event_windows.GraphedDetector)"}
         model.train()
+
+    # ---- scope (i): the aggregation kernels alone (BASELINE metric "SpMM HBM GB/s vs peak"), outside the step ----
+    agg_alone = None
+    if rank == 0 and hidden % 32 == 0:
+        from leak_det_gnn_b200 import ops
+
+        xa = torch.randn(args.batch, net["n_nodes"], hidden, device=dev)
+        staged = ops._staged_ok(model.pipe_graph, hidden)
+        live = ops.new_live_mask(args.batch, net["n_nodes"], hidden, dev) if staged and net["n_nodes"] <= 1024 else None
+        bias = torch.zeros(hidden, device=dev)
+        forms = {
+            "aggregate": lambda: ops.spmm(model.pipe_graph, xa),
+            "aggregate_transpose": lambda: ops.spmm(model.pipe_graph, xa, transpose=True),
+            "aggregate+bias+relu+dropout+mask": lambda: ops.spmm_fused(model.pipe_graph, xa, bias=bias, relu=True, drop_p=0.1,
+                                                                       drop_seed=7, live_out=live),
+        }
+        if live is not None:
+            forms["gate+aggregate_transpose+colsum"] = lambda: ops.spmm_fused(model.pipe_graph, xa, transpose=True,
+                                                                              live_in=live, gate_scale=1.1, want_colsum=True)
+        agg_alone = []
+        for name, fn in forms.items():
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(10):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            ms = a0.elapsed_time(a1) / 10
+            gbs = 2 * unit_bytes / (ms * 1e-3) / 1e9
+            agg_alone.append({"kernel": name, "ms": ms, "achieved": gbs, "unit": "GB/s", "peak": peaks()["hbm_gbs"],
+                              "frac": gbs / peaks()["hbm_gbs"], "algorithmic_bytes": 2 * unit_bytes,
+                              "path": "STAGED (TMA + shared-memory topology)" if staged else "GATHER (L2)"})
+        del xa, live
 
     # ---- rooflines, from the CUDA-event durations recorded live inside the timed region ----
     pk = peaks()
@@ -531,6 +581,7 @@ def run_ours(args, wl: dict) -> None:
         "spmm_fwd": ("hbm", 2 * unit_b), "spmm_bwd": ("hbm", 2 * unit_b),
         "spmm_fused_fwd": ("hbm", 2 * unit_b + unit_b // 32),   # read XW, write X_l and its 1-bit live mask
         "spmm_fused_bwd": ("hbm", 2 * unit_b + unit_b // 32),   # read dX_l and the live mask of X_l (gate), write G
+        "gcn_layer_fwd": ("hbm", 2 * unit_b + unit_b // 32),     # fused layer: read X_{l-1}, write X_l and its live mask
         "linear_tc": ("hbm", 2 * unit_b), "wgrad_tc": ("hbm", 2 * unit_b), "wgrad": ("hbm", 2 * unit_b),
         "node_init_fwd": ("hbm", unit_b + unit_b // 32),          # write X_0 and its live mask
         "node_init_bwd": ("hbm", unit_b + unit_b // 32),          # read dX_0 and the live mask (sensor rows: 4 %)
@@ -593,7 +644,8 @@ def run_ours(args, wl: dict) -> None:
             "warmup": args.warmup, "ms_per_step": ms_stack_net / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl, net, world),
-            "roofline": roof, "roofline_aggregation": agg, "roofline_all": roofs, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_aggregation": agg, "aggregation_alone": agg_alone, "roofline_all": roofs,
+            "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e_net / e2e_steps, "steps": e2e_steps,
                     "scope": ("build_residual_sequence_from_segment (frozen TCN) + " if full_step else "")
