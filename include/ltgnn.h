@@ -203,6 +203,18 @@ int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P, int32_t D
                           void* stream);
 int64_t ltgnn_pipe_head_ws_floats(int device);
 
+/* ---- frozen TCN predictor, one dilated causal convolution over gathered rows ---------
+ * Reference: models/predictor.py:17-52 (CausalConv1d -> LayerNorm -> ReLU, residual add), evaluated only on the
+ * (window, position) rows the last time step depends on (models/utils.py:169-216 reads nothing else).
+ *   Y[m, :] = [res[res_row[m], :] +] relu(LayerNorm(bias + sum_tap X[src[tap * M + m], :] W[tap]^T))
+ * X [x_rows, C], src int32 [taps, M] (-1 = zero row: the left padding), W [taps, C, C] (tap 0 = the oldest input;
+ * torch's conv weight permuted (2, 0, 1)), bias / gamma / beta [C] (gamma = beta = null: no LayerNorm), res [r_rows, C]
+ * with res_row int32 [M] or both null, Y [M, C].  C = 128.  tcgen05, 3xTF32, the weight streamed through shared memory.
+ */
+int ltgnn_tcn_conv(int device, int64_t M, int32_t C, int32_t taps, const float* X, const int32_t* src, const float* W,
+                   const float* bias, const float* gamma, const float* beta, float eps, int relu, const float* res,
+                   const int32_t* res_row, float* Y, void* stream);
+
 /* ---- shared per-sensor GRU encoder (detector.py:28-73) -----------------------
  * Sequence q = b*S + s has input [r[b,t,s], tf[b,t,0..F)] at step t (the reference's cat([rr, tf]) order);
  * weights in torch.nn.GRU layout (gate order r, z, n): w_ih [3H, 1+F], w_hh [3H, H], b_ih, b_hh [3H].  H = 64.

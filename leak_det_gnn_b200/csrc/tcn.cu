@@ -1,0 +1,332 @@
+// tcn.cu -- one dilated causal convolution of the frozen TCN predictor, evaluated only where the last time step
+// needs it (reference models/predictor.py:17-81, models/utils.py:169-216).
+//
+// The reference slides the predictor over l_det overlapping windows of every segment and evaluates all 36 time steps
+// of all 8 convolutions, although the model reads only the last step (predictor.py:80).  The host side keeps, per
+// convolution, the list of (window, position) rows the last step depends on (99 of 288 position evaluations) and for
+// every such row the rows of the previous layer its three taps read (-1 = the zero left padding of CausalConv1d).
+// That makes every convolution ONE GEMM over gathered rows with a fused epilogue:
+//
+//     Y[m, :] = [res[res_row[m], :] +] relu(LayerNorm(bias + sum_tap X[src[tap][m], :] W_tap^T))      K = taps * C = 384
+//
+//   warps 0-3   A LOADERS  gather the rows of one (tile, tap, 32-channel block) with cp.async into a ring of
+//                          transposition patches, split fp32 -> TF32 hi/lo, tcgen05.st into an A slot (as linear.cu)
+//   warps 4-7   B LOADERS  stream the weight: the 3 x 128 x 128 fp32 weight is 393 KB as hi + lo and cannot be resident, so
+//                          a ring of k-atom stages (32 K values x 128 outputs, hi + lo = 32 KB) is refilled from L2 --
+//                          and every stage is used by THREE row tiles before it is released, which divides that traffic
+//   warp  8     MMA        3xTF32, A from tensor memory; three 128-column accumulators (tiles t, t+1, t+2 of the group)
+//   warps 9-16  EPILOGUE   bias, LayerNorm over the 128 channels (two-pass mean / variance; the two warps that share a
+//                          row exchange partial sums through shared memory), ReLU, residual, coalesced stores via patches
+// fp32-faithful like every GEMM of this library (the residual is a small difference of pressures).
+#include "patch.cuh"
+#include "rowgemm_ts.cuh"
+
+using namespace ltgnn;
+
+namespace {
+namespace tc {
+using namespace ltgnn::ptx;
+using namespace ltgnn::umma;
+
+constexpr int kC = 128;                  // channels: K per tap and N
+constexpr int kALd = 4, kBLd = 4, kMmaWarp = 8, kEp = 8, kThreads = (kALd + kBLd + 1 + kEp) * 32;  // 17 warps
+constexpr int kTiles = 3;                // row tiles per group (accumulators in tensor memory)
+constexpr int kASlots = 2, kSlotCols = 64;
+constexpr int kBStages = 4, kADepth = 3;
+constexpr uint32_t kBStageBytes = 2u * kC * 128;  // one k-atom of the weight: 128 rows x 128 B, hi then lo
+
+struct Params {
+    const float4* X;           // [x_rows, 32] float4 rows of the previous layer
+    const int32_t* src;        // [taps][M]
+    const float* W;            // [taps][128][128]  (tap 0 = the oldest input)
+    const float* bias;         // [128]
+    const float* gamma;        // [128] or nullptr (no LayerNorm)
+    const float* beta;
+    const float4* res;         // [res_rows, 32] or nullptr
+    const int32_t* res_row;    // [M]
+    float4* Y;                 // [M, 32]
+    uint32_t M;
+    int32_t taps, relu;
+    float eps;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tcn_conv_kernel(const Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBStages], b_empty[kBStages], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float stat_s[2][2][128];   // [pass][half][row]: partial sums the two warps of a row exchange
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_ring = smem;                                             // kBStages x 32 KB
+    uint8_t* a_rings = b_ring + kBStages * kBStageBytes;                // kALd x kADepth patches
+    uint8_t* ep_patches = a_rings + kALd * kADepth * patch::kPatchBytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        for (int s = 0; s < kASlots; ++s) {
+            mbar_init(&a_full[s], kALd);
+            mbar_init(&a_empty[s], 1);
+        }
+        for (int s = 0; s < kBStages; ++s) {
+            mbar_init(&b_full[s], kBLd);
+            mbar_init(&b_empty[s], 1);
+        }
+        mbar_init(&acc_full, 1);
+        mbar_init(&acc_empty, kEp);
+        fence_mbar_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t acc_base = tmem_base, a_base = tmem_base + kTiles * kC;  // 384 accumulator columns + 2 A slots
+    const uint32_t rows_per_group = kTiles * 128;
+    const uint32_t n_groups = (p.M + rows_per_group - 1) / rows_per_group;
+    const uint32_t my_groups = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int n_katoms = p.taps * 4;        // k-atoms of 32 channels per group pass
+
+    if (warp < kALd) {
+        // ---------------- A loaders ----------------
+        const int quad = warp;
+        uint8_t* ring = a_rings + static_cast<size_t>(warp) * kADepth * patch::kPatchBytes;
+        const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
+        const int sub = lane >> 3, ch = lane & 7;
+        const uint32_t fills_per_group = n_katoms * kTiles, n_fills = my_groups * fills_per_group;
+        auto fetch = [&](uint32_t f, int slot_p) {
+            const patch::Patch pt(ring + slot_p * patch::kPatchBytes, lane);
+            if (f < n_fills) {
+                const uint32_t gi = f / fills_per_group, rem = f - gi * fills_per_group, j = rem / kTiles, tile = rem - j * kTiles;
+                const uint32_t tap = j >> 2, kg = j & 3;
+                const uint32_t row0 = (blockIdx.x + gi * gridDim.x) * rows_per_group + tile * 128 + quad * 32 + sub;
+                const int32_t* srct = p.src + static_cast<size_t>(tap) * p.M;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t row = row0 + 4 * k;
+                    const int32_t s = row < p.M ? __ldg(srct + row) : -1;   // -1: left padding / past the end -> zeros
+                    const float4* from = p.X + static_cast<size_t>(s < 0 ? 0 : s) * (kC / 4) + kg * 8 + ch;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(pt.co(k))), "l"(from),
+                                 "r"(s < 0 ? 0 : 16)
+                                 : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int d = 0; d < kADepth; ++d) fetch(d, d);
+        for (uint32_t f = 0; f < n_fills; ++f) {
+            const int slot_p = static_cast<int>(f % kADepth);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
+            __syncwarp();
+            float v[32];
+            {
+                const patch::Patch pt(ring + slot_p * patch::kPatchBytes, lane);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = *pt.row(j);
+                    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+                }
+            }
+            __syncwarp();
+            fetch(f + kADepth, slot_p);
+            const uint32_t slot = f & (kASlots - 1);
+            mbar_wait_relaxed(&a_empty[slot], ((f / kASlots) & 1) ^ 1);
+            fence_after_sync();
+            const uint32_t st_addr = lane_base + slot * kSlotCols;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+                float hi[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    hi[j] = tf32_hi(v[c + j]);
+                    lo[j] = v[c + j] - hi[j];
+                }
+                tmem_st8(st_addr + c, hi);
+                tmem_st8(st_addr + 32 + c, lo);
+            }
+            rowgemm_ts::tmem_wait_st();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[slot]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (warp < kALd + kBLd) {
+        // ---------------- B loaders: k-atom j of the weight -> ring stage (K-major SWIZZLE_128B, hi then lo) ----------------
+        const int bt = tid - kALd * 32;  // 0 .. 127
+        const uint32_t n_fills = my_groups * n_katoms;
+        for (uint32_t f = 0; f < n_fills; ++f) {
+            const uint32_t j = f % n_katoms, tap = j >> 2, kg = j & 3, stage = f % kBStages;
+            float4 w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {  // 128 rows x 8 chunks of 16 B: thread bt takes chunk (bt & 7) of rows (bt >> 3) + 16 i
+                const int n = (bt >> 3) + 16 * i, c = bt & 7;
+                w[i] = __ldg(reinterpret_cast<const float4*>(p.W + (static_cast<size_t>(tap) * kC + n) * kC + kg * 32) + c);
+            }
+            mbar_wait_relaxed(&b_empty[stage], ((f / kBStages) & 1) ^ 1);
+            uint8_t* hi_base = b_ring + stage * kBStageBytes;
+            uint8_t* lo_base = hi_base + kC * 128;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int n = (bt >> 3) + 16 * i, c = bt & 7;
+                float4 hi, lo;
+                split4(w[i], hi, lo);
+                const uint32_t off = sw128_offset(n, c, kC);   // a single k-atom: katom index 0
+                *reinterpret_cast<float4*>(hi_base + off) = hi;
+                *reinterpret_cast<float4*>(lo_base + off) = lo;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[stage]);
+        }
+    } else if (warp == kMmaWarp) {
+        // ---------------- MMA ----------------
+        const uint32_t idesc = idesc_tf32(128, kC);
+        const uint32_t ring_lo = desc_lo(smem_u32(b_ring));
+        uint32_t fa = 0, fb = 0;
+        for (uint32_t gi = 0; gi < my_groups; ++gi) {
+            mbar_wait_relaxed(&acc_empty, (gi & 1) ^ 1);
+            fence_after_sync();
+            for (int j = 0; j < n_katoms; ++j, ++fb) {
+                const uint32_t stage = fb % kBStages;
+                mbar_wait_relaxed(&b_full[stage], (fb / kBStages) & 1);
+                const uint32_t bh = ring_lo + stage * (kBStageBytes >> 4), bl = bh + ((kC * 128) >> 4);
+                for (int tile = 0; tile < kTiles; ++tile, ++fa) {
+                    const uint32_t slot = fa & (kASlots - 1);
+                    mbar_wait_relaxed(&a_full[slot], (fa / kASlots) & 1);
+                    fence_after_sync();
+                    if (elect_one()) {
+                        const uint32_t d = acc_base + tile * kC;
+                        const uint32_t a_hi = a_base + slot * kSlotCols, a_lo = a_hi + 32;
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, idesc, (j == 0 && k == 0) ? 0u : 1u);
+                            rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, idesc, 1u);
+                            rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, idesc, 1u);
+                        }
+                        commit(&a_empty[slot]);
+                        if (tile == kTiles - 1) commit(&b_empty[stage]);
+                        if (tile == kTiles - 1 && j == n_katoms - 1) commit(&acc_full);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: thread = (row of the tile, 64-channel half) ----------------
+        const int ew = warp - kMmaWarp - 1;          // 0 .. 7
+        const int q = warp & 3, half = ew >> 2;      // tensor-memory lane quadrant = warp % 4
+        const int rt = q * 32 + lane;                // row within the tile
+        const patch::Patch pt(ep_patches + ew * patch::kPatchBytes, lane);
+        const int sub = lane >> 3, ch = lane & 7;
+        const float inv_c = 1.f / static_cast<float>(kC);
+        for (uint32_t gi = 0; gi < my_groups; ++gi) {
+            mbar_wait(&acc_full, gi & 1);
+            fence_after_sync();
+            const uint32_t g_row0 = (blockIdx.x + gi * gridDim.x) * rows_per_group;
+            for (int tile = 0; tile < kTiles; ++tile) {
+                const uint32_t taddr = acc_base + tile * kC + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
+                const uint32_t row0 = g_row0 + tile * 128 + q * 32;   // first row of this warp's 32
+                float mean = 0.f, rstd = 1.f;
+                if (p.gamma) {
+                    // pass 1: mean of bias + acc over the row's 128 channels
+                    float s = 0.f;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + c0, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) s += v[j] + __ldg(p.bias + half * 64 + c0 + j);
+                    }
+                    stat_s[0][half][rt] = s;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    mean = (stat_s[0][0][rt] + stat_s[0][1][rt]) * inv_c;
+                    // pass 2: variance around that mean
+                    float s2 = 0.f;
+#pragma unroll
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        float v[32];
+                        tmem_ld32(taddr + c0, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float d = v[j] + __ldg(p.bias + half * 64 + c0 + j) - mean;
+                            s2 = fmaf(d, d, s2);
+                        }
+                    }
+                    stat_s[1][half][rt] = s2;
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    rstd = 1.f / sqrtf((stat_s[1][0][rt] + stat_s[1][1][rt]) * inv_c + p.eps);
+                }
+                // pass 3: normalise, activation, residual, coalesced stores (4 rows x 128 B per instruction)
+                int32_t my_res = -1;
+                if (p.res && row0 + lane < p.M) my_res = __ldg(p.res_row + row0 + lane);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(taddr + c0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int col = half * 64 + c0 + j;
+                        float y = v[j] + __ldg(p.bias + col);
+                        if (p.gamma) y = fmaf((y - mean) * rstd, __ldg(p.gamma + col), __ldg(p.beta + col));
+                        v[j] = p.relu ? fmaxf(y, 0.f) : y;
+                    }
+                    float4 g[8];
+                    patch::transpose_out(pt, v, g);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const uint32_t r = row0 + 4 * k + sub;
+                        const int32_t rr = __shfl_sync(0xffffffffu, my_res, 4 * k + sub);
+                        if (r < p.M) {
+                            const int c4 = (half * 64 + c0) / 4 + ch;
+                            if (rr >= 0) {
+                                const float4 a = __ldg(p.res + static_cast<size_t>(rr) * (kC / 4) + c4);
+                                g[k].x += a.x; g[k].y += a.y; g[k].z += a.z; g[k].w += a.w;
+                            }
+                            p.Y[static_cast<size_t>(r) * (kC / 4) + c4] = g[k];
+                        }
+                    }
+                }
+                if (p.gamma) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // stat_s reusable for the next tile
+            }
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc
+}  // namespace
+
+extern "C" int ltgnn_tcn_conv(int device, int64_t M, int32_t C, int32_t taps, const float* X, const int32_t* src,
+                              const float* W, const float* bias, const float* gamma, const float* beta, float eps, int relu,
+                              const float* res, const int32_t* res_row, float* Y, void* stream_) {
+    LTGNN_REQUIRE(M >= 0 && M < (1ll << 31) - 512, LTGNN_E_ARG, "tcn_conv: M=%lld", static_cast<long long>(M));
+    LTGNN_REQUIRE(C == tc::kC, LTGNN_E_SHAPE, "tcn_conv: C=%d (the kernel is built for %d channels)", C, tc::kC);
+    LTGNN_REQUIRE(taps >= 1 && taps <= 8, LTGNN_E_SHAPE, "tcn_conv: taps=%d", taps);
+    LTGNN_REQUIRE((gamma == nullptr) == (beta == nullptr), LTGNN_E_ARG, "tcn_conv: gamma and beta come together");
+    LTGNN_REQUIRE((res == nullptr) == (res_row == nullptr), LTGNN_E_ARG, "tcn_conv: res and res_row come together");
+    if (M == 0) return LTGNN_OK;
+    LTGNN_REQUIRE(X && src && W && bias && Y, LTGNN_E_ARG, "tcn_conv: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(res), LTGNN_E_ALIGN, "tcn_conv: 16-byte alignment");
+    const DeviceInfo* di = device_info(device);
+    if (!di) return LTGNN_E_CUDA;
+    LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "tcn_conv: device is sm_%d%d, need sm_100", di->cc_major, di->cc_minor);
+    const size_t smem = 1024 + tc::kBStages * tc::kBStageBytes +
+                        static_cast<size_t>(tc::kALd * tc::kADepth + tc::kEp) * patch::kPatchBytes;
+    LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "tcn_conv: %zu B of shared memory", smem);
+    LTGNN_USE_DEVICE(device);
+    LTGNN_CUDA_TRY(cudaFuncSetAttribute(tc::tcn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    tc::Params p{reinterpret_cast<const float4*>(X), src, W, bias, gamma, beta, reinterpret_cast<const float4*>(res), res_row,
+                 reinterpret_cast<float4*>(Y), static_cast<uint32_t>(M), taps, relu, eps};
+    const int64_t groups = (M + tc::kTiles * 128 - 1) / (tc::kTiles * 128);
+    const int grid = static_cast<int>(groups < di->sm_count ? groups : di->sm_count);
+    tc::tcn_conv_kernel<<<grid, tc::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    return LTGNN_OK;
+}

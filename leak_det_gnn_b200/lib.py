@@ -57,6 +57,8 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
     "ltgnn_pipe_head_ws_floats": (c_int64, [c_int]),
+    "ltgnn_tcn_conv": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ltgnn_gru_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "ltgnn_gru_bwd_dg_hn": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

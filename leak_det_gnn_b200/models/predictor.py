@@ -66,6 +66,15 @@ class NormalPredictorTCN(nn.Module):
         h = self.input_proj(torch.cat([x, x_time], dim=-1).transpose(1, 2))
         return self.head(self.tcn(h)[:, :, -1])
 
+    # use the hand-written sm_100a kernels for ``forward_last`` on CUDA (csrc/tcn.cu + csrc/linear.cu) where the shapes
+    # allow; False = the same cone through torch ops (cuBLAS), kept as the cross-check
+    use_native = True
+
+    def _native_ok(self, x: torch.Tensor) -> bool:
+        blk = self.tcn[0]
+        return (self.use_native and x.is_cuda and x.dtype == torch.float32 and self.input_proj.out_channels == 128
+                and blk.conv1.conv.kernel_size[0] <= 8 and self.num_sensors + self.time_dim <= 64 and self.num_sensors <= 32)
+
     @torch.no_grad()
     def forward_last(self, x: torch.Tensor, x_time: torch.Tensor) -> torch.Tensor:
         """Same result as ``forward`` in eval mode, computing only what the last time step depends on.
@@ -73,6 +82,8 @@ class NormalPredictorTCN(nn.Module):
         zero rows where a tap reaches before the window start (the left padding of CausalConv1d)."""
         if self.training:
             raise RuntimeError("forward_last is the inference path of the frozen predictor (call .eval() first)")
+        if self._native_ok(x):
+            return self._forward_last_native(x, x_time)
         b, length, _ = x.shape
         gather = self._cone_plan(length, x.device)
         h = F.linear(torch.cat([x, x_time], dim=-1), self.input_proj.weight[:, :, 0], self.input_proj.bias)  # (B, L, C)
@@ -86,6 +97,75 @@ class NormalPredictorTCN(nn.Module):
                 y = F.relu(norm(F.linear(rows, w, conv.conv.bias)))
             h = h.index_select(1, keep) + y
         return self.head(h[:, 0, :])
+
+    def _forward_last_native(self, x: torch.Tensor, x_time: torch.Tensor) -> torch.Tensor:
+        """The cone on the tensor cores: input projection and output head through ``ops.linear_tc`` (zero-padded to the
+        kernel's K / N granularity), every convolution + LayerNorm + ReLU (+ residual) through ``ops.tcn_conv``."""
+        from .. import ops
+
+        b, length, _ = x.shape
+        dev = x.device
+        prep = self._native_weights(dev)
+        rows = self._native_rows(length, b, dev)
+        c_in = self.num_sensors + self.time_dim
+        inp = torch.zeros(b, length, 64, device=dev, dtype=torch.float32)
+        inp[:, :, :self.num_sensors] = x
+        inp[:, :, self.num_sensors:c_in] = x_time
+        h = ops.linear_tc(inp.view(b * length, 64), prep["w_in"], prep["b_in"])                 # (B * L, 128)
+        for blk, (w1, w2), (src1, src2, keep_rows) in zip(self.tcn, prep["convs"], rows):
+            y = ops.tcn_conv(h, src1, w1, blk.conv1.conv.bias, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, True)
+            h = ops.tcn_conv(y, src2, w2, blk.conv2.conv.bias, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, True,
+                             res=h, res_row=keep_rows)
+        return ops.linear_tc(h, prep["w_out"], prep["b_out"])[:, :self.num_sensors]
+
+    def _native_weights(self, device):
+        """Weights in the kernels' layouts, rebuilt when a parameter changes (the predictor is frozen in practice)."""
+        cache = self.__dict__.setdefault("_native_w", {})
+        ver = tuple(p._version for p in self.parameters()) + (str(device),)
+        if cache.get("ver") == ver:
+            return cache["prep"]
+        c_in = self.num_sensors + self.time_dim
+        w_in = torch.zeros(128, 64, device=device)
+        w_in[:, :c_in] = self.input_proj.weight[:, :, 0]
+        w_out = torch.zeros(32, 128, device=device)
+        w_out[: self.num_sensors] = self.head.weight
+        b_out = torch.zeros(32, device=device)
+        b_out[: self.num_sensors] = self.head.bias
+        convs = [(blk.conv1.conv.weight.permute(2, 0, 1).contiguous(), blk.conv2.conv.weight.permute(2, 0, 1).contiguous())
+                 for blk in self.tcn]                       # (taps, C_out, C_in): tap 0 = the oldest input
+        prep = {"w_in": w_in, "b_in": self.input_proj.bias.detach().contiguous(), "w_out": w_out, "b_out": b_out,
+                "convs": convs}
+        cache.update(ver=ver, prep=prep)
+        return prep
+
+    def _native_rows(self, length: int, batch: int, device):
+        """Global row indices of the gathered convolutions for ``batch`` windows: per block (src1, src2, keep_rows) with
+        src int32 (taps, batch * n_out), -1 = zero padding; activations are laid out (window, position, channel)."""
+        cache = self.__dict__.setdefault("_native_r", {})
+        key = (length, batch, str(device))
+        if key in cache:
+            return cache[key]
+        ks = self.tcn[0].conv1.conv.kernel_size[0]
+        win = torch.arange(batch, device=device, dtype=torch.int64).unsqueeze(1)
+        out = []
+        n_in = length
+        for taps1, taps2, keep in self._cone_plan(length, device):
+            rows = []
+            n_src = n_in
+            for taps in (taps1, taps2):
+                rel = taps.view(-1, ks).t()                                   # (ks, n_out), value n_src = the zero row
+                n_out = rel.shape[1]
+                glob = torch.where(rel.unsqueeze(1) == n_src, torch.full((), -1, device=device, dtype=torch.int64),
+                                   win.unsqueeze(0) * n_src + rel.unsqueeze(1))   # (ks, batch, n_out)
+                rows.append(glob.reshape(ks, batch * n_out).to(torch.int32).contiguous())
+                n_src = n_out
+            keep_rows = (win * n_in + keep.unsqueeze(0)).reshape(-1).to(torch.int32).contiguous()
+            out.append((rows[0], rows[1], keep_rows))
+            n_in = keep.numel()
+        if len(cache) > 8:
+            cache.clear()
+        cache[key] = out
+        return out
 
     def _cone_plan(self, length: int, device):
         """Per block: flat tap indices of conv1 / conv2 (oldest tap first, `n_in` = the zero row) and the positions of

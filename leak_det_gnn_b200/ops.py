@@ -757,6 +757,33 @@ def gru_encode(r: torch.Tensor, tf: Optional[torch.Tensor], w_ih, w_hh, b_ih, b_
     return _GruEncoder.apply(r, tf, w_ih, w_hh, b_ih, b_hh)
 
 
+def tcn_conv(x: torch.Tensor, src: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+             gamma: Optional[torch.Tensor] = None, beta: Optional[torch.Tensor] = None, eps: float = 1e-5, relu: bool = True,
+             res: Optional[torch.Tensor] = None, res_row: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw gathered-row convolution of the frozen TCN predictor (see ltgnn_tcn_conv):
+    ``y[m] = [res[res_row[m]] +] relu(LayerNorm(bias + sum_tap x[src[tap, m]] @ weight[tap].T))``.
+    x (rows, 128) fp32 CUDA, src int32 (taps, M) with -1 for the zero padding, weight (taps, 128, 128)."""
+    _check_act(x, "x")
+    _check_act(weight, "weight")
+    taps, m = src.shape
+    c = x.shape[-1]
+    if src.dtype != torch.int32 or not src.is_cuda or not src.is_contiguous():
+        raise ValueError("src must be a contiguous int32 CUDA tensor (taps, M)")
+    if tuple(weight.shape) != (taps, c, c):
+        raise ValueError(f"weight must be {(taps, c, c)}, got {tuple(weight.shape)}")
+    if (res is None) != (res_row is None):
+        raise ValueError("res and res_row come together")
+    y = torch.empty(m, c, device=x.device, dtype=torch.float32)
+    L = _lib.load()
+    tok = _inst.begin("tcn_conv")
+    _lib.check(L.ltgnn_tcn_conv(_dev_index(x), m, c, taps, x.data_ptr(), src.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                None if gamma is None else gamma.data_ptr(), None if beta is None else beta.data_ptr(),
+                                float(eps), int(relu), None if res is None else res.data_ptr(),
+                                None if res_row is None else res_row.data_ptr(), y.data_ptr(), _stream(x)))
+    _inst.end(tok)
+    return y
+
+
 def unblock32(t: torch.Tensor, l: int, q: int) -> torch.Tensor:
     """Blocked-32 saved tensor [L*Qp/32, W/4, 32, 4] -> logical (L, Q, W) (tests / debugging)."""
     w = t.shape[1] * 4
