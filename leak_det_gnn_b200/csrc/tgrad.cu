@@ -23,70 +23,167 @@ namespace {
 // 6 loads per thread the kernel is latency bound unless the next chunk's loads are in flight while this one is stored
 // (a first version that computed inside the fetch ran at 5.4 ms).
 constexpr int kHeadSlices = 3;
-struct HeadLive {
-    static constexpr bool kRowFast = true;  // a warp = 32 rows x one chunk pair
-    static constexpr bool kExact = true;
-    using Raw = uint32_t;   // the 32-unit gate word that holds this chunk's 4 hidden units
-    using Side = float4;    // this thread's share of a[4 c .. 4 c + 3] (slice-0 CTAs only)
-    const uint32_t* hmask;  // [Mp, 4]: hidden unit j of a row <-> bit 31 - j % 32 of word j / 32 (heads.cu)
-    const float* dlogit;    // [M]
-    float scale;
-    float* side_part;       // [2 * gridDim.x][128]: one partial of a[] per (CTA, loader group)
-    __device__ __forceinline__ Raw raw(uint32_t row, int c) const { return __ldg(hmask + static_cast<size_t>(row) * 4 + (c >> 3)); }
-    __device__ __forceinline__ float aux(uint32_t row) const { return __ldg(dlogit + row); }
-    __device__ __forceinline__ float4 convert(const Raw& w, float d, int c, Side& side) const {
-        const uint32_t sh = 28 - 4 * (c & 7);  // units 4 (c % 8) .. + 3 sit at bits 31 - 4 (c % 8) .. 28 - 4 (c % 8)
-        const float4 live = make_float4((w >> (sh + 3)) & 1u ? 1.f : 0.f, (w >> (sh + 2)) & 1u ? 1.f : 0.f,
-                                        (w >> (sh + 1)) & 1u ? 1.f : 0.f, (w >> sh) & 1u ? 1.f : 0.f);
-        if (blockIdx.x % kHeadSlices == 0) {
-            const float g = d * scale;
-            side.x = fmaf(g, live.x, side.x); side.y = fmaf(g, live.y, side.y);
-            side.z = fmaf(g, live.z, side.z); side.w = fmaf(g, live.w, side.w);
-        }
-        return live;
-    }
-    // the 32 lanes of a loader warp hold 32 different rows of the same columns: butterfly sum, lane 0 writes
-    __device__ __forceinline__ void finish(Side* side, const int* cols, int n, uint32_t cta, int group, int lane) const {
-        for (int j = 0; j < n; ++j) {
-            float4 t = side[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
-                t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
-            }
-            if (lane == 0) reinterpret_cast<float4*>(side_part + (static_cast<size_t>(cta) * 2 + group) * 128)[cols[j]] = t;
-        }
-    }
-};
-struct FeatRaw {
-    float4 a, b;
-};
+constexpr int kSideParts = tgrad::kGroups * tgrad::kLoaderWarps / tgrad::kGroups;  // partials of a[] per CTA: one per loader warp
 struct HeadFeatSlice {
-    static constexpr bool kRowFast = false;
     static constexpr int kSlices = kHeadSlices;
-    using Raw = FeatRaw;
     const float4* x;   // node states [B*N, 16]
     const int2* ends;
-    const float* dlogit;
-    float scale;
     uint32_t P, N;
-    uint64_t magic;
-    __device__ __forceinline__ Raw raw(uint32_t row, int c) const {  // c < 16: chunk of this CTA's 64-column slice
-        const uint32_t b = magic ? ptx::fastdiv(row, magic) : row;
-        const int2 e = __ldg(ends + (row - b * P));
-        const float4* xb = x + static_cast<int64_t>(b) * N * 16 + c;
-        const int slice = blockIdx.x % kHeadSlices;
-        Raw r;
-        r.a = __ldg(xb + (slice == 1 ? e.y : e.x) * 16);
-        r.b = slice == 2 ? __ldg(xb + e.y * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
-        return r;
+    uint64_t magic;    // fastdiv by P (0: P = 1)
+};
+struct HeadFill;
+struct HeadLive {
+    static constexpr bool kExact = true;
+    using Fill = HeadFill;   // both operands are produced by the hand-written loop below
+    const uint4* hmask;     // [Mp]: hidden unit j of a row <-> bit 31 - j % 32 of word j / 32 (heads.cu)
+    const float* dlogit;    // [M]
+    float scale;
+    float* side_part;       // [kSideParts * gridDim.x][128]: one partial of a[] per (CTA, loader warp)
+};
+
+// The loader loop of the pipe-head weight gradient (tgrad.cuh, `Fill`).  A group = 256 threads = 32 rows x 8 threads;
+// thread (r, q) owns, in row r, the 16-byte chunks q, q + 8, q + 16, q + 24 of G (hidden units 4 q + 32 blk ..+ 3: one
+// nibble of gate word blk) and the chunks q, q + 8 of this CTA's 64-column feature slice -- the same swizzled offset
+// inside every 32-column block, computed once.  Three-deep software pipeline: the pipe ends of chunk n + 2, the node
+// rows / gate words / dlogit of chunk n + 1 and the stores of chunk n are in flight together; (window, pipe) advance
+// incrementally (no division per chunk).  kSlice is a template parameter: slice 0 (h_u) also sums a[], slice 2
+// (|h_u - h_v|) loads two node rows -- no CTA pays registers for both.
+struct HeadFill {
+    struct Rows {           // what one thread loads for one chunk
+        uint4 w;
+        float d;
+        float4 a[2], b[2];
+    };
+    template <int kSlice>
+    static __device__ __forceinline__ void loop(const HeadLive& g, const HeadFeatSlice& x, uint8_t* g_hi, uint8_t* x_hi,
+                                                uint8_t* x_lo, int gtid, int grp, uint32_t c_begin, uint32_t c_end, uint32_t M,
+                                                uint64_t* full, uint64_t* empty) {
+        using namespace ltgnn::ptx;
+        using namespace ltgnn::umma;
+        constexpr uint32_t kStep = tgrad::kGroups * tgrad::kChunk;   // rows between two chunks of this group
+        const int r = gtid >> 3, q = gtid & 7, lane = gtid & 31;
+        const uint32_t off = static_cast<uint32_t>(r * 128 + ((((q >> 1) ^ (r & 3)) << 5) | ((q & 1) << 4)));
+        const uint32_t sh = 28 - 4 * q;
+        float4 side[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) side[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t last_b = x.magic ? fastdiv(M - 1, x.magic) : M - 1, last_p = M - 1 - last_b * x.P;
+
+        // (b, p) of this thread's row in the chunk being fetched; rows past M read row M - 1 and are zeroed at store time
+        uint32_t row = (c_begin + grp) * tgrad::kChunk + r;
+        uint32_t b = x.magic ? fastdiv(row < M ? row : M - 1, x.magic) : (row < M ? row : M - 1);
+        uint32_t p = (row < M ? row : M - 1) - b * x.P;
+        auto advance = [&]() {          // to the same row of the group's next chunk
+            row += kStep;
+            p += kStep;
+            while (p >= x.P) {
+                p -= x.P;
+                ++b;
+            }
+            if (row >= M) {
+                b = last_b;
+                p = last_p;
+            }
+        };
+        auto load_ends = [&]() { return __ldg(x.ends + p); };
+        auto load_rows = [&](Rows& t, const int2 e, uint32_t rw, uint32_t bb) {
+            const uint32_t rc = rw < M ? rw : M - 1;
+            t.w = __ldg(g.hmask + rc);
+            t.d = __ldg(g.dlogit + rc);
+            const float4* xb = x.x + static_cast<int64_t>(bb) * x.N * 16 + q;
+            const float4* pa = xb + (kSlice == 1 ? e.y : e.x) * 16;
+            t.a[0] = __ldg(pa);
+            t.a[1] = __ldg(pa + 8);
+            if (kSlice == 2) {
+                const float4* pb = xb + e.y * 16;
+                t.b[0] = __ldg(pb);
+                t.b[1] = __ldg(pb + 8);
+            }
+        };
+
+        const uint32_t first = c_begin + grp;
+        if (first >= c_end) {
+            finish<kSlice>(g, side, grp, gtid, q, lane);
+            return;
+        }
+        Rows nxt;
+        uint32_t row_n = row, b_n = b;      // row / window of the chunk held in `nxt`
+        load_rows(nxt, load_ends(), row, b);
+        advance();
+        int2 e_n = load_ends();             // pipe ends of the chunk after `nxt` (garbage-free: p is always valid)
+        uint32_t use = 0;
+        for (uint32_t ch = first; ch < c_end; ch += tgrad::kGroups, ++use) {
+            const Rows cur = nxt;
+            const bool ok = row_n < M;
+            if (ch + tgrad::kGroups < c_end) {
+                row_n = row;
+                b_n = b;
+                load_rows(nxt, e_n, row, b);
+                advance();
+                e_n = load_ends();
+            }
+            const float gs = ok ? cur.d * g.scale : 0.f;
+            // G: four nibbles -> 0 / 1 floats (a row past M stores zeros: its gate word belongs to row M - 1)
+            float4 live[4];
+            const uint32_t wd[4] = {cur.w.x, cur.w.y, cur.w.z, cur.w.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t nib = ok ? wd[k] >> sh : 0u;
+                live[k] = make_float4(nib & 8u ? 1.f : 0.f, nib & 4u ? 1.f : 0.f, nib & 2u ? 1.f : 0.f, nib & 1u ? 1.f : 0.f);
+                if (kSlice == 0) {
+                    side[k].x += nib & 8u ? gs : 0.f;
+                    side[k].y += nib & 4u ? gs : 0.f;
+                    side[k].z += nib & 2u ? gs : 0.f;
+                    side[k].w += nib & 1u ? gs : 0.f;
+                }
+            }
+            // X: g * feature chunk, split into TF32 hi / lo
+            float4 hi[2], lo[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float4 v = cur.a[j];
+                if (kSlice == 2) v = make_float4(fabsf(v.x - cur.b[j].x), fabsf(v.y - cur.b[j].y), fabsf(v.z - cur.b[j].z), fabsf(v.w - cur.b[j].w));
+                split4(make_float4(gs * v.x, gs * v.y, gs * v.z, gs * v.w), hi[j], lo[j]);
+            }
+            mbar_wait(empty, (use & 1) ^ 1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(g_hi + off + k * tgrad::kBlockBytes) = live[k];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                *reinterpret_cast<float4*>(x_hi + off + j * tgrad::kBlockBytes) = hi[j];
+                *reinterpret_cast<float4*>(x_lo + off + j * tgrad::kBlockBytes) = lo[j];
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full);
+        }
+        finish<kSlice>(g, side, grp, gtid, q, lane);
     }
-    __device__ __forceinline__ float aux(uint32_t row) const { return __ldg(dlogit + row); }
-    __device__ __forceinline__ float4 convert(const Raw& r, float d, int) const {
-        const float g = d * scale;
-        if (blockIdx.x % kHeadSlices == 2)
-            return make_float4(g * fabsf(r.a.x - r.b.x), g * fabsf(r.a.y - r.b.y), g * fabsf(r.a.z - r.b.z), g * fabsf(r.a.w - r.b.w));
-        return make_float4(g * r.a.x, g * r.a.y, g * r.a.z, g * r.a.w);
+    // a[]: the four lanes of a warp with the same q hold four rows' shares of the same 16 hidden units
+    template <int kSlice>
+    static __device__ __forceinline__ void finish(const HeadLive& g, float4 (&side)[4], int grp, int gtid, int q, int lane) {
+        float4* out = reinterpret_cast<float4*>(g.side_part + (static_cast<size_t>(blockIdx.x) * kSideParts +
+                                                               grp * (tgrad::kLoaderWarps / tgrad::kGroups) + (gtid >> 5)) * 128);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 t = side[k];
+            if (kSlice == 0) {
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                    t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+                    t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+                }
+            }
+            if (lane < 8) out[8 * k + q] = t;      // hidden units 32 k + 4 q .. + 3 (zeros from the other slices' CTAs)
+        }
+    }
+    static __device__ __forceinline__ void run(const HeadLive& g, const HeadFeatSlice& x, uint8_t* g_hi, uint8_t* x_hi,
+                                               uint8_t* x_lo, int gtid, int grp, uint32_t c_begin, uint32_t c_end, uint32_t M,
+                                               uint64_t* full, uint64_t* empty) {
+        const int slice = blockIdx.x % kHeadSlices;
+        if (slice == 0) loop<0>(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin, c_end, M, full, empty);
+        else if (slice == 1) loop<1>(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin, c_end, M, full, empty);
+        else loop<2>(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin, c_end, M, full, empty);
     }
 };
 
@@ -116,8 +213,8 @@ head_param_epilogue_kernel(const float* __restrict__ A, const float* __restrict_
 }  // namespace
 
 extern "C" int64_t ltgnn_pipe_head_ws_floats(int device) {
-    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][64] + partials of a[] [2 sm][128] + A [128][192] + a [128]
-    return di ? static_cast<int64_t>(di->sm_count) * (tgrad::kMo * 64 + 2 * 128) + 128 * 192 + 128 : -1;
+    const DeviceInfo* di = device_info(device);  // tgrad partials [sm][128][64] + partials of a[] [16 sm][128] + A [128][192] + a [128]
+    return di ? static_cast<int64_t>(di->sm_count) * (tgrad::kMo * 64 + kSideParts * 128) + 128 * 192 + 128 : -1;
 }
 
 extern "C" int64_t ltgnn_tgrad_ws_floats(int device, int32_t No) {
@@ -172,20 +269,20 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
     const DeviceInfo* di = device_info(device);
     LTGNN_REQUIRE(di, LTGNN_E_CUDA, "pipe_head_bwd_w: device %d", device);
     const int No = D;  // one 64-column slice of the 192 feature columns per CTA
-    float* part = ws + static_cast<size_t>(di->sm_count) * tgrad::kMo * No;  // [2 sm][128] partials of a[]
-    float* A = part + static_cast<size_t>(di->sm_count) * 2 * 128;           // [128][192]
+    float* part = ws + static_cast<size_t>(di->sm_count) * tgrad::kMo * No;  // [16 sm][128] partials of a[]
+    float* A = part + static_cast<size_t>(di->sm_count) * kSideParts * 128;  // [128][192]
     float* a = A + 128 * 192;                                                // [128]
-    HeadLive g{hmask, dlogit, gate_scale, part};
-    HeadFeatSlice x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), dlogit, gate_scale,
-                    static_cast<uint32_t>(P), static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
+    HeadLive g{reinterpret_cast<const uint4*>(hmask), dlogit, gate_scale, part};
+    HeadFeatSlice x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
+                    static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
     int grid = 0;
-    int rc = tgrad::launch<1, 4, 2, -1>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
+    int rc = tgrad::launch<1, 4, 2, -2>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
     if (rc) return rc;
     for (int sl = 0; sl < kHeadSlices; ++sl) {  // A[:, 64 sl : 64 sl + 64] = sum over the row ranges of slice sl
         rc = tgrad::gather(ws, grid, No, 0, H, 0, No, A + sl * No, 3 * D, 0, stream, tgrad::kMo, sl, kHeadSlices);
         if (rc) return rc;
     }
-    rc = reduce_parts(part, 128, a, 2 * grid, H, 0, stream);
+    rc = reduce_parts(part, 128, a, kSideParts * grid, H, 0, stream);
     if (rc) return rc;
     head_param_epilogue_kernel<<<(H + 3) / 4, 128, 0, stream>>>(A, a, W1, b1, w2, dW1, db1, dw2, H, 3 * D);
     LTGNN_CUDA_TRY(cudaGetLastError());

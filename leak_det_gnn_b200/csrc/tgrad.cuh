@@ -109,6 +109,20 @@ struct exact_of { static constexpr bool value = false; };
 template <class T>
 struct exact_of<T, std::void_t<decltype(T::kExact)>> { static constexpr bool value = T::kExact; };
 
+// GLoader::Fill: a hand-written loader loop for one (G, X) pair.  `Fill::run(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin,
+// c_end, M, full, empty)` is called by every thread of loader group `grp` (gtid = thread index inside the group) and owns
+// the whole protocol for the group's chunks c_begin + grp, c_begin + grp + kGroups, ...: wait for `empty` (parity
+// (use & 1) ^ 1), write the stage in the mn_offset layout, fence_proxy_async_smem, one arrive per warp on `full`.  The
+// generic loop below costs ~430 instructions per thread and chunk for the pipe head (spills under the 72-register cap,
+// per-chunk index arithmetic) and its issue slots paced that kernel; a bespoke loop needs a third of that.
+template <class T, class = void>
+struct fill_of { using type = void; };
+template <class T>
+struct fill_of<T, std::void_t<typename T::Fill>> { using type = typename T::Fill; };
+
+// chunks per flush of `main` in the register-total form (kSeg = -1, -2)
+__host__ __device__ constexpr uint32_t flush_chunks(int seg) { return seg < 0 ? static_cast<uint32_t>(-(seg + 1)) + 1u : 1u; }
+
 // float4 index of (row, columns 4 c4 .. 4 c4 + 3) inside one [128 x No] partial of the workspace: row-fast, so that a
 // read-out warp (lane = row) touches 512 contiguous bytes per instruction
 __host__ __device__ inline size_t ws_f4(int row, int c4) { return static_cast<size_t>(c4) * kMo + row; }
@@ -129,6 +143,8 @@ __host__ inline size_t smem_bytes(int No, int mt) { return 1024 + kGroups * stag
 // kSeg = -1: the accurate form for narrow results (No <= 64, kMT = 1; the GCN layers): the totals stay in REGISTERS
 // of eight read-out warps (32 columns each), so a flush is one tensor-memory read of `main` -- tensor memory moves
 // 64 B / clock / SM, and the load / add / store of a total that lives there costs three times that.
+// kSeg = -2: the same with `main` flushed every SECOND chunk (64 rows = 8 truncating accumulations instead of 4: the
+// bias doubles to ~4e-7 of the sum, still 25 x inside the 1e-5 bar) -- for kernels whose pace is the tensor-memory read.
 template <class GLoader, class XLoader, int kMT, int kGJ = 4 * kMT, int kXJ = 8, int kSeg = 0>
 __global__ void __launch_bounds__(kSeg < 0 ? kThreadsReg : kThreads, 1)
 tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols,
@@ -183,139 +199,147 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     const uint32_t c_begin = (blockIdx.x / kSl) * per;
     const uint32_t c_end = c_begin + per < n_chunks ? c_begin + per : n_chunks;
 
+    using Fill = typename fill_of<GLoader>::type;
     if (warp < kLoaderWarps) {
         const int grp = warp / (kLoaderWarps / kGroups);
-        const int gtid = tid - grp * kGroupThreads;
-        uint8_t* g_hi = smem + grp * stage;
-        uint8_t* g_lo = g_hi + g_half;
-        uint8_t* x_hi = g_lo + g_half;
-        uint8_t* x_lo = x_hi + x_half;
-        // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of an operand, so the
-        // row-dependent part of a gather (division, end-node lookup) is done once and all loads go out together
-        // kRowFast sources (blocked-32 tensors: 32 consecutive rows of one chunk are contiguous) flip the mapping:
-        // a warp = 32 rows x one chunk (512 contiguous bytes) at the price of 2-way conflicts on the STS.  The two
-        // operands choose independently.
-        const int rg = GLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qg = GLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
-        const int rx = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qx = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
-        const int x4 = No / 4;
-        constexpr bool kPipe = (kGJ + kXJ) <= 6;
-        // chunk j of a thread: q, q + 8, ... for the 8-threads-per-row mapping; for kRowFast sources the warp owns
-        // PAIRS of neighbouring chunks (2 q, 2 q + 1, 2 q + 16, ...) so that the store below can be conflict-free
-        static_assert(!GLoader::kRowFast || kGJ % 2 == 0, "kRowFast operands need an even chunk count");
-        static_assert(!XLoader::kRowFast || kXJ % 2 == 0, "kRowFast operands need an even chunk count");
-        auto cg = [&](int j) { return GLoader::kRowFast ? 2 * qg + (j & 1) + 16 * (j >> 1) : qg + 8 * j; };
-        auto cx = [&](int j) { return XLoader::kRowFast ? 2 * qx + (j & 1) + 16 * (j >> 1) : qx + 8 * j; };
-        using GRaw = typename raw_of<GLoader>::type;
-        using XRaw = typename raw_of<XLoader>::type;
-        static_assert(!has_side<GLoader>::value || has_raw<GLoader>::value, "side accumulation needs a raw-style loader");
-        GRaw gv[kGJ];
-        XRaw xv[kXJ];
-        float gaux_v = 0.f, xaux_v = 0.f;
-        typename side_of<GLoader>::type side[kGJ] = {};
-        // raw-style loaders: rows past M are fetched from row M - 1 and zeroed at convert time -- a select on the loaded
-        // value would be a use of it, and the thread would wait for memory inside the fetch
-        auto fetch = [&](uint32_t ch, GRaw (&gd)[kGJ], XRaw (&xd)[kXJ], float& gaux, float& xaux) {
-            const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
-            const uint32_t row_gc = row_g < M ? row_g : M - 1, row_xc = row_x < M ? row_x : M - 1;
-#pragma unroll
-            for (int j = 0; j < kGJ; ++j) {
-                if constexpr (has_raw<GLoader>::value) gd[j] = gload.raw(row_gc, cg(j));
-                else gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if constexpr (has_raw<GLoader>::value) gaux = gload.aux(row_gc);
-#pragma unroll
-            for (int j = 0; j < kXJ; ++j) {
-                if constexpr (has_raw<XLoader>::value) xd[j] = xload.raw(row_xc, cx(j) < x4 ? cx(j) : 0);
-                else xd[j] = (row_x < M && cx(j) < x4) ? xload(row_x, cx(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if constexpr (has_raw<XLoader>::value) xaux = xload.aux(row_xc);
-        };
-        // store one operand's chunks (hi and lo).  kRowFast: the 32 lanes of a warp hold 32 rows of the SAME chunk,
-        // whose swizzled offsets share only 4 bank groups (2-way conflicts on every quarter-warp).  Lanes whose row
-        // has bit 2 set therefore store the two chunks of a pair in the opposite order: a quarter-warp then covers
-        // both parities x 4 swizzle phases = all 8 bank groups.
-        auto store = [&](auto fast, auto with_lo, const auto& v, int nj, int r, auto cj, int climit, uint8_t* hi_base,
-                         uint8_t* lo_base) {
-            if constexpr (decltype(fast)::value) {
-                const bool swap = (r >> 2) & 1;
-#pragma unroll
-                for (int j = 0; j < nj; j += 2) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const bool second = swap != (h == 1);
-                        const float4 val = second ? v[j + 1] : v[j];
-                        const int c = cj(j) + (second ? 1 : 0);
-                        if (c < climit) {
+        if constexpr (!std::is_void<Fill>::value) {
+            uint8_t* g_hi = smem + grp * stage;
+            Fill::run(gload, xload, g_hi, g_hi + 2 * g_half, g_hi + 2 * g_half + x_half, tid - grp * kGroupThreads, grp, c_begin,
+                      c_end, M, &bar_full[grp], &bar_empty[grp]);
+        } else {
+            const int gtid = tid - grp * kGroupThreads;
+            uint8_t* g_hi = smem + grp * stage;
+            uint8_t* g_lo = g_hi + g_half;
+            uint8_t* x_hi = g_lo + g_half;
+            uint8_t* x_lo = x_hi + x_half;
+            // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of an operand, so the
+            // row-dependent part of a gather (division, end-node lookup) is done once and all loads go out together
+            // kRowFast sources (blocked-32 tensors: 32 consecutive rows of one chunk are contiguous) flip the mapping:
+            // a warp = 32 rows x one chunk (512 contiguous bytes) at the price of 2-way conflicts on the STS.  The two
+            // operands choose independently.
+            const int rg = GLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qg = GLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
+            const int rx = XLoader::kRowFast ? (gtid & 31) : (gtid >> 3), qx = XLoader::kRowFast ? (gtid >> 5) : (gtid & 7);
+            const int x4 = No / 4;
+            constexpr bool kPipe = (kGJ + kXJ) <= 6;
+            // chunk j of a thread: q, q + 8, ... for the 8-threads-per-row mapping; for kRowFast sources the warp owns
+            // PAIRS of neighbouring chunks (2 q, 2 q + 1, 2 q + 16, ...) so that the store below can be conflict-free
+            static_assert(!GLoader::kRowFast || kGJ % 2 == 0, "kRowFast operands need an even chunk count");
+            static_assert(!XLoader::kRowFast || kXJ % 2 == 0, "kRowFast operands need an even chunk count");
+            auto cg = [&](int j) { return GLoader::kRowFast ? 2 * qg + (j & 1) + 16 * (j >> 1) : qg + 8 * j; };
+            auto cx = [&](int j) { return XLoader::kRowFast ? 2 * qx + (j & 1) + 16 * (j >> 1) : qx + 8 * j; };
+            using GRaw = typename raw_of<GLoader>::type;
+            using XRaw = typename raw_of<XLoader>::type;
+            static_assert(!has_side<GLoader>::value || has_raw<GLoader>::value, "side accumulation needs a raw-style loader");
+            GRaw gv[kGJ];
+            XRaw xv[kXJ];
+            float gaux_v = 0.f, xaux_v = 0.f;
+            typename side_of<GLoader>::type side[kGJ] = {};
+            // raw-style loaders: rows past M are fetched from row M - 1 and zeroed at convert time -- a select on the loaded
+            // value would be a use of it, and the thread would wait for memory inside the fetch
+            auto fetch = [&](uint32_t ch, GRaw (&gd)[kGJ], XRaw (&xd)[kXJ], float& gaux, float& xaux) {
+                const uint32_t row_g = ch * kChunk + rg, row_x = ch * kChunk + rx;
+                const uint32_t row_gc = row_g < M ? row_g : M - 1, row_xc = row_x < M ? row_x : M - 1;
+    #pragma unroll
+                for (int j = 0; j < kGJ; ++j) {
+                    if constexpr (has_raw<GLoader>::value) gd[j] = gload.raw(row_gc, cg(j));
+                    else gd[j] = row_g < M ? gload(row_g, cg(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if constexpr (has_raw<GLoader>::value) gaux = gload.aux(row_gc);
+    #pragma unroll
+                for (int j = 0; j < kXJ; ++j) {
+                    if constexpr (has_raw<XLoader>::value) xd[j] = xload.raw(row_xc, cx(j) < x4 ? cx(j) : 0);
+                    else xd[j] = (row_x < M && cx(j) < x4) ? xload(row_x, cx(j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if constexpr (has_raw<XLoader>::value) xaux = xload.aux(row_xc);
+            };
+            // store one operand's chunks (hi and lo).  kRowFast: the 32 lanes of a warp hold 32 rows of the SAME chunk,
+            // whose swizzled offsets share only 4 bank groups (2-way conflicts on every quarter-warp).  Lanes whose row
+            // has bit 2 set therefore store the two chunks of a pair in the opposite order: a quarter-warp then covers
+            // both parities x 4 swizzle phases = all 8 bank groups.
+            auto store = [&](auto fast, auto with_lo, const auto& v, int nj, int r, auto cj, int climit, uint8_t* hi_base,
+                             uint8_t* lo_base) {
+                if constexpr (decltype(fast)::value) {
+                    const bool swap = (r >> 2) & 1;
+    #pragma unroll
+                    for (int j = 0; j < nj; j += 2) {
+    #pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const bool second = swap != (h == 1);
+                            const float4 val = second ? v[j + 1] : v[j];
+                            const int c = cj(j) + (second ? 1 : 0);
+                            if (c < climit) {
+                                float4 hi, lo;
+                                split4(val, hi, lo);
+                                const uint32_t off = mn_offset(r, c, kChunk);
+                                *reinterpret_cast<float4*>(hi_base + off) = hi;
+                                if constexpr (decltype(with_lo)::value) *reinterpret_cast<float4*>(lo_base + off) = lo;
+                            }
+                        }
+                    }
+                } else {
+    #pragma unroll
+                    for (int j = 0; j < nj; ++j) {
+                        if (cj(j) < climit) {
                             float4 hi, lo;
-                            split4(val, hi, lo);
-                            const uint32_t off = mn_offset(r, c, kChunk);
+                            split4(v[j], hi, lo);
+                            const uint32_t off = mn_offset(r, cj(j), kChunk);
                             *reinterpret_cast<float4*>(hi_base + off) = hi;
                             if constexpr (decltype(with_lo)::value) *reinterpret_cast<float4*>(lo_base + off) = lo;
                         }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < nj; ++j) {
-                    if (cj(j) < climit) {
-                        float4 hi, lo;
-                        split4(v[j], hi, lo);
-                        const uint32_t off = mn_offset(r, cj(j), kChunk);
-                        *reinterpret_cast<float4*>(hi_base + off) = hi;
-                        if constexpr (decltype(with_lo)::value) *reinterpret_cast<float4*>(lo_base + off) = lo;
-                    }
+            };
+            uint32_t use = 0;
+            if (kPipe && c_begin + grp < c_end) fetch(c_begin + grp, gv, xv, gaux_v, xaux_v);
+            for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
+                GRaw gc[kGJ];
+                XRaw xc[kXJ];
+                float gaux = 0.f, xaux = 0.f;
+                if (kPipe) {
+    #pragma unroll
+                    for (int j = 0; j < kGJ; ++j) gc[j] = gv[j];
+    #pragma unroll
+                    for (int j = 0; j < kXJ; ++j) xc[j] = xv[j];
+                    gaux = gaux_v;
+                    xaux = xaux_v;
+                    if (ch + kGroups < c_end) fetch(ch + kGroups, gv, xv, gaux_v, xaux_v);  // in flight while this chunk is stored
+                } else {
+                    fetch(ch, gc, xc, gaux, xaux);
                 }
+                float4 gval[kGJ], xval[kXJ];
+                const bool g_ok = ch * kChunk + rg < M, x_ok = ch * kChunk + rx < M;
+                if constexpr (has_raw<GLoader>::value) gaux = g_ok ? gaux : 0.f;   // (a zero aux keeps the side sums clean)
+    #pragma unroll
+                for (int j = 0; j < kGJ; ++j) {
+                    if constexpr (has_side<GLoader>::value) gval[j] = gload.convert(gc[j], gaux, cg(j), side[j]);
+                    else if constexpr (has_raw<GLoader>::value) gval[j] = gload.convert(gc[j], gaux, cg(j));
+                    else gval[j] = gc[j];
+                    if (has_raw<GLoader>::value && !g_ok) gval[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+    #pragma unroll
+                for (int j = 0; j < kXJ; ++j) {
+                    if constexpr (has_raw<XLoader>::value) xval[j] = xload.convert(xc[j], xaux, cx(j));
+                    else xval[j] = xc[j];
+                    if (has_raw<XLoader>::value && !(x_ok && cx(j) < x4)) xval[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
+                store(std::integral_constant<bool, GLoader::kRowFast>{}, std::integral_constant<bool, !kExactG>{}, gval, kGJ, rg, cg,
+                      kG / 4, g_hi, g_lo);
+                store(std::integral_constant<bool, XLoader::kRowFast>{}, std::true_type{}, xval, kXJ, rx, cx, x4, x_hi, x_lo);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_full[grp]);
             }
-        };
-        uint32_t use = 0;
-        if (kPipe && c_begin + grp < c_end) fetch(c_begin + grp, gv, xv, gaux_v, xaux_v);
-        for (uint32_t ch = c_begin + grp; ch < c_end; ch += kGroups, ++use) {
-            GRaw gc[kGJ];
-            XRaw xc[kXJ];
-            float gaux = 0.f, xaux = 0.f;
-            if (kPipe) {
-#pragma unroll
-                for (int j = 0; j < kGJ; ++j) gc[j] = gv[j];
-#pragma unroll
-                for (int j = 0; j < kXJ; ++j) xc[j] = xv[j];
-                gaux = gaux_v;
-                xaux = xaux_v;
-                if (ch + kGroups < c_end) fetch(ch + kGroups, gv, xv, gaux_v, xaux_v);  // in flight while this chunk is stored
-            } else {
-                fetch(ch, gc, xc, gaux, xaux);
+            if constexpr (has_side<GLoader>::value) {
+                static_assert(GLoader::kRowFast, "side accumulation reduces over the lanes = rows of the row-fast mapping");
+                int cols[kGJ];
+    #pragma unroll
+                for (int j = 0; j < kGJ; ++j) cols[j] = cg(j);
+                gload.finish(side, cols, kGJ, blockIdx.x, grp, lane);
             }
-            float4 gval[kGJ], xval[kXJ];
-            const bool g_ok = ch * kChunk + rg < M, x_ok = ch * kChunk + rx < M;
-            if constexpr (has_raw<GLoader>::value) gaux = g_ok ? gaux : 0.f;   // (a zero aux keeps the side sums clean)
-#pragma unroll
-            for (int j = 0; j < kGJ; ++j) {
-                if constexpr (has_side<GLoader>::value) gval[j] = gload.convert(gc[j], gaux, cg(j), side[j]);
-                else if constexpr (has_raw<GLoader>::value) gval[j] = gload.convert(gc[j], gaux, cg(j));
-                else gval[j] = gc[j];
-                if (has_raw<GLoader>::value && !g_ok) gval[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < kXJ; ++j) {
-                if constexpr (has_raw<XLoader>::value) xval[j] = xload.convert(xc[j], xaux, cx(j));
-                else xval[j] = xc[j];
-                if (has_raw<XLoader>::value && !(x_ok && cx(j) < x4)) xval[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            mbar_wait(&bar_empty[grp], (use & 1) ^ 1);
-            store(std::integral_constant<bool, GLoader::kRowFast>{}, std::integral_constant<bool, !kExactG>{}, gval, kGJ, rg, cg,
-                  kG / 4, g_hi, g_lo);
-            store(std::integral_constant<bool, XLoader::kRowFast>{}, std::true_type{}, xval, kXJ, rx, cx, x4, x_hi, x_lo);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_full[grp]);
-        }
-        if constexpr (has_side<GLoader>::value) {
-            static_assert(GLoader::kRowFast, "side accumulation reduces over the lanes = rows of the row-fast mapping");
-            int cols[kGJ];
-#pragma unroll
-            for (int j = 0; j < kGJ; ++j) cols[j] = cg(j);
-            gload.finish(side, cols, kGJ, blockIdx.x, grp, lane);
         }
     } else if (warp == kMmaWarp && kSeg < 0) {
+        constexpr uint32_t kFl = flush_chunks(kSeg);   // chunks per flush of `main` (1 or 2)
         // register-total form: one block per chunk.  This warp is a single serial instruction stream that every chunk
         // passes through (an earlier, general version of this loop -- runtime block widths, a division for the rotation
         // index -- ran 190 instructions per chunk and set the kernel's pace), so everything loop-invariant is hoisted.
@@ -331,8 +355,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         }
         const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
         for (uint32_t n = 0; n < n_local; ++n) {
-            const uint32_t s = n & 1, a = n & nbuf_mask;
-            mbar_wait(&bar_tmp_empty[a], ((n >> nbuf_log2) & 1) ^ 1);  // the read-out drained this temporary
+            const uint32_t s = n & 1, f = n / kFl, in_f = n % kFl, a = f & nbuf_mask;
+            if (in_f == 0) mbar_wait(&bar_tmp_empty[a], ((f >> nbuf_log2) & 1) ^ 1);  // the read-out drained this temporary
             mbar_wait(&bar_full[s], (n >> 1) & 1);
             fence_after_sync();
             if (elect_one()) {
@@ -348,8 +372,9 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                     }
                 }
 #pragma unroll
-                for (uint32_t k = 0; k < kChunk / 8; ++k) mma_tf32_mn(d_main, g_h + 64 * k, x_h + 64 * k, idesc, k ? 1u : 0u);
-                commit(&bar_tmp_full[a]);
+                for (uint32_t k = 0; k < kChunk / 8; ++k)
+                    mma_tf32_mn(d_main, g_h + 64 * k, x_h + 64 * k, idesc, (k || in_f) ? 1u : 0u);
+                if (in_f == kFl - 1 || n + 1 == n_local) commit(&bar_tmp_full[a]);
                 commit(&bar_empty[s]);
             }
             __syncwarp();
@@ -429,7 +454,9 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         // read-out, register-total form: warp (q, half) owns columns [32 half, +32) of lane quadrant q
         const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2, row = q * 32 + lane;
         const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
+        constexpr uint32_t kFl = flush_chunks(kSeg);
+        const uint32_t n_chunks_local = c_begin < c_end ? c_end - c_begin : 0;
+        const uint32_t n_local = (n_chunks_local + kFl - 1) / kFl;   // flushes
         float tot[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) tot[j] = 0.f;
