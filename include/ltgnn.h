@@ -164,24 +164,24 @@ int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_t D, const 
  *      part[b*P + p] = sum over the H hidden units of hidden * w2
  *   so pipe_logit = part + b2 (edge_head.mlp.3).  hpost (optional; logical [Mp, H], Mp = B*P rounded up to 128,
  *   stored blocked-32 as [Mp/32][H/4][32][4]) receives `hidden` for the backward.  X [B,N,D] node states; ends int32 [P,2] on the device.  D = 64, H = 128.
- *   hmask (optional; uint32 [Mp, H/32]) receives the 1-bit form of hidden > 0: bit j % 32 of word j / 32 of a row.
+ *   hmask (optional; uint32 [Mp, H/32]) receives the 1-bit form of hidden > 0: bit 31 - j % 32 of word j / 32 of a row.
+ *   hsign (optional; uint32 [Mp, 4]) receives sign(x_u - x_v) as two bits per feature: words 2 g / 2 g + 1 of a row hold
+ *   the `> 0` / `< 0` bits of features 32 g .. 32 g + 31 (feature j at bit 31 - j % 32).  The backward needs both.
  * pipe_head_bwd_dx: dX[b, i, :] = dpooled[b, :] / N (the mean-pool gradient; dpooled may be null) + the input gradient
  *   of the pipe head given dlogit [B*P], summed over the pipe ends at node i in the order of the incidence lists
  *   inc_ptr int32 [N+1], inc int32 [2P] (entry = pipe << 1 | end, grouped by node): a gather, bit-reproducible, dX is
- *   written exactly once.  inc_ell (optional, int32 [N, 8]): the same lists padded with -1 to 8 slots per node, for
- *   graphs whose nodes touch at most 8 class-pipe ends (faster: branch-free loads).
+ *   written exactly once.  The node states are not read: hmask and hsign carry everything the forward knew.
  *   ws: ltgnn_pipe_head_dx_ws_floats(device, P) floats.
  * mean_pool_fwd / mean_pool_bwd_fill: pooled[b,:] = mean_i X[b,i,:];  dX[b,i,:] = dpooled[b,:] / N.
  */
 int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
                         const int32_t* ends, const float* W1, const float* b1, const float* w2, float drop_p,
-                        uint64_t drop_seed, float* part, float* hpost, uint32_t* hmask, void* stream);
+                        uint64_t drop_seed, float* part, float* hpost, uint32_t* hmask, uint32_t* hsign, void* stream);
 int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t P);
-int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
-                           const int32_t* ends, const int32_t* inc_ptr, const int32_t* inc, const int32_t* inc_ell,
-                           const float* W1,
-                           const float* w2, const uint32_t* hmask, const float* dlogit, float gate_scale,
-                           const float* dpooled, float* ws, float* dX, void* stream);
+int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const int32_t* inc_ptr,
+                           const int32_t* inc, const float* W1, const float* w2, const uint32_t* hmask,
+                           const uint32_t* hsign, const float* dlogit, float gate_scale, const float* dpooled, float* ws,
+                           float* dX, void* stream);
 int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, const float* X, float* pooled, void* stream);
 int ltgnn_mean_pool_bwd_fill(int device, int64_t B, int32_t N, int32_t D, const float* dpooled, float* dX, void* stream);
 

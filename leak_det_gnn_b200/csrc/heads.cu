@@ -116,7 +116,7 @@ constexpr uint32_t kScrBytes = 4096;
 
 __global__ void __launch_bounds__(kThreads, 1)
 pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends, uint32_t P, uint32_t N, uint64_t magic,
-                     const HeadFwdEpilogue epilogue, const float* __restrict__ W1, uint32_t M) {
+                     const HeadFwdEpilogue epilogue, const float* __restrict__ W1, uint32_t M, uint2* __restrict__ hsign) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
     __shared__ uint32_t tmem_base_s;
@@ -202,6 +202,19 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
             emit(0, [&](int j) { return u[j]; });   // h_v still in flight
             patch::transpose_in(patch, gv, v);
             emit(1, [&](int j) { return v[j]; });
+            if (hsign && row < M) {
+                // sign(h_u - h_v) of this row's 32 features for the backward (d|x| = sign(x), 0 at 0): two words, feature
+                // j at bit 31 - j.  d < 0 <=> the top bit of its pattern; d > 0 <=> the top bit of minus its pattern
+                // taken as an integer (h >= +0, so d is never -0).  One funnel shift each.
+                uint32_t pos = 0, neg = 0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t bits = __float_as_uint(u[j] - v[j]);
+                    neg = __funnelshift_l(bits, neg, 1);
+                    pos = __funnelshift_l(0u - bits, pos, 1);
+                }
+                hsign[static_cast<size_t>(row) * 2 + grp] = make_uint2(pos, neg);
+            }
             emit(2, [&](int j) { return fabsf(u[j] - v[j]); });
         }
     } else if (warp == kMmaWarp) {
@@ -272,36 +285,45 @@ struct DpreLoader {
     float scale;
 };
 
-__device__ __forceinline__ float sgn(float d) { return (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f); }
-
 // dfeat[row, 0:3D] = dpre[row, :] W1 goes back to the two end nodes: +u for the h_u block, +v for the h_v block,
-// +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0).  Several pipes share a node, and the reference
-// adds them with index_add_ (atomics on a GPU).  Here the sum is a GATHER in a fixed order, so the gradient is
-// bit-reproducible: a CTA works through whole windows; the epilogue warps park the per-pipe rows [du | dv] of the window
-// in a CTA-private scratch (P x 128 floats, reused window after window: it lives in L2) and then walk the node ->
-// incident pipe-end lists: dx[b, i, :] = dpooled[b, :] / N + sum over the pipe ends at node i, written exactly once
-// (the mean-pool gradient rides along: no separate fill pass, no read-modify-write of dx).
+// +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0; the signs come as 2 bits per feature from the
+// forward, `hsign` -- re-reading the node states for them cost a third of this kernel).  Several pipes share a node, and
+// the reference adds them with index_add_ (atomics on a GPU).  Here the sum is a GATHER in a fixed order, so the gradient
+// is bit-reproducible: a CTA works through whole windows; the epilogue warps park the per-pipe-end rows of the window in a
+// CTA-private scratch (2P x 64 floats, reused window after window: it lives in L2) at the position the end has in the
+// node-sorted incidence list, so the ends of a node are contiguous.  When the window is complete the scratch comes back
+// through 1-D bulk copies (TMA) in chunks of whole nodes, double-buffered in the shared memory the epilogue's transpose
+// patches occupy during the tiles, and every node adds its rows in list order:
+//     dx[b, i, :] = dpooled[b, :] / N + sum over the pipe ends at node i,        written exactly once
+// (the mean-pool gradient rides along: no separate fill pass, no read-modify-write of dx).  A per-thread gather from L2
+// (round 2's first version) was latency bound: 45 000 clocks per window against ~7 000 for the bulk copies.
 //
 // Same warp roles as the forward kernel.  The epilogue warps (two per TMEM lane quadrant, 32 of the 64 node
 // features each) turn the row-per-thread accumulator blocks into 128-byte row segments through the swizzled
-// shared-memory patch, so that the node-state reads for the sign and the scratch stores touch 4 full lines per
-// instruction instead of 32 partial ones.
+// shared-memory patch, so that the scratch stores touch 4 full lines per instruction instead of 32 partial ones.
 namespace hb {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
 constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;  // 13 warps: 128 regs
 constexpr int kK = 128, kN = 192, kStages = 2, kStageCols = 64;
 constexpr uint32_t kScrBytes = 4096;
+constexpr uint32_t kCapRows = kEpWarps * kScrBytes / 2 / (kD * 4);  // pipe-end rows per gather buffer (two buffers): 64
 
 __device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory"); }
 
+// end_pos[2 p + end] = position of that pipe end in the node-sorted incidence list `inc` (its inverse permutation)
+__global__ void invert_incidence_kernel(const int32_t* __restrict__ inc, int32_t* __restrict__ end_pos, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) end_pos[__ldg(inc + e)] = e;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, float4* __restrict__ dx,
-                        const int2* __restrict__ ends, const int32_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc,
-                        const int4* __restrict__ inc_ell, const float4* __restrict__ dpooled, float4* __restrict__ scratch, uint32_t P, uint32_t N, uint32_t B,
+pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const int2* __restrict__ end_pos,
+                        const int32_t* __restrict__ inc_ptr, const uint2* __restrict__ hsign,
+                        const float4* __restrict__ dpooled, float4* __restrict__ scratch, uint32_t P, uint32_t N, uint32_t B,
                         const float* __restrict__ W1) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2], bar_gather[2];
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_hi = smem;  // B[n = feature column (192)][k = hidden unit (128)] = W1[k][n]
@@ -318,6 +340,7 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
             mbar_init(&bar_tempty[a], kEpWarps);
+            mbar_init(&bar_gather[a], 1);
         }
         fence_mbar_init();
     }
@@ -428,32 +451,28 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
         const patch::Patch patch(scr_patch + (warp - kMmaWarp - 1) * kScrBytes, lane);
         const int sub = lane >> 3, ch = lane & 7;
         const int et = (warp - kMmaWarp - 1) * 32 + lane;           // 0..255 among the epilogue threads
-        float4* scr = scratch + static_cast<size_t>(blockIdx.x) * T * 128 * 32;  // [T * 128 rows][du 16 | dv 16] float4
+        float4* scr = scratch + static_cast<size_t>(blockIdx.x) * P * 2 * kD4;   // [2 P pipe ends, node-sorted][16] float4
         const float inv_n = 1.f / static_cast<float>(N);
+        uint32_t gph[2] = {0, 0};                                   // phases of the two gather buffers
+        // sign words of this lane's 8 row segments (rows p0 + 4 k + sub, features [32 half, +32)), fetched one tile ahead
+        uint2 sg_next[8];
+        auto fetch_signs = [&](uint32_t t) {
+            const uint32_t w = w_begin + t / T, p = (t % T) * 128 + q * 32 + sub;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                sg_next[k] = (t < n_tiles && p + 4 * k < P) ? __ldg(hsign + (static_cast<size_t>(w) * P + p + 4 * k) * 2 + half)
+                                                            : make_uint2(0u, 0u);
+        };
+        fetch_signs(0);
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t a = t & 1;
             const uint32_t w = w_begin + t / T, tt = t % T;
             const uint32_t p0 = tt * 128 + q * 32;                  // first pipe of this warp's 32 rows
-            uint32_t iu = 0, iv = 0;
-            if (p0 + lane < P) {
-                const int2 e = __ldg(ends + p0 + lane);
-                iu = w * N + e.x;
-                iv = w * N + e.y;
-            }
-            // sign(h_u - h_v) of this lane's 8 row segments, packed as two bit masks (bit 4 k + component): the
-            // node states do not depend on the accumulator, so their latency is paid before the wait
-            uint32_t pos = 0, neg = 0;
+            const int2 pos_l = p0 + lane < P ? __ldg(end_pos + p0 + lane) : make_int2(-1, -1);
+            uint2 sg[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t ru = __shfl_sync(0xffffffffu, iu, 4 * k + sub), rv = __shfl_sync(0xffffffffu, iv, 4 * k + sub);
-                const float4 pu = __ldg(x + ru * kD4 + half * 8 + ch), pv = __ldg(x + rv * kD4 + half * 8 + ch);
-                const float d[4] = {pu.x - pv.x, pu.y - pv.y, pu.z - pv.z, pu.w - pv.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    pos |= (d[i] > 0.f ? 1u : 0u) << (4 * k + i);
-                    neg |= (d[i] < 0.f ? 1u : 0u) << (4 * k + i);
-                }
-            }
+            for (int k = 0; k < 8; ++k) sg[k] = sg_next[k];
+            fetch_signs(t + 1);
             mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
             fence_after_sync();
             const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16) + 32 * half;
@@ -462,96 +481,90 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, const float4* __restrict__ x, f
                 tmem_ld32(taddr + col, v);
                 patch::transpose_out(patch, v, g);
             };
-            auto signed_c = [&](float c, int bit) { return (pos >> bit) & 1u ? c : ((neg >> bit) & 1u ? -c : 0.f); };
+            // feature 4 ch + i of the half sits at bit 31 - (4 ch + i) of the pos / neg words
+            auto signed_c = [&](float c, const uint2& s2, int i) {
+                const uint32_t sh = 4 * ch + i;
+                return static_cast<int32_t>(s2.x << sh) < 0 ? c : (static_cast<int32_t>(s2.y << sh) < 0 ? -c : 0.f);
+            };
             float4 gc[8], ga[8];
             pull32(2 * kD, gc);  // d / d |x_u - x_v|  ->  +- sign
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                gc[k].x = signed_c(gc[k].x, 4 * k); gc[k].y = signed_c(gc[k].y, 4 * k + 1);
-                gc[k].z = signed_c(gc[k].z, 4 * k + 2); gc[k].w = signed_c(gc[k].w, 4 * k + 3);
+                gc[k].x = signed_c(gc[k].x, sg[k], 0); gc[k].y = signed_c(gc[k].y, sg[k], 1);
+                gc[k].z = signed_c(gc[k].z, sg[k], 2); gc[k].w = signed_c(gc[k].w, sg[k], 3);
             }
             pull32(0, ga);       // d / d x_u
 #pragma unroll
-            for (int k = 0; k < 8; ++k)  // rows past P are never read back
-                __stcg(scr + static_cast<size_t>(p0 + 4 * k + sub) * 32 + half * 8 + ch,
-                       make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
+            for (int k = 0; k < 8; ++k) {
+                const int pu = __shfl_sync(0xffffffffu, pos_l.x, 4 * k + sub);
+                if (pu >= 0)
+                    __stcg(scr + static_cast<size_t>(pu) * kD4 + half * 8 + ch,
+                           make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
+            }
             pull32(kD, ga);      // d / d x_v
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                __stcg(scr + static_cast<size_t>(p0 + 4 * k + sub) * 32 + 16 + half * 8 + ch,
-                       make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+            for (int k = 0; k < 8; ++k) {
+                const int pv = __shfl_sync(0xffffffffu, pos_l.y, 4 * k + sub);
+                if (pv >= 0)
+                    __stcg(scr + static_cast<size_t>(pv) * kD4 + half * 8 + ch,
+                           make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+            }
             if (tt == T - 1) {
-                // the window is complete: every node gathers its pipe ends in list order (16 threads = the 256 bytes of a node)
+                // The window is complete.  Chunks of whole nodes (at most 32 nodes and kCapRows pipe ends; every warp
+                // derives the same chunk sequence from inc_ptr) come back from the scratch by bulk copy into the two
+                // buffers in turn; 16 threads = the 256 bytes of a node add its rows in list order.
+                fence_proxy_async_all();   // my scratch stores and patch accesses, before the async proxy touches either
                 ep_bar();
                 const int f = et & 15;
                 const float4 pl = dpooled ? __ldg(dpooled + static_cast<size_t>(w) * kD4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                if (inc_ell) {
-                    // fixed-width lists (8 slots per node, -1 = empty): the loads of three nodes go out together -- the
-                    // scratch sits in L2, and a dependent chain per node made this phase longer than the six tiles
-                    constexpr int kNodes = 2, kStep = (kEpWarps * 32) >> 4;
-                    auto load_ent = [&](uint32_t i0, int h4, int4 (&ent)[kNodes]) {
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) {
-                            const uint32_t i = i0 + u * kStep;
-                            ent[u] = i < N ? __ldg(inc_ell + 2 * i + h4) : make_int4(-1, -1, -1, -1);
-                        }
-                    };
-                    auto add_slots = [&](const int4 (&ent)[kNodes], float4 (&acc)[kNodes]) {
-                        float4 c[kNodes][4];
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) {
-                            const int e4[4] = {ent[u].x, ent[u].y, ent[u].z, ent[u].w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (e4[k] >= 0) c[u][k] = __ldcg(scr + static_cast<size_t>(e4[k] >> 1) * 32 + (e4[k] & 1) * 16 + f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) {
-                            const int e4[4] = {ent[u].x, ent[u].y, ent[u].z, ent[u].w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                if (e4[k] >= 0) {
-                                    acc[u].x += c[u][k].x; acc[u].y += c[u][k].y; acc[u].z += c[u][k].z; acc[u].w += c[u][k].w;
-                                }
-                        }
-                    };
-                    int4 ent_next[kNodes];
-                    load_ent(et >> 4, 0, ent_next);
-                    for (uint32_t i0 = et >> 4; i0 < N; i0 += kNodes * kStep) {
-                        int4 ent[kNodes], ent_hi[kNodes];
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) ent[u] = ent_next[u];
-                        load_ent(i0, 1, ent_hi);                       // slots 4-7 of this batch (rarely occupied)
-                        load_ent(i0 + kNodes * kStep, 0, ent_next);    // slots 0-3 of the next batch: in flight during the adds
-                        float4 acc[kNodes];
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) acc[u] = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
-                        add_slots(ent, acc);
-                        bool any = false;
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) any = any || ent_hi[u].x >= 0;
-                        if (__any_sync(0xffffffffu, any)) add_slots(ent_hi, acc);
-#pragma unroll
-                        for (int u = 0; u < kNodes; ++u) {
-                            const uint32_t i = i0 + u * kStep;
-                            if (i < N) stg_stream(dx + (static_cast<size_t>(w) * N + i) * kD4 + f, acc[u]);
-                        }
+                const float4 base = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
+                auto bounds = [&](uint32_t n0, uint32_t& n1, uint32_t& r0, uint32_t& r1) {
+                    r0 = static_cast<uint32_t>(__ldg(inc_ptr + n0));
+                    const uint32_t i = n0 + 1 + lane;
+                    const uint32_t re = i <= N ? static_cast<uint32_t>(__ldg(inc_ptr + i)) : 0xffffffffu;
+                    uint32_t cnt = __popc(__ballot_sync(0xffffffffu, i <= N && re - r0 <= kCapRows));
+                    cnt = cnt ? cnt : 1;   // a node with more than kCapRows ends goes alone, straight from L2
+                    n1 = n0 + cnt;
+                    r1 = __shfl_sync(0xffffffffu, re, cnt - 1);
+                };
+                auto issue = [&](uint32_t buf, uint32_t r0, uint32_t r1) {
+                    if (et == 0 && r1 > r0 && r1 - r0 <= kCapRows) {
+                        const uint32_t bytes = (r1 - r0) * kD * 4;
+                        mbar_arrive_expect_tx(&bar_gather[buf], bytes);
+                        bulk_load(scr_patch + buf * (kCapRows * kD * 4), scr + static_cast<size_t>(r0) * kD4, bytes, &bar_gather[buf]);
                     }
-                } else
-                    for (uint32_t i = et >> 4; i < N; i += (kEpWarps * 32) >> 4) {
-                    float4 acc = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
-                    const int e_end = __ldg(inc_ptr + i + 1);
-                    for (int e = __ldg(inc_ptr + i); e < e_end; ++e) {
-                        const int ent = __ldg(inc + e);  // pipe << 1 | end
-                        const float4 c = __ldcg(scr + static_cast<size_t>(ent >> 1) * 32 + (ent & 1) * 16 + f);
-                        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+                };
+                uint32_t n0 = 0, n1, r0, r1;
+                bounds(0, n1, r0, r1);
+                issue(0, r0, r1);
+                for (uint32_t c = 0; n0 < N; ++c) {
+                    const uint32_t buf = c & 1;
+                    uint32_t m1 = n1, s0 = r1, s1 = r1;
+                    if (n1 < N) {
+                        bounds(n1, m1, s0, s1);
+                        issue(buf ^ 1, s0, s1);
                     }
-                    stg_stream(dx + (static_cast<size_t>(w) * N + i) * kD4 + f, acc);
+                    const bool staged = r1 > r0 && r1 - r0 <= kCapRows;
+                    if (staged) {
+                        mbar_wait(&bar_gather[buf], gph[buf] & 1);
+                        ++gph[buf];
+                    }
+                    const float4* stage = reinterpret_cast<const float4*>(scr_patch + buf * (kCapRows * kD * 4)) + f;
+                    for (uint32_t node = n0 + (et >> 4); node < n1; node += (kEpWarps * 32) >> 4) {
+                        const uint32_t e0 = static_cast<uint32_t>(__ldg(inc_ptr + node)), e1 = static_cast<uint32_t>(__ldg(inc_ptr + node + 1));
+                        float4 acc = base;
+                        for (uint32_t e = e0; e < e1; ++e) {
+                            const float4 v = staged ? stage[(e - r0) * kD4] : __ldcg(scr + static_cast<size_t>(e) * kD4 + f);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                        stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + f, acc);
+                    }
+                    ep_bar();  // this buffer may be refilled; after the last chunk: the next window may overwrite the scratch
+                    n0 = n1; n1 = m1; r0 = s0; r1 = s1;
                 }
-                ep_bar();  // the next window's rows may overwrite the scratch
             }
         }
     }
@@ -624,15 +637,16 @@ int head_shape_check(int D, int H, const char* who) {
 extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
                                    const int32_t* ends, const float* W1, const float* b1, const float* w2,
                                    float drop_p, uint64_t drop_seed, float* part, float* hpost, uint32_t* hmask,
-                                   void* stream_) {
+                                   uint32_t* hsign, void* stream_) {
     LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_fwd: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
     int rc = head_shape_check(D, H, "pipe_head_fwd");
     if (rc) return rc;
     LTGNN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LTGNN_E_ARG, "pipe_head_fwd: dropout p=%f", drop_p);
     if (B == 0) return LTGNN_OK;
     LTGNN_REQUIRE(X && ends && W1 && b1 && w2 && part, LTGNN_E_ARG, "pipe_head_fwd: null tensor");
-    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(b1) && aligned16(w2) && aligned16(hpost) && aligned16(hmask), LTGNN_E_ALIGN,
-                  "pipe_head_fwd: 16-byte alignment required");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(b1) && aligned16(w2) && aligned16(hpost) && aligned16(hmask) &&
+                      aligned16(hsign),
+                  LTGNN_E_ALIGN, "pipe_head_fwd: 16-byte alignment required");
     const int64_t M = B * P;
     LTGNN_REQUIRE(M < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*P too large");
     const uint32_t t16 = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
@@ -651,29 +665,27 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
     const int grid = static_cast<int>(tiles < di->sm_count ? tiles : di->sm_count);
     hf::pipe_head_fwd_kernel<<<grid, hf::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
         reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
-        static_cast<uint32_t>(N), magic_of(P), ep, W1, static_cast<uint32_t>(M));
+        static_cast<uint32_t>(N), magic_of(P), ep, W1, static_cast<uint32_t>(M), reinterpret_cast<uint2*>(hsign));
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }
 
 extern "C" int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t P) {
-    const DeviceInfo* di = device_info(device);  // per CTA: the window's pipe rows [du | dv], padded to whole tiles
-    return di ? static_cast<int64_t>(di->sm_count) * ((P + 127) / 128) * 128 * 128 : -1;
+    const DeviceInfo* di = device_info(device);  // positions of the 2 P pipe ends + per CTA: one window's 2 P rows of 64
+    return di ? (2ll * P + 3) / 4 * 4 + static_cast<int64_t>(di->sm_count) * 2 * P * kD : -1;
 }
 
-extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
-                                      const int32_t* ends, const int32_t* inc_ptr, const int32_t* inc,
-                                      const int32_t* inc_ell, const float* W1,
-                                      const float* w2, const uint32_t* hmask, const float* dlogit, float gate_scale,
+extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H,
+                                      const int32_t* inc_ptr, const int32_t* inc, const float* W1, const float* w2,
+                                      const uint32_t* hmask, const uint32_t* hsign, const float* dlogit, float gate_scale,
                                       const float* dpooled, float* ws, float* dX, void* stream_) {
     LTGNN_REQUIRE(B >= 0 && N > 0 && P > 0, LTGNN_E_ARG, "pipe_head_bwd_dx: B=%lld N=%d P=%d", static_cast<long long>(B), N, P);
     int rc = head_shape_check(D, H, "pipe_head_bwd_dx");
     if (rc) return rc;
     if (B == 0) return LTGNN_OK;
-    LTGNN_REQUIRE(X && ends && inc_ptr && inc && W1 && w2 && hmask && dlogit && ws && dX, LTGNN_E_ARG,
+    LTGNN_REQUIRE(inc_ptr && inc && W1 && w2 && hmask && hsign && dlogit && ws && dX, LTGNN_E_ARG,
                   "pipe_head_bwd_dx: null tensor");
-    LTGNN_REQUIRE(aligned16(X) && aligned16(W1) && aligned16(hmask) && aligned16(dX) && aligned16(ws) && aligned16(dpooled) &&
-                      aligned16(inc_ell),
+    LTGNN_REQUIRE(aligned16(W1) && aligned16(hmask) && aligned16(hsign) && aligned16(dX) && aligned16(ws) && aligned16(dpooled),
                   LTGNN_E_ALIGN, "pipe_head_bwd_dx: 16-byte alignment required");
     DpreLoader ld{reinterpret_cast<const uint4*>(hmask), dlogit, w2, gate_scale};
     const DeviceInfo* di = device_info(device);
@@ -684,13 +696,18 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
     const size_t smem = 1024 + 2ull * hb::kN * hb::kK * 4 + hb::kEpWarps * hb::kScrBytes;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_bwd_dx: %zu B of shared memory", smem);
     LTGNN_USE_DEVICE(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int32_t* end_pos = reinterpret_cast<int32_t*>(ws);
+    float* scratch = ws + (2ll * P + 3) / 4 * 4;
+    hb::invert_incidence_kernel<<<(2 * P + 255) / 256, 256, 0, stream>>>(inc, end_pos, 2 * P);
+    LTGNN_CUDA_TRY(cudaGetLastError());
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(hb::pipe_head_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
     const int grid = static_cast<int>(B < di->sm_count ? B : di->sm_count);
-    hb::pipe_head_bwd_dx_kernel<<<grid, hb::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(
-        ld, reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(ends), inc_ptr,
-        inc, reinterpret_cast<const int4*>(inc_ell), reinterpret_cast<const float4*>(dpooled), reinterpret_cast<float4*>(ws), static_cast<uint32_t>(P),
-        static_cast<uint32_t>(N), static_cast<uint32_t>(B), W1);
+    hb::pipe_head_bwd_dx_kernel<<<grid, hb::kThreads, smem, stream>>>(
+        ld, reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(end_pos), inc_ptr,
+        reinterpret_cast<const uint2*>(hsign), reinterpret_cast<const float4*>(dpooled), reinterpret_cast<float4*>(scratch),
+        static_cast<uint32_t>(P), static_cast<uint32_t>(N), static_cast<uint32_t>(B), W1);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

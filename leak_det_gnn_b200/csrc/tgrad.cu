@@ -34,6 +34,7 @@ struct HeadFeatSlice {
 struct HeadFill;
 struct HeadLive {
     static constexpr bool kExact = true;
+    static constexpr int kStages = 4;   // 32 KB each (no lo copy of G)
     using Fill = HeadFill;   // both operands are produced by the hand-written loop below
     const uint4* hmask;     // [Mp]: hidden unit j of a row <-> bit 31 - j % 32 of word j / 32 (heads.cu)
     const float* dlogit;    // [M]
@@ -55,9 +56,8 @@ struct HeadFill {
         float4 a[2], b[2];
     };
     template <int kSlice>
-    static __device__ __forceinline__ void loop(const HeadLive& g, const HeadFeatSlice& x, uint8_t* g_hi, uint8_t* x_hi,
-                                                uint8_t* x_lo, int gtid, int grp, uint32_t c_begin, uint32_t c_end, uint32_t M,
-                                                uint64_t* full, uint64_t* empty) {
+    static __device__ __forceinline__ void loop(const HeadLive& g, const HeadFeatSlice& x, const tgrad::Ring& ring, int gtid,
+                                                int grp, uint32_t c_begin, uint32_t c_end, uint32_t M) {
         using namespace ltgnn::ptx;
         using namespace ltgnn::umma;
         constexpr uint32_t kStep = tgrad::kGroups * tgrad::kChunk;   // rows between two chunks of this group
@@ -111,6 +111,7 @@ struct HeadFill {
         load_rows(nxt, load_ends(), row, b);
         advance();
         int2 e_n = load_ends();             // pipe ends of the chunk after `nxt` (garbage-free: p is always valid)
+        constexpr uint32_t kPer = HeadLive::kStages / tgrad::kGroups;   // stages this group rotates through
         uint32_t use = 0;
         for (uint32_t ch = first; ch < c_end; ch += tgrad::kGroups, ++use) {
             const Rows cur = nxt;
@@ -145,17 +146,19 @@ struct HeadFill {
                 if (kSlice == 2) v = make_float4(fabsf(v.x - cur.b[j].x), fabsf(v.y - cur.b[j].y), fabsf(v.z - cur.b[j].z), fabsf(v.w - cur.b[j].w));
                 split4(make_float4(gs * v.x, gs * v.y, gs * v.z, gs * v.w), hi[j], lo[j]);
             }
-            mbar_wait(empty, (use & 1) ^ 1);
+            const uint32_t st = grp + tgrad::kGroups * (use % kPer);
+            uint8_t* g_hi = ring.base + st * ring.stage + off;
+            mbar_wait(ring.empty + st, ((use / kPer) & 1) ^ 1);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(g_hi + off + k * tgrad::kBlockBytes) = live[k];
+            for (int k = 0; k < 4; ++k) *reinterpret_cast<float4*>(g_hi + k * tgrad::kBlockBytes) = live[k];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                *reinterpret_cast<float4*>(x_hi + off + j * tgrad::kBlockBytes) = hi[j];
-                *reinterpret_cast<float4*>(x_lo + off + j * tgrad::kBlockBytes) = lo[j];
+                *reinterpret_cast<float4*>(g_hi + ring.x_hi + j * tgrad::kBlockBytes) = hi[j];
+                *reinterpret_cast<float4*>(g_hi + ring.x_lo + j * tgrad::kBlockBytes) = lo[j];
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(full);
+            if (lane == 0) mbar_arrive(ring.full + st);
         }
         finish<kSlice>(g, side, grp, gtid, q, lane);
     }
@@ -177,13 +180,12 @@ struct HeadFill {
             if (lane < 8) out[8 * k + q] = t;      // hidden units 32 k + 4 q .. + 3 (zeros from the other slices' CTAs)
         }
     }
-    static __device__ __forceinline__ void run(const HeadLive& g, const HeadFeatSlice& x, uint8_t* g_hi, uint8_t* x_hi,
-                                               uint8_t* x_lo, int gtid, int grp, uint32_t c_begin, uint32_t c_end, uint32_t M,
-                                               uint64_t* full, uint64_t* empty) {
+    static __device__ __forceinline__ void run(const HeadLive& g, const HeadFeatSlice& x, const tgrad::Ring& ring, int gtid,
+                                               int grp, uint32_t c_begin, uint32_t c_end, uint32_t M) {
         const int slice = blockIdx.x % kHeadSlices;
-        if (slice == 0) loop<0>(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin, c_end, M, full, empty);
-        else if (slice == 1) loop<1>(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin, c_end, M, full, empty);
-        else loop<2>(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin, c_end, M, full, empty);
+        if (slice == 0) loop<0>(g, x, ring, gtid, grp, c_begin, c_end, M);
+        else if (slice == 1) loop<1>(g, x, ring, gtid, grp, c_begin, c_end, M);
+        else loop<2>(g, x, ring, gtid, grp, c_begin, c_end, M);
     }
 };
 

@@ -109,16 +109,31 @@ struct exact_of { static constexpr bool value = false; };
 template <class T>
 struct exact_of<T, std::void_t<decltype(T::kExact)>> { static constexpr bool value = T::kExact; };
 
-// GLoader::Fill: a hand-written loader loop for one (G, X) pair.  `Fill::run(g, x, g_hi, x_hi, x_lo, gtid, grp, c_begin,
-// c_end, M, full, empty)` is called by every thread of loader group `grp` (gtid = thread index inside the group) and owns
-// the whole protocol for the group's chunks c_begin + grp, c_begin + grp + kGroups, ...: wait for `empty` (parity
-// (use & 1) ^ 1), write the stage in the mn_offset layout, fence_proxy_async_smem, one arrive per warp on `full`.  The
+// GLoader::Fill: a hand-written loader loop for one (G, X) pair.  `Fill::run(g, x, ring, gtid, grp, c_begin, c_end, M)`
+// is called by every thread of loader group `grp` (gtid = thread index inside the group) and owns
+// the whole protocol for the group's chunks c_begin + grp, c_begin + grp + kGroups, ...: the group's use-th chunk goes to
+// stage grp + kGroups * (use % (kStages / kGroups)): wait for its `empty` (parity ((use / (kStages / kGroups)) & 1) ^ 1),
+// write the stage in the mn_offset layout, fence_proxy_async_smem, one arrive per warp on its `full`.  The
 // generic loop below costs ~430 instructions per thread and chunk for the pipe head (spills under the 72-register cap,
 // per-chunk index arithmetic) and its issue slots paced that kernel; a bespoke loop needs a third of that.
 template <class T, class = void>
 struct fill_of { using type = void; };
 template <class T>
 struct fill_of<T, std::void_t<typename T::Fill>> { using type = typename T::Fill; };
+
+// GLoader::kStages (with a Fill): ring stages, a multiple of kGroups; group g fills stages g, g + kGroups, ... in turn.
+// With one stage per group the loaders and the MMA warp wait for each other half of the time (measured on the pipe
+// head: loaders 45 % on `empty`, MMA warp 45 % on `full`); an exact-G stage has no lo copy, so four stages fit.
+constexpr int kMaxStages = 4;
+template <class T, class = void>
+struct stages_of { static constexpr int value = kGroups; };
+template <class T>
+struct stages_of<T, std::void_t<decltype(T::kStages)>> { static constexpr int value = T::kStages; };
+struct Ring {   // what a Fill needs to know about the ring
+    uint8_t* base;                  // stage 0 (operand G, hi)
+    uint32_t stage, x_hi, x_lo;     // bytes per stage; offsets of the X copies inside a stage
+    uint64_t *full, *empty;         // [stages]
+};
 
 // chunks per flush of `main` in the register-total form (kSeg = -1, -2)
 __host__ __device__ constexpr uint32_t flush_chunks(int seg) { return seg < 0 ? static_cast<uint32_t>(-(seg + 1)) + 1u : 1u; }
@@ -127,8 +142,12 @@ __host__ __device__ constexpr uint32_t flush_chunks(int seg) { return seg < 0 ? 
 // read-out warp (lane = row) touches 512 contiguous bytes per instruction
 __host__ __device__ inline size_t ws_f4(int row, int c4) { return static_cast<size_t>(c4) * kMo + row; }
 
-__host__ inline size_t stage_bytes(int No, int mt) { return 2ull * (kMo * mt + No) * kChunk * 4; }
-__host__ inline size_t smem_bytes(int No, int mt) { return 1024 + kGroups * stage_bytes(No, mt); }
+__host__ inline size_t stage_bytes(int No, int mt, bool exact_g = false) {
+    return ((exact_g ? 1ull : 2ull) * kMo * mt + 2ull * No) * kChunk * 4;
+}
+__host__ inline size_t smem_bytes(int No, int mt, bool exact_g = false, int stages = kGroups) {
+    return 1024 + stages * stage_bytes(No, mt, exact_g);
+}
 
 // GLoader: float4 operator()(uint32_t row, int c16) for c16 < kMo/4;  XLoader: same for c16 < No/4.
 // Both are only called for row < M.  ws: [gridDim.x][kMo][No].
@@ -150,19 +169,24 @@ __global__ void __launch_bounds__(kSeg < 0 ? kThreadsReg : kThreads, 1)
 tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols,
              int nb, uint32_t nbuf_log2) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kGroups], bar_empty[kGroups], bar_tmp_full[kMaxBuf], bar_tmp_empty[kMaxBuf];
+    __shared__ uint64_t bar_full[kMaxStages], bar_empty[kMaxStages], bar_tmp_full[kMaxBuf], bar_tmp_empty[kMaxBuf];
+    constexpr bool kExactG = exact_of<GLoader>::value;
+    constexpr int kStages = stages_of<GLoader>::value;
+    static_assert(kStages % kGroups == 0 && kStages <= kMaxStages, "ring stages: a multiple of the loader groups");
+    static_assert(kStages == kGroups || kSeg < 0, "only the register-total form walks a deeper ring");
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int kG = kMo * kMT;                        // operand-G columns
-    const uint32_t g_half = kG * kChunk * 4;             // G hi (then G lo)
+    const uint32_t g_half = kG * kChunk * 4;             // G hi (then G lo, unless G is exact)
+    const uint32_t g_all = (kExactG ? 1 : 2) * g_half;
     const uint32_t x_half = static_cast<uint32_t>(No) * kChunk * 4;
-    const uint32_t stage = 2 * (g_half + x_half);
+    const uint32_t stage = g_all + 2 * x_half;
 
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, tmem_cols);
     if (tid == 0) {
-        for (int s = 0; s < kGroups; ++s) {
+        for (int s = 0; s < kStages; ++s) {
             mbar_init(&bar_full[s], kLoaderWarps / kGroups);
             mbar_init(&bar_empty[s], 1);
         }
@@ -173,8 +197,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         fence_mbar_init();
     }
     if (kGJ < 4 * kMT) {  // operand-G columns the loaders never write: zero in every stage, hi and lo
-        for (uint32_t i = tid; i < kGroups * 2 * (g_half / 16); i += blockDim.x) {
-            const uint32_t st = i / (2 * (g_half / 16)), r = i - st * 2 * (g_half / 16);
+        for (uint32_t i = tid; i < kStages * (g_all / 16); i += blockDim.x) {
+            const uint32_t st = i / (g_all / 16), r = i - st * (g_all / 16);
             *reinterpret_cast<float4*>(smem + st * stage + r * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         fence_proxy_async_smem();
@@ -191,7 +215,6 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
 
     // contiguous range of row chunks per CTA
     constexpr uint32_t kSl = slices_of<XLoader>::value;
-    constexpr bool kExactG = exact_of<GLoader>::value;
     static_assert(!kExactG || kSeg < 0, "exact-G operands are only handled by the register-total form");
     const uint32_t n_chunks = (M + kChunk - 1) / kChunk;
     const uint32_t n_ranges = gridDim.x / kSl;
@@ -203,14 +226,13 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     if (warp < kLoaderWarps) {
         const int grp = warp / (kLoaderWarps / kGroups);
         if constexpr (!std::is_void<Fill>::value) {
-            uint8_t* g_hi = smem + grp * stage;
-            Fill::run(gload, xload, g_hi, g_hi + 2 * g_half, g_hi + 2 * g_half + x_half, tid - grp * kGroupThreads, grp, c_begin,
-                      c_end, M, &bar_full[grp], &bar_empty[grp]);
+            const Ring ring{smem, stage, g_all, g_all + x_half, bar_full, bar_empty};
+            Fill::run(gload, xload, ring, tid - grp * kGroupThreads, grp, c_begin, c_end, M);
         } else {
             const int gtid = tid - grp * kGroupThreads;
             uint8_t* g_hi = smem + grp * stage;
             uint8_t* g_lo = g_hi + g_half;
-            uint8_t* x_hi = g_lo + g_half;
+            uint8_t* x_hi = g_hi + g_all;
             uint8_t* x_lo = x_hi + x_half;
             // 8 threads per row: thread (r, q) owns 16-byte chunks q, q + 8, ... of row r of an operand, so the
             // row-dependent part of a gather (division, end-node lookup) is done once and all loads go out together
@@ -345,22 +367,16 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
         // index -- ran 190 instructions per chunk and set the kernel's pace), so everything loop-invariant is hoisted.
         const uint32_t idesc = idesc_tf32_mn(kMo, No);
         const uint32_t base = smem_u32(smem);
-        uint32_t gh[kGroups], gl[kGroups], xh[kGroups], xl[kGroups];
-#pragma unroll
-        for (int s = 0; s < kGroups; ++s) {
-            gh[s] = mn_desc_lo(base + s * stage);
-            gl[s] = mn_desc_lo(base + s * stage + g_half);
-            xh[s] = mn_desc_lo(base + s * stage + 2 * g_half);
-            xl[s] = mn_desc_lo(base + s * stage + 2 * g_half + x_half);
-        }
+        const uint32_t gh0 = mn_desc_lo(base), gl0 = mn_desc_lo(base + g_half), xh0 = mn_desc_lo(base + g_all);
+        const uint32_t xl0 = mn_desc_lo(base + g_all + x_half), st16 = stage >> 4;   // descriptors advance by stage / 16
         const uint32_t n_local = c_begin < c_end ? c_end - c_begin : 0;
         for (uint32_t n = 0; n < n_local; ++n) {
-            const uint32_t s = n & 1, f = n / kFl, in_f = n % kFl, a = f & nbuf_mask;
+            const uint32_t s = n % kStages, f = n / kFl, in_f = n % kFl, a = f & nbuf_mask;
             if (in_f == 0) mbar_wait(&bar_tmp_empty[a], ((f >> nbuf_log2) & 1) ^ 1);  // the read-out drained this temporary
-            mbar_wait(&bar_full[s], (n >> 1) & 1);
+            mbar_wait(&bar_full[s], (n / kStages) & 1);
             fence_after_sync();
             if (elect_one()) {
-                const uint32_t g_h = s ? gh[1] : gh[0], g_l = s ? gl[1] : gl[0], x_h = s ? xh[1] : xh[0], x_l = s ? xl[1] : xl[0];
+                const uint32_t so = s * st16, g_h = gh0 + so, g_l = gl0 + so, x_h = xh0 + so, x_l = xl0 + so;
                 const uint32_t d_main = t_tmp + a * nb;
 #pragma unroll
                 for (uint32_t k = 0; k < kChunk / 8; ++k) {
@@ -391,8 +407,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
             fence_after_sync();
             if (elect_one()) {
                 const uint32_t gh = mn_desc_lo(base + s * stage), gl = mn_desc_lo(base + s * stage + g_half);
-                const uint32_t xh = mn_desc_lo(base + s * stage + 2 * g_half);
-                const uint32_t xl = mn_desc_lo(base + s * stage + 2 * g_half + x_half);
+                const uint32_t xh = mn_desc_lo(base + s * stage + g_all);
+                const uint32_t xl = mn_desc_lo(base + s * stage + g_all + x_half);
 #pragma unroll
                 for (uint32_t k = 0; k < kChunk / 8; ++k) {  // 8 rows = 1024 B = 64 descriptor units per K-step
 #pragma unroll
@@ -404,7 +420,7 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                     }
                 }
                 commit(&bar_empty[s]);
-                if (in_seg == kSeg - 1 || ch + 1 == c_end) commit(&bar_tmp_full[a]);
+                if (in_seg + 1 == static_cast<uint32_t>(kSeg > 0 ? kSeg : 1) || ch + 1 == c_end) commit(&bar_tmp_full[a]);
             }
             __syncwarp();
         }
@@ -416,8 +432,8 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
             mbar_wait(&bar_full[s], (n / kGroups) & 1);
             fence_after_sync();
             const uint32_t gh = mn_desc_lo(base + s * stage), gl = mn_desc_lo(base + s * stage + g_half);
-            const uint32_t xh = mn_desc_lo(base + s * stage + 2 * g_half);
-            const uint32_t xl = mn_desc_lo(base + s * stage + 2 * g_half + x_half);
+            const uint32_t xh = mn_desc_lo(base + s * stage + g_all);
+            const uint32_t xl = mn_desc_lo(base + s * stage + g_all + x_half);
             const uint32_t idesc_full = idesc_tf32_mn(kMo, No);
 #pragma unroll 1
             for (uint32_t mt = 0; mt < kMT; ++mt) {  // accumulator tile mt <- operand-G columns [128 mt, +128)
@@ -614,7 +630,7 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "%s: device is sm_%d%d, need sm_100", who, di->cc_major,
                   di->cc_minor);
-    const size_t smem = smem_bytes(No, kMT);
+    const size_t smem = smem_bytes(No, kMT, exact_of<GLoader>::value, stages_of<GLoader>::value);
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "%s: %zu B of shared memory", who, smem);
     LTGNN_USE_DEVICE(device);
     auto kern = tgrad_kernel<GLoader, XLoader, kMT, kGJ, kXJ, kSeg>;

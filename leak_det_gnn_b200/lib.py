@@ -44,11 +44,11 @@ SIGNATURES = {
     "ltgnn_gcn_layer_fwd": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                     c_uint64, c_void_p, c_void_p, c_void_p]),
     "ltgnn_pipe_head_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                    c_void_p, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ltgnn_pipe_head_dx_ws_floats": (c_int64, [c_int, c_int32]),
     "ltgnn_pipe_head_bwd_dx": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
-                                       c_void_p, c_void_p, c_void_p]),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
     "ltgnn_mean_pool_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "ltgnn_mean_pool_bwd_fill": (c_int, [c_int, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "ltgnn_tgrad_ws_floats": (c_int64, [c_int, c_int32]),

@@ -446,22 +446,14 @@ def heads_supported(d: int, h: int) -> bool:
 
 def pipe_incidence(ends: torch.Tensor, num_nodes: int):
     """Node -> incident pipe-end lists of the class pipes, for the gather form of the pipe head's input gradient:
-    ``(inc_ptr int32 [N+1], inc int32 [2P], inc_ell int32 [N, 8] or None)`` on the device of ``ends``, entry =
-    pipe << 1 | end, grouped by node in (pipe, end) order; ``inc_ell`` is the same lists padded with -1 to 8 slots per
-    node (None if some node touches more than 8 pipe ends).  Host work, once per model (the detector caches it next to
-    its other index tensors)."""
+    ``(inc_ptr int32 [N+1], inc int32 [2P])`` on the device of ``ends``, entry = pipe << 1 | end, grouped by node in
+    (pipe, end) order.  Host work, once per model (the detector caches it next to its other index tensors)."""
     e = ends.detach().cpu().numpy().astype(np.int64).reshape(-1)           # element 2 p + end = node of that pipe end
     order = np.argsort(e, kind="stable").astype(np.int32)
     cnt = np.bincount(e, minlength=num_nodes)
     ptr = np.zeros(num_nodes + 1, dtype=np.int32)
     np.cumsum(cnt, out=ptr[1:])
-    ell = None
-    if cnt.max(initial=0) <= 8:
-        ell_np = np.full((num_nodes, 8), -1, dtype=np.int32)
-        node_of = e[order]
-        ell_np[node_of, np.arange(order.size) - ptr[node_of]] = order
-        ell = torch.from_numpy(ell_np).to(ends.device)
-    return torch.from_numpy(ptr).to(ends.device), torch.from_numpy(order).to(ends.device), ell
+    return torch.from_numpy(ptr).to(ends.device), torch.from_numpy(order).to(ends.device)
 
 
 class _Heads(torch.autograd.Function):
@@ -469,7 +461,7 @@ class _Heads(torch.autograd.Function):
     writes d loss / d x exactly once: every node gathers the pool gradient and its incident pipe ends in a fixed order."""
 
     @staticmethod
-    def forward(ctx, x, ends, inc_ptr, inc, inc_ell, w1, b1, w2, drop_p, training):
+    def forward(ctx, x, ends, inc_ptr, inc, w1, b1, w2, drop_p, training):
         x = x.contiguous()
         b, n, d = x.shape
         p_cnt, h = ends.shape[0], w1.shape[0]
@@ -479,19 +471,21 @@ class _Heads(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)
         part = torch.empty(1, b, p_cnt, device=x.device, dtype=torch.float32)
         # saved for the backward: ONE BIT per hidden unit, the ReLU-and-dropout gate [Mp, H/32] (rows padded to Mp = B*P
-        # rounded up to 128).  The hidden activations themselves (1.6 GB at B = 4096) are not needed: they are linear in
-        # W1, b1 under the gate, and d w2 follows from the accumulators of the d W1 GEMM (csrc/tgrad.cu).  The test hook
-        # still asks for them.
+        # rounded up to 128), and TWO BITS per feature, sign(x_u - x_v) [Mp, 4].  The hidden activations themselves
+        # (1.6 GB at B = 4096) are not needed: they are linear in W1, b1 under the gate, and d w2 follows from the
+        # accumulators of the d W1 GEMM (csrc/tgrad.cu).  The test hook still asks for them.
         mp = (b * p_cnt + 127) // 128 * 128
         hpost = (torch.empty(mp // 32, h // 4, 32, 4, device=x.device, dtype=torch.float32)
                  if DEBUG_CAPTURE is not None else None)
         hmask = torch.empty(mp, h // 32, device=x.device, dtype=torch.int32) if need_grad else None
+        hsign = torch.empty(mp, 4, device=x.device, dtype=torch.int32) if need_grad else None
         w2v = w2.reshape(-1).contiguous()
         tok = _inst.begin("pipe_head_fwd")
         _lib.check(L.ltgnn_pipe_head_fwd(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), w1.data_ptr(),
                                          b1.data_ptr(), w2v.data_ptr(), p, new_dropout_seed() if p > 0 else 0,
                                          part.data_ptr(), None if hpost is None else hpost.data_ptr(),
-                                         None if hmask is None else hmask.data_ptr(), _stream(x)))
+                                         None if hmask is None else hmask.data_ptr(),
+                                         None if hsign is None else hsign.data_ptr(), _stream(x)))
         _inst.end(tok)
         pooled = torch.empty(b, d, device=x.device, dtype=torch.float32)
         tok = _inst.begin("mean_pool_fwd")
@@ -501,15 +495,14 @@ class _Heads(torch.autograd.Function):
             DEBUG_CAPTURE["head_live"] = unblock32(hpost, 1, b * p_cnt)[0] != 0   # (B*P, H) bool
             DEBUG_CAPTURE["head_mask_words"] = hmask[: b * p_cnt]
         if need_grad:
-            ctx.save_for_backward(x, ends, inc_ptr, inc, w1, b1, w2v, hmask)
-            ctx.inc_ell = inc_ell
+            ctx.save_for_backward(x, ends, inc_ptr, inc, w1, b1, w2v, hmask, hsign)
         # the kernel draws 16 random bits per hidden unit: its keep probability is 1 - round(p * 2^16) / 2^16
         ctx.scale = 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
         return part, pooled
 
     @staticmethod
     def backward(ctx, dpart, dpooled):
-        x, ends, inc_ptr, inc, w1, b1, w2v, hmask = ctx.saved_tensors
+        x, ends, inc_ptr, inc, w1, b1, w2v, hmask, hsign = ctx.saved_tensors
         b, n, d = x.shape
         p_cnt, h = ends.shape[0], w1.shape[0]
         dev = _dev_index(x)
@@ -519,11 +512,10 @@ class _Heads(torch.autograd.Function):
         dpooled = None if dpooled is None else dpooled.contiguous()
         ws = torch.empty(int(L.ltgnn_pipe_head_dx_ws_floats(dev, p_cnt)), device=x.device, dtype=torch.float32)
         tok = _inst.begin("pipe_head_bwd_dx")
-        _lib.check(L.ltgnn_pipe_head_bwd_dx(dev, b, n, p_cnt, d, h, x.data_ptr(), ends.data_ptr(), inc_ptr.data_ptr(),
-                                            inc.data_ptr(), None if ctx.inc_ell is None else ctx.inc_ell.data_ptr(),
-                                            w1.data_ptr(), w2v.data_ptr(), hmask.data_ptr(),
-                                            dlogit.data_ptr(), ctx.scale, None if dpooled is None else dpooled.data_ptr(),
-                                            ws.data_ptr(), dx.data_ptr(), _stream(x)))
+        _lib.check(L.ltgnn_pipe_head_bwd_dx(dev, b, n, p_cnt, d, h, inc_ptr.data_ptr(), inc.data_ptr(), w1.data_ptr(),
+                                            w2v.data_ptr(), hmask.data_ptr(), hsign.data_ptr(), dlogit.data_ptr(), ctx.scale,
+                                            None if dpooled is None else dpooled.data_ptr(), ws.data_ptr(), dx.data_ptr(),
+                                            _stream(x)))
         _inst.end(tok)
         del ws
         # parameter gradients: dW1 on tensor cores with operands formed on the fly; db1 and dw2 from the same accumulators
@@ -536,7 +528,7 @@ class _Heads(torch.autograd.Function):
                                            b1.data_ptr(), w2v.data_ptr(), hmask.data_ptr(), dlogit.data_ptr(), ctx.scale,
                                            dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), ws.data_ptr(), _stream(x)))
         _inst.end(tok)
-        return dx, None, None, None, None, dw1, db1, dw2, None, None
+        return dx, None, None, None, dw1, db1, dw2, None, None
 
 
 def heads(x: torch.Tensor, ends: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, drop_p: float,
@@ -547,7 +539,7 @@ def heads(x: torch.Tensor, ends: torch.Tensor, w1: torch.Tensor, b1: torch.Tenso
     _check_act(x.contiguous(), "x")
     if incidence is None:
         incidence = pipe_incidence(ends, x.shape[1])
-    return _Heads.apply(x, ends, incidence[0], incidence[1], incidence[2], w1, b1, w2, drop_p, training)
+    return _Heads.apply(x, ends, incidence[0], incidence[1], w1, b1, w2, drop_p, training)
 
 
 # ----------------------------------------------------------------------------------------------
