@@ -171,13 +171,13 @@ int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_t D, const 
  *   of the pipe head given dlogit [B*P], summed over the pipe ends at node i in the order of the incidence lists
  *   inc_ptr int32 [N+1], inc int32 [2P] (entry = pipe << 1 | end, grouped by node): a gather, bit-reproducible, dX is
  *   written exactly once.  The node states are not read: hmask and hsign carry everything the forward knew.
- *   ws: ltgnn_pipe_head_dx_ws_floats(device, P) floats.
+ *   ws: ltgnn_pipe_head_dx_ws_floats(device, N, P) floats.
  * mean_pool_fwd / mean_pool_bwd_fill: pooled[b,:] = mean_i X[b,i,:];  dX[b,i,:] = dpooled[b,:] / N.
  */
 int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const float* X,
                         const int32_t* ends, const float* W1, const float* b1, const float* w2, float drop_p,
                         uint64_t drop_seed, float* part, float* hpost, uint32_t* hmask, uint32_t* hsign, void* stream);
-int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t P);
+int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t N, int32_t P);
 int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H, const int32_t* inc_ptr,
                            const int32_t* inc, const float* W1, const float* w2, const uint32_t* hmask,
                            const uint32_t* hsign, const float* dlogit, float gate_scale, const float* dpooled, float* ws,

@@ -277,7 +277,10 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
 }  // namespace hf
 
 // ------------------------------------------------------------------ backward (input gradient)
-// A[row, j] = d loss / d pre[row, j] = dlogit[row] * scale * w2[j] * live[row, j]
+// d loss / d pre[row, j] = g[row] * w2[j] * live[row, j] with g = dlogit * scale is rank one up to the 0 / 1 gate, so
+//      dfeat[row, c] = g[row] * sum_j live[row, j] * (w2[j] * W1[j, c]):
+// the A operand is the gate itself (exact in TF32: no lo copy, two MMAs per K step instead of three), the resident B
+// operand is W1 with its rows scaled by w2, and g multiplies the accumulator row in the epilogue.
 struct DpreLoader {
     const uint4* hmask;    // [Mp] rows of 128 bits: hidden unit j of a row is live <=> bit 31 - j % 32 of word j / 32
     const float* dlogit;   // [M]
@@ -285,51 +288,89 @@ struct DpreLoader {
     float scale;
 };
 
-// dfeat[row, 0:3D] = dpre[row, :] W1 goes back to the two end nodes: +u for the h_u block, +v for the h_v block,
-// +-sign(h_u - h_v) for the |.| block (torch: d|x| = sign(x), 0 at 0; the signs come as 2 bits per feature from the
-// forward, `hsign` -- re-reading the node states for them cost a third of this kernel).  Several pipes share a node, and
-// the reference adds them with index_add_ (atomics on a GPU).  Here the sum is a GATHER in a fixed order, so the gradient
-// is bit-reproducible: a CTA works through whole windows; the epilogue warps park the per-pipe-end rows of the window in a
-// CTA-private scratch (2P x 64 floats, reused window after window: it lives in L2) at the position the end has in the
-// node-sorted incidence list, so the ends of a node are contiguous.  When the window is complete the scratch comes back
-// through 1-D bulk copies (TMA) in chunks of whole nodes, double-buffered in the shared memory the epilogue's transpose
-// patches occupy during the tiles, and every node adds its rows in list order:
+// dfeat goes back to the two end nodes: +u for the h_u block, +v for the h_v block, +-sign(h_u - h_v) for the |.| block
+// (torch: d|x| = sign(x), 0 at 0; the signs come as 2 bits per feature from the forward, `hsign` -- re-reading the node
+// states for them cost a third of this kernel).  Several pipes share a node, and the reference adds them with index_add_
+// (atomics on a GPU).  Here the sum is a GATHER in a fixed order, so the gradient is bit-reproducible: a CTA works through
+// whole windows; the epilogue warps park the per-pipe-end rows of the window in a CTA-private scratch (reused window
+// after window: it lives in L2) at the position the end has in the node-sorted incidence list, so the ends of a node are
+// contiguous.  When the window is complete the scratch comes back through 1-D bulk copies (TMA) in chunks of whole nodes
+// and every node adds its rows in list order:
 //     dx[b, i, :] = dpooled[b, :] / N + sum over the pipe ends at node i,        written exactly once
-// (the mean-pool gradient rides along: no separate fill pass, no read-modify-write of dx).  A per-thread gather from L2
-// (round 2's first version) was latency bound: 45 000 clocks per window against ~7 000 for the bulk copies.
+// (the mean-pool gradient rides along: no separate fill pass, no read-modify-write of dx).
 //
-// Same warp roles as the forward kernel.  The epilogue warps (two per TMEM lane quadrant, 32 of the 64 node
-// features each) turn the row-per-thread accumulator blocks into 128-byte row segments through the swizzled
-// shared-memory patch, so that the scratch stores touch 4 full lines per instruction instead of 32 partial ones.
+// The gather must not sit on the epilogue warps' critical path: done by them at the end of every window it cost as much
+// as the GEMM (45 000 clocks per window as a per-thread gather from L2; still 20 000 with bulk copies, the loop around
+// them and the refill of the drained MMA pipeline), and done by the loader warps in between their tiles it held up the A
+// operand.  So the scratch is double-buffered by window parity and four GATHER warps work on window w - 1 while the tiles
+// of window w are in flight (chunks are warp-private: no barrier inside the gather).  The staging buffers do not fit next
+// to a resident [192 x 128] hi + lo weight, so a CTA owns one HALF of the 64 node features (32 columns of each of the
+// three blocks: B is [96 x 128], 96 KB) and two CTAs share a window range.
+//
+//   warps 0-3   LOADERS   thread = pipe row = TMEM lane: gate bits -> 0 / 1 floats -> tcgen05.st, four K blocks per tile
+//                         into a ring two tiles deep
+//   warp  4     MMA       elected lane, A from tensor memory, B resident
+//   warps 5-8   EPILOGUE  one per TMEM lane quadrant: u + s c and v - s c of its 32 pipe rows; row-per-thread accumulator
+//                         blocks become 128-byte row segments through the swizzled shared-memory patch (scratch stores
+//                         touch 4 full lines per instruction, not 32 partial ones)
+//   warps 9-12  GATHER    bulk copies scratch -> shared memory, node sums, dx
 namespace hb {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
-constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 8, kThreads = (kLdWarps + 1 + kEpWarps) * 32;  // 13 warps: 128 regs
-constexpr int kK = 128, kN = 192, kStages = 2, kStageCols = 64;
+constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 4, kGaWarps = 4;
+constexpr int kThreads = (kLdWarps + 1 + kEpWarps + kGaWarps) * 32;  // 13 warps: 128 registers
+constexpr int kK = 128, kHalf = 32, kN = 3 * kHalf, kStages = 8, kStageCols = 32;  // A ring: two tiles deep
 constexpr uint32_t kScrBytes = 4096;
-constexpr uint32_t kCapRows = kEpWarps * kScrBytes / 2 / (kD * 4);  // pipe-end rows per gather buffer (two buffers): 64
+constexpr uint32_t kRowBytes = kHalf * 4;                    // one pipe end's share of this CTA: 128 B
+constexpr uint32_t kBufs = 2 * kGaWarps, kCapRows = 88;   // gather buffers: two per gather warp, 11 KB each
+constexpr uint32_t kBufBytes = kCapRows * kRowBytes;      // (a chunk: <= 32 nodes, <= 88 pipe ends)
+constexpr uint32_t kTblWords = 2048;           // shared-memory copy of the chunk table and of inc_ptr, when they fit
+constexpr int kH4 = kHalf / 4;
 
-__device__ __forceinline__ void ep_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpWarps * 32) : "memory"); }
-
-// end_pos[2 p + end] = position of that pipe end in the node-sorted incidence list `inc` (its inverse permutation)
-__global__ void invert_incidence_kernel(const int32_t* __restrict__ inc, int32_t* __restrict__ end_pos, int n) {
+// Index tables of the gather, rebuilt per call (microseconds):
+//   end_pos[2 p + end] = position of that pipe end in the node-sorted incidence list `inc` (its inverse permutation)
+//   chunks: tbl[0] = number of chunks C, tbl[1 .. C + 1] = first node of every chunk (tbl[C + 1] = N); a chunk is a run
+//   of at most kCapNodes nodes with at most kCapRows pipe ends (a node with more ends than that is a chunk of its own)
+__global__ void __launch_bounds__(256)
+prep_incidence_kernel(const int32_t* __restrict__ inc_ptr, const int32_t* __restrict__ inc, int32_t* __restrict__ end_pos,
+                      int32_t* __restrict__ tbl, int n_ends, uint32_t N) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) end_pos[__ldg(inc + e)] = e;
+    if (e < n_ends) end_pos[__ldg(inc + e)] = e;
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const uint32_t lane = threadIdx.x;
+        uint32_t n0 = 0, c = 0;
+        while (n0 < N) {
+            if (lane == 0) tbl[1 + c] = static_cast<int32_t>(n0);
+            const uint32_t r0 = static_cast<uint32_t>(__ldg(inc_ptr + n0)), i = n0 + 1 + lane;
+            const uint32_t re = i <= N ? static_cast<uint32_t>(__ldg(inc_ptr + i)) : 0xffffffffu;
+            const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, i <= N && re - r0 <= kCapRows));
+            n0 += cnt ? cnt : 1;
+            ++c;
+        }
+        if (lane == 0) {
+            tbl[1 + c] = static_cast<int32_t>(N);
+            tbl[0] = static_cast<int32_t>(c);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
 pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const int2* __restrict__ end_pos,
-                        const int32_t* __restrict__ inc_ptr, const uint2* __restrict__ hsign,
-                        const float4* __restrict__ dpooled, float4* __restrict__ scratch, uint32_t P, uint32_t N, uint32_t B,
-                        const float* __restrict__ W1) {
+                        const int32_t* __restrict__ tbl, const int32_t* __restrict__ inc_ptr,
+                        const uint2* __restrict__ hsign, const float4* __restrict__ dpooled, float4* __restrict__ scratch,
+                        uint32_t P, uint32_t N, uint32_t B, const float* __restrict__ W1) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2], bar_gather[2];
+    __shared__ uint64_t bar_full[kStages], bar_empty[kStages], bar_tfull[2], bar_tempty[2], bar_gather[kBufs];
+    __shared__ uint64_t bar_wdone[2], bar_wfree[2];   // scratch of window parity p: complete (epilogue) / gathered
     __shared__ uint32_t tmem_base_s;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* b_hi = smem;  // B[n = feature column (192)][k = hidden unit (128)] = W1[k][n]
+    uint8_t* b_hi = smem;  // B[n][k] = w2[k] * W1[k][column n of this CTA's half], n = 32 * block + feature
     uint8_t* b_lo = b_hi + kN * kK * 4;
     uint8_t* scr_patch = b_lo + kN * kK * 4;
+    uint8_t* gbuf = scr_patch + kEpWarps * kScrBytes;
+    int32_t* tbl_s = reinterpret_cast<int32_t*>(gbuf + kBufs * kBufBytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t fh = blockIdx.x & 1;  // which half of the node features this CTA produces
 
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
@@ -340,78 +381,72 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
             mbar_init(&bar_tempty[a], kEpWarps);
-            mbar_init(&bar_gather[a], 1);
+        }
+        for (uint32_t b = 0; b < kBufs; ++b) mbar_init(&bar_gather[b], 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar_wdone[a], kEpWarps);
+            mbar_init(&bar_wfree[a], kGaWarps);
         }
         fence_mbar_init();
     }
-    rowgemm_ts::fill_b(b_hi, b_lo, W1, kN, 1, kK, kN, tid, kThreads);
+    // the gather's index tables (first_node -> inc_ptr -> rows: dependent loads) fit shared memory for any graph this
+    // head is used on
+    const uint32_t n_chunks = static_cast<uint32_t>(__ldg(tbl));
+    const bool tbl_fits = n_chunks + 2 + N + 1 <= kTblWords;
+    if (tbl_fits) {
+        for (uint32_t i = tid; i < n_chunks + 1; i += kThreads) tbl_s[i] = __ldg(tbl + 1 + i);
+        for (uint32_t i = tid; i <= N; i += kThreads) tbl_s[n_chunks + 1 + i] = __ldg(inc_ptr + i);
+    }
+    const int32_t* first_node = tbl_fits ? tbl_s : tbl + 1;
+    const int32_t* node_ptr = tbl_fits ? tbl_s + n_chunks + 1 : inc_ptr;
+    for (int i = tid; i < kN * kK; i += kThreads) {   // resident B, K-major SW128, hi / lo
+        const int k = i / kN, n = i - k * kN;
+        const float w = __ldg(W1 + static_cast<size_t>(k) * (3 * kD) + (n >> 5) * kD + fh * kHalf + (n & 31)) * __ldg(loader.w2 + k);
+        const float hi = tf32_hi(w), lo = w - hi;
+        const uint32_t off = sw128_offset(n, k >> 2, kN) + (k & 3) * 4;
+        *reinterpret_cast<float*>(b_hi + off) = hi;
+        *reinterpret_cast<float*>(b_lo + off) = lo;
+    }
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
     const uint32_t acc_base = tmem_base, a_base = tmem_base + 2 * kN;
-    // each CTA owns a contiguous range of windows; a window is T tiles of 128 pipe rows (the last one padded)
+    // two CTAs (the two feature halves) share a contiguous range of windows; a window is T tiles of 128 pipe rows
     const uint32_t T = (P + 127) / 128;
-    const uint32_t per_cta = (B + gridDim.x - 1) / gridDim.x;
-    const uint32_t w_begin = min(blockIdx.x * per_cta, B), w_end = min(w_begin + per_cta, B);
+    const uint32_t n_ranges = gridDim.x >> 1;
+    const uint32_t per_cta = (B + n_ranges - 1) / n_ranges;
+    const uint32_t w_begin = min((blockIdx.x >> 1) * per_cta, B), w_end = min(w_begin + per_cta, B);
     const uint32_t n_tiles = (w_end - w_begin) * T;
 
+    // scratch: [window parity][2 P pipe ends, node-sorted][8] float4 per CTA
+    float4* scr_cta = scratch + static_cast<size_t>(blockIdx.x) * 2 * P * 2 * kH4;
+    const size_t scr_par = static_cast<size_t>(P) * 2 * kH4;
     if (warp < kLdWarps) {
-        // The four loader warps (thread = pipe row = TMEM lane) emit the four 32-wide K blocks of every tile into the
-        // two A slots in turn.  A row needs 16 bytes of gate bits and one dlogit: fetched one tile ahead.
         const int quad = warp & 3;
         const uint32_t st_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
-        const float* w2 = loader.w2;
         uint32_t stage = 0;
         uint4 m_next = make_uint4(0, 0, 0, 0);
-        float g_next = 0.f;
         auto fetch = [&](uint32_t t) {
             const uint32_t w = w_begin + t / T, p = (t % T) * 128 + quad * 32 + lane;
-            if (t < n_tiles && p < P) {
-                const size_t row = static_cast<size_t>(w) * P + p;
-                m_next = __ldg(loader.hmask + row);
-                g_next = __ldg(loader.dlogit + row) * loader.scale;
-            } else {
-                m_next = make_uint4(0, 0, 0, 0);
-                g_next = 0.f;
-            }
+            m_next = (t < n_tiles && p < P) ? __ldg(loader.hmask + static_cast<size_t>(w) * P + p) : make_uint4(0, 0, 0, 0);
         };
         fetch(0);
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint4 m = m_next;
-            const float g = g_next;
             fetch(t + 1);
-            const uint32_t words[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll 1
             for (int kg = 0; kg < 4; ++kg) {
-                // the 32 operand values of this K block are formed BEFORE the slot is waited for
-                const uint32_t bits = words[kg];
-                float v[32];
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 wv = __ldg(reinterpret_cast<const float4*>(w2) + kg * 8 + j4);
-                    v[4 * j4 + 0] = (bits >> (31 - 4 * j4)) & 1u ? g * wv.x : 0.f;
-                    v[4 * j4 + 1] = (bits >> (30 - 4 * j4)) & 1u ? g * wv.y : 0.f;
-                    v[4 * j4 + 2] = (bits >> (29 - 4 * j4)) & 1u ? g * wv.z : 0.f;
-                    v[4 * j4 + 3] = (bits >> (28 - 4 * j4)) & 1u ? g * wv.w : 0.f;
-                }
-                const uint32_t slot = stage & 1;
-                mbar_wait_relaxed(&bar_empty[slot], ((stage >> 1) & 1) ^ 1);
+                const uint32_t slot = stage & (kStages - 1);
+                mbar_wait_relaxed(&bar_empty[slot], ((stage / kStages) & 1) ^ 1);   // the MMA that read it two tiles ago is done
                 ++stage;
                 fence_after_sync();
-                const uint32_t st_addr = st_base + slot * kStageCols;
+                const uint32_t bits = kg == 0 ? m.x : (kg == 1 ? m.y : (kg == 2 ? m.z : m.w));
+                float v[32];
 #pragma unroll
-                for (int c = 0; c < 32; c += 8) {
-                    float hi[8], lo[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        hi[j] = tf32_hi(v[c + j]);
-                        lo[j] = v[c + j] - hi[j];
-                    }
-                    tmem_st8(st_addr + c, hi);
-                    tmem_st8(st_addr + 32 + c, lo);
-                }
+                for (int j = 0; j < 32; ++j) v[j] = static_cast<int32_t>(bits << j) < 0 ? 1.f : 0.f;
+                rowgemm_ts::tmem_st32(st_base + slot * kStageCols, v);
                 rowgemm_ts::tmem_wait_st();
                 fence_before_sync();
                 __syncwarp();
@@ -428,17 +463,16 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
             const uint32_t d = acc_base + a * kN;
 #pragma unroll 1
             for (uint32_t kg = 0; kg < 4; ++kg) {
-                const uint32_t stage = 4 * t + kg, slot = stage & 1;
-                mbar_wait_relaxed(&bar_full[slot], (stage >> 1) & 1);
+                const uint32_t stage = 4 * t + kg, slot = stage & (kStages - 1);
+                mbar_wait_relaxed(&bar_full[slot], (stage / kStages) & 1);
                 fence_after_sync();
                 if (elect_one()) {
-                    const uint32_t a_hi = a_base + slot * kStageCols, a_lo = a_hi + 32;
+                    const uint32_t a_op = a_base + slot * kStageCols;
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k) {
                         const uint32_t boff = kg * kg_units + 2 * k;
-                        rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (kg == 0 && k == 0) ? 0u : 1u);
-                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
-                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
+                        rowgemm_ts::mma_tf32_ts(d, a_op + 8 * k, bl + boff, idesc, (kg == 0 && k == 0) ? 0u : 1u);
+                        rowgemm_ts::mma_tf32_ts(d, a_op + 8 * k, bh + boff, idesc, 1u);
                     }
                     commit(&bar_empty[slot]);
                     if (kg == 3) commit(&bar_tfull[a]);
@@ -446,125 +480,147 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
                 __syncwarp();
             }
         }
-    } else {
-        const int q = warp & 3, half = (warp - kMmaWarp - 1) >> 2;  // TMEM lane quadrant = warp % 4
-        const patch::Patch patch(scr_patch + (warp - kMmaWarp - 1) * kScrBytes, lane);
-        const int sub = lane >> 3, ch = lane & 7;
-        const int et = (warp - kMmaWarp - 1) * 32 + lane;           // 0..255 among the epilogue threads
-        float4* scr = scratch + static_cast<size_t>(blockIdx.x) * P * 2 * kD4;   // [2 P pipe ends, node-sorted][16] float4
+    } else if (warp > kMmaWarp + kEpWarps) {
+        // ---- gather: this warp owns chunks j, j + 4, ... of every window and two staging buffers; a chunk's bulk copy
+        // travels while the previous chunk is added up; 8 lanes = the 128 bytes of a node, 4 nodes per pass
+        const uint32_t j = static_cast<uint32_t>(warp - kMmaWarp - kEpWarps - 1);
+        const uint32_t n_win = w_end - w_begin;
+        const uint32_t own = n_chunks > j ? (n_chunks - j + kGaWarps - 1) / kGaWarps : 0;   // chunks per window
         const float inv_n = 1.f / static_cast<float>(N);
-        uint32_t gph[2] = {0, 0};                                   // phases of the two gather buffers
-        // sign words of this lane's 8 row segments (rows p0 + 4 k + sub, features [32 half, +32)), fetched one tile ahead
+        const uint32_t f = lane & 7;
+        uint8_t* my_buf = gbuf + 2 * j * kBufBytes;
+        uint64_t* my_bar = bar_gather + 2 * j;
+        uint32_t cnt = 0;                                     // chunks so far: buffer = cnt & 1, phase = (cnt >> 1) & 1
+        auto chunk_rows = [&](uint32_t k, uint32_t& n0, uint32_t& n1, uint32_t& r0, uint32_t& r1) {
+            const uint32_t c = j + k * kGaWarps;
+            n0 = static_cast<uint32_t>(first_node[c]);
+            n1 = static_cast<uint32_t>(first_node[c + 1]);
+            r0 = static_cast<uint32_t>(node_ptr[n0]);
+            r1 = static_cast<uint32_t>(node_ptr[n1]);
+        };
+        auto issue = [&](uint32_t k, uint32_t idx, const float4* scr) {
+            uint32_t n0, n1, r0, r1;
+            chunk_rows(k, n0, n1, r0, r1);
+            if (lane == 0) {
+                uint64_t* bar = my_bar + (idx & 1);
+                if (r1 > r0 && r1 - r0 <= kCapRows) {
+                    const uint32_t bytes = (r1 - r0) * kRowBytes;
+                    fence_proxy_async_smem();   // my reads of this buffer (two chunks ago), before the async proxy refills it
+                    mbar_arrive_expect_tx(bar, bytes);
+                    bulk_load(my_buf + (idx & 1) * kBufBytes, scr + static_cast<size_t>(r0) * kH4, bytes, bar);
+                } else {
+                    mbar_arrive(bar);   // nothing to stage (no pipe ends, or one node above the cap): keeps the phase in step
+                }
+            }
+        };
+        for (uint32_t win = 0; win < n_win; ++win) {
+            const uint32_t w = w_begin + win;
+            float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dpooled) {
+                const float4 pl = __ldg(dpooled + static_cast<size_t>(w) * kD4 + fh * kH4 + f);
+                base = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
+            }
+            const float4* scr = scr_cta + (win & 1) * scr_par;
+            mbar_wait_relaxed(&bar_wdone[win & 1], (win >> 1) & 1);   // the epilogue has parked all rows of the window
+            if (own) issue(0, cnt, scr);
+            for (uint32_t k = 0; k < own; ++k, ++cnt) {
+                __syncwarp();
+                if (k + 1 < own) issue(k + 1, cnt + 1, scr);
+                uint32_t n0, n1, r0, r1;
+                chunk_rows(k, n0, n1, r0, r1);
+                const bool staged = r1 > r0 && r1 - r0 <= kCapRows;
+                mbar_wait(my_bar + (cnt & 1), (cnt >> 1) & 1);
+                const float4* stage = reinterpret_cast<const float4*>(my_buf + (cnt & 1) * kBufBytes) + f;
+                for (uint32_t node = n0 + (lane >> 3); node < n1; node += 4) {
+                    const uint32_t e0 = static_cast<uint32_t>(node_ptr[node]), e1 = static_cast<uint32_t>(node_ptr[node + 1]);
+                    float4 acc = base;
+                    for (uint32_t e = e0; e < e1; ++e) {
+                        const float4 v = staged ? stage[(e - r0) * kH4] : __ldcg(scr + static_cast<size_t>(e) * kH4 + f);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                    stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + fh * kH4 + f, acc);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_wfree[win & 1]);   // this warp is done with the window's scratch
+        }
+    } else {
+        const int e_warp = warp - kMmaWarp - 1;
+        const int q = warp & 3;                                     // TMEM lane quadrant = warp % 4
+        const patch::Patch patch(scr_patch + e_warp * kScrBytes, lane);
+        const int sub = lane >> 3, ch = lane & 7;
+        // per tile, fetched one tile ahead: g of this thread's row, and the sign words of the 8 row segments this lane
+        // holds after the transpose (rows p0 + 4 k + sub)
+        float g_next = 0.f;
         uint2 sg_next[8];
-        auto fetch_signs = [&](uint32_t t) {
-            const uint32_t w = w_begin + t / T, p = (t % T) * 128 + q * 32 + sub;
+        auto fetch = [&](uint32_t t) {
+            const uint32_t w = w_begin + t / T, p0 = (t % T) * 128 + q * 32;
+            const bool live = t < n_tiles;
+            g_next = (live && p0 + lane < P) ? __ldg(loader.dlogit + static_cast<size_t>(w) * P + p0 + lane) * loader.scale : 0.f;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                sg_next[k] = (t < n_tiles && p + 4 * k < P) ? __ldg(hsign + (static_cast<size_t>(w) * P + p + 4 * k) * 2 + half)
+                sg_next[k] = (live && p0 + 4 * k + sub < P) ? __ldg(hsign + (static_cast<size_t>(w) * P + p0 + 4 * k + sub) * 2 + fh)
                                                             : make_uint2(0u, 0u);
         };
-        fetch_signs(0);
+        fetch(0);
         for (uint32_t t = 0; t < n_tiles; ++t) {
-            const uint32_t a = t & 1;
-            const uint32_t w = w_begin + t / T, tt = t % T;
+            const uint32_t a = t & 1, widx = t / T, tt = t % T;
+            float4* scr = scr_cta + (widx & 1) * scr_par;
+            // the gather of the window that used this half of the scratch two windows ago must be over
+            if (tt == 0 && widx >= 2) mbar_wait(&bar_wfree[widx & 1], ((widx >> 1) - 1) & 1);
             const uint32_t p0 = tt * 128 + q * 32;                  // first pipe of this warp's 32 rows
             const int2 pos_l = p0 + lane < P ? __ldg(end_pos + p0 + lane) : make_int2(-1, -1);
+            const float g = g_next;
             uint2 sg[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) sg[k] = sg_next[k];
-            fetch_signs(t + 1);
+            fetch(t + 1);
             mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
             fence_after_sync();
-            const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16) + 32 * half;
-            auto pull32 = [&](uint32_t col, float4 (&g)[8]) {
+            const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16);
+            auto pull32 = [&](uint32_t col, float4 (&out)[8]) {
                 float v[32];
                 tmem_ld32(taddr + col, v);
-                patch::transpose_out(patch, v, g);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= g;
+                patch::transpose_out(patch, v, out);
             };
             // feature 4 ch + i of the half sits at bit 31 - (4 ch + i) of the pos / neg words
             auto signed_c = [&](float c, const uint2& s2, int i) {
                 const uint32_t sh = 4 * ch + i;
                 return static_cast<int32_t>(s2.x << sh) < 0 ? c : (static_cast<int32_t>(s2.y << sh) < 0 ? -c : 0.f);
             };
-            float4 gc[8], ga[8];
-            pull32(2 * kD, gc);  // d / d |x_u - x_v|  ->  +- sign
+            float4 gc4[8], ga[8];
+            pull32(2 * kHalf, gc4);  // d / d |x_u - x_v|  ->  +- sign
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                gc[k].x = signed_c(gc[k].x, sg[k], 0); gc[k].y = signed_c(gc[k].y, sg[k], 1);
-                gc[k].z = signed_c(gc[k].z, sg[k], 2); gc[k].w = signed_c(gc[k].w, sg[k], 3);
+                gc4[k].x = signed_c(gc4[k].x, sg[k], 0); gc4[k].y = signed_c(gc4[k].y, sg[k], 1);
+                gc4[k].z = signed_c(gc4[k].z, sg[k], 2); gc4[k].w = signed_c(gc4[k].w, sg[k], 3);
             }
-            pull32(0, ga);       // d / d x_u
+            pull32(0, ga);           // d / d x_u
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int pu = __shfl_sync(0xffffffffu, pos_l.x, 4 * k + sub);
-                if (pu >= 0)
-                    __stcg(scr + static_cast<size_t>(pu) * kD4 + half * 8 + ch,
-                           make_float4(ga[k].x + gc[k].x, ga[k].y + gc[k].y, ga[k].z + gc[k].z, ga[k].w + gc[k].w));
+                const int ps = __shfl_sync(0xffffffffu, pos_l.x, 4 * k + sub);
+                if (ps >= 0)
+                    __stcg(scr + static_cast<size_t>(ps) * kH4 + ch,
+                           make_float4(ga[k].x + gc4[k].x, ga[k].y + gc4[k].y, ga[k].z + gc4[k].z, ga[k].w + gc4[k].w));
             }
-            pull32(kD, ga);      // d / d x_v
+            pull32(kHalf, ga);       // d / d x_v
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const int pv = __shfl_sync(0xffffffffu, pos_l.y, 4 * k + sub);
-                if (pv >= 0)
-                    __stcg(scr + static_cast<size_t>(pv) * kD4 + half * 8 + ch,
-                           make_float4(ga[k].x - gc[k].x, ga[k].y - gc[k].y, ga[k].z - gc[k].z, ga[k].w - gc[k].w));
+                const int ps = __shfl_sync(0xffffffffu, pos_l.y, 4 * k + sub);
+                if (ps >= 0)
+                    __stcg(scr + static_cast<size_t>(ps) * kH4 + ch,
+                           make_float4(ga[k].x - gc4[k].x, ga[k].y - gc4[k].y, ga[k].z - gc4[k].z, ga[k].w - gc4[k].w));
             }
             if (tt == T - 1) {
-                // The window is complete.  Chunks of whole nodes (at most 32 nodes and kCapRows pipe ends; every warp
-                // derives the same chunk sequence from inc_ptr) come back from the scratch by bulk copy into the two
-                // buffers in turn; 16 threads = the 256 bytes of a node add its rows in list order.
-                fence_proxy_async_all();   // my scratch stores and patch accesses, before the async proxy touches either
-                ep_bar();
-                const int f = et & 15;
-                const float4 pl = dpooled ? __ldg(dpooled + static_cast<size_t>(w) * kD4 + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 base = make_float4(pl.x * inv_n, pl.y * inv_n, pl.z * inv_n, pl.w * inv_n);
-                auto bounds = [&](uint32_t n0, uint32_t& n1, uint32_t& r0, uint32_t& r1) {
-                    r0 = static_cast<uint32_t>(__ldg(inc_ptr + n0));
-                    const uint32_t i = n0 + 1 + lane;
-                    const uint32_t re = i <= N ? static_cast<uint32_t>(__ldg(inc_ptr + i)) : 0xffffffffu;
-                    uint32_t cnt = __popc(__ballot_sync(0xffffffffu, i <= N && re - r0 <= kCapRows));
-                    cnt = cnt ? cnt : 1;   // a node with more than kCapRows ends goes alone, straight from L2
-                    n1 = n0 + cnt;
-                    r1 = __shfl_sync(0xffffffffu, re, cnt - 1);
-                };
-                auto issue = [&](uint32_t buf, uint32_t r0, uint32_t r1) {
-                    if (et == 0 && r1 > r0 && r1 - r0 <= kCapRows) {
-                        const uint32_t bytes = (r1 - r0) * kD * 4;
-                        mbar_arrive_expect_tx(&bar_gather[buf], bytes);
-                        bulk_load(scr_patch + buf * (kCapRows * kD * 4), scr + static_cast<size_t>(r0) * kD4, bytes, &bar_gather[buf]);
-                    }
-                };
-                uint32_t n0 = 0, n1, r0, r1;
-                bounds(0, n1, r0, r1);
-                issue(0, r0, r1);
-                for (uint32_t c = 0; n0 < N; ++c) {
-                    const uint32_t buf = c & 1;
-                    uint32_t m1 = n1, s0 = r1, s1 = r1;
-                    if (n1 < N) {
-                        bounds(n1, m1, s0, s1);
-                        issue(buf ^ 1, s0, s1);
-                    }
-                    const bool staged = r1 > r0 && r1 - r0 <= kCapRows;
-                    if (staged) {
-                        mbar_wait(&bar_gather[buf], gph[buf] & 1);
-                        ++gph[buf];
-                    }
-                    const float4* stage = reinterpret_cast<const float4*>(scr_patch + buf * (kCapRows * kD * 4)) + f;
-                    for (uint32_t node = n0 + (et >> 4); node < n1; node += (kEpWarps * 32) >> 4) {
-                        const uint32_t e0 = static_cast<uint32_t>(__ldg(inc_ptr + node)), e1 = static_cast<uint32_t>(__ldg(inc_ptr + node + 1));
-                        float4 acc = base;
-                        for (uint32_t e = e0; e < e1; ++e) {
-                            const float4 v = staged ? stage[(e - r0) * kD4] : __ldcg(scr + static_cast<size_t>(e) * kD4 + f);
-                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                        }
-                        stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + f, acc);
-                    }
-                    ep_bar();  // this buffer may be refilled; after the last chunk: the next window may overwrite the scratch
-                    n0 = n1; n1 = m1; r0 = s0; r1 = s1;
-                }
+                // my rows of this window are parked: hand the scratch to the gather warps
+                fence_proxy_async_all();   // my scratch stores, before the async proxy reads them
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_wdone[widx & 1]);
             }
         }
     }
@@ -670,9 +726,11 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
     return LTGNN_OK;
 }
 
-extern "C" int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t P) {
-    const DeviceInfo* di = device_info(device);  // positions of the 2 P pipe ends + per CTA: one window's 2 P rows of 64
-    return di ? (2ll * P + 3) / 4 * 4 + static_cast<int64_t>(di->sm_count) * 2 * P * kD : -1;
+// index tables (2 P end positions, the chunk table: 1 + N + 1 entries) + per CTA two windows' 2 P rows of 32 floats
+static int64_t dx_table_words(int32_t N, int32_t P) { return (2ll * P + N + 2 + 3) / 4 * 4; }
+extern "C" int64_t ltgnn_pipe_head_dx_ws_floats(int device, int32_t N, int32_t P) {
+    const DeviceInfo* di = device_info(device);
+    return di ? dx_table_words(N, P) + static_cast<int64_t>(di->sm_count) * 2 * 2 * P * hb::kHalf : -1;
 }
 
 extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t D, int32_t H,
@@ -693,19 +751,21 @@ extern "C" int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t 
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_bwd_dx: device is sm_%d%d, need sm_100",
                   di->cc_major, di->cc_minor);
     LTGNN_REQUIRE(B * P < (1ll << 31) && B * N < (1ll << 28), LTGNN_E_SHAPE, "pipe_head_bwd_dx: B*P or B*N too large");
-    const size_t smem = 1024 + 2ull * hb::kN * hb::kK * 4 + hb::kEpWarps * hb::kScrBytes;
+    const size_t smem = 1024 + 2ull * hb::kN * hb::kK * 4 + hb::kEpWarps * hb::kScrBytes + hb::kBufs * hb::kBufBytes + hb::kTblWords * 4;
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "pipe_head_bwd_dx: %zu B of shared memory", smem);
     LTGNN_USE_DEVICE(device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     int32_t* end_pos = reinterpret_cast<int32_t*>(ws);
-    float* scratch = ws + (2ll * P + 3) / 4 * 4;
-    hb::invert_incidence_kernel<<<(2 * P + 255) / 256, 256, 0, stream>>>(inc, end_pos, 2 * P);
+    int32_t* tbl = end_pos + 2 * P;
+    float* scratch = ws + dx_table_words(N, P);
+    hb::prep_incidence_kernel<<<(2 * P + 255) / 256, 256, 0, stream>>>(inc_ptr, inc, end_pos, tbl, 2 * P, static_cast<uint32_t>(N));
     LTGNN_CUDA_TRY(cudaGetLastError());
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(hb::pipe_head_bwd_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    const int grid = static_cast<int>(B < di->sm_count ? B : di->sm_count);
-    hb::pipe_head_bwd_dx_kernel<<<grid, hb::kThreads, smem, stream>>>(
-        ld, reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(end_pos), inc_ptr,
+    // two CTAs (feature halves) per window range
+    const int64_t ranges = B < di->sm_count / 2 ? B : di->sm_count / 2;
+    hb::pipe_head_bwd_dx_kernel<<<static_cast<int>(2 * ranges), hb::kThreads, smem, stream>>>(
+        ld, reinterpret_cast<float4*>(dX), reinterpret_cast<const int2*>(end_pos), tbl, inc_ptr,
         reinterpret_cast<const uint2*>(hsign), reinterpret_cast<const float4*>(dpooled), reinterpret_cast<float4*>(scratch),
         static_cast<uint32_t>(P), static_cast<uint32_t>(N), static_cast<uint32_t>(B), W1);
     LTGNN_CUDA_TRY(cudaGetLastError());

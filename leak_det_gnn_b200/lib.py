@@ -45,7 +45,7 @@ SIGNATURES = {
                                     c_uint64, c_void_p, c_void_p, c_void_p]),
     "ltgnn_pipe_head_fwd": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_float, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "ltgnn_pipe_head_dx_ws_floats": (c_int64, [c_int, c_int32]),
+    "ltgnn_pipe_head_dx_ws_floats": (c_int64, [c_int, c_int32, c_int32]),
     "ltgnn_pipe_head_bwd_dx": (c_int, [c_int, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                        c_void_p]),

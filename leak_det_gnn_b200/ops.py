@@ -510,7 +510,7 @@ class _Heads(torch.autograd.Function):
         dlogit = dpart[0].contiguous().view(-1)
         dx = torch.empty_like(x)
         dpooled = None if dpooled is None else dpooled.contiguous()
-        ws = torch.empty(int(L.ltgnn_pipe_head_dx_ws_floats(dev, p_cnt)), device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(L.ltgnn_pipe_head_dx_ws_floats(dev, n, p_cnt)), device=x.device, dtype=torch.float32)
         tok = _inst.begin("pipe_head_bwd_dx")
         _lib.check(L.ltgnn_pipe_head_bwd_dx(dev, b, n, p_cnt, d, h, inc_ptr.data_ptr(), inc.data_ptr(), w1.data_ptr(),
                                             w2v.data_ptr(), hmask.data_ptr(), hsign.data_ptr(), dlogit.data_ptr(), ctx.scale,
