@@ -135,7 +135,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef LTGNN_DEBUG_WAIT
+        if (++spins > (1u << 22)) {
+            if ((threadIdx.x & 31) == 0) printf("mbar_wait timeout: block %d warp %d bar %x parity %u\n", blockIdx.x, threadIdx.x >> 5, smem_u32(bar), parity);
+            __trap();
+        }
+#else
         if (++spins > (1u << 26)) __trap();
+#endif
     }
 }
 // Same for waits that are NOT on the critical path (a producer running ahead of its consumer): the explicit
@@ -153,7 +160,14 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) break;
+#ifdef LTGNN_DEBUG_WAIT
+        if (++spins > (1u << 16)) {
+            if ((threadIdx.x & 31) == 0) printf("mbar_wait_relaxed timeout: block %d warp %d bar %x parity %u\n", blockIdx.x, threadIdx.x >> 5, smem_u32(bar), parity);
+            __trap();
+        }
+#else
         if (++spins > (1u << 24)) __trap();
+#endif
     }
 }
 

@@ -310,20 +310,21 @@ struct DpreLoader {
 //   warps 0-3   LOADERS   thread = pipe row = TMEM lane: gate bits -> 0 / 1 floats -> tcgen05.st, four K blocks per tile
 //                         into a ring two tiles deep
 //   warp  4     MMA       elected lane, A from tensor memory, B resident
-//   warps 5-8   EPILOGUE  one per TMEM lane quadrant: u + s c and v - s c of its 32 pipe rows; row-per-thread accumulator
-//                         blocks become 128-byte row segments through the swizzled shared-memory patch (scratch stores
-//                         touch 4 full lines per instruction, not 32 partial ones)
-//   warps 9-12  GATHER    bulk copies scratch -> shared memory, node sums, dx
+//   warps 5-12  EPILOGUE  two per TMEM lane quadrant, one per accumulator (even / odd tiles): u + s c and v - s c of its
+//                         32 pipe rows; row-per-thread accumulator blocks become 128-byte row segments through the
+//                         swizzled shared-memory patch (scratch stores touch 4 full lines per instruction, not 32
+//                         partial ones)
+//   warps 13-15 GATHER    bulk copies scratch -> shared memory, node sums, dx   (16 warps: still 128 registers each)
 namespace hb {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
-constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 4, kGaWarps = 4;
-constexpr int kThreads = (kLdWarps + 1 + kEpWarps + kGaWarps) * 32;  // 13 warps: 128 registers
+constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 4, kGaWarps = 7;
+constexpr int kThreads = (kLdWarps + 1 + kEpWarps + kGaWarps) * 32;  // 16 warps: 128 registers
 constexpr int kK = 128, kHalf = 32, kN = 3 * kHalf, kStages = 8, kStageCols = 32;  // A ring: two tiles deep
 constexpr uint32_t kScrBytes = 4096;
 constexpr uint32_t kRowBytes = kHalf * 4;                    // one pipe end's share of this CTA: 128 B
-constexpr uint32_t kBufs = 2 * kGaWarps, kCapRows = 88;   // gather buffers: two per gather warp, 11 KB each
-constexpr uint32_t kBufBytes = kCapRows * kRowBytes;      // (a chunk: <= 32 nodes, <= 88 pipe ends)
+constexpr uint32_t kBufs = 2 * kGaWarps, kCapRows = 56;   // gather buffers: two per gather warp, 7 KB each
+constexpr uint32_t kBufBytes = kCapRows * kRowBytes;      // (a chunk: <= 32 nodes, <= 56 pipe ends)
 constexpr uint32_t kTblWords = 2048;           // shared-memory copy of the chunk table and of inc_ptr, when they fit
 constexpr int kH4 = kHalf / 4;
 
@@ -380,7 +381,7 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], kEpWarps);
+            mbar_init(&bar_tempty[a], 4);   // the four quadrant warps that drain this accumulator
         }
         for (uint32_t b = 0; b < kBufs; ++b) mbar_init(&bar_gather[b], 1);
         for (int a = 0; a < 2; ++a) {
@@ -531,14 +532,45 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
                 const bool staged = r1 > r0 && r1 - r0 <= kCapRows;
                 mbar_wait(my_bar + (cnt & 1), (cnt >> 1) & 1);
                 const float4* stage = reinterpret_cast<const float4*>(my_buf + (cnt & 1) * kBufBytes) + f;
-                for (uint32_t node = n0 + (lane >> 3); node < n1; node += 4) {
-                    const uint32_t e0 = static_cast<uint32_t>(node_ptr[node]), e1 = static_cast<uint32_t>(node_ptr[node + 1]);
-                    float4 acc = base;
-                    for (uint32_t e = e0; e < e1; ++e) {
-                        const float4 v = staged ? stage[(e - r0) * kH4] : __ldcg(scr + static_cast<size_t>(e) * kH4 + f);
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                // the row ranges of this lane's nodes are read one pass ahead; two rows per trip, two partial sums (the
+                // order of the additions stays a fixed function of the graph)
+                uint32_t node = n0 + (lane >> 3);
+                uint32_t e0 = 0, e1 = 0;
+                if (node < n1) {
+                    e0 = static_cast<uint32_t>(node_ptr[node]);
+                    e1 = static_cast<uint32_t>(node_ptr[node + 1]);
+                }
+                while (node < n1) {
+                    const uint32_t nxt = node + 4;
+                    uint32_t f0 = 0, f1 = 0;
+                    if (nxt < n1) {
+                        f0 = static_cast<uint32_t>(node_ptr[nxt]);
+                        f1 = static_cast<uint32_t>(node_ptr[nxt + 1]);
                     }
-                    stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + fh * kH4 + f, acc);
+                    float4 acc = base, acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (staged) {
+                        const float4* row = stage + (e0 - r0) * kH4;
+                        uint32_t n = e1 - e0;
+                        for (; n >= 2; n -= 2, row += 2 * kH4) {
+                            const float4 v0 = row[0], v1 = row[kH4];
+                            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                            acc2.x += v1.x; acc2.y += v1.y; acc2.z += v1.z; acc2.w += v1.w;
+                        }
+                        if (n) {
+                            const float4 v0 = row[0];
+                            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+                        }
+                    } else {
+                        for (uint32_t e = e0; e < e1; ++e) {
+                            const float4 v = __ldcg(scr + static_cast<size_t>(e) * kH4 + f);
+                            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                        }
+                    }
+                    stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + fh * kH4 + f,
+                               make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w));
+                    node = nxt;
+                    e0 = f0;
+                    e1 = f1;
                 }
             }
             __syncwarp();
@@ -547,9 +579,11 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
     } else {
         const int e_warp = warp - kMmaWarp - 1;
         const int q = warp & 3;                                     // TMEM lane quadrant = warp % 4
+        constexpr uint32_t kGroups = kEpWarps / 4;                  // 1: every warp takes every tile; 2: even / odd tiles
+        const uint32_t par = static_cast<uint32_t>(e_warp >> 2);    // this warp's group
         const patch::Patch patch(scr_patch + e_warp * kScrBytes, lane);
         const int sub = lane >> 3, ch = lane & 7;
-        // per tile, fetched one tile ahead: g of this thread's row, and the sign words of the 8 row segments this lane
+        // per tile, fetched one of this warp's tiles ahead: g of this thread's row, and the sign words of the 8 row segments this lane
         // holds after the transpose (rows p0 + 4 k + sub)
         float g_next = 0.f;
         uint2 sg_next[8];
@@ -562,19 +596,20 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
                 sg_next[k] = (live && p0 + 4 * k + sub < P) ? __ldg(hsign + (static_cast<size_t>(w) * P + p0 + 4 * k + sub) * 2 + fh)
                                                             : make_uint2(0u, 0u);
         };
-        fetch(0);
+        fetch(par);
         for (uint32_t t = 0; t < n_tiles; ++t) {
             const uint32_t a = t & 1, widx = t / T, tt = t % T;
             float4* scr = scr_cta + (widx & 1) * scr_par;
             // the gather of the window that used this half of the scratch two windows ago must be over
             if (tt == 0 && widx >= 2) mbar_wait(&bar_wfree[widx & 1], ((widx >> 1) - 1) & 1);
+            if (t % kGroups == par) {
             const uint32_t p0 = tt * 128 + q * 32;                  // first pipe of this warp's 32 rows
             const int2 pos_l = p0 + lane < P ? __ldg(end_pos + p0 + lane) : make_int2(-1, -1);
             const float g = g_next;
             uint2 sg[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) sg[k] = sg_next[k];
-            fetch(t + 1);
+            fetch(t + kGroups);
             mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
             fence_after_sync();
             const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16);
@@ -615,6 +650,7 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
                 if (ps >= 0)
                     __stcg(scr + static_cast<size_t>(ps) * kH4 + ch,
                            make_float4(ga[k].x - gc4[k].x, ga[k].y - gc4[k].y, ga[k].z - gc4[k].z, ga[k].w - gc4[k].w));
+            }
             }
             if (tt == T - 1) {
                 // my rows of this window are parked: hand the scratch to the gather warps
