@@ -532,45 +532,49 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
                 const bool staged = r1 > r0 && r1 - r0 <= kCapRows;
                 mbar_wait(my_bar + (cnt & 1), (cnt >> 1) & 1);
                 const float4* stage = reinterpret_cast<const float4*>(my_buf + (cnt & 1) * kBufBytes) + f;
-                // the row ranges of this lane's nodes are read one pass ahead; two rows per trip, two partial sums (the
-                // order of the additions stays a fixed function of the graph)
+                // The row range of a lane's node is read one pass ahead.  The row loop is warp-uniform (it runs to the
+                // longest of the pass's four nodes, shorter ones add zeros): as a per-lane loop the compiler unrolled it
+                // into a thicket of divergent remainders, 120 instructions and 650 clocks per pass.  Two rows per trip,
+                // two partial sums: the order of the additions is a fixed function of the graph.
                 uint32_t node = n0 + (lane >> 3);
-                uint32_t e0 = 0, e1 = 0;
+                uint32_t e0 = 0, rows = 0;
                 if (node < n1) {
                     e0 = static_cast<uint32_t>(node_ptr[node]);
-                    e1 = static_cast<uint32_t>(node_ptr[node + 1]);
+                    rows = static_cast<uint32_t>(node_ptr[node + 1]) - e0;
                 }
-                while (node < n1) {
+                const uint32_t n_pass = (n1 - n0 + 3) >> 2;
+#pragma unroll 1
+                for (uint32_t ps = 0; ps < n_pass; ++ps) {
                     const uint32_t nxt = node + 4;
-                    uint32_t f0 = 0, f1 = 0;
+                    uint32_t f0 = 0, frows = 0;
                     if (nxt < n1) {
                         f0 = static_cast<uint32_t>(node_ptr[nxt]);
-                        f1 = static_cast<uint32_t>(node_ptr[nxt + 1]);
+                        frows = static_cast<uint32_t>(node_ptr[nxt + 1]) - f0;
                     }
                     float4 acc = base, acc2 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (staged) {
-                        const float4* row = stage + (e0 - r0) * kH4;
-                        uint32_t n = e1 - e0;
-                        for (; n >= 2; n -= 2, row += 2 * kH4) {
-                            const float4 v0 = row[0], v1 = row[kH4];
+                        const uint32_t longest = __reduce_max_sync(0xffffffffu, rows);
+                        const float4* row = stage + static_cast<int32_t>(e0 - r0) * kH4;   // (never read when rows == 0)
+#pragma unroll 1
+                        for (uint32_t i = 0; i < longest; i += 2, row += 2 * kH4) {
+                            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                            if (i < rows) v0 = row[0];
+                            if (i + 1 < rows) v1 = row[kH4];
                             acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
                             acc2.x += v1.x; acc2.y += v1.y; acc2.z += v1.z; acc2.w += v1.w;
                         }
-                        if (n) {
-                            const float4 v0 = row[0];
-                            acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-                        }
                     } else {
-                        for (uint32_t e = e0; e < e1; ++e) {
+                        for (uint32_t e = e0; e < e0 + rows; ++e) {
                             const float4 v = __ldcg(scr + static_cast<size_t>(e) * kH4 + f);
                             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                         }
                     }
-                    stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + fh * kH4 + f,
-                               make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w));
+                    if (node < n1)
+                        stg_stream(dx + (static_cast<size_t>(w) * N + node) * kD4 + fh * kH4 + f,
+                                   make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w));
                     node = nxt;
                     e0 = f0;
-                    e1 = f1;
+                    rows = frows;
                 }
             }
             __syncwarp();
