@@ -168,9 +168,9 @@ int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_t D, const 
  *   hsign (optional; uint32 [Mp, 4]) receives sign(x_u - x_v) as two bits per feature: words 2 g / 2 g + 1 of a row hold
  *   the `> 0` / `< 0` bits of features 32 g .. 32 g + 31 (feature j at bit 31 - j % 32).  The backward needs both.
  * pipe_head_bwd_dx: dX[b, i, :] = dpooled[b, :] / N (the mean-pool gradient; dpooled may be null) + the input gradient
- *   of the pipe head given dlogit [B*P], summed over the pipe ends at node i in the order of the incidence lists
- *   inc_ptr int32 [N+1], inc int32 [2P] (entry = pipe << 1 | end, grouped by node): a gather, bit-reproducible, dX is
- *   written exactly once.  The node states are not read: hmask and hsign carry everything the forward knew.
+ *   of the pipe head given dlogit [B*P], summed over the pipe ends at node i -- the entries of the incidence lists
+ *   inc_ptr int32 [N+1], inc int32 [2P] (entry = pipe << 1 | end, grouped by node) -- in a fixed order (the even and
+ *   the odd positions of a node's list as two partial sums): a gather, bit-reproducible, dX is written exactly once.  The node states are not read: hmask and hsign carry everything the forward knew.
  *   ws: ltgnn_pipe_head_dx_ws_floats(device, N, P) floats.
  * mean_pool_fwd / mean_pool_bwd_fill: pooled[b,:] = mean_i X[b,i,:];  dX[b,i,:] = dpooled[b,:] / N.
  */

@@ -114,6 +114,21 @@ def full(rep: str, out: str, key: str = "") -> None:
         data = json.loads(tp.read_text()) if tp.exists() else {}
         data.setdefault(key, {}).update({k: v for k, v in traffic.items() if v is not None})
         tp.write_text(json.dumps(data, indent=1))
+        # the per-op table bench.py reads (profiles/ncu_traffic.json): kernel -> the instrument name of the op it implements
+        op_of = {"gcn_layer_fwd_kernel": "gcn_layer_fwd", "pipe_head_fwd_kernel": "pipe_head_fwd", "mean_pool_kernel": "mean_pool_fwd",
+                 "pipe_head_bwd_dx_kernel": "pipe_head_bwd_dx", "tgrad<HeadLive,HeadFeatSlice,mt=1,seg=-2>": "pipe_head_bwd_w",
+                 "tgrad<StackedRows,StackedRows,mt=1,seg=-1>": "wgrad_tc", "linear_ts_kernel": "linear_tc",
+                 "spmm_staged_kernel<epi=0,gate=1>": "spmm_fused_bwd", "spmm_staged_kernel<epi=1,gate=0>": "spmm_fused_fwd",
+                 "node_init_fwd_kernel": "node_init_fwd", "gate_extract_kernel": "node_init_bwd"}
+        bp = REPO / "profiles" / "ncu_traffic.json"
+        table = json.loads(bp.read_text()) if bp.exists() else {}
+        ops = table.setdefault(key, {})
+        for k, v in traffic.items():
+            if v is not None and k in op_of:
+                ops[op_of[k]] = v
+        table["_note_r02"] = ("GNN-stack entries refreshed from profiles/r02*_kernels_ncu_full.csv (ncu --set full, per launch); "
+                              "node_init_bwd = its streaming pass (gate_extract_kernel) only; GRU entries are round 1's (kernels unchanged)")
+        bp.write_text(json.dumps(table, indent=1))
 
 
 if __name__ == "__main__":
