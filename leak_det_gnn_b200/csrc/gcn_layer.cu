@@ -211,7 +211,7 @@ gcn_layer_fwd_kernel(const Params p) {
         const int g = lane >> 3, q = lane & 7;       // aggregation: row within the warp's group of 4, float4 of the slice
         for (uint32_t wi = 0; wi < n_win; ++wi) {
             const int64_t b = w_first + static_cast<int64_t>(wi) * w_step;
-            mbar_wait(&bar_acc_full, wi & 1);
+            mbar_wait_relaxed(&bar_acc_full, wi & 1);   // 24 warps polling would take issue slots from the four loader warps
             fence_after_sync();
           for (int sl = 0; sl < p.n_slices; ++sl) {
             for (int t = dj; t < p.T; t += kCons / 4) {

@@ -7,7 +7,7 @@ from collections import Counter, OrderedDict
 from pathlib import Path
 
 LIB = Path(__file__).resolve().parents[1] / "leak_det_gnn_b200" / "libltgnn.so"
-WATCH = ["UTCHMMA", "UTCBAR", "UTMALDG", "LDTM", "STTM", "SYNCS", "LDGSTS", "ATOM", "RED", "LDL", "STL", "HMMA", "FFMA"]
+WATCH = ["UTCHMMA", "UTCBAR", "UTMALDG", "UBLKCP", "LDTM", "STTM", "SYNCS", "LDGSTS", "ATOM", "RED", "LDL", "STL", "HMMA", "FFMA"]
 
 
 def main() -> None:
@@ -29,7 +29,7 @@ def main() -> None:
             cur["total"] += 1
             if op in WATCH:
                 cur[op] += 1
-    print(f"# {LIB.name}: SASS instruction counts per kernel (cuobjdump -sass); UTCHMMA = tcgen05.mma, UTMALDG = TMA load,")
+    print(f"# {LIB.name}: SASS instruction counts per kernel (cuobjdump -sass); UTCHMMA = tcgen05.mma, UTMALDG = TMA tensor load, UBLKCP = TMA 1-D bulk copy,")
     print("# LDTM / STTM = tcgen05.ld / st (tensor memory), UTCBAR = tcgen05.commit, LDGSTS = cp.async, ATOM / RED = global atomics,")
     print("# LDL / STL = register spills")
     print(f"{'kernel':112s} {'total':>7s} " + " ".join(f"{w:>7s}" for w in WATCH))
