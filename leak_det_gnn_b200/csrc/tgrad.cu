@@ -278,7 +278,7 @@ extern "C" int ltgnn_pipe_head_bwd_w(int device, int64_t B, int32_t N, int32_t P
     HeadFeatSlice x{reinterpret_cast<const float4*>(X), reinterpret_cast<const int2*>(ends), static_cast<uint32_t>(P),
                     static_cast<uint32_t>(N), P >= 2 ? (~0ull / static_cast<uint64_t>(P)) + 1 : 0ull};
     int grid = 0;
-    int rc = tgrad::launch<1, 4, 2, -2>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
+    int rc = tgrad::launch<1, 4, 2, -4>(device, g, x, ws, M, No, &grid, stream, "pipe_head_bwd_w");
     if (rc) return rc;
     for (int sl = 0; sl < kHeadSlices; ++sl) {  // A[:, 64 sl : 64 sl + 64] = sum over the row ranges of slice sl
         rc = tgrad::gather(ws, grid, No, 0, H, 0, No, A + sl * No, 3 * D, 0, stream, tgrad::kMo, sl, kHeadSlices);

@@ -162,8 +162,9 @@ __host__ inline size_t smem_bytes(int No, int mt, bool exact_g = false, int stag
 // kSeg = -1: the accurate form for narrow results (No <= 64, kMT = 1; the GCN layers): the totals stay in REGISTERS
 // of eight read-out warps (32 columns each), so a flush is one tensor-memory read of `main` -- tensor memory moves
 // 64 B / clock / SM, and the load / add / store of a total that lives there costs three times that.
-// kSeg = -2: the same with `main` flushed every SECOND chunk (64 rows = 8 truncating accumulations instead of 4: the
-// bias doubles to ~4e-7 of the sum, still 25 x inside the 1e-5 bar) -- for kernels whose pace is the tensor-memory read.
+// kSeg = -2, -4: the same with `main` flushed every second / fourth chunk (64 / 128 rows = 8 / 16 truncating accumulations
+// instead of 4: the bias grows to ~4e-7 / 9e-7 of the sum, still inside the 1e-5 bar) -- for kernels whose pace is the
+// tensor-memory read.  With an exact G the cross products are flushed too (width 2 No per temporary).
 template <class GLoader, class XLoader, int kMT, int kGJ = 4 * kMT, int kXJ = 8, int kSeg = 0>
 __global__ void __launch_bounds__(kSeg < 0 ? kThreadsReg : kThreads, 1)
 tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, uint32_t M, int No, uint32_t tmem_cols,
@@ -210,8 +211,9 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
     const uint32_t nbuf_mask = (1u << nbuf_log2) - 1;  // 2 or 4 temporaries in rotation
     // tensor memory: total [kMT][No] | cross [kMT][No] | main [nbuf][nb]   (nb = 64 or 32 columns per block)
     // (register-total form: cross [No] | main [nbuf][nb])
+    // (register-total form with an exact G: [nbuf][main No | cross No] -- one MMA of width 2 No per K step, see below)
     const uint32_t t_cross = kSeg < 0 ? tmem_base : tmem_base + kMT * No;
-    const uint32_t t_tmp = kSeg < 0 ? tmem_base + No : tmem_base + 2 * kMT * No;
+    const uint32_t t_tmp = kSeg < 0 ? (kExactG ? tmem_base : tmem_base + No) : tmem_base + 2 * kMT * No;
 
     // contiguous range of row chunks per CTA
     constexpr uint32_t kSl = slices_of<XLoader>::value;
@@ -378,18 +380,25 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
             if (elect_one()) {
                 const uint32_t so = s * st16, g_h = gh0 + so, g_l = gl0 + so, x_h = xh0 + so, x_l = xl0 + so;
                 const uint32_t d_main = t_tmp + a * nb;
+                if constexpr (kExactG) {
+                    // G x [X hi | X lo]: the two copies of X are adjacent in the stage, so they are ONE operand of width
+                    // 2 No -- G is fetched from shared memory once per K step instead of twice (an SS-form MMA this narrow
+                    // is paced by its operand fetch), and the warp issues half as many instructions.  The cross products
+                    // land in the upper No columns of the temporary and are flushed with the main ones.
+                    const uint32_t idesc2 = idesc_tf32_mn(kMo, 2 * No);
 #pragma unroll
-                for (uint32_t k = 0; k < kChunk / 8; ++k) {
-                    if constexpr (!kExactG) {
+                    for (uint32_t k = 0; k < kChunk / 8; ++k)
+                        mma_tf32_mn(d_main, g_h + 64 * k, x_h + 64 * k, idesc2, (k || in_f) ? 1u : 0u);
+                } else {
+#pragma unroll
+                    for (uint32_t k = 0; k < kChunk / 8; ++k) {
                         mma_tf32_mn(t_cross, g_l + 64 * k, x_h + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
                         mma_tf32_mn(t_cross, g_h + 64 * k, x_l + 64 * k, idesc, 1u);
-                    } else {
-                        mma_tf32_mn(t_cross, g_h + 64 * k, x_l + 64 * k, idesc, (n == 0 && k == 0) ? 0u : 1u);
                     }
-                }
 #pragma unroll
-                for (uint32_t k = 0; k < kChunk / 8; ++k)
-                    mma_tf32_mn(d_main, g_h + 64 * k, x_h + 64 * k, idesc, (k || in_f) ? 1u : 0u);
+                    for (uint32_t k = 0; k < kChunk / 8; ++k)
+                        mma_tf32_mn(d_main, g_h + 64 * k, x_h + 64 * k, idesc, (k || in_f) ? 1u : 0u);
+                }
                 if (in_f == kFl - 1 || n + 1 == n_local) commit(&bar_tmp_full[a]);
                 commit(&bar_empty[s]);
             }
@@ -484,6 +493,18 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                 float m0[16], m1[16];
                 tmem_ld16_nowait(t_tmp + lane_off + a * nb + 32 * half, m0);
                 tmem_ld16_nowait(t_tmp + lane_off + a * nb + 32 * half + 16, m1);
+                if constexpr (kExactG) {   // the flushed cross products sit No columns further; read in two rounds (registers)
+                    tmem_wait_ld();
+                    tmem_pin16(m0);
+                    tmem_pin16(m1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        tot[j] += m0[j];
+                        tot[16 + j] += m1[j];
+                    }
+                    tmem_ld16_nowait(t_tmp + lane_off + a * nb + No + 32 * half, m0);
+                    tmem_ld16_nowait(t_tmp + lane_off + a * nb + No + 32 * half + 16, m1);
+                }
                 tmem_wait_ld();
                 tmem_pin16(m0);
                 tmem_pin16(m1);
@@ -496,7 +517,7 @@ tgrad_kernel(const GLoader gload, const XLoader xload, float* __restrict__ ws, u
                     tot[16 + j] += m1[j];
                 }
             }
-            if (n_local) {  // the last `main` commit also covers every cross MMA issued before it
+            if (n_local && !kExactG) {  // the last `main` commit also covers every cross MMA issued before it
                 float c0v[16], c1v[16];
                 tmem_ld16(t_cross + lane_off + 32 * half, c0v);
                 tmem_ld16(t_cross + lane_off + 32 * half + 16, c1v);
@@ -641,13 +662,14 @@ int launch(int device, const GLoader& g, const XLoader& x, float* ws, int64_t M,
     static_assert(kSeg >= 0 || kMT == 1, "the register-total form handles one accumulator tile");
     LTGNN_REQUIRE(kSeg >= 0 || No <= 64, LTGNN_E_SHAPE, "%s: the register-total form needs No <= 64, got %d", who, No);
     const int left = 512 - 2 * No * kMT;
-    const int nb = kSeg < 0 ? No : (left >= 2 * 64 ? 64 : 32);
+    constexpr bool kExact = exact_of<GLoader>::value;
+    const int nb = kSeg < 0 ? (kExact ? 2 * No : No) : (left >= 2 * 64 ? 64 : 32);
     int nbuf = kSeg > 0 ? 2 : (kSeg < 0 ? kMaxBuf : left / nb);
     nbuf = nbuf >= 4 ? 4 : nbuf;  // rotation counts are powers of two
     if (nbuf == 3) nbuf = 2;
     LTGNN_REQUIRE(nbuf >= 2 && left >= 0, LTGNN_E_SHAPE, "%s: 2 x %d accumulator columns leave no room in tensor memory", who,
                   No * kMT);
-    const uint32_t need = kSeg > 0 ? 2 * No * kMT : (kSeg < 0 ? No + nbuf * nb : 2 * No * kMT + nbuf * nb);
+    const uint32_t need = kSeg > 0 ? 2 * No * kMT : (kSeg < 0 ? (kExact ? 0 : No) + nbuf * nb : 2 * No * kMT + nbuf * nb);
     while (cols < need) cols <<= 1;
     constexpr int kSl = slices_of<XLoader>::value;
     const int grid = di->sm_count / kSl * kSl;
