@@ -310,21 +310,26 @@ struct DpreLoader {
 //   warps 0-3   LOADERS   thread = pipe row = TMEM lane: gate bits -> 0 / 1 floats -> tcgen05.st, four K blocks per tile
 //                         into a ring two tiles deep
 //   warp  4     MMA       elected lane, A from tensor memory, B resident
-//   warps 5-12  EPILOGUE  two per TMEM lane quadrant, one per accumulator (even / odd tiles): u + s c and v - s c of its
-//                         32 pipe rows; row-per-thread accumulator blocks become 128-byte row segments through the
-//                         swizzled shared-memory patch (scratch stores touch 4 full lines per instruction, not 32
-//                         partial ones)
-//   warps 13-15 GATHER    bulk copies scratch -> shared memory, node sums, dx   (16 warps: still 128 registers each)
+//   warps 5-8   EPILOGUE  one per TMEM lane quadrant, thread = pipe row: g * (u + s c) and g * (v - s c) of its 32
+//                         features (the row's own 64 sign bits come with one load, the shifts are constants), written as
+//                         two 128-byte rows into a shared-memory staging area (row pitch 144 B: row-per-thread stores and
+//                         8-lanes-per-row loads are both conflict-free), read back as coalesced row segments and stored
+//                         to their node-sorted scratch positions, 4 full lines per instruction.  (The first version
+//                         transposed the three accumulator blocks separately and applied the signs afterwards: 850
+//                         instructions per tile and warp, and the four epilogue warps were the kernel's pace.  One
+//                         128-byte bulk store per row instead of the read-back was slower still: 1.21 ms.)
+//   warps 9-15  GATHER    bulk copies scratch -> shared memory, node sums, dx   (16 warps: still 128 registers each)
 namespace hb {
 using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
 constexpr int kLdWarps = 4, kMmaWarp = 4, kEpWarps = 4, kGaWarps = 7;
 constexpr int kThreads = (kLdWarps + 1 + kEpWarps + kGaWarps) * 32;  // 16 warps: 128 registers
 constexpr int kK = 128, kHalf = 32, kN = 3 * kHalf, kStages = 8, kStageCols = 32;  // A ring: two tiles deep
-constexpr uint32_t kScrBytes = 4096;
+constexpr uint32_t kRowPitch = 144;                          // staging row: 128 B + 16 (bank spread)
+constexpr uint32_t kScrBytes = 2 * 32 * kRowPitch;           // per epilogue warp: the u rows, then the v rows
 constexpr uint32_t kRowBytes = kHalf * 4;                    // one pipe end's share of this CTA: 128 B
-constexpr uint32_t kBufs = 2 * kGaWarps, kCapRows = 56;   // gather buffers: two per gather warp, 7 KB each
-constexpr uint32_t kBufBytes = kCapRows * kRowBytes;      // (a chunk: <= 32 nodes, <= 56 pipe ends)
+constexpr uint32_t kBufs = 2 * kGaWarps, kCapRows = 48;   // gather buffers: two per gather warp, 6 KB each
+constexpr uint32_t kBufBytes = kCapRows * kRowBytes;      // (a chunk: <= 32 nodes, <= 48 pipe ends)
 constexpr uint32_t kTblWords = 2048;           // shared-memory copy of the chunk table and of inc_ptr, when they fit
 constexpr int kH4 = kHalf / 4;
 
@@ -585,20 +590,27 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
         const int q = warp & 3;                                     // TMEM lane quadrant = warp % 4
         constexpr uint32_t kGroups = kEpWarps / 4;                  // 1: every warp takes every tile; 2: even / odd tiles
         const uint32_t par = static_cast<uint32_t>(e_warp >> 2);    // this warp's group
-        const patch::Patch patch(scr_patch + e_warp * kScrBytes, lane);
+        uint8_t* row_u = scr_patch + e_warp * kScrBytes + lane * kRowPitch;   // this thread's two staging rows
+        uint8_t* row_v = row_u + 32 * kRowPitch;
         const int sub = lane >> 3, ch = lane & 7;
-        // per tile, fetched one of this warp's tiles ahead: g of this thread's row, and the sign words of the 8 row segments this lane
-        // holds after the transpose (rows p0 + 4 k + sub)
+        const uint8_t* seg = scr_patch + e_warp * kScrBytes + sub * kRowPitch + ch * 16;   // read-back: row 4 k + sub, chunk ch
+        // per tile, fetched one of this warp's tiles ahead: g, the scratch positions of the two ends and the 2 x 32 sign bits
+        // of this thread's pipe row
         float g_next = 0.f;
-        uint2 sg_next[8];
+        int2 pos_next = make_int2(-1, -1);
+        uint2 sg_next = make_uint2(0u, 0u);
         auto fetch = [&](uint32_t t) {
-            const uint32_t w = w_begin + t / T, p0 = (t % T) * 128 + q * 32;
-            const bool live = t < n_tiles;
-            g_next = (live && p0 + lane < P) ? __ldg(loader.dlogit + static_cast<size_t>(w) * P + p0 + lane) * loader.scale : 0.f;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                sg_next[k] = (live && p0 + 4 * k + sub < P) ? __ldg(hsign + (static_cast<size_t>(w) * P + p0 + 4 * k + sub) * 2 + fh)
-                                                            : make_uint2(0u, 0u);
+            const uint32_t w = w_begin + t / T, p = (t % T) * 128 + q * 32 + lane;
+            if (t < n_tiles && p < P) {
+                const size_t row = static_cast<size_t>(w) * P + p;
+                g_next = __ldg(loader.dlogit + row) * loader.scale;
+                pos_next = __ldg(end_pos + p);
+                sg_next = __ldg(hsign + row * 2 + fh);
+            } else {
+                g_next = 0.f;
+                pos_next = make_int2(-1, -1);
+                sg_next = make_uint2(0u, 0u);
+            }
         };
         fetch(par);
         for (uint32_t t = 0; t < n_tiles; ++t) {
@@ -607,54 +619,44 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
             // the gather of the window that used this half of the scratch two windows ago must be over
             if (tt == 0 && widx >= 2) mbar_wait(&bar_wfree[widx & 1], ((widx >> 1) - 1) & 1);
             if (t % kGroups == par) {
-            const uint32_t p0 = tt * 128 + q * 32;                  // first pipe of this warp's 32 rows
-            const int2 pos_l = p0 + lane < P ? __ldg(end_pos + p0 + lane) : make_int2(-1, -1);
-            const float g = g_next;
-            uint2 sg[8];
+                const float g = g_next;
+                const int2 pos = pos_next;
+                const uint2 sg = sg_next;    // .x: x_u > x_v, .y: x_u < x_v; feature j of the half at bit 31 - j
+                fetch(t + kGroups);
+                mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
+                fence_after_sync();
+                const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16);
+                float c[32], e[32];
+                tmem_ld32(taddr + 2 * kHalf, c);     // d / d |x_u - x_v|  ->  g * sign * c
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sg[k] = sg_next[k];
-            fetch(t + kGroups);
-            mbar_wait_relaxed(&bar_tfull[a], (t >> 1) & 1);
-            fence_after_sync();
-            const uint32_t taddr = acc_base + a * kN + (static_cast<uint32_t>(q * 32) << 16);
-            auto pull32 = [&](uint32_t col, float4 (&out)[8]) {
-                float v[32];
-                tmem_ld32(taddr + col, v);
+                for (int j = 0; j < 32; ++j) {
+                    const float gc = g * c[j];
+                    c[j] = static_cast<int32_t>(sg.x << j) < 0 ? gc : (static_cast<int32_t>(sg.y << j) < 0 ? -gc : 0.f);
+                }
+                tmem_ld32(taddr, e);                 // d / d x_u
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= g;
-                patch::transpose_out(patch, v, out);
-            };
-            // feature 4 ch + i of the half sits at bit 31 - (4 ch + i) of the pos / neg words
-            auto signed_c = [&](float c, const uint2& s2, int i) {
-                const uint32_t sh = 4 * ch + i;
-                return static_cast<int32_t>(s2.x << sh) < 0 ? c : (static_cast<int32_t>(s2.y << sh) < 0 ? -c : 0.f);
-            };
-            float4 gc4[8], ga[8];
-            pull32(2 * kHalf, gc4);  // d / d |x_u - x_v|  ->  +- sign
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(row_u + 4 * j) = make_float4(fmaf(g, e[j], c[j]), fmaf(g, e[j + 1], c[j + 1]),
+                                                                            fmaf(g, e[j + 2], c[j + 2]), fmaf(g, e[j + 3], c[j + 3]));
+                tmem_ld32(taddr + kHalf, e);         // d / d x_v
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                gc4[k].x = signed_c(gc4[k].x, sg[k], 0); gc4[k].y = signed_c(gc4[k].y, sg[k], 1);
-                gc4[k].z = signed_c(gc4[k].z, sg[k], 2); gc4[k].w = signed_c(gc4[k].w, sg[k], 3);
-            }
-            pull32(0, ga);           // d / d x_u
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(row_v + 4 * j) = make_float4(fmaf(g, e[j], -c[j]), fmaf(g, e[j + 1], -c[j + 1]),
+                                                                            fmaf(g, e[j + 2], -c[j + 2]), fmaf(g, e[j + 3], -c[j + 3]));
+                __syncwarp();
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ps = __shfl_sync(0xffffffffu, pos_l.x, 4 * k + sub);
-                if (ps >= 0)
-                    __stcg(scr + static_cast<size_t>(ps) * kH4 + ch,
-                           make_float4(ga[k].x + gc4[k].x, ga[k].y + gc4[k].y, ga[k].z + gc4[k].z, ga[k].w + gc4[k].w));
-            }
-            pull32(kHalf, ga);       // d / d x_v
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[a]);  // accumulator drained
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int ps = __shfl_sync(0xffffffffu, pos_l.y, 4 * k + sub);
-                if (ps >= 0)
-                    __stcg(scr + static_cast<size_t>(ps) * kH4 + ch,
-                           make_float4(ga[k].x - gc4[k].x, ga[k].y - gc4[k].y, ga[k].z - gc4[k].z, ga[k].w - gc4[k].w));
-            }
+                for (int k = 0; k < 8; ++k) {        // rows 4 k + sub: 8 lanes = one 128-byte row
+                    const int pu = __shfl_sync(0xffffffffu, pos.x, 4 * k + sub), pv = __shfl_sync(0xffffffffu, pos.y, 4 * k + sub);
+                    if (pu >= 0) {
+                        __stcg(scr + static_cast<size_t>(pu) * kH4 + ch, *reinterpret_cast<const float4*>(seg + 4 * k * kRowPitch));
+                        __stcg(scr + static_cast<size_t>(pv) * kH4 + ch,
+                               *reinterpret_cast<const float4*>(seg + (32 + 4 * k) * kRowPitch));
+                    }
+                }
+                __syncwarp();                        // the staging rows may be overwritten
             }
             if (tt == T - 1) {
                 // my rows of this window are parked: hand the scratch to the gather warps
