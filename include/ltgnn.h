@@ -47,6 +47,14 @@ int ltgnn_version(void);
 /* Copies the calling thread's last error message (NUL terminated) into buf; returns its length. */
 size_t ltgnn_last_error(char* buf, size_t cap);
 
+/* Device-resident dropout seed, for CUDA-graph capture of a TRAINING step (the reference draws fresh dropout masks on
+ * every call of train_detector.py:310; a captured launch would otherwise replay the drop_seed it was captured with).
+ * After ltgnn_seed_source(w), every dropout-bearing launch made FROM THE CALLING THREAD (ltgnn_node_init_fwd,
+ * ltgnn_gcn_layer_fwd, ltgnn_spmm_fused, ltgnn_pipe_head_fwd) keys its random stream with drop_seed + *w, where the
+ * 64-bit device word *w is read when the kernel runs: bump it between replays (on the stream) and every replay draws
+ * new masks.  ltgnn_seed_source(NULL) (the default) restores drop_seed alone.  The word must outlive the launches. */
+void ltgnn_seed_source(const uint64_t* dev_word);
+
 /* ---- graph handle -------------------------------------------------------------------
  * Replaces the per-forward work of detector.py:195-196 (_batchify_edge_index) and of
  * torch_geometric gcn_norm inside every GCNConv.forward (detector.py:199): the normalised

@@ -80,6 +80,10 @@ const DeviceInfo* device_info(int device);
 int reduce_parts(const float* parts, int64_t stride, float* out, int n_parts, int n, int accumulate,
                  cudaStream_t stream);
 
+// Device word the calling thread registered with ltgnn_seed_source (or nullptr): every dropout-bearing launch made from
+// that thread hands it to its kernel, which adds the word -- read when the kernel RUNS -- to its drop_seed argument.
+const uint64_t* seed_source();
+
 }  // namespace ltgnn
 
 struct ltgnn_graph {
@@ -222,6 +226,10 @@ __device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t
         k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+// seed of this launch: the drop_seed argument, plus the device-resident word of ltgnn_seed_source when one is set
+__device__ __forceinline__ uint64_t launch_seed(uint64_t seed, const uint64_t* src) {
+    return src ? seed + __ldg(reinterpret_cast<const unsigned long long*>(src)) : seed;
 }
 // inverted dropout on the float4 whose linear float4 index is `idx4`; thresh = p * 2^32
 __device__ __forceinline__ void dropout4(float4& v, uint64_t idx4, uint64_t seed, uint32_t thresh, float keep_scale) {

@@ -54,6 +54,7 @@ struct Params {
     uint32_t drop_thresh;
     float keep_scale;
     uint64_t drop_seed;
+    const uint64_t* seed_src;  // ltgnn_seed_source word or nullptr
     uint32_t off_stage, off_rowptr, off_colval, off_ring;  // byte offsets after the 1024-aligned base (W hi/lo first)
 };
 
@@ -209,6 +210,7 @@ gcn_layer_fwd_kernel(const Params p) {
         const int cw = warp - kMmaWarp - 1;          // 0 .. 23
         const int q4 = warp & 3, dj = cw >> 2;       // tensor-memory lane quadrant = warp % 4; this warp drains tiles dj, dj + 6
         const int g = lane >> 3, q = lane & 7;       // aggregation: row within the warp's group of 4, float4 of the slice
+        const uint64_t seed = launch_seed(p.drop_seed, p.seed_src);
         for (uint32_t wi = 0; wi < n_win; ++wi) {
             const int64_t b = w_first + static_cast<int64_t>(wi) * w_step;
             mbar_wait_relaxed(&bar_acc_full, wi & 1);   // 24 warps polling would take issue slots from the four loader warps
@@ -277,7 +279,7 @@ gcn_layer_fwd_kernel(const Params p) {
                 }
                 if (p.drop_thresh) {  // one Philox call (16 random bits per element) decides both float4, as in spmm.cu
                     float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    dropout8(v, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * d4), p.drop_seed, p.drop_thresh,
+                    dropout8(v, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * d4), seed, p.drop_thresh,
                              p.keep_scale);
                     a0 = make_float4(v[0], v[1], v[2], v[3]);
                     a1 = make_float4(v[4], v[5], v[6], v[7]);
@@ -358,6 +360,7 @@ extern "C" int ltgnn_gcn_layer_fwd(ltgnn_graph_t g, int64_t B, int32_t K, int32_
     p.drop_thresh = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
     p.keep_scale = 1.f / (1.f - static_cast<float>(p.drop_thresh) / 65536.f);
     p.drop_seed = drop_seed;
+    p.seed_src = seed_source();
     p.n_slots = (512 - p.T * D) / gl::kSlotCols >= gl::kMaxSlots ? gl::kMaxSlots : 2;  // a power of two
     p.off_stage = 2u * D * K * 4;
     p.off_rowptr = p.off_stage + gl::align_up(static_cast<uint32_t>(g->n) * 128, 128);

@@ -104,6 +104,12 @@ using namespace ltgnn;
 
 extern "C" int ltgnn_version(void) { return LTGNN_VERSION; }
 
+static thread_local const uint64_t* g_seed_src = nullptr;
+namespace ltgnn {
+const uint64_t* seed_source() { return g_seed_src; }
+}  // namespace ltgnn
+extern "C" void ltgnn_seed_source(const uint64_t* dev_word) { g_seed_src = dev_word; }
+
 extern "C" size_t ltgnn_last_error(char* buf, size_t cap) {
     size_t n = strlen(g_err);
     if (buf && cap) {

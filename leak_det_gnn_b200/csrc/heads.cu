@@ -37,6 +37,7 @@ struct HeadFwdEpilogue {
     uint32_t drop_thresh16;  // round(p * 2^16), 0 = no dropout
     float keep_scale;        // 1 / (1 - drop_thresh16 / 2^16)
     uint64_t drop_seed;
+    const uint64_t* seed_src;  // ltgnn_seed_source word or nullptr
     template <class Pull>
     __device__ __forceinline__ float operator()(uint32_t row, int c_begin, int c_end, Pull&& pull) const {
         float acc = 0.f;
@@ -60,8 +61,9 @@ struct HeadFwdEpilogue {
             }
             if (drop_thresh16) {
                 const uint64_t i8 = static_cast<uint64_t>(row) * (H >> 3) + (col >> 3);
-                ptx::dropout8_mask(v, i8, drop_seed, thresh_hi);
-                ptx::dropout8_mask(v + 8, i8 + 1, drop_seed, thresh_hi);
+                const uint64_t seed = ptx::launch_seed(drop_seed, seed_src);
+                ptx::dropout8_mask(v, i8, seed, thresh_hi);
+                ptx::dropout8_mask(v + 8, i8 + 1, seed, thresh_hi);
             }
             if (hmask) {
                 // v >= +0 here, so v > 0 <=> its bit pattern u != 0 <=> the top bit of -u is set; one funnel shift moves
@@ -748,7 +750,8 @@ extern "C" int ltgnn_pipe_head_fwd(int device, int64_t B, int32_t N, int32_t P, 
     const int64_t M = B * P;
     LTGNN_REQUIRE(M < (1ll << 31), LTGNN_E_SHAPE, "pipe_head_fwd: B*P too large");
     const uint32_t t16 = drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(drop_p) * 65536.0 + 0.5) : 0u;
-    HeadFwdEpilogue ep{b1, w2, part, hpost, hmask, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed};
+    HeadFwdEpilogue ep{b1, w2, part, hpost, hmask, H, t16, 1.f / (1.f - static_cast<float>(t16) / 65536.f), drop_seed,
+                       seed_source()};
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "pipe_head_fwd: device is sm_%d%d, need sm_100", di->cc_major,

@@ -26,6 +26,7 @@ struct InitParams {
     uint32_t drop_thresh;
     float keep_scale;
     uint64_t drop_seed;
+    const uint64_t* seed_src;  // ltgnn_seed_source word or nullptr
 };
 
 // ---------------------------------------- forward ----------------------------------------
@@ -83,7 +84,8 @@ node_init_fwd_kernel(const InitParams p, float* __restrict__ X0, uint32_t* __res
             *reinterpret_cast<float4*>(v) = src[0];
             *reinterpret_cast<float4*>(v + 4) = src[1];
             if (p.drop_thresh)
-                ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
+                ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), ptx::launch_seed(p.drop_seed, p.seed_src), p.drop_thresh,
+                              p.keep_scale);
             ptx::stg_stream(out + 2 * i, *reinterpret_cast<const float4*>(v));
             ptx::stg_stream(out + 2 * i + 1, *reinterpret_cast<const float4*>(v + 4));
             if (live_out) {
@@ -158,7 +160,8 @@ node_init_fwd_direct_kernel(const InitParams p, float* __restrict__ X0, uint32_t
                 for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j] + cst[c * 4 + j], 0.f);
             }
             if (p.drop_thresh)
-                ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), p.drop_seed, p.drop_thresh, p.keep_scale);
+                ptx::dropout8(v, static_cast<uint64_t>(b * p.N * d8 + i), ptx::launch_seed(p.drop_seed, p.seed_src), p.drop_thresh,
+                              p.keep_scale);
             ptx::stg_stream(out + 2 * i, *reinterpret_cast<const float4*>(v));
             ptx::stg_stream(out + 2 * i + 1, *reinterpret_cast<const float4*>(v + 4));
             if (live_out) {  // same word layout as node_init_fwd_kernel
@@ -282,7 +285,7 @@ extern "C" int ltgnn_node_init_fwd(int device, int64_t B, int32_t N, int32_t S, 
     LTGNN_REQUIRE(hs && slot && W && bias && X0, LTGNN_E_ARG, "node_init_fwd: null tensor");
     LTGNN_REQUIRE(aligned16(X0), LTGNN_E_ALIGN, "node_init_fwd: X0 must be 16-byte aligned");
     LTGNN_USE_DEVICE(device);
-    InitParams p{hs, W, bias, slot, B, N, S, ds, D, thresh_of(drop_p), scale_of(drop_p), drop_seed};
+    InitParams p{hs, W, bias, slot, B, N, S, ds, D, thresh_of(drop_p), scale_of(drop_p), drop_seed, seed_source()};
     const size_t smem = sizeof(float) * (static_cast<size_t>(ds + 1) * D + 2 * D + static_cast<size_t>(S) * ds +
                                          static_cast<size_t>(S) * D);
     LTGNN_REQUIRE(!live_out || D % 32 == 0, LTGNN_E_SHAPE, "node_init_fwd: live_out needs D %% 32 == 0 (D=%d)", D);

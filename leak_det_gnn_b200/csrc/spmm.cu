@@ -47,6 +47,7 @@ struct StagedParams {
     uint32_t drop_thresh;  // round(p * 2^16), 0 = no dropout (16 random bits per element)
     float keep_scale;      // 1 / (1 - drop_thresh / 2^16): exactly unbiased
     uint64_t drop_seed;
+    const uint64_t* seed_src;  // ltgnn_seed_source word or nullptr
     // input gate (kGate): x *= gate > 0 ? gate_scale : 0 before aggregation; column sums of the gated x
     const float* gate;
     float gate_scale;
@@ -225,7 +226,7 @@ spmm_staged_kernel(const __grid_constant__ CUtensorMap tmap, const StagedParams 
                 }
                 if (p.drop_thresh) {  // one Philox call (16 random bits per element) decides both float4
                     float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                    dropout8(v, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * p.d4), p.drop_seed,
+                    dropout8(v, static_cast<uint64_t>(base4 + static_cast<int64_t>(r0) * p.d4), launch_seed(p.drop_seed, p.seed_src),
                              p.drop_thresh, p.keep_scale);
                     a0 = make_float4(v[0], v[1], v[2], v[3]);
                     a1 = make_float4(v[4], v[5], v[6], v[7]);
@@ -291,8 +292,9 @@ template <bool kEpi, bool kGate>
 __global__ void __launch_bounds__(256)
 spmm_gather_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ colval, const float4* __restrict__ X,
                    float4* __restrict__ Y, int32_t n, int32_t d4, int64_t total, const float4* __restrict__ bias, int relu,
-                   uint32_t drop_thresh, float keep_scale, uint64_t drop_seed, const float4* __restrict__ gate,
-                   float gate_scale) {
+                   uint32_t drop_thresh, float keep_scale, uint64_t drop_seed_arg, const uint64_t* seed_src,
+                   const float4* __restrict__ gate, float gate_scale) {
+    const uint64_t drop_seed = launch_seed(drop_seed_arg, seed_src);
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
         const int64_t row = e / d4;
@@ -473,6 +475,7 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
         p.drop_thresh = f.drop_p > 0.f ? static_cast<uint32_t>(static_cast<double>(f.drop_p) * 65536.0 + 0.5) : 0u;
         p.keep_scale = 1.f / (1.f - static_cast<float>(p.drop_thresh) / 65536.f);
         p.drop_seed = f.drop_seed;
+        p.seed_src = seed_source();
         p.gate = f.gate;
         p.gate_scale = f.gate_scale;
         p.colsum_ws = f.colsum ? f.ws : nullptr;
@@ -512,7 +515,7 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
     auto launch_g = [&](auto kern) -> int {
         kern<<<static_cast<int>(blocks), 256, 0, stream>>>(
             g->rowptr[transpose], g->colval[transpose], reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
-            g->n, D / 4, total, reinterpret_cast<const float4*>(f.bias), f.relu, thresh, keep, f.drop_seed,
+            g->n, D / 4, total, reinterpret_cast<const float4*>(f.bias), f.relu, thresh, keep, f.drop_seed, seed_source(),
             reinterpret_cast<const float4*>(f.gate), f.gate_scale);
         LTGNN_CUDA_TRY(cudaGetLastError());
         return LTGNN_OK;

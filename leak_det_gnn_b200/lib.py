@@ -22,6 +22,7 @@ SPMM_AUTO, SPMM_STAGED, SPMM_GATHER = 0, 1, 2
 SIGNATURES = {
     "ltgnn_version": (c_int, []),
     "ltgnn_last_error": (c_size_t, [c_char_p, c_size_t]),
+    "ltgnn_seed_source": (None, [c_void_p]),
     "ltgnn_graph_create": (c_int, [c_int, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, POINTER(c_void_p)]),
     "ltgnn_graph_destroy": (c_int, [c_void_p]),

@@ -17,7 +17,7 @@ from . import instrument as _inst
 from . import lib as _lib
 from .graph import GCNCsr, build_gcn_csr
 
-__all__ = ["PipeGraph", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported", "pipe_incidence", "gru_encode", "gru_supported"]
+__all__ = ["PipeGraph", "device_seed", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported", "pipe_incidence", "gru_encode", "gru_supported"]
 
 
 # Test hook: when set to a dict, the autograd nodes drop the masks they saved into it (``lives``: the 1-bit ReLU-and-
@@ -158,6 +158,25 @@ def new_dropout_seed() -> int:
     """A fresh 63-bit key for one in-kernel dropout stream, drawn from torch's CPU generator so that
     ``torch.manual_seed`` makes training runs reproducible."""
     return int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+
+
+class device_seed:
+    """``with device_seed(word): ...`` -- every dropout-bearing kernel launched from this thread inside the block keys
+    its random stream with ``drop_seed + word[0]``, the int64 CUDA tensor ``word`` being read when the kernel RUNS
+    (``ltgnn_seed_source``).  This is what lets a captured CUDA graph of a training step draw fresh masks on every
+    replay (graphed.GraphedTrainStep bumps the word inside the graph)."""
+
+    def __init__(self, word: torch.Tensor) -> None:
+        if not word.is_cuda or word.dtype != torch.int64 or word.numel() != 1:
+            raise ValueError("device_seed needs a one-element int64 CUDA tensor")
+        self.word = word
+
+    def __enter__(self):
+        _lib.load().ltgnn_seed_source(ctypes.c_void_p(self.word.data_ptr()))
+        return self
+
+    def __exit__(self, *exc) -> None:
+        _lib.load().ltgnn_seed_source(None)
 
 
 def new_live_mask(b: int, n: int, d: int, device) -> torch.Tensor:

@@ -13,7 +13,9 @@ pipe_ids_in_order, num_classes, predictor_ckpt, args``; ``detector_best.ckpt`` b
 * every rank takes the indices ``rank, rank + W, ...`` of the reference's deterministic ``seed + idx`` dataset
   (models/datasets.py:489-541), so W ranks with ``--batch_size B`` reproduce one process with batch ``W * B``; gradients
   live in one flat 242 KB bucket and are averaged by ONE NCCL all-reduce per step, BEFORE the clip (parallel.py);
-* validation uses the vectorised evaluator (evaluator.py: no per-sample ``.item()``).
+* validation uses the vectorised evaluator (evaluator.py: no per-sample ``.item()``);
+* the step is one fixed launch sequence (the loader drops the last partial batch), so it is captured once and replayed as
+  a CUDA graph (graphed.py; ``--cuda_graph 0`` issues it call by call).
 
 The datasets stay the reference's own code (host-side CSV loaders, out of scope here): ``--reference_root`` is put on
 ``sys.path`` and ``models.datasets.AbruptLeakDetectorDataset`` is imported from it unchanged.  ``--synthetic N`` replaces
@@ -39,6 +41,7 @@ from torch.utils.data import DataLoader, Dataset, Subset
 from .evaluator import BUCKETS, DetectorEvaluator
 from .graph import parse_epanet_inp
 from .models import LeakDetector, NormalPredictorGRU, NormalPredictorTCN, build_residual_sequence_from_segment
+from .graphed import GraphedTrainStep
 from .parallel import FlatGradBucket, broadcast_parameters, shard_indices
 
 
@@ -73,6 +76,8 @@ def build_argparser() -> argparse.ArgumentParser:
     ap.add_argument("--synthetic", type=int, default=0, help="use N synthetic windows per epoch instead of --leak_root")
     ap.add_argument("--synthetic_sensors", type=str, default=None, help="comma-separated sensor node ids (synthetic mode)")
     ap.add_argument("--synthetic_pipes", type=int, default=0, help="number of class pipes, 0 = all [PIPES] (synthetic mode)")
+    ap.add_argument("--cuda_graph", type=int, default=1, help="1: replay the training step as a CUDA graph (graphed.py); "
+                                                              "0: one call per kernel")
     return ap
 
 
@@ -205,6 +210,9 @@ def main(argv: Optional[List[str]] = None) -> Dict[str, float]:
     evaluator = DetectorEvaluator(predictor, detector, device, l_pred=args.l_pred, l_det=args.l_det, topk=args.topk,
                                   metric_groups=("basic", "binary", "bucket"))
 
+    # the loader drops the last partial batch, so every step has one shape: capture it once (graphed.py)
+    graphed = (GraphedTrainStep(detector, opt, bucket, args.batch_size, args.l_det, predictor=predictor, l_pred=args.l_pred,
+                                grad_clip=args.grad_clip, loss_fn=loss_fn) if args.cuda_graph else None)
     best_acc, metrics = -1.0, {}
     if rank == 0:
         meta = {"inp_path": str(args.inp_path), "predictor_ckpt": str(args.predictor_ckpt), "sensor_ids": sensor_ids,
@@ -218,7 +226,11 @@ def main(argv: Optional[List[str]] = None) -> Dict[str, float]:
         running = torch.zeros((), device=device)
         seen = 0
         for it, batch in enumerate(train_loader, start=1):
-            loss = train_step(detector, predictor, bucket, opt, loss_fn, batch, device, args.l_pred, args.l_det, args.grad_clip)
+            if graphed is not None:
+                loss = graphed(batch["noisy_seg"], batch["time_seg"], torch.as_tensor(batch["label"], dtype=torch.long))
+            else:
+                loss = train_step(detector, predictor, bucket, opt, loss_fn, batch, device, args.l_pred, args.l_det,
+                                  args.grad_clip)
             running += loss * batch["noisy_seg"].size(0)     # stays on the device: the reference's per-step loss.item() sync is gone
             seen += batch["noisy_seg"].size(0)
             if rank == 0 and (it % args.log_every) == 0:
