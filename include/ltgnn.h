@@ -190,6 +190,34 @@ int ltgnn_pipe_head_bwd_dx(int device, int64_t B, int32_t N, int32_t P, int32_t 
                            const int32_t* inc, const float* W1, const float* w2, const uint32_t* hmask,
                            const uint32_t* hsign, const float* dlogit, float gate_scale, const float* dpooled, float* ws,
                            float* dX, void* stream);
+/* ---- the pipe head for node widths the fused kernels above do not take (csrc/heads_wide.cu) -------------------------
+ * Same reference lines (detector.py:76-88,204-211) at D = 128 (BASELINE configs[4]): the features are materialised,
+ * F [3][B*P][D] = h_u | h_v | |h_u - h_v|; Linear(3D, H) + ReLU runs as the three-tap gathered-row GEMM ltgnn_tcn_conv
+ * (tap t reads row t*B*P + m of F against W1[:, tD:(t+1)D]); these four streaming kernels do the rest.
+ *   ltgnn_pipe_feat_fwd   X [B,N,D], ends int32 [P,2] -> F
+ *   ltgnn_head_out_fwd    h [M,H] = relu(pre) -> (in place) hd = dropout(h);  part[m] = sum_j hd[m,j] w2[j]
+ *   ltgnn_head_out_bwd    gq[m,j] = hd[m,j] > 0 ? dlogit[m] scale : 0;  dh = gq * w2;  cs[j] = sum_m gq[m,j];
+ *                         ws: ltgnn_head_out_ws_floats(device, H) floats
+ *   ltgnn_head_wide_finish  T [3][H][D] = gq^T F[t] (three ltgnn_wgrad_tc products) -> dW1 [H,3D] = w2[j] T,
+ *                         db1 = w2 * cs,  dw2[j] = b1[j] cs[j] + sum W1[j,:] . T[:,j,:]  (the hidden layer is linear in
+ *                         W1, b1 under the gate, so dw2 needs no pass over the hidden activations)
+ *   ltgnn_pipe_feat_bwd   dX[b,n] = dpooled[b]/N (if given) + sum over the pipe ends at n, in the order of inc
+ *                         (inc_ptr int32 [N+1], inc int32 [2P]: pipe << 1 | end), of  end u: dF0[m] + s dF2[m],
+ *                         end v: dF1[m] - s dF2[m],  s = sign(x_u - x_v).  dX written once; deterministic.
+ */
+int ltgnn_pipe_feat_fwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, const float* X, const int32_t* ends,
+                        float* F, void* stream);
+int ltgnn_head_out_fwd(int device, int64_t M, int32_t H, float* h, const float* w2, float drop_p, uint64_t drop_seed,
+                       float* part, void* stream);
+int64_t ltgnn_head_out_ws_floats(int device, int32_t H);
+int ltgnn_head_out_bwd(int device, int64_t M, int32_t H, const float* hd, const float* w2, const float* dlogit, float scale,
+                       float* dh, float* gq, float* cs, float* ws, void* stream);
+int ltgnn_head_wide_finish(int device, int32_t H, int32_t D, const float* T, const float* W1, const float* b1,
+                           const float* w2, const float* cs, float* dW1, float* db1, float* dw2, void* stream);
+int ltgnn_pipe_feat_bwd(int device, int64_t B, int32_t N, int32_t P, int32_t D, const float* X, const int32_t* ends,
+                        const int32_t* inc_ptr, const int32_t* inc, const float* dF, const float* dpooled, float* dX,
+                        void* stream);
+
 int ltgnn_mean_pool_fwd(int device, int64_t B, int32_t N, int32_t D, const float* X, float* pooled, void* stream);
 int ltgnn_mean_pool_bwd_fill(int device, int64_t B, int32_t N, int32_t D, const float* dpooled, float* dX, void* stream);
 

@@ -286,73 +286,107 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ ws, float* __rest
 
 // kEpi: y = dropout(relu(acc + bias)) as in the STAGED kernel (same Philox counter: the float4 pair (r, r + 96) of a
 // window shares one call there; here a thread owns one float4, so it draws for its own index with dropout4h -- the two
-// paths are statistically, not bitwise, the same stream).  kGate: every neighbour value is gated on the fly by the float
-// gate tensor (the upstream layer's output): x * (gate > 0 ? gate_scale : 0).
+// paths are statistically, not bitwise, the same stream).  kGate: every neighbour value is gated on the fly, either by the
+// float gate tensor (the upstream layer's output): x * (gate > 0 ? gate_scale : 0), or -- D % 32 == 0 -- by its 1-bit
+// form live_in [B, D/32, N] (4 bytes per neighbour and 32-feature slice instead of a second 16-byte gather per float4).
+// live_out: the same record of y > 0, written by the q == 0 lane of every 8-lane slice group (word layout of new_live_mask:
+// bit 8 c + q <-> element 4 q + c of the slice).  Lanes of a warp stay together (the ballots need all 32).
 template <bool kEpi, bool kGate>
 __global__ void __launch_bounds__(256)
 spmm_gather_kernel(const int32_t* __restrict__ rowptr, const int2* __restrict__ colval, const float4* __restrict__ X,
                    float4* __restrict__ Y, int32_t n, int32_t d4, int64_t total, const float4* __restrict__ bias, int relu,
                    uint32_t drop_thresh, float keep_scale, uint64_t drop_seed_arg, const uint64_t* seed_src,
-                   const float4* __restrict__ gate, float gate_scale) {
+                   const float4* __restrict__ gate, float gate_scale, uint32_t* __restrict__ live_out,
+                   const uint32_t* __restrict__ live_in) {
     const uint64_t drop_seed = launch_seed(drop_seed_arg, seed_src);
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const int64_t row = e / d4;
-        const int c4 = static_cast<int>(e - row * d4);
+    const int lane = threadIdx.x & 31, n_slices = d4 >> 3;
+    for (int64_t e0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); e0 < total; e0 += stride) {
+        const int64_t e = e0 + lane;
+        const bool valid = e < total;
+        const int64_t row = (valid ? e : 0) / d4;
+        const int c4 = static_cast<int>((valid ? e : 0) - row * d4);
         const int64_t b = row / n;
         const int r = static_cast<int>(row - b * n);
         const float4* xb = X + b * n * d4 + c4;
-        const float4* gb = kGate ? gate + b * n * d4 + c4 : nullptr;
+        const float4* gb = (kGate && gate) ? gate + b * n * d4 + c4 : nullptr;
+        const uint32_t* lb = (kGate && live_in) ? live_in + (b * n_slices + (c4 >> 3)) * n : nullptr;
+        const int q = c4 & 7;
         auto fetch = [&](int col) {
             float4 x = __ldg(xb + static_cast<int64_t>(col) * d4);
             if (kGate) {
-                const float4 m = __ldg(gb + static_cast<int64_t>(col) * d4);
-                x.x = m.x > 0.f ? x.x * gate_scale : 0.f; x.y = m.y > 0.f ? x.y * gate_scale : 0.f;
-                x.z = m.z > 0.f ? x.z * gate_scale : 0.f; x.w = m.w > 0.f ? x.w * gate_scale : 0.f;
+                if (lb) {
+                    const uint32_t w = __ldg(lb + col) >> q;
+                    x.x = (w & 1u) ? x.x * gate_scale : 0.f; x.y = (w & 0x100u) ? x.y * gate_scale : 0.f;
+                    x.z = (w & 0x10000u) ? x.z * gate_scale : 0.f; x.w = (w & 0x1000000u) ? x.w * gate_scale : 0.f;
+                } else {
+                    const float4 m = __ldg(gb + static_cast<int64_t>(col) * d4);
+                    x.x = m.x > 0.f ? x.x * gate_scale : 0.f; x.y = m.y > 0.f ? x.y * gate_scale : 0.f;
+                    x.z = m.z > 0.f ? x.z * gate_scale : 0.f; x.w = m.w > 0.f ? x.w * gate_scale : 0.f;
+                }
             }
             return x;
         };
-        int k = __ldg(rowptr + r);
-        const int end = __ldg(rowptr + r + 1);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (; k + 1 < end; k += 2) {
-            const int2 c0 = __ldg(colval + k);
-            const int2 c1 = __ldg(colval + k + 1);
-            const float4 x0 = fetch(c0.x);
-            const float4 x1 = fetch(c1.x);
-            fma2(acc, __int_as_float(c0.y), x0);
-            fma2(acc, __int_as_float(c1.y), x1);
-        }
-        if (k < end) {
-            const int2 c0 = __ldg(colval + k);
-            fma2(acc, __int_as_float(c0.y), fetch(c0.x));
-        }
-        if (kEpi) {
-            if (bias) {
-                const float4 bb = __ldg(bias + c4);
-                acc.x = __fadd_rn(acc.x, bb.x); acc.y = __fadd_rn(acc.y, bb.y);
-                acc.z = __fadd_rn(acc.z, bb.z); acc.w = __fadd_rn(acc.w, bb.w);
+        if (valid) {
+            int k = __ldg(rowptr + r);
+            const int end = __ldg(rowptr + r + 1);
+            for (; k + 1 < end; k += 2) {
+                const int2 c0 = __ldg(colval + k);
+                const int2 c1 = __ldg(colval + k + 1);
+                const float4 x0 = fetch(c0.x);
+                const float4 x1 = fetch(c1.x);
+                fma2(acc, __int_as_float(c0.y), x0);
+                fma2(acc, __int_as_float(c1.y), x1);
             }
-            if (relu) {
-                acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            if (k < end) {
+                const int2 c0 = __ldg(colval + k);
+                fma2(acc, __int_as_float(c0.y), fetch(c0.x));
             }
-            if (drop_thresh) dropout4h(acc, static_cast<uint64_t>(e), drop_seed, drop_thresh, keep_scale);
+            if (kEpi) {
+                if (bias) {
+                    const float4 bb = __ldg(bias + c4);
+                    acc.x = __fadd_rn(acc.x, bb.x); acc.y = __fadd_rn(acc.y, bb.y);
+                    acc.z = __fadd_rn(acc.z, bb.z); acc.w = __fadd_rn(acc.w, bb.w);
+                }
+                if (relu) {
+                    acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                }
+                if (drop_thresh) dropout4h(acc, static_cast<uint64_t>(e), drop_seed, drop_thresh, keep_scale);
+            }
+            stg_stream(Y + e, acc);
         }
-        stg_stream(Y + e, acc);
+        if (kEpi && live_out) {   // d4 % 8 == 0: an 8-lane group is one 32-feature slice of one row, valid as a whole
+            const uint32_t bx = __ballot_sync(0xffffffffu, acc.x > 0.f), by = __ballot_sync(0xffffffffu, acc.y > 0.f);
+            const uint32_t bz = __ballot_sync(0xffffffffu, acc.z > 0.f), bw = __ballot_sync(0xffffffffu, acc.w > 0.f);
+            const uint32_t g8 = static_cast<uint32_t>(lane >> 3), sel = g8 | ((4u + g8) << 4);
+            if (valid && q == 0)
+                live_out[(b * n_slices + (c4 >> 3)) * n + r] =
+                    __byte_perm(__byte_perm(bx, by, sel), __byte_perm(bz, bw, sel), 0x5410);
+        }
     }
 }
 
-// colsum[c] = sum over all rows of gate(x): per-CTA partials, fixed order (the d bias of the gather path)
+// colsum[c] = sum over all rows of gate(x): per-CTA partials, fixed order (the d bias of the gather path); the gate as
+// floats or as the 1-bit record `live` [B, D/32, N]
 __global__ void __launch_bounds__(256)
-gated_colsum_kernel(const float4* __restrict__ X, const float4* __restrict__ gate, float gate_scale, int64_t rows, int d4,
-                    float* __restrict__ part) {
+gated_colsum_kernel(const float4* __restrict__ X, const float4* __restrict__ gate, const uint32_t* __restrict__ live,
+                    float gate_scale, int64_t rows, int d4, int n, float* __restrict__ part) {
     __shared__ float4 red[256];
-    const int tid = threadIdx.x, c = tid % d4, rstep = 256 / d4;
+    const int tid = threadIdx.x, c = tid % d4, rstep = 256 / d4, q = c & 7, n_slices = d4 >> 3;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * rstep + tid / d4; r < rows; r += static_cast<int64_t>(gridDim.x) * rstep) {
-        const float4 x = ldg_stream(X + r * d4 + c), m = ldg_stream(gate + r * d4 + c);
-        s.x += m.x > 0.f ? x.x * gate_scale : 0.f; s.y += m.y > 0.f ? x.y * gate_scale : 0.f;
-        s.z += m.z > 0.f ? x.z * gate_scale : 0.f; s.w += m.w > 0.f ? x.w * gate_scale : 0.f;
+        const float4 x = ldg_stream(X + r * d4 + c);
+        if (live) {
+            const int64_t b = r / n;
+            const uint32_t w = __ldg(live + (b * n_slices + (c >> 3)) * n + (r - b * n)) >> q;
+            s.x += (w & 1u) ? x.x * gate_scale : 0.f; s.y += (w & 0x100u) ? x.y * gate_scale : 0.f;
+            s.z += (w & 0x10000u) ? x.z * gate_scale : 0.f; s.w += (w & 0x1000000u) ? x.w * gate_scale : 0.f;
+        } else {
+            const float4 m = ldg_stream(gate + r * d4 + c);
+            s.x += m.x > 0.f ? x.x * gate_scale : 0.f; s.y += m.y > 0.f ? x.y * gate_scale : 0.f;
+            s.z += m.z > 0.f ? x.z * gate_scale : 0.f; s.w += m.w > 0.f ? x.w * gate_scale : 0.f;
+        }
     }
     red[tid] = s;
     __syncthreads();
@@ -436,7 +470,7 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
         LTGNN_REQUIRE(pl.ok, LTGNN_E_SHAPE, "%s: the STAGED kernel needs D %% 32 == 0 and a 32-feature slice of the "
                       "graph (%d rows) to fit shared memory", who, g->n);
     if (fused && !want_staged) {  // large graphs: the L2-gather kernel carries the same epilogue / gate
-        LTGNN_REQUIRE(!f.live_in && !f.live_out, LTGNN_E_SHAPE, "%s: 1-bit gates need the STAGED kernel (graph too large)", who);
+        LTGNN_REQUIRE((!f.live_in && !f.live_out) || D % 32 == 0, LTGNN_E_SHAPE, "%s: 1-bit gates need D %% 32 == 0", who);
         LTGNN_REQUIRE(256 % (D / 4) == 0 || !f.colsum, LTGNN_E_SHAPE, "%s: colsum on the gather path needs D/4 | 256", who);
     }
 
@@ -516,7 +550,7 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
         kern<<<static_cast<int>(blocks), 256, 0, stream>>>(
             g->rowptr[transpose], g->colval[transpose], reinterpret_cast<const float4*>(X), reinterpret_cast<float4*>(Y),
             g->n, D / 4, total, reinterpret_cast<const float4*>(f.bias), f.relu, thresh, keep, f.drop_seed, seed_source(),
-            reinterpret_cast<const float4*>(f.gate), f.gate_scale);
+            reinterpret_cast<const float4*>(f.gate), f.gate_scale, f.live_out, f.live_in);
         LTGNN_CUDA_TRY(cudaGetLastError());
         return LTGNN_OK;
     };
@@ -529,8 +563,8 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
         float* part = nullptr;
         LTGNN_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&part), sizeof(float) * n_parts * D, stream));
         gated_colsum_kernel<<<n_parts, 256, 0, stream>>>(reinterpret_cast<const float4*>(X),
-                                                          reinterpret_cast<const float4*>(f.gate), f.gate_scale,
-                                                          B * g->n, D / 4, part);
+                                                          reinterpret_cast<const float4*>(f.gate), f.live_in, f.gate_scale,
+                                                          B * g->n, D / 4, g->n, part);
         cudaError_t e = cudaGetLastError();
         int rr = e == cudaSuccess ? reduce_parts(part, D, f.colsum, n_parts, D, 0, stream) : LTGNN_OK;
         cudaFreeAsync(part, stream);

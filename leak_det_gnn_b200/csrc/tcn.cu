@@ -12,9 +12,11 @@
 //   warps 0-3   A LOADERS  gather the rows of one (tile, tap, 32-channel block) with cp.async into a ring of
 //                          transposition patches, split fp32 -> TF32 hi/lo, tcgen05.st into an A slot (as linear.cu)
 //   warps 4-7   B LOADERS  stream the weight: the 3 x 128 x 128 fp32 weight is 393 KB as hi + lo and cannot be resident, so
-//                          a ring of k-atom stages (32 K values x 128 outputs, hi + lo = 32 KB) is refilled from L2 --
-//                          and every stage is used by THREE row tiles before it is released, which divides that traffic
-//   warp  8     MMA        3xTF32, A from tensor memory; three 128-column accumulators (tiles t, t+1, t+2 of the group)
+//                          a ring of k-atom stages (32 K values x 128 outputs, hi + lo = 32 KB) is refilled from L2 (the
+//                          weight is prefetched into L2 at kernel start); a stage may serve the `tiles` row tiles of a
+//                          group before it is released -- measured, one tile per group with overlapped epilogues wins
+//   warp  8     MMA        3xTF32, A from tensor memory; two 128-column accumulators ROTATING over the CTA's row tiles, so
+//                          that tile n + 1 is multiplied while the epilogue normalises tile n
 //   warps 9-16  EPILOGUE   bias, LayerNorm over the 128 channels (two-pass mean / variance; the two warps that share a
 //                          row exchange partial sums through shared memory), ReLU, residual, coalesced stores via patches
 // fp32-faithful like every GEMM of this library (the residual is a small difference of pressures).
@@ -30,9 +32,9 @@ using namespace ltgnn::umma;
 
 constexpr int kC = 128;                  // channels: K per tap and N
 constexpr int kALd = 4, kBLd = 4, kMmaWarp = 8, kEp = 8, kThreads = (kALd + kBLd + 1 + kEp) * 32;  // 17 warps
-constexpr int kTiles = 3;                // row tiles per group (accumulators in tensor memory)
-constexpr int kASlots = 2, kSlotCols = 64;
-constexpr int kBStages = 4, kADepth = 3;
+constexpr int kTiles = 2;                // accumulators in tensor memory (and the most row tiles a group may have)
+constexpr int kASlots = 4, kSlotCols = 64;   // 2 x 128 accumulator columns + 4 x 64 A columns = the 512 of tensor memory
+constexpr int kBStages = 3, kADepth = 5;   // 80 KB of gathered rows in flight per SM: the gather is latency-bound
 constexpr uint32_t kBStageBytes = 2u * kC * 128;  // one k-atom of the weight: 128 rows x 128 B, hi then lo
 
 struct Params {
@@ -48,14 +50,18 @@ struct Params {
     uint32_t M;
     int32_t taps, relu;
     float eps;
+    int32_t tiles;             // row tiles per group, 1 .. kTiles (fewer for small M: more CTAs, shorter chains)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 tcn_conv_kernel(const Params p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBStages], b_empty[kBStages], acc_full, acc_empty;
+    __shared__ uint64_t a_full[kASlots], a_empty[kASlots], b_full[kBStages], b_empty[kBStages], acc_full[kTiles],
+        acc_empty[kTiles];
     __shared__ uint32_t tmem_base_s;
     __shared__ float stat_s[2][2][128];   // [pass][half][row]: partial sums the two warps of a row exchange
+    __shared__ float4 prm_s[3][kC / 4];   // bias | gamma | beta: read as broadcast LDS.128 by the epilogue (a per-element
+                                          // __ldg was 320 load instructions per thread and tile and paced the kernel)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_ring = smem;                                             // kBStages x 32 KB
     uint8_t* a_rings = b_ring + kBStages * kBStageBytes;                // kALd x kADepth patches
@@ -72,16 +78,23 @@ tcn_conv_kernel(const Params p) {
             mbar_init(&b_full[s], kBLd);
             mbar_init(&b_empty[s], 1);
         }
-        mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, kEp);
+        for (int t = 0; t < kTiles; ++t) {   // per tile: the tensor core refills tile t of the next group while the
+            mbar_init(&acc_full[t], 1);      // epilogue is still normalising tiles t + 1, ...
+            mbar_init(&acc_empty[t], kEp);
+        }
         fence_mbar_init();
+    }
+    if (tid < kC) {
+        reinterpret_cast<float*>(prm_s[0])[tid] = __ldg(p.bias + tid);
+        reinterpret_cast<float*>(prm_s[1])[tid] = p.gamma ? __ldg(p.gamma + tid) : 1.f;
+        reinterpret_cast<float*>(prm_s[2])[tid] = p.gamma ? __ldg(p.beta + tid) : 0.f;
     }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t acc_base = tmem_base, a_base = tmem_base + kTiles * kC;  // 384 accumulator columns + 2 A slots
-    const uint32_t rows_per_group = kTiles * 128;
+    const uint32_t acc_base = tmem_base, a_base = tmem_base + kTiles * kC;  // 256 accumulator columns + 4 A slots
+    const uint32_t rows_per_group = p.tiles * 128;
     const uint32_t n_groups = (p.M + rows_per_group - 1) / rows_per_group;
     const uint32_t my_groups = blockIdx.x < n_groups ? (n_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int n_katoms = p.taps * 4;        // k-atoms of 32 channels per group pass
@@ -92,19 +105,44 @@ tcn_conv_kernel(const Params p) {
         uint8_t* ring = a_rings + static_cast<size_t>(warp) * kADepth * patch::kPatchBytes;
         const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int sub = lane >> 3, ch = lane & 7;
-        const uint32_t fills_per_group = n_katoms * kTiles, n_fills = my_groups * fills_per_group;
-        auto fetch = [&](uint32_t f, int slot_p) {
-            const patch::Patch pt(ring + slot_p * patch::kPatchBytes, lane);
-            if (f < n_fills) {
-                const uint32_t gi = f / fills_per_group, rem = f - gi * fills_per_group, j = rem / kTiles, tile = rem - j * kTiles;
-                const uint32_t tap = j >> 2, kg = j & 3;
-                const uint32_t row0 = (blockIdx.x + gi * gridDim.x) * rows_per_group + tile * 128 + quad * 32 + sub;
+        const uint32_t fills_per_group = n_katoms * p.tiles, n_fills = my_groups * fills_per_group;
+        // The source-row indices of a fill are loaded one iteration BEFORE its cp.async are issued (idx / ok / kg_i): the
+        // dependent index -> address -> copy chain was ~600 clocks of every fill, on a warp that runs its fills in series.
+        // (gi_n, j_n, tile_n) walk the fills incrementally -- no divisions.
+        int32_t idx[8];
+        uint32_t ok = 0, kg_i = 0, have = 0;
+        uint32_t gi_n = 0, j_n = 0, tile_n = 0, f_n = 0;
+        auto load_idx = [&]() {
+            have = f_n < n_fills;
+            if (have) {
+                const uint32_t tap = j_n >> 2;
+                kg_i = j_n & 3;
+                const uint32_t row0 = (blockIdx.x + gi_n * gridDim.x) * rows_per_group + tile_n * 128 + quad * 32 + sub;
                 const int32_t* srct = p.src + static_cast<size_t>(tap) * p.M;
+                ok = 0;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const uint32_t row = row0 + 4 * k;
-                    const int32_t s = row < p.M ? __ldg(srct + row) : -1;   // -1: left padding / past the end -> zeros
-                    const float4* from = p.X + static_cast<size_t>(s < 0 ? 0 : s) * (kC / 4) + kg * 8 + ch;
+                    idx[k] = __ldg(srct + (row < p.M ? row : p.M - 1));   // unconditional: the value is not used here
+                    ok |= (row < p.M ? 1u : 0u) << k;
+                }
+                ++f_n;
+                if (++tile_n == static_cast<uint32_t>(p.tiles)) {
+                    tile_n = 0;
+                    if (++j_n == static_cast<uint32_t>(n_katoms)) {
+                        j_n = 0;
+                        ++gi_n;
+                    }
+                }
+            }
+        };
+        auto issue = [&](int slot_p) {   // the fill whose indices load_idx fetched last
+            if (have) {
+                const patch::Patch pt(ring + slot_p * patch::kPatchBytes, lane);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int32_t s = (ok >> k) & 1 ? idx[k] : -1;   // -1: left padding / past the end -> zeros
+                    const float4* from = p.X + static_cast<size_t>(s < 0 ? 0 : s) * (kC / 4) + kg_i * 8 + ch;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(pt.co(k))), "l"(from),
                                  "r"(s < 0 ? 0 : 16)
                                  : "memory");
@@ -112,7 +150,11 @@ tcn_conv_kernel(const Params p) {
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        for (int d = 0; d < kADepth; ++d) fetch(d, d);
+        for (int d = 0; d < kADepth; ++d) {
+            load_idx();
+            issue(d);
+        }
+        load_idx();
         for (uint32_t f = 0; f < n_fills; ++f) {
             const int slot_p = static_cast<int>(f % kADepth);
             asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
@@ -127,7 +169,8 @@ tcn_conv_kernel(const Params p) {
                 }
             }
             __syncwarp();
-            fetch(f + kADepth, slot_p);
+            issue(slot_p);     // fill f + kADepth: its indices arrived during the previous iteration
+            load_idx();        // fill f + kADepth + 1: in flight until the next iteration
             const uint32_t slot = f & (kASlots - 1);
             mbar_wait_relaxed(&a_empty[slot], ((f / kASlots) & 1) ^ 1);
             fence_after_sync();
@@ -153,6 +196,11 @@ tcn_conv_kernel(const Params p) {
         // ---------------- B loaders: k-atom j of the weight -> ring stage (K-major SWIZZLE_128B, hi then lo) ----------------
         const int bt = tid - kALd * 32;  // 0 .. 127
         const uint32_t n_fills = my_groups * n_katoms;
+        if (my_groups) {   // the first pass over the weight would otherwise pay one HBM round trip per k-atom, in series
+            const uint32_t lines = static_cast<uint32_t>(p.taps) * kC * kC * 4 / 128;
+            for (uint32_t l = bt; l < lines; l += kBLd * 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.W) + l * 128ull));
+        }
         for (uint32_t f = 0; f < n_fills; ++f) {
             const uint32_t j = f % n_katoms, tap = j >> 2, kg = j & 3, stage = f % kBStages;
             float4 w[8];
@@ -183,18 +231,18 @@ tcn_conv_kernel(const Params p) {
         const uint32_t ring_lo = desc_lo(smem_u32(b_ring));
         uint32_t fa = 0, fb = 0;
         for (uint32_t gi = 0; gi < my_groups; ++gi) {
-            mbar_wait_relaxed(&acc_empty, (gi & 1) ^ 1);
-            fence_after_sync();
             for (int j = 0; j < n_katoms; ++j, ++fb) {
                 const uint32_t stage = fb % kBStages;
                 mbar_wait_relaxed(&b_full[stage], (fb / kBStages) & 1);
                 const uint32_t bh = ring_lo + stage * (kBStageBytes >> 4), bl = bh + ((kC * 128) >> 4);
-                for (int tile = 0; tile < kTiles; ++tile, ++fa) {
+                for (int tile = 0; tile < p.tiles; ++tile, ++fa) {
                     const uint32_t slot = fa & (kASlots - 1);
+                    const uint32_t nt = gi * p.tiles + tile, acc = nt % kTiles;   // accumulators rotate over the CTA's tiles
+                    if (j == 0) mbar_wait_relaxed(&acc_empty[acc], ((nt / kTiles) & 1) ^ 1);   // the epilogue drained it
                     mbar_wait_relaxed(&a_full[slot], (fa / kASlots) & 1);
                     fence_after_sync();
                     if (elect_one()) {
-                        const uint32_t d = acc_base + tile * kC;
+                        const uint32_t d = acc_base + acc * kC;
                         const uint32_t a_hi = a_base + slot * kSlotCols, a_lo = a_hi + 32;
 #pragma unroll
                         for (uint32_t k = 0; k < 4; ++k) {
@@ -203,8 +251,8 @@ tcn_conv_kernel(const Params p) {
                             rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, idesc, 1u);
                         }
                         commit(&a_empty[slot]);
-                        if (tile == kTiles - 1) commit(&b_empty[stage]);
-                        if (tile == kTiles - 1 && j == n_katoms - 1) commit(&acc_full);
+                        if (tile == p.tiles - 1) commit(&b_empty[stage]);
+                        if (j == n_katoms - 1) commit(&acc_full[acc]);
                     }
                     __syncwarp();
                 }
@@ -219,11 +267,12 @@ tcn_conv_kernel(const Params p) {
         const int sub = lane >> 3, ch = lane & 7;
         const float inv_c = 1.f / static_cast<float>(kC);
         for (uint32_t gi = 0; gi < my_groups; ++gi) {
-            mbar_wait(&acc_full, gi & 1);
-            fence_after_sync();
             const uint32_t g_row0 = (blockIdx.x + gi * gridDim.x) * rows_per_group;
-            for (int tile = 0; tile < kTiles; ++tile) {
-                const uint32_t taddr = acc_base + tile * kC + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
+            for (int tile = 0; tile < p.tiles; ++tile) {
+                const uint32_t nt = gi * p.tiles + tile, acc = nt % kTiles;
+                mbar_wait(&acc_full[acc], (nt / kTiles) & 1);
+                fence_after_sync();
+                const uint32_t taddr = acc_base + acc * kC + (static_cast<uint32_t>(q * 32) << 16) + half * 64;
                 const uint32_t row0 = g_row0 + tile * 128 + q * 32;   // first row of this warp's 32
                 float mean = 0.f, rstd = 1.f;
                 if (p.gamma) {
@@ -234,7 +283,10 @@ tcn_conv_kernel(const Params p) {
                         float v[32];
                         tmem_ld32(taddr + c0, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) s += v[j] + __ldg(p.bias + half * 64 + c0 + j);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = prm_s[0][(half * 64 + c0 + j) >> 2];
+                            s += (v[j] + b4.x) + (v[j + 1] + b4.y) + (v[j + 2] + b4.z) + (v[j + 3] + b4.w);
+                        }
                     }
                     stat_s[0][half][rt] = s;
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
@@ -246,9 +298,11 @@ tcn_conv_kernel(const Params p) {
                         float v[32];
                         tmem_ld32(taddr + c0, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float d = v[j] + __ldg(p.bias + half * 64 + c0 + j) - mean;
-                            s2 = fmaf(d, d, s2);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = prm_s[0][(half * 64 + c0 + j) >> 2];
+                            const float d0 = v[j] + b4.x - mean, d1 = v[j + 1] + b4.y - mean;
+                            const float d2 = v[j + 2] + b4.z - mean, d3 = v[j + 3] + b4.w - mean;
+                            s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
                         }
                     }
                     stat_s[1][half][rt] = s2;
@@ -262,12 +316,23 @@ tcn_conv_kernel(const Params p) {
                 for (int c0 = 0; c0 < 64; c0 += 32) {
                     float v[32];
                     tmem_ld32(taddr + c0, v);
+                    if (c0 == 32) {  // last read of this tile's accumulator: hand it back before the stores
+                        fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int col = half * 64 + c0 + j;
-                        float y = v[j] + __ldg(p.bias + col);
-                        if (p.gamma) y = fmaf((y - mean) * rstd, __ldg(p.gamma + col), __ldg(p.beta + col));
-                        v[j] = p.relu ? fmaxf(y, 0.f) : y;
+                    for (int j = 0; j < 32; j += 4) {
+                        const int c4 = (half * 64 + c0 + j) >> 2;
+                        const float4 b4 = prm_s[0][c4], g4 = prm_s[1][c4], e4 = prm_s[2][c4];
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w},
+                                    ee[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float y = v[j + i] + bb[i];
+                            if (p.gamma) y = fmaf((y - mean) * rstd, gg[i], ee[i]);
+                            v[j + i] = p.relu ? fmaxf(y, 0.f) : y;
+                        }
                     }
                     float4 g[8];
                     patch::transpose_out(pt, v, g);
@@ -287,9 +352,6 @@ tcn_conv_kernel(const Params p) {
                 }
                 if (p.gamma) asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // stat_s reusable for the next tile
             }
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty);
         }
     }
     fence_before_sync();
@@ -322,9 +384,14 @@ extern "C" int ltgnn_tcn_conv(int device, int64_t M, int32_t C, int32_t taps, co
     LTGNN_REQUIRE(smem <= static_cast<size_t>(di->smem_optin), LTGNN_E_SHAPE, "tcn_conv: %zu B of shared memory", smem);
     LTGNN_USE_DEVICE(device);
     LTGNN_CUDA_TRY(cudaFuncSetAttribute(tc::tcn_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // One row tile per group: with the accumulators rotating over a CTA's tiles, the tensor core then works on tile n + 1
+    // (and n + 2) while the epilogue normalises tile n.  Larger groups reuse every weight k-atom for 2 or 3 tiles, but the
+    // B loaders are idle most of the time anyway and the epilogue of a group is then exposed (measured: never faster).
+    const int64_t n_tiles = (M + 127) / 128;
+    int tiles = 1;
     tc::Params p{reinterpret_cast<const float4*>(X), src, W, bias, gamma, beta, reinterpret_cast<const float4*>(res), res_row,
-                 reinterpret_cast<float4*>(Y), static_cast<uint32_t>(M), taps, relu, eps};
-    const int64_t groups = (M + tc::kTiles * 128 - 1) / (tc::kTiles * 128);
+                 reinterpret_cast<float4*>(Y), static_cast<uint32_t>(M), taps, relu, eps, tiles};
+    const int64_t groups = (n_tiles + tiles - 1) / tiles;
     const int grid = static_cast<int>(groups < di->sm_count ? groups : di->sm_count);
     tc::tcn_conv_kernel<<<grid, tc::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
     LTGNN_CUDA_TRY(cudaGetLastError());

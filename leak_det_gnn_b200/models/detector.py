@@ -140,20 +140,15 @@ class LeakDetector(nn.Module):
         message-passing hot path."""
         if not h_s.is_cuda:
             raise ValueError("LeakDetector runs on CUDA only (sm_100a kernels; no CPU fallback)")
-        slot, ends, ends32, incidence = self._index_tensors(h_s.device)
+        slot, _, ends32, incidence = self._index_tensors(h_s.device)
         conv_params = [t for conv in self.convs for t in (conv.lin.weight, conv.bias)]
         x = ops.gnn_body(h_s, slot, self.pipe_graph, self.dropout.p, self.training, self.sensor_to_node.weight,
                          self.sensor_to_node.bias, conv_params)
         lin1, lin2 = self.edge_head.mlp[0], self.edge_head.mlp[3]
-        if ops.heads_supported(x.shape[-1], lin1.out_features):
-            # fused pipe head (features formed on the fly, tcgen05) + mean pool; the H -> 1 layer's bias and the
-            # tiny no-leak MLP on the pooled (B, D) vector stay in torch
-            part, pooled = ops.heads(x, ends32, lin1.weight, lin1.bias, lin2.weight, self.dropout.p, self.training,
-                                     incidence)
-            pipe_logits = part.sum(0) + lin2.bias
-        else:
-            pipe_logits = self.edge_head(x[:, ends[:, 0], :], x[:, ends[:, 1], :])
-            pooled = ops.mean_pool(x)
+        # pipe head (features formed on the fly, tcgen05) + mean pool; the H -> 1 layer's bias and the tiny no-leak MLP
+        # on the pooled (B, D) vector stay in torch.  Node widths other than 64 / 128 raise inside ops.heads.
+        part, pooled = ops.heads(x, ends32, lin1.weight, lin1.bias, lin2.weight, self.dropout.p, self.training, incidence)
+        pipe_logits = part.sum(0) + lin2.bias
         noleak_logit = self.noleak_head(pooled).unsqueeze(-1)
         return torch.cat([pipe_logits, noleak_logit], dim=-1)
 

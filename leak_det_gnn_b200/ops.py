@@ -17,7 +17,7 @@ from . import instrument as _inst
 from . import lib as _lib
 from .graph import GCNCsr, build_gcn_csr
 
-__all__ = ["PipeGraph", "device_seed", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported", "pipe_incidence", "gru_encode", "gru_supported"]
+__all__ = ["PipeGraph", "device_seed", "spmm", "spmm_fused", "aggregate", "linear_tc", "wgrad", "gcn_conv", "mean_pool", "gnn_body", "heads", "heads_supported", "heads_wide_supported", "pipe_incidence", "gru_encode", "gru_supported"]
 
 
 # Test hook: when set to a dict, the autograd nodes drop the masks they saved into it (``lives``: the 1-bit ReLU-and-
@@ -130,7 +130,8 @@ def _dev_index(x: torch.Tensor) -> int:
 
 
 def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False,
-              transposed: bool = False, gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0) -> torch.Tensor:
+              transposed: bool = False, gate: Optional[torch.Tensor] = None, gate_scale: float = 1.0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Raw (non-differentiable) tensor-core dense layer (tcgen05, 3xTF32):
     ``gate(act(x @ weight.T + bias))``, or ``x @ weight`` when ``transposed``; see ltgnn_linear."""
     _check_act(x, "x")
@@ -140,7 +141,13 @@ def linear_tc(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     if (weight.shape[0] if transposed else weight.shape[1]) != k:
         raise ValueError(f"weight {tuple(weight.shape)} does not match x[..., {k}] (transposed={transposed})")
     m = x.numel() // k
-    y = torch.empty(*x.shape[:-1], n, device=x.device, dtype=torch.float32)
+    if out is None:
+        y = torch.empty(*x.shape[:-1], n, device=x.device, dtype=torch.float32)
+    else:
+        _check_act(out, "out")
+        if out.numel() != m * n:
+            raise ValueError(f"out must hold {m} x {n} values")
+        y = out
     if gate is not None:
         _check_act(gate, "gate")
         if gate.numel() != y.numel():
@@ -276,8 +283,9 @@ def _linear_any(x, weight, transposed=False):
     return x @ weight if transposed else torch.nn.functional.linear(x, weight)
 
 
-def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW[Do, Di] = sum_rows g[row, :]^T x[row, :]; g: (..., Do), x: (..., Di), same leading shape."""
+def wgrad(g: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[Do, Di] = sum_rows g[row, :]^T x[row, :]; g: (..., Do), x: (..., Di), same leading shape.
+    ``out``: a contiguous (Do, Di) fp32 CUDA tensor to write into."""
     _check_act(g, "g")
     _check_act(x, "x")
     do, di = g.shape[-1], x.shape[-1]
@@ -286,7 +294,11 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         raise ValueError("wgrad: row counts differ")
     L = _lib.load()
     dev = _dev_index(g)
-    dw = torch.empty(do, di, device=g.device, dtype=torch.float32)
+    if out is not None:
+        _check_act(out, "out")
+        if tuple(out.shape) != (do, di):
+            raise ValueError(f"out must be {(do, di)}")
+    dw = torch.empty(do, di, device=g.device, dtype=torch.float32) if out is None else out
     if do in (64, 128) and di % 32 == 0 and 0 < di <= 192 and m > 0:
         ws = torch.empty(int(L.ltgnn_tgrad_ws_floats(dev, di)), device=g.device, dtype=torch.float32)
         tok = _inst.begin("wgrad_tc")
@@ -295,7 +307,8 @@ def wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
         _inst.end(tok)
         return dw
     if not _wgrad_ok(do, di):
-        return g.reshape(m, do).t() @ x.reshape(m, di)
+        res = g.reshape(m, do).t() @ x.reshape(m, di)
+        return res if out is None else out.copy_(res)
     ws = torch.empty(int(L.ltgnn_wgrad_ws_floats(dev, do, di)), device=g.device, dtype=torch.float32)
     tok = _inst.begin("wgrad")
     _lib.check(L.ltgnn_wgrad(dev, m, do, di, g.data_ptr(), x.data_ptr(), dw.data_ptr(), 0, ws.data_ptr(), _stream(g)))
@@ -550,15 +563,125 @@ class _Heads(torch.autograd.Function):
         return dx, None, None, None, dw1, db1, dw2, None, None
 
 
+def heads_wide_supported(d: int, h: int) -> bool:
+    """Shapes of the composed pipe head (csrc/heads_wide.cu + the gathered-row GEMM of csrc/tcn.cu, 128 channels)."""
+    return d == 128 and h == 128
+
+
+_ROWS3_CACHE: Dict = {}
+
+
+def _rows3(m: int, device) -> torch.Tensor:
+    """src of the three-tap GEMM over F [3][M][D]: tap t of output row r reads row t * M + r."""
+    key = (m, str(device))
+    hit = _ROWS3_CACHE.get(key)
+    if hit is None:
+        if len(_ROWS3_CACHE) > 8:
+            _ROWS3_CACHE.clear()
+        hit = (torch.arange(m, dtype=torch.int32).unsqueeze(0) + torch.arange(3, dtype=torch.int32).unsqueeze(1) * m
+               ).contiguous().to(device)
+        _ROWS3_CACHE[key] = hit
+    return hit
+
+
+class _HeadsWide(torch.autograd.Function):
+    """The pipe head + mean pool for D = H = 128 (BASELINE configs[4]): features materialised once, the 3D -> H product
+    as a three-tap gathered-row GEMM on the tensor cores, the H -> 1 layer / dropout / feature gradient as streaming
+    kernels (csrc/heads_wide.cu).  Same contract as :class:`_Heads`; gradients are gathers and fixed-order sums."""
+
+    @staticmethod
+    def forward(ctx, x, ends, inc_ptr, inc, w1, b1, w2, drop_p, training):
+        x = x.contiguous()
+        b, n, d = x.shape
+        p_cnt, h = ends.shape[0], w1.shape[0]
+        m = b * p_cnt
+        if 3 * m >= 2**31:
+            raise ValueError("heads: B * P too large for int32 row indices")
+        dev = _dev_index(x)
+        L = _lib.load()
+        p = float(drop_p) if training else 0.0
+        feat = torch.empty(3, m, d, device=x.device, dtype=torch.float32)
+        tok = _inst.begin("pipe_feat_fwd")
+        _lib.check(L.ltgnn_pipe_feat_fwd(dev, b, n, p_cnt, d, x.data_ptr(), ends.data_ptr(), feat.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        w3 = w1.detach().view(h, 3, d).permute(1, 0, 2).contiguous()          # [tap][H][D]: W1[:, tD:(t+1)D]
+        hid = tcn_conv(feat.view(3 * m, d), _rows3(m, x.device), w3, b1.detach().contiguous(), relu=True)   # relu(pre), (M, H)
+        part = torch.empty(1, b, p_cnt, device=x.device, dtype=torch.float32)
+        w2v = w2.detach().reshape(-1).contiguous()
+        tok = _inst.begin("head_out_fwd")
+        _lib.check(L.ltgnn_head_out_fwd(dev, m, h, hid.data_ptr(), w2v.data_ptr(), p, new_dropout_seed() if p > 0 else 0,
+                                        part.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        pooled = torch.empty(b, d, device=x.device, dtype=torch.float32)
+        tok = _inst.begin("mean_pool_fwd")
+        _lib.check(L.ltgnn_mean_pool_fwd(dev, b, n, d, x.data_ptr(), pooled.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        if DEBUG_CAPTURE is not None:
+            DEBUG_CAPTURE["head_live"] = hid > 0
+        ctx.save_for_backward(x, ends, inc_ptr, inc, w3, w2v, feat, hid, w1, b1)
+        ctx.scale = 1.0 / (1.0 - int(p * 65536.0 + 0.5) / 65536.0)
+        return part, pooled
+
+    @staticmethod
+    def backward(ctx, dpart, dpooled):
+        x, ends, inc_ptr, inc, w3, w2v, feat, hid, w1, b1 = ctx.saved_tensors
+        b, n, d = x.shape
+        p_cnt, h = ends.shape[0], w3.shape[1]
+        m = b * p_cnt
+        dev = _dev_index(x)
+        L = _lib.load()
+        dlogit = dpart[0].contiguous().view(-1)
+        dh = torch.empty(m, h, device=x.device, dtype=torch.float32)
+        gq = torch.empty(m, h, device=x.device, dtype=torch.float32)
+        cs = torch.empty(h, device=x.device, dtype=torch.float32)
+        ws = torch.empty(int(L.ltgnn_head_out_ws_floats(dev, h)), device=x.device, dtype=torch.float32)
+        tok = _inst.begin("head_out_bwd")
+        _lib.check(L.ltgnn_head_out_bwd(dev, m, h, hid.data_ptr(), w2v.data_ptr(), dlogit.data_ptr(), ctx.scale, dh.data_ptr(),
+                                        gq.data_ptr(), cs.data_ptr(), ws.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        # parameter gradients: T[t] = gq^T F[t] on the tensor cores; dW1, db1, dw2 follow from T and cs (the hidden layer is
+        # linear in W1, b1 under the gate -- no second pass over the hidden activations)
+        t3 = torch.empty(3, h, d, device=x.device, dtype=torch.float32)
+        for t in range(3):
+            wgrad(gq, feat[t], out=t3[t])
+        dw1 = torch.empty_like(w1)
+        db1 = torch.empty(h, device=x.device, dtype=torch.float32)
+        dw2 = torch.empty(1, h, device=x.device, dtype=torch.float32)
+        w1c, b1c = w1.detach().contiguous(), b1.detach().contiguous()
+        tok = _inst.begin("head_wide_finish")
+        _lib.check(L.ltgnn_head_wide_finish(dev, h, d, t3.data_ptr(), w1c.data_ptr(), b1c.data_ptr(), w2v.data_ptr(),
+                                            cs.data_ptr(), dw1.data_ptr(), db1.data_ptr(), dw2.data_ptr(), _stream(x)))
+        _inst.end(tok)
+        dfeat = torch.empty_like(feat)
+        for t in range(3):
+            linear_tc(dh, w3[t], transposed=True, out=dfeat[t])                        # dF_t = dh W1[:, tD:(t+1)D]
+        dx = torch.empty_like(x)
+        dpooled = None if dpooled is None else dpooled.contiguous()
+        tok = _inst.begin("pipe_feat_bwd")
+        _lib.check(L.ltgnn_pipe_feat_bwd(dev, b, n, p_cnt, d, x.data_ptr(), ends.data_ptr(), inc_ptr.data_ptr(), inc.data_ptr(),
+                                         dfeat.data_ptr(), None if dpooled is None else dpooled.data_ptr(), dx.data_ptr(),
+                                         _stream(x)))
+        _inst.end(tok)
+        return dx, None, None, None, dw1, db1, dw2, None, None
+
+
 def heads(x: torch.Tensor, ends: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, drop_p: float,
           training: bool, incidence=None):
-    """x (B,N,64), ends int32 (P,2) -> (part (1,B,P), pooled (B,64)); pipe_logits = part.sum(0) + b2.
+    """x (B,N,D), ends int32 (P,2) -> (part (1,B,P), pooled (B,D)); pipe_logits = part.sum(0) + b2.
+    D = 64: the fused tensor-memory kernels (csrc/heads.cu); D = 128: the composed form (csrc/heads_wide.cu); the hidden
+    width is the reference's 128.  Other widths raise -- there is no library fallback.
     ``incidence``: the result of :func:`pipe_incidence` for these ends (built on the fly, with a host round trip, when
     omitted)."""
     _check_act(x.contiguous(), "x")
+    d, h = x.shape[-1], w1.shape[0]
     if incidence is None:
         incidence = pipe_incidence(ends, x.shape[1])
-    return _Heads.apply(x, ends, incidence[0], incidence[1], w1, b1, w2, drop_p, training)
+    if heads_supported(d, h):
+        return _Heads.apply(x, ends, incidence[0], incidence[1], w1, b1, w2, drop_p, training)
+    if heads_wide_supported(d, h):
+        return _HeadsWide.apply(x, ends, incidence[0], incidence[1], w1, b1, w2, drop_p, training)
+    raise ValueError(f"heads: node width {d} / hidden width {h} not built (64 or 128 / 128); the sm_100a kernels have no "
+                     "library fallback")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -594,9 +717,11 @@ class _GnnBody(torch.autograd.Function):
                 xs.append(x)
                 continue
             xw = _linear_any(x, w)
-            # graphs that fit shared memory: STAGED kernel + 1-bit live mask; larger ones: the L2-gather kernel with the
-            # same fused epilogue (the backward then gates with the float activations)
-            lives.append(live_for(xw.shape[-1]) if _staged_ok(graph, xw.shape[-1]) else None)
+            # graphs that fit shared memory: STAGED kernel; larger ones: the L2-gather kernel with the same fused epilogue.
+            # Both write the 1-bit live mask the backward gates with (D % 32 == 0; else the float activations gate)
+            d_out = xw.shape[-1]
+            lives.append(live_for(d_out) if _staged_ok(graph, d_out)
+                         else (new_live_mask(bsz, n, d_out, h_s.device) if need_grad and d_out % 32 == 0 else None))
             x = spmm_fused(graph, xw.view(bsz, n, -1), bias=b, relu=True, drop_p=p,
                            drop_seed=new_dropout_seed() if p > 0 else 0, live_out=lives[-1])
             del xw

@@ -131,6 +131,69 @@ def test_heads_fwd_bwd(bsz, n, p):
     assert rel_err(b2c.grad, t[4].grad) <= TOL
 
 
+@pytest.mark.parametrize("bsz,n,p", [(3, 661, 764), (1, 50, 2), (40, 300, 600), (2, 20000, 1000)])
+def test_heads_wide_fwd_bwd(bsz, n, p):
+    """Node width 128 (BASELINE configs[4]; detector.py:76-88,204-216 at node_hidden = 128): the composed pipe head of
+    csrc/heads_wide.cu + the three-tap gathered-row GEMM, forward and every gradient against fp64.  40 x 600 rows = 188
+    row tiles through the GEMM; 20 000 nodes with 1 000 class pipes = mostly nodes without an incident pipe."""
+    gen = torch.Generator().manual_seed(bsz * 7 + p)
+    x = torch.randn(bsz, n, 128, generator=gen).relu()
+    ends = torch.randint(0, n, (p, 2), generator=gen)
+    ends[0, 1] = ends[0, 0]  # a degenerate pipe: |h_u - h_v| = 0 and sign(0) = 0
+    w1 = torch.randn(128, 384, generator=gen) * 0.1
+    b1 = torch.randn(128, generator=gen) * 0.1
+    w2 = torch.randn(1, 128, generator=gen) * 0.2
+    b2 = torch.randn(1, generator=gen)
+    dlog = torch.randn(bsz, p, generator=gen)
+    dpool = torch.randn(bsz, 128, generator=gen)
+
+    o = [v.cuda().requires_grad_(True) for v in (x, w1, b1, w2)]
+    b2c = b2.cuda().requires_grad_(True)
+    ops.DEBUG_CAPTURE = cap = {}
+    try:
+        part, pooled = ops.heads(o[0], ends.to(torch.int32).cuda(), o[1], o[2], o[3], 0.1, False)
+    finally:
+        ops.DEBUG_CAPTURE = None
+    logits = part.sum(0) + b2c
+    ((logits * dlog.cuda()).sum() + (pooled * dpool.cuda()).sum()).backward()
+
+    # fp64 truth with the ReLU decisions the kernel took (a pre-activation within fp32 rounding of zero may flip in fp64)
+    live = cap["head_live"].cpu().double().view(bsz, p, 128)
+    t = [v.double().requires_grad_(True) for v in (x, w1, b1, w2, b2)]
+    h_u, h_v = t[0][:, ends[:, 0], :], t[0][:, ends[:, 1], :]
+    feat = torch.cat([h_u, h_v, (h_u - h_v).abs()], dim=-1)
+    hid = torch.nn.functional.linear(feat, t[1], t[2]) * live
+    lr, pr = torch.nn.functional.linear(hid, t[3], t[4]).squeeze(-1), t[0].mean(dim=1)
+    ((lr * dlog.double()).sum() + (pr * dpool.double()).sum()).backward()
+    assert rel_err(logits, lr) <= TOL and rel_err(pooled, pr) <= TOL
+    for got, want in zip(o + [b2c], t):
+        assert rel_err(got.grad, want.grad) <= TOL
+
+
+def test_heads_wide_dropout_and_determinism():
+    gen = torch.Generator().manual_seed(6)
+    x = (torch.randn(8, 300, 128, generator=gen).relu()).cuda().requires_grad_(True)
+    ends = torch.randint(0, 300, (500, 2), generator=gen).to(torch.int32).cuda()
+    w1 = (torch.randn(128, 384, generator=gen) * 0.05).cuda().requires_grad_(True)
+    b1 = (torch.rand(128, generator=gen) + 5.0).cuda().requires_grad_(True)   # all hidden units live: dropout is the only zero source
+    w2 = (torch.rand(1, 128, generator=gen) + 0.5).cuda().requires_grad_(True)
+
+    def run(train):
+        for t in (x, w1, b1, w2):
+            t.grad = None
+        torch.manual_seed(1)
+        part, pooled = ops.heads(x, ends, w1, b1, w2, 0.1, train)
+        (part.sum() + pooled.sum()).backward()
+        return part.detach().clone(), [t.grad.clone() for t in (x, w1, b1, w2)]
+
+    part, grads = run(True)
+    part2, grads2 = run(True)
+    base, _ = run(False)
+    assert torch.equal(part, part2) and all(torch.equal(a, b) for a, b in zip(grads, grads2))   # bitwise run to run
+    assert not torch.equal(part, base)
+    assert abs((part.sum(0) / base.sum(0)).mean().item() - 1.0) < 5e-3                            # unbiased
+
+
 def test_heads_dropout_train_mode():
     gen = torch.Generator().manual_seed(5)
     x = (torch.randn(16, 661, 64, generator=gen).relu()).cuda()

@@ -170,6 +170,31 @@ def test_spmm_fused_live_mask_bit_exact(graph_golden, net, b, d):
         spmm_fused(pg, g, transpose=True, gate=y, live_in=live)
 
 
+@pytest.mark.parametrize("n,b,d", [(12000, 3, 128), (9001, 2, 64), (20000, 1, 32)])
+def test_gather_path_live_mask_bit_exact(n, b, d):
+    """Graphs too large for shared memory (BASELINE configs[4] shape, scaled down): the L2-gather kernel writes and reads
+    the same 1-bit gates -- identical to gating with the float activations, column sums included."""
+    from leak_det_gnn_b200 import ops
+    from leak_det_gnn_b200.ops import PipeGraph, new_live_mask, spmm_fused, unpack_live_mask
+    rng = np.random.default_rng(n)
+    par = np.arange(1, n) - 1 - rng.integers(0, np.minimum(np.arange(1, n), 64))
+    ei = torch.from_numpy(np.stack([np.concatenate([np.arange(1, n), par]), np.concatenate([par, np.arange(1, n)])]))
+    pg = PipeGraph(ei, n)
+    assert not ops._staged_ok(pg, d)
+    gen = torch.Generator().manual_seed(n + b)
+    x = torch.randn(b, n, d, generator=gen).cuda()
+    bias = torch.randn(d, generator=gen).cuda()
+    live = new_live_mask(b, n, d, x.device)
+    live.fill_(-1)
+    y = spmm_fused(pg, x, bias=bias, relu=True, drop_p=0.25, drop_seed=99, live_out=live)
+    assert torch.equal(y, spmm_fused(pg, x, bias=bias, relu=True, drop_p=0.25, drop_seed=99))
+    assert torch.equal(unpack_live_mask(live), y > 0)
+    g = torch.randn(b, n, d, generator=gen).cuda()
+    want, want_cs = spmm_fused(pg, g, transpose=True, gate=y, gate_scale=4.0 / 3.0, want_colsum=True)
+    got, got_cs = spmm_fused(pg, g, transpose=True, live_in=live, gate_scale=4.0 / 3.0, want_colsum=True)
+    assert torch.equal(got, want) and torch.equal(got_cs, want_cs)
+
+
 def test_spmm_fused_dropout_statistics(graph_golden):
     from leak_det_gnn_b200.ops import spmm_fused
     pg = _graph(graph_golden, "LTA")
