@@ -375,17 +375,28 @@ gated_colsum_kernel(const float4* __restrict__ X, const float4* __restrict__ gat
     __shared__ float4 red[256];
     const int tid = threadIdx.x, c = tid % d4, rstep = 256 / d4, q = c & 7, n_slices = d4 >> 3;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * rstep + tid / d4; r < rows; r += static_cast<int64_t>(gridDim.x) * rstep) {
+    const int64_t step = static_cast<int64_t>(gridDim.x) * rstep;
+    const int64_t step_b = step / n;                     // (window, node) of a thread's row advance without divisions
+    const int step_r = static_cast<int>(step - step_b * n);
+    int64_t r = static_cast<int64_t>(blockIdx.x) * rstep + tid / d4;
+    int64_t b = r / n;
+    int rl = static_cast<int>(r - b * n);
+    for (; r < rows; r += step) {
         const float4 x = ldg_stream(X + r * d4 + c);
         if (live) {
-            const int64_t b = r / n;
-            const uint32_t w = __ldg(live + (b * n_slices + (c >> 3)) * n + (r - b * n)) >> q;
+            const uint32_t w = __ldg(live + (b * n_slices + (c >> 3)) * n + rl) >> q;
             s.x += (w & 1u) ? x.x * gate_scale : 0.f; s.y += (w & 0x100u) ? x.y * gate_scale : 0.f;
             s.z += (w & 0x10000u) ? x.z * gate_scale : 0.f; s.w += (w & 0x1000000u) ? x.w * gate_scale : 0.f;
         } else {
             const float4 m = ldg_stream(gate + r * d4 + c);
             s.x += m.x > 0.f ? x.x * gate_scale : 0.f; s.y += m.y > 0.f ? x.y * gate_scale : 0.f;
             s.z += m.z > 0.f ? x.z * gate_scale : 0.f; s.w += m.w > 0.f ? x.w * gate_scale : 0.f;
+        }
+        b += step_b;
+        rl += step_r;
+        if (rl >= n) {
+            rl -= n;
+            ++b;
         }
     }
     red[tid] = s;
@@ -559,7 +570,7 @@ int spmm_impl(ltgnn_graph_t g, int transpose, int64_t B, int32_t D, const float*
     else rc = epi ? launch_g(spmm_gather_kernel<true, false>) : launch_g(spmm_gather_kernel<false, false>);
     if (rc) return rc;
     if (f.colsum) {
-        const int n_parts = g->sm_count;  // ws holds sm_count * 32 floats >= n_parts * D only for D <= 32: use our own
+        const int n_parts = g->sm_count * 8;  // 8 CTAs per SM keep enough loads in flight; ws is too small for this: use our own
         float* part = nullptr;
         LTGNN_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&part), sizeof(float) * n_parts * D, stream));
         gated_colsum_kernel<<<n_parts, 256, 0, stream>>>(reinterpret_cast<const float4*>(X),
