@@ -244,8 +244,8 @@ def spmm_fused(graph: PipeGraph, x: torch.Tensor, transpose: bool = False, bias:
 
 
 # ----------------------------------------------------------------------------------------------
-# shape support predicates (mirrors of the checks in csrc/; unsupported shapes use cuBLAS via torch
-# for the plain GEMMs -- still on the GPU, never on the CPU)
+# shape support predicates (mirrors of the checks in csrc/).  Channel counts off the kernels' granularity are zero-padded
+# to it (operator-level GCNConv); anything larger raises -- no cuBLAS / eager-torch path anywhere
 # ----------------------------------------------------------------------------------------------
 _SMEM_LIMIT = 232448  # sm_100: 227 KB opt-in dynamic shared memory per block
 
@@ -275,12 +275,31 @@ def _staged_ok(graph: PipeGraph, d: int) -> bool:
     return _SMEM_LIMIT - 128 - off >= stage
 
 
+def _pad_cols(t: torch.Tensor, cols: int) -> torch.Tensor:
+    """Zero-pad the last dimension to ``cols`` (a copy; no arithmetic)."""
+    if t.shape[-1] == cols:
+        return t
+    out = torch.zeros(*t.shape[:-1], cols, device=t.device, dtype=t.dtype)
+    out[..., : t.shape[-1]] = t
+    return out
+
+
 def _linear_any(x, weight, transposed=False):
+    """``x @ weight.T`` (or ``x @ weight``) for any channel counts up to 256: shapes off the tensor-core kernel's
+    granularity (K % 32, N % 16) are zero-padded to it -- the operator-level ``GCNConv`` drop-in takes the channel counts PyG
+    takes, and there is no library GEMM behind it."""
     k = x.shape[-1]
     n = weight.shape[1] if transposed else weight.shape[0]
     if _linear_tc_ok(k, n):
         return linear_tc(x, weight, transposed=transposed)
-    return x @ weight if transposed else torch.nn.functional.linear(x, weight)
+    kp, np_ = (k + 31) // 32 * 32, (n + 15) // 16 * 16
+    if not _linear_tc_ok(kp, np_):
+        raise ValueError(f"linear: {k} -> {n} channels exceed what the sm_100a kernel holds resident (<= 256, K*N*8 bytes of "
+                         "shared memory); there is no library fallback")
+    w = weight.detach()
+    wp = torch.zeros((kp, np_) if transposed else (np_, kp), device=w.device, dtype=w.dtype)
+    wp[: w.shape[0], : w.shape[1]] = w
+    return linear_tc(_pad_cols(x, kp), wp, transposed=transposed)[..., :n].contiguous()
 
 
 def wgrad(g: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -307,7 +326,11 @@ def wgrad(g: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None) 
         _inst.end(tok)
         return dw
     if not _wgrad_ok(do, di):
-        res = g.reshape(m, do).t() @ x.reshape(m, di)
+        # off-granularity channel counts (operator-level GCNConv only): zero-pad to the tensor-core kernel's shapes
+        dop, dip = (64 if do <= 64 else 128), (di + 31) // 32 * 32
+        if do > 128 or dip > 192 or m == 0:
+            raise ValueError(f"wgrad: ({do}, {di}) not built (<= 128 x 192 channels); there is no library fallback")
+        res = wgrad(_pad_cols(g.reshape(m, do), dop), _pad_cols(x.reshape(m, di), dip))[:do, :di].contiguous()
         return res if out is None else out.copy_(res)
     ws = torch.empty(int(L.ltgnn_wgrad_ws_floats(dev, do, di)), device=g.device, dtype=torch.float32)
     tok = _inst.begin("wgrad")
@@ -375,13 +398,8 @@ def node_init_bwd(h_s, slot, weight, dx0, x0, gate_scale, live=None):
     b, s, ds = h_s.shape
     n, d = x0.shape[1], x0.shape[2]
     if d not in (64, 128) or ds % 32:
-        # shapes outside the tensor-core kernels (never the reference's 64/64): same maths with torch ops on the GPU
-        dz = torch.where(x0 > 0, dx0 * gate_scale, torch.zeros((), device=x0.device))
-        rows = torch.nonzero(slot >= 0).flatten()
-        dzs = torch.zeros(b, s, d, device=x0.device)
-        dzs[:, slot[rows].long()] = dz[:, rows]
-        dw = torch.cat([torch.einsum("bsd,bsk->dk", dzs, h_s), dzs.sum(dim=(0, 1)).unsqueeze(1)], dim=1)
-        return dzs @ weight[:, :ds], dw, dz.sum(dim=(0, 1))
+        raise ValueError(f"node_init_bwd: node width {d} / sensor width {ds} not built (64 or 128 / a multiple of 32); the "
+                         "sm_100a kernels have no library fallback")
     L = _lib.load()
     dev = _dev_index(h_s)
     dhs = torch.empty_like(h_s)
@@ -468,7 +486,7 @@ def mean_pool(x: torch.Tensor) -> torch.Tensor:
     """(B, N, D) -> (B, D): ``global_mean_pool`` for equal-sized graphs (detector.py:214-215)."""
     _check_act(x.contiguous(), "x")
     if x.shape[-1] % 4 or 256 % (x.shape[-1] // 4):
-        return x.mean(dim=1)
+        raise ValueError(f"mean_pool: width {x.shape[-1]} not built (D / 4 must divide 256); no library fallback")
     return _MeanPool.apply(x)
 
 

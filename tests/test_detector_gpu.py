@@ -11,7 +11,7 @@ than 3x the reference's own distance."""
 import pytest
 import torch
 
-from conftest import TOPO, rel_err
+from conftest import parity_log, TOPO, rel_err
 from leak_det_gnn_b200.models import LeakDetector
 
 pytestmark = pytest.mark.gpu
@@ -56,14 +56,14 @@ def test_gnn_stack_matches_reference_golden(detector_golden, case):
             continue
         _check(p.grad, g["grads"][name], g["stack_grads64"][name], name, report)
     assert len(report) == len(g["state_dict"]) - 4 + 1
+    parity_log(f"golden stack {case}", {k: {"ours": a, "reference_fp32": b} for k, (a, b) in report.items()})
     assert sum(o <= TOL for o, _ in report.values()) >= len(report) - 2, report
 
 
 @pytest.mark.parametrize("case", ["LTA_P2", "LTA_Pall", "LT_Pall", "LTA_D128_L3"])
 def test_forward_backward_match_reference_golden(detector_golden, case):
-    """Whole module, through the cuDNN GRU the reference also calls on a GPU.  The four GRU gradients
-    are produced by cuDNN's RNN backward (fast-math gate functions): held to 1e-4, everything else to
-    the fp32 bar."""
+    """Whole module, sensor GRU encoder included (the native tensor-memory GRU, csrc/gru.cu).  The four GRU gradients
+    come out of back-propagation through the whole window: held to 1e-4, everything else to the fp32 bar."""
     g = detector_golden(case)
     m = _build(g)
     logits = m(g["residual"].cuda(), g["tfeat"].cuda())

@@ -20,7 +20,8 @@ kern = next((r[1] for r in rows if r and r[0] == "Kernel Name"), "")
 hi = next(i for i, r in enumerate(rows) if "Address" in r and "Source" in r)
 h = rows[hi]
 idx = {k: i for i, k in enumerate(h)}
-data = [r for r in rows[hi + 1:] if len(r) == len(h)]
+nxt = next((i for i in range(hi + 1, len(rows)) if "Address" in rows[i] and "Source" in rows[i]), len(rows))
+data = [r for r in rows[hi + 1:nxt] if len(r) == len(h)]   # an export of several launches repeats the header: first one
 S = lambda r: int(r[idx["# Samples"]] or 0)
 E = lambda r: int(r[idx["Instructions Executed"]] or 0)
 if note:
