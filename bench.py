@@ -60,6 +60,9 @@ WORKLOADS = {
                    cfg="BASELINE configs[1] shape: the reference's training batch"),
     "ltown_dp256": dict(net="LT", batch=256, l_det=36, pipes=905, hidden=64, full_step=True, cpu_sample=16, graphed=True,
                         cfg="BASELINE configs[3]: whole training step incl. frozen predictor, clip, AdamW"),
+    "predictor_train": dict(net="LTA", batch=256, l_det=36, pipes=2, hidden=64, full_step=False, cpu_sample=256,
+                            cfg="BASELINE configs[0]: train_predictor (TCN, batch 256) -- the reference's CPU-runnable case; "
+                                "no graph work, baseline only: --impl reference"),
     "scaled100k": dict(net="SYN100K", batch=16, l_det=36, pipes=2000, hidden=128, full_step=False, cpu_sample=1,
                        cfg="BASELINE configs[4]: N=100k, mean degree 2.3, hidden 128"),
 }
@@ -292,6 +295,50 @@ def cpu_full_step_fn(net: dict, wl: dict, sample_b: int, l_det: int, with_predic
             loss.backward()
             return loss.item()
     return step
+
+
+def run_predictor_train(args, wl: dict) -> None:
+    """BASELINE configs[0]: one optimisation step of reference models/train_predictor.py:203-228 (TCN, MSE, AdamW lr 1e-3,
+    weight decay 1e-4, clip 1.0, batch 256) on synthetic normal windows in the dataset's batch layout (x (B, 36, S),
+    x_time (B, 36, 9), y (B, S)), on the host cores.  The predictor has no graph layers: nothing of this step
+    is on the sm_100a path; the line exists so that every BASELINE config has a number on this box."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from leak_det_gnn_b200.models import NormalPredictorTCN   # state_dict-compatible mirror of models/predictor.py:55-81
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(198)
+    b, l, n_s = args.batch, 36, SENSORS
+    model = NormalPredictorTCN(n_s, 9).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    rng = np.random.default_rng(198)
+    hour = (np.arange(l)[None, :] * 5 / 60.0 + rng.uniform(0, 24, (b, 1))) % 24
+    x = torch.from_numpy((8 * np.sin(2 * np.pi * hour / 24)[:, :, None] / 8 + 0.05 * rng.standard_normal((b, l, n_s))).astype(np.float32))
+    xt = torch.from_numpy(np.stack([time_features(l, int(i)) for i in rng.integers(0, 2016, b)]))
+    y = x[:, -1, :] + 0.01
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(x, xt), y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+
+    for _ in range(max(1, args.warmup)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    t = (time.perf_counter() - t0) / args.steps
+    line = {"impl": "reference", "metric": "predictor_windows_per_sec_train_step", "value": b / t, "unit": "windows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"predictor_train: NormalPredictorTCN (405 021 parameters), batch {b} x 36 steps x {n_s} sensors, "
+                                   f"one AdamW step ({wl['cfg']})"},
+            "cpu_baseline": {"value": b / t, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{args.steps} steps of batch {b}, {t * 1e3:.0f} ms/step"},
+            "e2e": {"value": b / t, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
 
 
 def run_reference(args, wl: dict) -> None:
@@ -726,6 +773,12 @@ def main() -> None:
     args.pipes = wl["pipes"] if args.pipes is None else args.pipes
     args.cpu_sample = wl["cpu_sample"] if args.cpu_sample is None else args.cpu_sample
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload == "predictor_train":
+        if args.impl != "reference":
+            raise SystemExit("predictor_train is BASELINE configs[0], the reference's CPU baseline: run it with --impl reference "
+                             "(the predictor has no graph layers; its training step is not on the sm_100a path)")
+        run_predictor_train(args, wl)
+        return
     if args.impl == "reference":
         run_reference(args, wl)
         return

@@ -67,6 +67,11 @@ def test_node_init_fwd_bwd(bsz, n, s, ds, d):
     non = torch.ones(n, dtype=torch.bool)
     non[idx] = False
     assert torch.equal(x0[:, non.cuda(), :].cpu(), torch.relu(b).expand(bsz, int(non.sum()), d))
+    if d not in (64, 128) or ds % 32:
+        # widths the backward kernels are not built for: a loud error, not a library fallback
+        with pytest.raises(ValueError, match="not built"):
+            ops.node_init_bwd(h_s.cuda(), slot.cuda(), w.cuda(), dx.cuda(), x0, 1.0)
+        return
     dhs, dw, db = ops.node_init_bwd(h_s.cuda(), slot.cuda(), w.cuda(), dx.cuda(), x0, 1.0)
     assert rel_err(dhs, h64.grad) <= TOL
     assert rel_err(dw, w64.grad) <= 5 * TOL
