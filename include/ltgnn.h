@@ -245,11 +245,13 @@ int64_t ltgnn_pipe_head_ws_floats(int device);
  *   Y[m, :] = [res[res_row[m], :] +] relu(LayerNorm(bias + sum_tap X[src[tap * M + m], :] W[tap]^T))
  * X [x_rows, C], src int32 [taps, M] (-1 = zero row: the left padding), W [taps, C, C] (tap 0 = the oldest input;
  * torch's conv weight permuted (2, 0, 1)), bias / gamma / beta [C] (gamma = beta = null: no LayerNorm), res [r_rows, C]
- * with res_row int32 [M] or both null, Y [M, C].  C = 128.  tcgen05, 3xTF32, the weight streamed through shared memory.
+ * with res_row int32 [M] or both null, Y [M, C].  C = 128.  tcgen05, 3xTF32; the weight is split into TF32 hi / lo and laid
+ * out as shared-memory operand stages once per call (into ws: ltgnn_tcn_ws_floats(taps) floats) and streamed by bulk copies.
  */
+int64_t ltgnn_tcn_ws_floats(int32_t taps);
 int ltgnn_tcn_conv(int device, int64_t M, int32_t C, int32_t taps, const float* X, const int32_t* src, const float* W,
                    const float* bias, const float* gamma, const float* beta, float eps, int relu, const float* res,
-                   const int32_t* res_row, float* Y, void* stream);
+                   const int32_t* res_row, float* Y, float* ws, void* stream);
 
 /* ---- shared per-sensor GRU encoder (detector.py:28-73) -----------------------
  * Sequence q = b*S + s has input [r[b,t,s], tf[b,t,0..F)] at step t (the reference's cat([rr, tf]) order);

@@ -9,14 +9,15 @@
 //
 //     Y[m, :] = [res[res_row[m], :] +] relu(LayerNorm(bias + sum_tap X[src[tap][m], :] W_tap^T))      K = taps * C = 384
 //
-//   warps 0-3   A LOADERS  gather the rows of one (tile, tap, 32-channel block) with cp.async into a ring of
-//                          transposition patches, split fp32 -> TF32 hi/lo, tcgen05.st into an A slot (as linear.cu)
-//   warps 4-7   B LOADERS  stream the weight: the 3 x 128 x 128 fp32 weight is 393 KB as hi + lo and cannot be resident, so
-//                          a ring of k-atom stages (32 K values x 128 outputs, hi + lo = 32 KB) is refilled from L2 (the
-//                          weight is prefetched into L2 at kernel start); a stage may serve the `tiles` row tiles of a
-//                          group before it is released -- measured, one tile per group with overlapped epilogues wins
-//   warp  8     MMA        3xTF32, A from tensor memory; two 128-column accumulators ROTATING over the CTA's row tiles, so
-//                          that tile n + 1 is multiplied while the epilogue normalises tile n
+//   warps 0-7   A LOADERS  gather the rows of one (tile, tap, 32-channel block) = one "fill" with cp.async into a ring of
+//                          transposition patches, split fp32 -> TF32 hi/lo, tcgen05.st into an A slot (as linear.cu).  Two
+//                          sets of four warps take the even and the odd fills: a warp runs its fills in series (~2 200
+//                          clocks each: copy latency, split, tensor-memory store, hand-over), the tensor core needs ~860
+//   warp  8     MMA + B    3xTF32, A from tensor memory; two 128-column accumulators ROTATING over the CTA's row tiles, so
+//                          that tile n + 1 is multiplied while the epilogue normalises tile n.  The weight (393 KB as
+//                          hi + lo: cannot be resident) is split and laid out ONCE per launch by tcn_pack_weight_kernel;
+//                          the elected lane brings k-atom stages (32 K values x 128 outputs, hi + lo = 32 KB) in with 1-D
+//                          bulk copies (TMA) two k-atoms ahead -- no warp converts weights inside the main loop
 //   warps 9-16  EPILOGUE   bias, LayerNorm over the 128 channels (two-pass mean / variance; the two warps that share a
 //                          row exchange partial sums through shared memory), ReLU, residual, coalesced stores via patches
 // fp32-faithful like every GEMM of this library (the residual is a small difference of pressures).
@@ -31,16 +32,16 @@ using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
 
 constexpr int kC = 128;                  // channels: K per tap and N
-constexpr int kALd = 4, kBLd = 4, kMmaWarp = 8, kEp = 8, kThreads = (kALd + kBLd + 1 + kEp) * 32;  // 17 warps
+constexpr int kALd = 8, kMmaWarp = 8, kEp = 8, kThreads = (kALd + 1 + kEp) * 32;  // 17 warps; kALd = 2 sets of 4
 constexpr int kTiles = 2;                // accumulators in tensor memory (and the most row tiles a group may have)
 constexpr int kASlots = 4, kSlotCols = 64;   // 2 x 128 accumulator columns + 4 x 64 A columns = the 512 of tensor memory
-constexpr int kBStages = 3, kADepth = 5;   // 80 KB of gathered rows in flight per SM: the gather is latency-bound
+constexpr int kBStages = 3, kADepth = 2;   // 8 warps x 2 patches = 64 KB of gathered rows in flight per SM
 constexpr uint32_t kBStageBytes = 2u * kC * 128;  // one k-atom of the weight: 128 rows x 128 B, hi then lo
 
 struct Params {
     const float4* X;           // [x_rows, 32] float4 rows of the previous layer
     const int32_t* src;        // [taps][M]
-    const float* W;            // [taps][128][128]  (tap 0 = the oldest input)
+    const uint8_t* Wp;         // packed weight: [taps * 4 k-atoms][hi | lo][128 x 128 B, SWIZZLE_128B] (tcn_pack_weight_kernel)
     const float* bias;         // [128]
     const float* gamma;        // [128] or nullptr (no LayerNorm)
     const float* beta;
@@ -52,6 +53,23 @@ struct Params {
     float eps;
     int32_t tiles;             // row tiles per group, 1 .. kTiles (fewer for small M: more CTAs, shorter chains)
 };
+
+// W [taps][128 outputs][128 inputs] fp32 -> the B operand stages the main kernel copies in verbatim: k-atom j = tap * 4 + kg
+// (32 inputs) is 32 KB: TF32 hi of the 128 x 32 block as a K-major SWIZZLE_128B tile (row n at (n / 8) * 1024 + (n % 8) * 128,
+// 16-byte chunk c at (c ^ n % 8) * 16), then lo the same way.  One thread per 16-byte chunk.
+__global__ void __launch_bounds__(256)
+tcn_pack_weight_kernel(const float* __restrict__ W, uint8_t* __restrict__ Wp, int taps) {
+    const int i = blockIdx.x * 256 + threadIdx.x;          // (j, n, c)
+    if (i >= taps * 4 * kC * 8) return;
+    const int c = i & 7, n = (i >> 3) & (kC - 1), j = i >> 10, tap = j >> 2, kg = j & 3;
+    const float4 w = __ldg(reinterpret_cast<const float4*>(W + (static_cast<size_t>(tap) * kC + n) * kC + kg * 32) + c);
+    float4 hi, lo;
+    split4(w, hi, lo);
+    uint8_t* stage = Wp + static_cast<size_t>(j) * kBStageBytes;
+    const uint32_t off = sw128_offset(n, c, kC);
+    *reinterpret_cast<float4*>(stage + off) = hi;
+    *reinterpret_cast<float4*>(stage + kC * 128 + off) = lo;
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 tcn_conv_kernel(const Params p) {
@@ -71,11 +89,11 @@ tcn_conv_kernel(const Params p) {
     if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) {
         for (int s = 0; s < kASlots; ++s) {
-            mbar_init(&a_full[s], kALd);
+            mbar_init(&a_full[s], 4);            // the four warps (lane quadrants) of the set that owns the fill
             mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < kBStages; ++s) {
-            mbar_init(&b_full[s], kBLd);
+            mbar_init(&b_full[s], 1);            // the expect_tx arrival of the lane that issues the bulk copy
             mbar_init(&b_empty[s], 1);
         }
         for (int t = 0; t < kTiles; ++t) {   // per tile: the tensor core refills tile t of the next group while the
@@ -100,18 +118,29 @@ tcn_conv_kernel(const Params p) {
     const int n_katoms = p.taps * 4;        // k-atoms of 32 channels per group pass
 
     if (warp < kALd) {
-        // ---------------- A loaders ----------------
-        const int quad = warp;
+        // ---------------- A loaders: set 0 (warps 0-3) takes the even fills, set 1 (warps 4-7) the odd ones ----------------
+        const int quad = warp & 3;
+        const uint32_t set = warp >> 2;
         uint8_t* ring = a_rings + static_cast<size_t>(warp) * kADepth * patch::kPatchBytes;
         const uint32_t lane_base = a_base + (static_cast<uint32_t>(quad * 32) << 16);
         const int sub = lane >> 3, ch = lane & 7;
         const uint32_t fills_per_group = n_katoms * p.tiles, n_fills = my_groups * fills_per_group;
-        // The source-row indices of a fill are loaded one iteration BEFORE its cp.async are issued (idx / ok / kg_i): the
-        // dependent index -> address -> copy chain was ~600 clocks of every fill, on a warp that runs its fills in series.
-        // (gi_n, j_n, tile_n) walk the fills incrementally -- no divisions.
+        // The source-row indices of a fill are loaded one iteration BEFORE its cp.async are issued (idx / ok / kg_i).
+        // (gi_n, j_n, tile_n) walk this set's fills incrementally -- no divisions.
         int32_t idx[8];
         uint32_t ok = 0, kg_i = 0, have = 0;
         uint32_t gi_n = 0, j_n = 0, tile_n = 0, f_n = 0;
+        auto advance = [&]() {
+            ++f_n;
+            if (++tile_n == static_cast<uint32_t>(p.tiles)) {
+                tile_n = 0;
+                if (++j_n == static_cast<uint32_t>(n_katoms)) {
+                    j_n = 0;
+                    ++gi_n;
+                }
+            }
+        };
+        if (set) advance();
         auto load_idx = [&]() {
             have = f_n < n_fills;
             if (have) {
@@ -126,14 +155,8 @@ tcn_conv_kernel(const Params p) {
                     idx[k] = __ldg(srct + (row < p.M ? row : p.M - 1));   // unconditional: the value is not used here
                     ok |= (row < p.M ? 1u : 0u) << k;
                 }
-                ++f_n;
-                if (++tile_n == static_cast<uint32_t>(p.tiles)) {
-                    tile_n = 0;
-                    if (++j_n == static_cast<uint32_t>(n_katoms)) {
-                        j_n = 0;
-                        ++gi_n;
-                    }
-                }
+                advance();
+                advance();
             }
         };
         auto issue = [&](int slot_p) {   // the fill whose indices load_idx fetched last
@@ -155,8 +178,9 @@ tcn_conv_kernel(const Params p) {
             issue(d);
         }
         load_idx();
-        for (uint32_t f = 0; f < n_fills; ++f) {
-            const int slot_p = static_cast<int>(f % kADepth);
+        uint32_t i = 0;
+        for (uint32_t f = set; f < n_fills; f += 2, ++i) {
+            const int slot_p = static_cast<int>(i % kADepth);
             asm volatile("cp.async.wait_group %0;" ::"n"(kADepth - 1) : "memory");
             __syncwarp();
             float v[32];
@@ -169,8 +193,8 @@ tcn_conv_kernel(const Params p) {
                 }
             }
             __syncwarp();
-            issue(slot_p);     // fill f + kADepth: its indices arrived during the previous iteration
-            load_idx();        // fill f + kADepth + 1: in flight until the next iteration
+            issue(slot_p);     // this set's fill kADepth ahead: its indices arrived during the previous iteration
+            load_idx();        // the one after that: in flight until the next iteration
             const uint32_t slot = f & (kASlots - 1);
             mbar_wait_relaxed(&a_empty[slot], ((f / kASlots) & 1) ^ 1);
             fence_after_sync();
@@ -192,43 +216,21 @@ tcn_conv_kernel(const Params p) {
             if (lane == 0) mbar_arrive(&a_full[slot]);
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp < kALd + kBLd) {
-        // ---------------- B loaders: k-atom j of the weight -> ring stage (K-major SWIZZLE_128B, hi then lo) ----------------
-        const int bt = tid - kALd * 32;  // 0 .. 127
-        const uint32_t n_fills = my_groups * n_katoms;
-        if (my_groups) {   // the first pass over the weight would otherwise pay one HBM round trip per k-atom, in series
-            const uint32_t lines = static_cast<uint32_t>(p.taps) * kC * kC * 4 / 128;
-            for (uint32_t l = bt; l < lines; l += kBLd * 32)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(p.W) + l * 128ull));
-        }
-        for (uint32_t f = 0; f < n_fills; ++f) {
-            const uint32_t j = f % n_katoms, tap = j >> 2, kg = j & 3, stage = f % kBStages;
-            float4 w[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {  // 128 rows x 8 chunks of 16 B: thread bt takes chunk (bt & 7) of rows (bt >> 3) + 16 i
-                const int n = (bt >> 3) + 16 * i, c = bt & 7;
-                w[i] = __ldg(reinterpret_cast<const float4*>(p.W + (static_cast<size_t>(tap) * kC + n) * kC + kg * 32) + c);
-            }
-            mbar_wait_relaxed(&b_empty[stage], ((f / kBStages) & 1) ^ 1);
-            uint8_t* hi_base = b_ring + stage * kBStageBytes;
-            uint8_t* lo_base = hi_base + kC * 128;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int n = (bt >> 3) + 16 * i, c = bt & 7;
-                float4 hi, lo;
-                split4(w[i], hi, lo);
-                const uint32_t off = sw128_offset(n, c, kC);   // a single k-atom: katom index 0
-                *reinterpret_cast<float4*>(hi_base + off) = hi;
-                *reinterpret_cast<float4*>(lo_base + off) = lo;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_full[stage]);
-        }
     } else if (warp == kMmaWarp) {
-        // ---------------- MMA ----------------
+        // ---------------- MMA, and the producer of the weight stages ----------------
         const uint32_t idesc = idesc_tf32(128, kC);
         const uint32_t ring_lo = desc_lo(smem_u32(b_ring));
+        const uint32_t total_katoms = my_groups * n_katoms;
+        auto refill = [&](uint32_t ka) {   // k-atom number `ka` of this CTA's sequence -> stage ka % kBStages
+            if (elect_one()) {
+                const uint32_t stage = ka % kBStages;
+                mbar_arrive_expect_tx(&b_full[stage], kBStageBytes);
+                bulk_load(b_ring + stage * kBStageBytes, p.Wp + static_cast<size_t>(ka % n_katoms) * kBStageBytes, kBStageBytes,
+                          &b_full[stage]);
+            }
+            __syncwarp();
+        };
+        for (uint32_t ka = 0; ka < kBStages && ka < total_katoms; ++ka) refill(ka);
         uint32_t fa = 0, fb = 0;
         for (uint32_t gi = 0; gi < my_groups; ++gi) {
             for (int j = 0; j < n_katoms; ++j, ++fb) {
@@ -255,6 +257,12 @@ tcn_conv_kernel(const Params p) {
                         if (j == n_katoms - 1) commit(&acc_full[acc]);
                     }
                     __syncwarp();
+                }
+                // the stage of the PREVIOUS k-atom is free once its MMAs are done -- they precede the ones just queued, so
+                // this wait ends while those still run -- and takes the k-atom kBStages ahead of it
+                if (fb >= 1 && fb - 1 + kBStages < total_katoms) {
+                    mbar_wait(&b_empty[(fb - 1) % kBStages], ((fb - 1) / kBStages) & 1);
+                    refill(fb - 1 + kBStages);
                 }
             }
         }
@@ -365,17 +373,22 @@ tcn_conv_kernel(const Params p) {
 }  // namespace tc
 }  // namespace
 
+extern "C" int64_t ltgnn_tcn_ws_floats(int32_t taps) {
+    return taps >= 1 && taps <= 8 ? static_cast<int64_t>(taps) * 4 * (tc::kBStageBytes / 4) : -1;
+}
+
 extern "C" int ltgnn_tcn_conv(int device, int64_t M, int32_t C, int32_t taps, const float* X, const int32_t* src,
                               const float* W, const float* bias, const float* gamma, const float* beta, float eps, int relu,
-                              const float* res, const int32_t* res_row, float* Y, void* stream_) {
+                              const float* res, const int32_t* res_row, float* Y, float* ws, void* stream_) {
     LTGNN_REQUIRE(M >= 0 && M < (1ll << 31) - 512, LTGNN_E_ARG, "tcn_conv: M=%lld", static_cast<long long>(M));
     LTGNN_REQUIRE(C == tc::kC, LTGNN_E_SHAPE, "tcn_conv: C=%d (the kernel is built for %d channels)", C, tc::kC);
     LTGNN_REQUIRE(taps >= 1 && taps <= 8, LTGNN_E_SHAPE, "tcn_conv: taps=%d", taps);
     LTGNN_REQUIRE((gamma == nullptr) == (beta == nullptr), LTGNN_E_ARG, "tcn_conv: gamma and beta come together");
     LTGNN_REQUIRE((res == nullptr) == (res_row == nullptr), LTGNN_E_ARG, "tcn_conv: res and res_row come together");
     if (M == 0) return LTGNN_OK;
-    LTGNN_REQUIRE(X && src && W && bias && Y, LTGNN_E_ARG, "tcn_conv: null tensor");
-    LTGNN_REQUIRE(aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(res), LTGNN_E_ALIGN, "tcn_conv: 16-byte alignment");
+    LTGNN_REQUIRE(X && src && W && bias && Y && ws, LTGNN_E_ARG, "tcn_conv: null tensor");
+    LTGNN_REQUIRE(aligned16(X) && aligned16(W) && aligned16(Y) && aligned16(res) && aligned16(ws), LTGNN_E_ALIGN,
+                  "tcn_conv: 16-byte alignment");
     const DeviceInfo* di = device_info(device);
     if (!di) return LTGNN_E_CUDA;
     LTGNN_REQUIRE(di->cc_major == 10, LTGNN_E_UNSUPPORTED, "tcn_conv: device is sm_%d%d, need sm_100", di->cc_major, di->cc_minor);
@@ -389,11 +402,15 @@ extern "C" int ltgnn_tcn_conv(int device, int64_t M, int32_t C, int32_t taps, co
     // B loaders are idle most of the time anyway and the epilogue of a group is then exposed (measured: never faster).
     const int64_t n_tiles = (M + 127) / 128;
     int tiles = 1;
-    tc::Params p{reinterpret_cast<const float4*>(X), src, W, bias, gamma, beta, reinterpret_cast<const float4*>(res), res_row,
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint8_t* wp = reinterpret_cast<uint8_t*>(ws);
+    tc::tcn_pack_weight_kernel<<<(taps * 4 * tc::kC * 8 + 255) / 256, 256, 0, stream>>>(W, wp, taps);
+    LTGNN_CUDA_TRY(cudaGetLastError());
+    tc::Params p{reinterpret_cast<const float4*>(X), src, wp, bias, gamma, beta, reinterpret_cast<const float4*>(res), res_row,
                  reinterpret_cast<float4*>(Y), static_cast<uint32_t>(M), taps, relu, eps, tiles};
     const int64_t groups = (n_tiles + tiles - 1) / tiles;
     const int grid = static_cast<int>(groups < di->sm_count ? groups : di->sm_count);
-    tc::tcn_conv_kernel<<<grid, tc::kThreads, smem, static_cast<cudaStream_t>(stream_)>>>(p);
+    tc::tcn_conv_kernel<<<grid, tc::kThreads, smem, stream>>>(p);
     LTGNN_CUDA_TRY(cudaGetLastError());
     return LTGNN_OK;
 }

@@ -929,11 +929,12 @@ def tcn_conv(x: torch.Tensor, src: torch.Tensor, weight: torch.Tensor, bias: tor
         raise ValueError("res and res_row come together")
     y = torch.empty(m, c, device=x.device, dtype=torch.float32)
     L = _lib.load()
+    ws = torch.empty(int(L.ltgnn_tcn_ws_floats(taps)), device=x.device, dtype=torch.float32)   # the packed hi / lo weight
     tok = _inst.begin("tcn_conv")
     _lib.check(L.ltgnn_tcn_conv(_dev_index(x), m, c, taps, x.data_ptr(), src.data_ptr(), weight.data_ptr(), bias.data_ptr(),
                                 None if gamma is None else gamma.data_ptr(), None if beta is None else beta.data_ptr(),
                                 float(eps), int(relu), None if res is None else res.data_ptr(),
-                                None if res_row is None else res_row.data_ptr(), y.data_ptr(), _stream(x)))
+                                None if res_row is None else res_row.data_ptr(), y.data_ptr(), ws.data_ptr(), _stream(x)))
     _inst.end(tok)
     return y
 
