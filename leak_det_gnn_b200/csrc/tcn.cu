@@ -13,11 +13,11 @@
 //                          transposition patches, split fp32 -> TF32 hi/lo, tcgen05.st into an A slot (as linear.cu).  Two
 //                          sets of four warps take the even and the odd fills: a warp runs its fills in series (~2 200
 //                          clocks each: copy latency, split, tensor-memory store, hand-over), the tensor core needs ~860
-//   warp  8     MMA + B    3xTF32, A from tensor memory; two 128-column accumulators ROTATING over the CTA's row tiles, so
-//                          that tile n + 1 is multiplied while the epilogue normalises tile n.  The weight (393 KB as
-//                          hi + lo: cannot be resident) is split and laid out ONCE per launch by tcn_pack_weight_kernel;
-//                          the elected lane brings k-atom stages (32 K values x 128 outputs, hi + lo = 32 KB) in with 1-D
-//                          bulk copies (TMA) two k-atoms ahead -- no warp converts weights inside the main loop
+//   warp  8     MMA        3xTF32, A from tensor memory; two 128-column accumulators ROTATING over the CTA's row tiles, so
+//                          that tile n + 1 is multiplied while the epilogue normalises tile n
+//   warp  17    B PRODUCER the weight (393 KB as hi + lo: cannot be resident) is split and laid out ONCE per launch by
+//                          tcn_pack_weight_kernel; this warp's elected lane brings k-atom stages (32 K values x 128 outputs,
+//                          hi + lo = 32 KB) in with 1-D bulk copies (TMA), up to three ahead of the tensor core
 //   warps 9-16  EPILOGUE   bias, LayerNorm over the 128 channels (two-pass mean / variance; the two warps that share a
 //                          row exchange partial sums through shared memory), ReLU, residual, coalesced stores via patches
 // fp32-faithful like every GEMM of this library (the residual is a small difference of pressures).
@@ -32,7 +32,7 @@ using namespace ltgnn::ptx;
 using namespace ltgnn::umma;
 
 constexpr int kC = 128;                  // channels: K per tap and N
-constexpr int kALd = 8, kMmaWarp = 8, kEp = 8, kThreads = (kALd + 1 + kEp) * 32;  // 17 warps; kALd = 2 sets of 4
+constexpr int kALd = 8, kMmaWarp = 8, kEp = 8, kBWarp = kALd + 1 + kEp, kThreads = (kALd + 1 + kEp + 1) * 32;  // 18 warps (96 registers, as with 17)
 constexpr int kTiles = 2;                // accumulators in tensor memory (and the most row tiles a group may have)
 constexpr int kASlots = 4, kSlotCols = 64;   // 2 x 128 accumulator columns + 4 x 64 A columns = the 512 of tensor memory
 constexpr int kBStages = 3, kADepth = 2;   // 8 warps x 2 patches = 64 KB of gathered rows in flight per SM
@@ -217,31 +217,61 @@ tcn_conv_kernel(const Params p) {
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == kMmaWarp) {
-        // ---------------- MMA, and the producer of the weight stages ----------------
+        // ---------------- MMA ----------------
+        // This warp is ONE serial instruction stream every fill passes through, and the tensor pipe drains whenever it is
+        // busy with anything else (a clock64 timeline showed ~900 clocks of index arithmetic, ring refills and modulo
+        // operations between two 720-clock bursts of MMA issue): ring positions and parities are carried incrementally,
+        // and the weight ring is refilled by a warp of its own.
         const uint32_t idesc = idesc_tf32(128, kC);
         const uint32_t ring_lo = desc_lo(smem_u32(b_ring));
-        const uint32_t total_katoms = my_groups * n_katoms;
-        auto refill = [&](uint32_t ka) {   // k-atom number `ka` of this CTA's sequence -> stage ka % kBStages
-            if (elect_one()) {
-                const uint32_t stage = ka % kBStages;
-                mbar_arrive_expect_tx(&b_full[stage], kBStageBytes);
-                bulk_load(b_ring + stage * kBStageBytes, p.Wp + static_cast<size_t>(ka % n_katoms) * kBStageBytes, kBStageBytes,
-                          &b_full[stage]);
+        uint32_t stage = 0, stage_par = 0, slot = 0, slot_par = 0, nt = 0;
+        if (p.tiles == 1) {
+            // one tile per group (what the host picks): two fills = two k-atoms per hand-over, 24 MMAs back to back --
+            // the tensor pipe only runs while this warp is issuing, so the waits, fences and commits are paid half as often
+            for (uint32_t gi = 0; gi < my_groups; ++gi, ++nt) {
+                const uint32_t acc = nt % kTiles, d = acc_base + acc * kC;
+                mbar_wait_relaxed(&acc_empty[acc], ((nt / kTiles) & 1) ^ 1);   // the epilogue drained it
+                for (int j = 0; j < n_katoms; j += 2) {   // n_katoms = 4 * taps: even
+                    const uint32_t stage1 = stage + 1 == kBStages ? 0 : stage + 1, par1 = stage1 ? stage_par : stage_par ^ 1;
+                    const uint32_t slot1 = slot + 1;      // slot is even here: the pair shares the parity
+                    mbar_wait_relaxed(&b_full[stage], stage_par);
+                    mbar_wait_relaxed(&b_full[stage1], par1);
+                    mbar_wait_relaxed(&a_full[slot], slot_par);
+                    mbar_wait_relaxed(&a_full[slot1], slot_par);
+                    fence_after_sync();
+                    if (elect_one()) {
+#pragma unroll
+                        for (uint32_t h = 0; h < 2; ++h) {
+                            const uint32_t st = h ? stage1 : stage, sl = h ? slot1 : slot;
+                            const uint32_t bh = ring_lo + st * (kBStageBytes >> 4), bl = bh + ((kC * 128) >> 4);
+                            const uint32_t a_hi = a_base + sl * kSlotCols, a_lo = a_hi + 32;
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + 2 * k, idesc, (j == 0 && h == 0 && k == 0) ? 0u : 1u);
+                                rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + 2 * k, idesc, 1u);
+                                rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + 2 * k, idesc, 1u);
+                            }
+                            commit(&a_empty[sl]);
+                            commit(&b_empty[st]);
+                        }
+                        if (j == n_katoms - 2) commit(&acc_full[acc]);
+                    }
+                    __syncwarp();
+                    slot = (slot + 2) & (kASlots - 1);
+                    slot_par ^= (slot == 0);
+                    stage = stage1 + 1 == kBStages ? 0 : stage1 + 1;
+                    stage_par = stage ? par1 : par1 ^ 1;
+                }
             }
-            __syncwarp();
-        };
-        for (uint32_t ka = 0; ka < kBStages && ka < total_katoms; ++ka) refill(ka);
-        uint32_t fa = 0, fb = 0;
+        } else {
         for (uint32_t gi = 0; gi < my_groups; ++gi) {
-            for (int j = 0; j < n_katoms; ++j, ++fb) {
-                const uint32_t stage = fb % kBStages;
-                mbar_wait_relaxed(&b_full[stage], (fb / kBStages) & 1);
+            for (int j = 0; j < n_katoms; ++j) {
+                mbar_wait_relaxed(&b_full[stage], stage_par);
                 const uint32_t bh = ring_lo + stage * (kBStageBytes >> 4), bl = bh + ((kC * 128) >> 4);
-                for (int tile = 0; tile < p.tiles; ++tile, ++fa) {
-                    const uint32_t slot = fa & (kASlots - 1);
-                    const uint32_t nt = gi * p.tiles + tile, acc = nt % kTiles;   // accumulators rotate over the CTA's tiles
-                    if (j == 0) mbar_wait_relaxed(&acc_empty[acc], ((nt / kTiles) & 1) ^ 1);   // the epilogue drained it
-                    mbar_wait_relaxed(&a_full[slot], (fa / kASlots) & 1);
+                for (int tile = 0; tile < p.tiles; ++tile) {
+                    const uint32_t ntile = nt + tile, acc = ntile % kTiles;   // accumulators rotate over the CTA's tiles
+                    if (j == 0) mbar_wait_relaxed(&acc_empty[acc], ((ntile / kTiles) & 1) ^ 1);   // the epilogue drained it
+                    mbar_wait_relaxed(&a_full[slot], slot_par);
                     fence_after_sync();
                     if (elect_one()) {
                         const uint32_t d = acc_base + acc * kC;
@@ -257,13 +287,32 @@ tcn_conv_kernel(const Params p) {
                         if (j == n_katoms - 1) commit(&acc_full[acc]);
                     }
                     __syncwarp();
+                    slot = (slot + 1) & (kASlots - 1);
+                    slot_par ^= (slot == 0);
                 }
-                // the stage of the PREVIOUS k-atom is free once its MMAs are done -- they precede the ones just queued, so
-                // this wait ends while those still run -- and takes the k-atom kBStages ahead of it
-                if (fb >= 1 && fb - 1 + kBStages < total_katoms) {
-                    mbar_wait(&b_empty[(fb - 1) % kBStages], ((fb - 1) / kBStages) & 1);
-                    refill(fb - 1 + kBStages);
+                if (++stage == kBStages) {
+                    stage = 0;
+                    stage_par ^= 1;
                 }
+            }
+            nt += p.tiles;
+        }
+        }
+    } else if (warp == kBWarp) {
+        // ---------------- weight ring producer: k-atom stages by 1-D bulk copies (TMA), up to kBStages ahead ----------------
+        const uint32_t total_katoms = my_groups * n_katoms;
+        uint32_t stage = 0, par = 1, j = 0;   // parity 1 passes on a fresh barrier: the first pass over the ring does not wait
+        for (uint32_t ka = 0; ka < total_katoms; ++ka) {
+            mbar_wait_relaxed(&b_empty[stage], par);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&b_full[stage], kBStageBytes);
+                bulk_load(b_ring + stage * kBStageBytes, p.Wp + static_cast<size_t>(j) * kBStageBytes, kBStageBytes, &b_full[stage]);
+            }
+            __syncwarp();
+            if (++j == static_cast<uint32_t>(n_katoms)) j = 0;
+            if (++stage == kBStages) {
+                stage = 0;
+                par ^= 1;
             }
         }
     } else {
@@ -342,18 +391,24 @@ tcn_conv_kernel(const Params p) {
                             v[j + i] = p.relu ? fmaxf(y, 0.f) : y;
                         }
                     }
+                    // residual rows: all eight loads of this chunk are in flight before the first is used (taken one by
+                    // one inside the store loop they were 16 serial L2 round trips per tile: the residual convolutions ran
+                    // 50 % longer per row than the others)
+                    float4 a[8];
+                    const int c4 = (half * 64 + c0) / 4 + ch;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int32_t rr = __shfl_sync(0xffffffffu, my_res, 4 * k + sub);
+                        a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rr >= 0) a[k] = __ldg(p.res + static_cast<size_t>(rr) * (kC / 4) + c4);
+                    }
                     float4 g[8];
                     patch::transpose_out(pt, v, g);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const uint32_t r = row0 + 4 * k + sub;
-                        const int32_t rr = __shfl_sync(0xffffffffu, my_res, 4 * k + sub);
                         if (r < p.M) {
-                            const int c4 = (half * 64 + c0) / 4 + ch;
-                            if (rr >= 0) {
-                                const float4 a = __ldg(p.res + static_cast<size_t>(rr) * (kC / 4) + c4);
-                                g[k].x += a.x; g[k].y += a.y; g[k].z += a.z; g[k].w += a.w;
-                            }
+                            g[k].x += a[k].x; g[k].y += a[k].y; g[k].z += a[k].z; g[k].w += a[k].w;
                             p.Y[static_cast<size_t>(r) * (kC / 4) + c4] = g[k];
                         }
                     }
