@@ -184,6 +184,36 @@ gcn_layer_fwd_kernel(const Params p) {
             fence_after_sync();
             for (int t = 0; t < p.T; ++t) {
                 const uint32_t d = acc_base + t * p.D;
+                if (p.n_slots == 4) {
+                    // the two slots of one patch (32 K values) per hand-over: 12 MMAs back to back.  The tensor pipe only
+                    // runs while this warp is issuing, and a wait + fence + election + commit round costs several times
+                    // the 192 clocks of one slot's six MMAs -- taken slot by slot, the window's GEMM (24 slots) was longer
+                    // than the aggregation of a slice it is meant to hide under
+                    for (int kh = 0; kh < 2 * n_kg; kh += 2, sf += 2) {
+                        const uint32_t slot = sf & 3, par = (sf >> 2) & 1;   // sf is even: slots (0, 1) or (2, 3), one parity
+                        mbar_wait_relaxed(&bar_full[slot], par);
+                        mbar_wait_relaxed(&bar_full[slot + 1], par);
+                        fence_after_sync();
+                        if (elect_one()) {
+#pragma unroll
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                const uint32_t a_hi = a_base + (slot + h) * kSlotCols, a_lo = a_hi + 16;
+                                const uint32_t bbase = static_cast<uint32_t>(kh >> 1) * kg_units + 4 * h;
+#pragma unroll
+                                for (uint32_t k = 0; k < 2; ++k) {
+                                    const uint32_t boff = bbase + 2 * k;
+                                    rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (kh == 0 && h == 0 && k == 0) ? 0u : 1u);
+                                    rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
+                                    rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
+                                }
+                                commit(&bar_empty[slot + h]);
+                            }
+                            if (t == p.T - 1 && kh == 2 * n_kg - 2) commit(&bar_acc_full);
+                        }
+                        __syncwarp();
+                    }
+                    continue;
+                }
                 for (int kh = 0; kh < 2 * n_kg; ++kh, ++sf) {  // 16 K values per slot
                     const uint32_t slot = sf & slot_mask;
                     mbar_wait_relaxed(&bar_full[slot], (sf >> slot_log2) & 1);

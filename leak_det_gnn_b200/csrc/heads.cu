@@ -228,23 +228,31 @@ pipe_head_fwd_kernel(const float4* __restrict__ x, const int2* __restrict__ ends
             const uint32_t a = t & 1;
             mbar_wait_relaxed(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
             const uint32_t d = acc_base + a * kN;
+            // two stages (24 MMAs) per hand-over: the tensor pipe only runs while this warp is issuing (its queue is
+            // shallow), so waits, fence, election and commits are paid once per pair.  6 t + s is even: the pair sits in
+            // slots (0, 1) or (2, 3) and shares the ring parity.
 #pragma unroll 1
-            for (uint32_t s = 0; s < 6; ++s) {
-                const uint32_t stage = 6 * t + s, slot = stage & 3;
-                const uint32_t kg = s < 3 ? 2 * s : 2 * (s - 3) + 1;  // K block of W1 this stage multiplies
-                mbar_wait_relaxed(&bar_full[slot], (stage >> 2) & 1);
+            for (uint32_t s = 0; s < 6; s += 2) {
+                const uint32_t stage = 6 * t + s, slot = stage & 3, par = (stage >> 2) & 1;
+                mbar_wait_relaxed(&bar_full[slot], par);
+                mbar_wait_relaxed(&bar_full[slot + 1], par);
                 fence_after_sync();
                 if (elect_one()) {
-                    const uint32_t a_hi = a_base + slot * kStageCols, a_lo = a_hi + 32;
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k) {
-                        const uint32_t boff = kg * kg_units + 2 * k;
-                        rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (s == 0 && k == 0) ? 0u : 1u);
-                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
-                        rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
+                    for (uint32_t h = 0; h < 2; ++h) {
+                        const uint32_t sh = s + h;
+                        const uint32_t kg = sh < 3 ? 2 * sh : 2 * (sh - 3) + 1;  // K block of W1 this stage multiplies
+                        const uint32_t a_hi = a_base + (slot + h) * kStageCols, a_lo = a_hi + 32;
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            const uint32_t boff = kg * kg_units + 2 * k;
+                            rowgemm_ts::mma_tf32_ts(d, a_lo + 8 * k, bh + boff, idesc, (sh == 0 && k == 0) ? 0u : 1u);
+                            rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bl + boff, idesc, 1u);
+                            rowgemm_ts::mma_tf32_ts(d, a_hi + 8 * k, bh + boff, idesc, 1u);
+                        }
+                        commit(&bar_empty[slot + h]);
                     }
-                    commit(&bar_empty[slot]);
-                    if (s == 5) commit(&bar_tfull[a]);
+                    if (s == 4) commit(&bar_tfull[a]);
                 }
                 __syncwarp();
             }
