@@ -477,24 +477,27 @@ pipe_head_bwd_dx_kernel(const DpreLoader loader, float4* __restrict__ dx, const 
             const uint32_t a = t & 1;
             mbar_wait_relaxed(&bar_tempty[a], ((t >> 1) & 1) ^ 1);
             const uint32_t d = acc_base + a * kN;
-#pragma unroll 1
-            for (uint32_t kg = 0; kg < 4; ++kg) {
-                const uint32_t stage = 4 * t + kg, slot = stage & (kStages - 1);
-                mbar_wait_relaxed(&bar_full[slot], (stage / kStages) & 1);
-                fence_after_sync();
-                if (elect_one()) {
-                    const uint32_t a_op = a_base + slot * kStageCols;
+            // the four stages of a tile per hand-over (32 MMAs back to back; the ring is two tiles deep, so the loaders
+            // fill the next tile meanwhile): the tensor pipe only runs while this warp is issuing
+            const uint32_t stage0 = 4 * t, slot0 = stage0 & (kStages - 1), par = (stage0 / kStages) & 1;
+#pragma unroll
+            for (uint32_t kg = 0; kg < 4; ++kg) mbar_wait_relaxed(&bar_full[slot0 + kg], par);
+            fence_after_sync();
+            if (elect_one()) {
+#pragma unroll
+                for (uint32_t kg = 0; kg < 4; ++kg) {
+                    const uint32_t a_op = a_base + (slot0 + kg) * kStageCols;
 #pragma unroll
                     for (uint32_t k = 0; k < 4; ++k) {
                         const uint32_t boff = kg * kg_units + 2 * k;
                         rowgemm_ts::mma_tf32_ts(d, a_op + 8 * k, bl + boff, idesc, (kg == 0 && k == 0) ? 0u : 1u);
                         rowgemm_ts::mma_tf32_ts(d, a_op + 8 * k, bh + boff, idesc, 1u);
                     }
-                    commit(&bar_empty[slot]);
-                    if (kg == 3) commit(&bar_tfull[a]);
+                    commit(&bar_empty[slot0 + kg]);
                 }
-                __syncwarp();
+                commit(&bar_tfull[a]);
             }
+            __syncwarp();
         }
     } else if (warp > kMmaWarp + kEpWarps) {
         // ---- gather: this warp owns chunks j, j + 4, ... of every window and two staging buffers; a chunk's bulk copy
