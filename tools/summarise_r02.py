@@ -124,8 +124,9 @@ def full(rep: str, out: str, key: str = "") -> None:
         table = json.loads(bp.read_text()) if bp.exists() else {}
         ops = table.setdefault(key, {})
         for k, v in traffic.items():
-            if v is not None and k in op_of:
-                ops[op_of[k]] = v
+            name = "pipe_head_bwd_w" if k.startswith("tgrad<HeadLive,HeadFeatSlice") else op_of.get(k)
+            if v is not None and name:
+                ops[name] = v
         table["_note_r02"] = ("GNN-stack entries refreshed from profiles/r02*_kernels_ncu_full.csv (ncu --set full, per launch); "
                               "node_init_bwd = its streaming pass (gate_extract_kernel) only; GRU entries are round 1's (kernels unchanged)")
         bp.write_text(json.dumps(table, indent=1))
