@@ -73,3 +73,17 @@ def test_live_mask_and_blocked32_layouts_documented_in_the_header():
     rows = logical.reshape(l * qp, w)
     blocked = rows.reshape(l * qp // 32, 32, w // 4, 4).permute(0, 2, 1, 3).contiguous()
     assert torch.equal(ops.unblock32(blocked, l, q_), logical[:, :q_])
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_graphed_step_and_device_seed_need_cuda():
+    """The CUDA-graph training step and the device-resident dropout seed have no CPU form either."""
+    from leak_det_gnn_b200 import ops
+    from leak_det_gnn_b200.graphed import GraphedStep
+    from leak_det_gnn_b200.parallel import FlatGradBucket
+
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.device_seed(torch.zeros(1, dtype=torch.int64))
+    m = torch.nn.Linear(4, 4)
+    with pytest.raises(ValueError, match="CUDA"):
+        GraphedStep(m, lambda: m(torch.zeros(1, 4)).sum(), None, FlatGradBucket(m.parameters()))
