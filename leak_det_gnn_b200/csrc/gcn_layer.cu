@@ -94,7 +94,13 @@ gcn_layer_fwd_kernel(const Params p) {
     }
     rowgemm_ts::fill_b(b_hi, b_lo, p.W, p.K, 0, p.K, p.D, tid, kThreads);
     for (int i = tid; i <= p.n; i += kThreads) s_rowptr[i] = __ldg(p.rowptr + i);
-    for (int i = tid; i < p.nnz; i += kThreads) s_colval[i] = __ldg(p.colval + i);
+    for (int i = tid; i < p.nnz; i += kThreads) {
+        // .x becomes the BYTE offset of chunk 0 of the neighbour's stage row, swizzle term included: chunk q of row c lives
+        // at c * 128 + ((q ^ (c & 7)) << 4) = (c * 128 + ((c & 7) << 4)) ^ (q << 4) -- one XOR per entry in the gather loop
+        int2 cv = __ldg(p.colval + i);
+        cv.x = cv.x * 128 + ((cv.x & 7) << 4);
+        s_colval[i] = cv;
+    }
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -240,6 +246,8 @@ gcn_layer_fwd_kernel(const Params p) {
         const int cw = warp - kMmaWarp - 1;          // 0 .. 23
         const int q4 = warp & 3, dj = cw >> 2;       // tensor-memory lane quadrant = warp % 4; this warp drains tiles dj, dj + 6
         const int g = lane >> 3, q = lane & 7;       // aggregation: row within the warp's group of 4, float4 of the slice
+        const uint8_t* stage_b = reinterpret_cast<const uint8_t*>(stage);
+        const int qx = q << 4;
         const uint64_t seed = launch_seed(p.drop_seed, p.seed_src);
         for (uint32_t wi = 0; wi < n_win; ++wi) {
             const int64_t b = w_first + static_cast<int64_t>(wi) * w_step;
@@ -284,18 +292,18 @@ gcn_layer_fwd_kernel(const Params p) {
                 while (k0 < e0 && k1 < e1) {
                     const int2 c0 = s_colval[k0++];
                     const int2 c1 = s_colval[k1++];
-                    const float4 x0 = stage[c0.x * 8 + (q ^ (c0.x & 7))];
-                    const float4 x1 = stage[c1.x * 8 + (q ^ (c1.x & 7))];
+                    const float4 x0 = *reinterpret_cast<const float4*>(stage_b + (c0.x ^ qx));
+                    const float4 x1 = *reinterpret_cast<const float4*>(stage_b + (c1.x ^ qx));
                     fma2(a0, __int_as_float(c0.y), x0);
                     fma2(a1, __int_as_float(c1.y), x1);
                 }
                 for (; k0 < e0; ++k0) {
                     const int2 c0 = s_colval[k0];
-                    fma2(a0, __int_as_float(c0.y), stage[c0.x * 8 + (q ^ (c0.x & 7))]);
+                    fma2(a0, __int_as_float(c0.y), *reinterpret_cast<const float4*>(stage_b + (c0.x ^ qx)));
                 }
                 for (; k1 < e1; ++k1) {
                     const int2 c1 = s_colval[k1];
-                    fma2(a1, __int_as_float(c1.y), stage[c1.x * 8 + (q ^ (c1.x & 7))]);
+                    fma2(a1, __int_as_float(c1.y), *reinterpret_cast<const float4*>(stage_b + (c1.x ^ qx)));
                 }
                 if (p.bias) {
                     a0.x = __fadd_rn(a0.x, bias4.x); a0.y = __fadd_rn(a0.y, bias4.y);
